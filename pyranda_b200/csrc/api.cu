@@ -1,0 +1,662 @@
+// C ABI of libparcop_b200 (include/parcop_b200.h): plan construction and operator dispatch.
+//
+// Replaces, for the hot path only: parcop.f90 (the f2py surface), objects.f90 (global object
+// tables -> one opaque plan), compact.f90:55-319 (operator suite setup), compact_operators.f90
+// (null-op rule, metric scale) and the Cartesian / curvilinear branches of operators.f90.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/parcop_b200.h"
+#include "kernels.cuh"
+#include "tables.hpp"
+
+using namespace pb;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+int g_chunk_len = 64;
+
+#define PB_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t err__ = (call);                                                            \
+    if (err__ != cudaSuccess)                                                              \
+      return fail(PB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));     \
+  } while (0)
+
+struct SweepPlan {
+  bool built = false, null_op = false, split = false;
+  int kind = 0, dir = 0, np = 1, rank = 0, n = 0;
+  Stencil st;
+  SweepDev dev;
+  double4 *RC = nullptr;  // rank-level spike columns [m]
+  double *GR = nullptr;   // rank-level reduced-system rows [4][4np]
+  std::vector<void *> owned;
+};
+
+}  // namespace
+
+struct pb_plan {
+  int n[3], p[3], c[3], a[3];
+  int coordsys = 0, device = 0;
+  double d[3], x1f[3], xnf[3];
+  bool periodic[3], null_dir[3];
+  size_t npts = 0;
+  SweepPlan sw[K_COUNT][3];
+  SweepPlan custom_d1[3];
+  std::vector<double *> scratch;   // device work fields, npts each
+  double *red_partial = nullptr, *red_result = nullptr, *red_host = nullptr;
+  std::map<std::string, double *> mesh;  // device mesh arrays
+  bool mesh_set = false;
+};
+
+namespace {
+
+template <typename T>
+int upload(SweepPlan &sp, const std::vector<T> &h, const T **dptr) {
+  T *d = nullptr;
+  PB_CUDA(cudaMalloc(&d, sizeof(T) * (h.empty() ? 1 : h.size())));
+  if (!h.empty()) PB_CUDA(cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  sp.owned.push_back(d);
+  *dptr = d;
+  return PB_OK;
+}
+
+void free_sweep(SweepPlan &sp) {
+  for (void *q : sp.owned) cudaFree(q);
+  sp.owned.clear();
+  sp.built = false;
+}
+
+// One operator along one axis: compact_basetype.f90:65-209 re-expressed for the chunked kernels.
+int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
+  sp.kind = kind; sp.dir = dir; sp.n = pl->n[dir]; sp.np = pl->p[dir]; sp.rank = pl->c[dir];
+  sp.st = make_stencil((Kind)kind);
+  sp.null_op = pl->n[dir] < 4;  // compact.f90:95-97, compact_basetype.f90:101-103
+  sp.split = sp.np > 1;
+  sp.built = true;
+  if (sp.null_op) return PB_OK;
+  const int n = sp.n, np = sp.np, m = n / np, r0 = sp.rank * m;
+  if (m < 16)
+    return fail(PB_ERR_UNSUPPORTED, "local extent " + std::to_string(m) + " along axis " + std::to_string(dir) +
+                                        " is below 16 (the reference's own decomposition bound, pyrandaMPI.py:785-792)");
+  const Stencil &st = sp.st;
+  std::vector<double> bands = assemble_bands(st, n, periodic);
+  std::vector<double> local(bands.begin() + (size_t)r0 * 5, bands.begin() + (size_t)(r0 + m) * 5);
+  const bool cyclic_local = periodic && np == 1;
+  const int P = choose_chunks(m, g_chunk_len);
+  if (P > kMaxChunks) return fail(PB_ERR_UNSUPPORTED, "too many chunks");
+
+  SweepDev &dv = sp.dev;
+  memset(&dv, 0, sizeof(dv));
+  dv.m = m; dv.P = P; dv.C = m / P;
+  const int ax = pl->a[0], ay = pl->a[1], az = pl->a[2];
+  if (dir == 0) { dv.nfast = ay * az; dv.nouter = 1; dv.rstride = 1; dv.ostride = 0; }
+  else if (dir == 1) { dv.nfast = ax; dv.nouter = az; dv.rstride = ax; dv.ostride = (long)ax * ay; }
+  else { dv.nfast = ax; dv.nouter = ay; dv.rstride = (long)ax * ay; dv.ostride = ax; }
+  for (int l = 0; l < 9; ++l) dv.ari[l] = st.ari[l];
+  // closure rows belong to the ranks that own the physical boundary
+  for (int r = 0; r < 4; ++r)
+    for (int l = 0; l < 9; ++l) { dv.arb_lo[r][l] = st.arb_lo[r][l]; dv.arb_hi[r][l] = st.arb_hi[r][l]; }
+  dv.phys_lo = (!periodic && sp.rank == 0) ? 1 : 0;
+  dv.phys_hi = (!periodic && sp.rank == np - 1) ? 1 : 0;
+  dv.wrap = cyclic_local ? 1 : 0;
+  dv.implicit = st.implicit ? 1 : 0;
+  dv.add_v = (st.null_option == 1) ? 1 : 0;
+  const double dd = pl->d[dir];
+  dv.scale = st.post == 1 ? 1.0 / dd : (st.post == 2 ? 1.0 / (dd * dd) : 1.0);  // compact_operators.f90:43,152
+
+  if (st.fam == F_R3 && (dv.phys_lo || dv.phys_hi)) {
+    // compact_r3.f90:89-104 multiplies zero ghost values by these weights; they must vanish
+    for (int r = 0; r < 3; ++r)
+      for (int l = 0; l < 3 - r; ++l)
+        if (st.arb_lo[r][l] != 0.0 || st.arb_hi[3 - r][6 - l] != 0.0)
+          return fail(PB_ERR_UNSUPPORTED, "r3 closure rows reach outside the domain");
+  }
+  if (st.implicit) {
+    Partition part;
+    try { part = build_partition(m, local, cyclic_local, P); }
+    catch (const std::exception &ex) { return fail(PB_ERR_ARG, ex.what()); }
+    for (int q = 0; q < P; ++q) dv.ctype[q] = part.ctype[q];
+    std::vector<double2> luf((size_t)part.ntypes * dv.C);
+    std::vector<double4> lub((size_t)part.ntypes * dv.C), rc((size_t)part.ntypes * dv.C);
+    for (size_t t = 0; t < luf.size(); ++t) {
+      luf[t] = make_double2(part.lu[t * 5 + 0], part.lu[t * 5 + 1]);
+      lub[t] = make_double4(part.lu[t * 5 + 2], part.lu[t * 5 + 3], part.lu[t * 5 + 4], 0.0);
+      rc[t] = make_double4(part.rc[t * 4 + 0], part.rc[t * 4 + 1], part.rc[t * 4 + 2], part.rc[t * 4 + 3]);
+    }
+    int rcv;
+    if ((rcv = upload(sp, luf, &dv.lu_f)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, lub, &dv.lu_b)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, rc, &dv.rc)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, part.G, &dv.G)) != PB_OK) return rcv;
+    if (sp.split) {
+      // rank level: the same partition algebra with ranks as chunks (compact_basetype.f90:150-198)
+      Partition rp;
+      try { rp = build_partition(n, bands, periodic, np); }
+      catch (const std::exception &ex) { return fail(PB_ERR_ARG, ex.what()); }
+      const int t = rp.ctype[sp.rank];
+      std::vector<double4> RC(m);
+      for (int i = 0; i < m; ++i) {
+        const double *q = &rp.rc[((size_t)t * m + i) * 4];
+        RC[i] = make_double4(q[0], q[1], q[2], q[3]);
+      }
+      std::vector<double> GR(rp.G.begin() + (size_t)sp.rank * 16 * np, rp.G.begin() + (size_t)(sp.rank + 1) * 16 * np);
+      const double4 *dRC; const double *dGR;
+      if ((rcv = upload(sp, RC, &dRC)) != PB_OK) return rcv;
+      if ((rcv = upload(sp, GR, &dGR)) != PB_OK) return rcv;
+      sp.RC = const_cast<double4 *>(dRC);
+      sp.GR = const_cast<double *>(dGR);
+    }
+  }
+  return PB_OK;
+}
+
+int bc_code(const char *s, int *code) {
+  if (!s) return PB_ERR_ARG;
+  if (!strncmp(s, "NONE", 4)) { *code = 0; return PB_OK; }
+  if (!strncmp(s, "PERI", 4)) { *code = 1; return PB_OK; }
+  if (!strncmp(s, "SYMM", 4)) { *code = 2; return PB_OK; }
+  return PB_ERR_ARG;
+}
+
+int get_scratch(pb_plan *pl, size_t k, double **out) {
+  while (pl->scratch.size() <= k) {
+    double *d = nullptr;
+    PB_CUDA(cudaMalloc(&d, sizeof(double) * pl->npts));
+    pl->scratch.push_back(d);
+  }
+  *out = pl->scratch[k];
+  return PB_OK;
+}
+
+const EpiArgs kStore = {EPI_STORE, 0.0, nullptr};
+
+// d1x..filterz of compact_operators.f90 for a non-split direction
+int apply_dir(pb_plan *pl, SweepPlan &sp, const double *in, double *out, const EpiArgs &epi, cudaStream_t st) {
+  const long N = (long)pl->npts;
+  if (!sp.built) return fail(PB_ERR_STATE, "operator not built");
+  if (in == out) return fail(PB_ERR_ARG, "operator output must not alias its input");
+  if (sp.null_op) {
+    // compact_operators.f90:24-29 (zero) / :397-402 (copy)
+    if (sp.st.null_option == 1) {
+      if (epi.mode != EPI_STORE) return fail(PB_ERR_ARG, "null filter with a composite epilogue");
+      PB_CUDA(launch_copy(N, in, out, st));
+    } else if (epi.mode == EPI_STORE || epi.mode == EPI_RING_SET) {
+      PB_CUDA(launch_fill(N, 0.0, out, st));
+    }
+    return PB_OK;
+  }
+  if (sp.split)
+    return fail(PB_ERR_STATE, "this axis is split across ranks: use pb_z_pack_halo / pb_z_local / pb_z_finish");
+  if (sp.dir == 0) PB_CUDA(launch_sweep_x(sp.st.fam, 0, sp.dev, in, out, epi, st));
+  else PB_CUDA(launch_sweep_yz(sp.st.fam, 0, sp.dev, in, out, nullptr, nullptr, nullptr, epi, st));
+  return PB_OK;
+}
+
+double *mesh_arr(const pb_plan *pl, const char *name) {
+  auto it = pl->mesh.find(name);
+  return it == pl->mesh.end() ? nullptr : it->second;
+}
+
+int new_mesh_arr(pb_plan *pl, const char *name, double **out) {
+  double *d = mesh_arr(pl, name);
+  if (!d) {
+    PB_CUDA(cudaMalloc(&d, sizeof(double) * pl->npts));
+    pl->mesh[name] = d;
+  }
+  *out = d;
+  return PB_OK;
+}
+
+int filter3(pb_plan *pl, int kind, const double *in, double *out, cudaStream_t st) {
+  // operators.f90:849-851 / :873-875: x -> y -> z through one work array
+  double *tmp;
+  int rc;
+  if ((rc = get_scratch(pl, 0, &tmp)) != PB_OK) return rc;
+  if ((rc = apply_dir(pl, pl->sw[kind][0], in, out, kStore, st)) != PB_OK) return rc;
+  if ((rc = apply_dir(pl, pl->sw[kind][1], out, tmp, kStore, st)) != PB_OK) return rc;
+  return apply_dir(pl, pl->sw[kind][2], tmp, out, kStore, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pb_last_error(void) { return g_err.c_str(); }
+const char *pb_version(void) { return "parcop_b200 0.1 (sm_100a)"; }
+long pb_launch_count(void) { return launch_count(); }
+
+int pb_set_tuning(int lines_yz, int lines_x, int chunk_len) {
+  if (lines_yz > 0) set_yz_lines(lines_yz);
+  if (lines_x > 0) set_x_lines(lines_x);
+  if (chunk_len >= 16) g_chunk_len = chunk_len;
+  return PB_OK;
+}
+
+int pb_plan_create(pb_plan **plan, int nx, int ny, int nz, int px, int py, int pz, int cx, int cy, int cz,
+                   int coordsys, double x1, double xn, double y1, double yn, double z1, double zn,
+                   const char *bx1, const char *bxn, const char *by1, const char *byn, const char *bz1,
+                   const char *bzn, int device) {
+  if (!plan) return fail(PB_ERR_ARG, "plan is NULL");
+  *plan = nullptr;
+  if (nx < 1 || ny < 1 || nz < 1 || px < 1 || py < 1 || pz < 1) return fail(PB_ERR_ARG, "sizes must be positive");
+  if (nx % px || ny % py || nz % pz) return fail(PB_ERR_ARG, "grid not divisible by the processor grid (comm.f90:189-206)");
+  if (px != 1 || py != 1) return fail(PB_ERR_UNSUPPORTED, "only z-slab decompositions (px = py = 1) are supported");
+  if (cx != 0 || cy != 0 || cz < 0 || cz >= pz) return fail(PB_ERR_ARG, "rank coordinates outside the processor grid");
+  if (coordsys != 0 && coordsys != 3) return fail(PB_ERR_UNSUPPORTED, "coordsys must be 0 (Cartesian) or 3 (curvilinear)");
+  const char *bs[3][2] = {{bx1, bxn}, {by1, byn}, {bz1, bzn}};
+  int bcode[3][2];
+  for (int d = 0; d < 3; ++d)
+    for (int s = 0; s < 2; ++s) {
+      if (bc_code(bs[d][s], &bcode[d][s]) != PB_OK) return fail(PB_ERR_ARG, "boundary strings must be NONE, PERI or SYMM");
+      if (bcode[d][s] == 2) return fail(PB_ERR_UNSUPPORTED, "SYMM boundaries are not implemented on the CUDA path");
+    }
+  if (device >= 0) PB_CUDA(cudaSetDevice(device));
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+
+  pb_plan *pl = new pb_plan();
+  pl->device = dev; pl->coordsys = coordsys;
+  const int nn[3] = {nx, ny, nz}, pp[3] = {px, py, pz}, cc[3] = {cx, cy, cz};
+  const double lo[3] = {x1, y1, z1}, hi[3] = {xn, yn, zn};
+  for (int d = 0; d < 3; ++d) {
+    pl->n[d] = nn[d]; pl->p[d] = pp[d]; pl->c[d] = cc[d]; pl->a[d] = nn[d] / pp[d];
+    // parcop.f90:46-56 (nodes -> faces) then patch.f90:83-85
+    const double dn = (hi[d] - lo[d]) / (double)(nn[d] - 1 > 1 ? nn[d] - 1 : 1);
+    pl->x1f[d] = lo[d] - dn / 2.0; pl->xnf[d] = hi[d] + dn / 2.0;
+    pl->d[d] = (pl->xnf[d] - pl->x1f[d]) / (double)nn[d];
+    pl->periodic[d] = bcode[d][0] == 1;  // patch.f90:89-109: periodicity follows the lower string
+    pl->null_dir[d] = nn[d] < 4;
+  }
+  pl->npts = (size_t)pl->a[0] * pl->a[1] * pl->a[2];
+  for (int k = 0; k < K_COUNT; ++k)
+    for (int d = 0; d < 3; ++d) {
+      int rc = build_sweep(pl, pl->sw[k][d], k, d, pl->periodic[d]);
+      if (rc != PB_OK) { pb_plan_destroy(pl); return rc; }
+    }
+  if (cudaMalloc(&pl->red_partial, sizeof(double) * 2048) != cudaSuccess ||
+      cudaMalloc(&pl->red_result, sizeof(double)) != cudaSuccess ||
+      cudaMallocHost(&pl->red_host, sizeof(double)) != cudaSuccess) {
+    pb_plan_destroy(pl);
+    return fail(PB_ERR_CUDA, "allocation of reduction buffers failed");
+  }
+  *plan = pl;
+  return PB_OK;
+}
+
+int pb_plan_destroy(pb_plan *pl) {
+  if (!pl) return PB_OK;
+  for (int k = 0; k < K_COUNT; ++k)
+    for (int d = 0; d < 3; ++d) free_sweep(pl->sw[k][d]);
+  for (int d = 0; d < 3; ++d) free_sweep(pl->custom_d1[d]);
+  for (double *q : pl->scratch) cudaFree(q);
+  for (auto &kv : pl->mesh) cudaFree(kv.second);
+  if (pl->red_partial) cudaFree(pl->red_partial);
+  if (pl->red_result) cudaFree(pl->red_result);
+  if (pl->red_host) cudaFreeHost(pl->red_host);
+  delete pl;
+  return PB_OK;
+}
+
+int pb_plan_extents(const pb_plan *pl, int *ax, int *ay, int *az) {
+  if (!pl) return fail(PB_ERR_ARG, "plan is NULL");
+  if (ax) *ax = pl->a[0];
+  if (ay) *ay = pl->a[1];
+  if (az) *az = pl->a[2];
+  return PB_OK;
+}
+int pb_plan_spacing(const pb_plan *pl, double *dx, double *dy, double *dz) {
+  if (!pl) return fail(PB_ERR_ARG, "plan is NULL");
+  if (dx) *dx = pl->d[0];
+  if (dy) *dy = pl->d[1];
+  if (dz) *dz = pl->d[2];
+  return PB_OK;
+}
+
+int pb_plan_set_mesh(pb_plan *pl, const double *x, const double *y, const double *z, int periodic_grid) {
+  if (!pl) return fail(PB_ERR_ARG, "plan is NULL");
+  const size_t N = pl->npts;
+  const int ax = pl->a[0], ay = pl->a[1], az = pl->a[2];
+  const bool given = x && y && z;
+  if (pl->coordsys == 3 && !given) return fail(PB_ERR_ARG, "curvilinear meshes need x, y, z (setup_mesh_x3)");
+  double *dxg, *dyg, *dzg, *d1, *d2, *d3, *cv, *gl;
+  int rc;
+  if ((rc = new_mesh_arr(pl, "x", &dxg)) || (rc = new_mesh_arr(pl, "y", &dyg)) || (rc = new_mesh_arr(pl, "z", &dzg)) ||
+      (rc = new_mesh_arr(pl, "d1", &d1)) || (rc = new_mesh_arr(pl, "d2", &d2)) || (rc = new_mesh_arr(pl, "d3", &d3)) ||
+      (rc = new_mesh_arr(pl, "CellVol", &cv)) || (rc = new_mesh_arr(pl, "GridLen", &gl)))
+    return rc;
+  if (given) {
+    PB_CUDA(cudaMemcpy(dxg, x, sizeof(double) * N, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(dyg, y, sizeof(double) * N, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(dzg, z, sizeof(double) * N, cudaMemcpyHostToDevice));
+  } else {
+    // mesh.f90:173-177: cell centres of the uniform grid, global index offset by the rank's slab
+    std::vector<double> hx(N), hy(N), hz(N);
+    for (int k = 0; k < az; ++k)
+      for (int j = 0; j < ay; ++j)
+        for (int i = 0; i < ax; ++i) {
+          const size_t t = i + (size_t)ax * (j + (size_t)ay * k);
+          hx[t] = pl->x1f[0] + (double)(2 * (pl->c[0] * ax + i + 1) - 1) * 0.5 * pl->d[0];
+          hy[t] = pl->x1f[1] + (double)(2 * (pl->c[1] * ay + j + 1) - 1) * 0.5 * pl->d[1];
+          hz[t] = pl->x1f[2] + (double)(2 * (pl->c[2] * az + k + 1) - 1) * 0.5 * pl->d[2];
+        }
+    PB_CUDA(cudaMemcpy(dxg, hx.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(dyg, hy.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(dzg, hz.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  }
+  cudaStream_t st = 0;
+  if (pl->coordsys == 0) {
+    // mesh.f90:191-212
+    const double dx = pl->d[0], dy = pl->d[1], dz = pl->d[2];
+    const double v1 = pl->n[0] == 1 ? fmax(dy, dz) : dx, v2 = pl->n[1] == 1 ? fmax(dx, dz) : dy,
+                 v3 = pl->n[2] == 1 ? fmax(dx, dy) : dz;
+    PB_CUDA(launch_fill((long)N, v1, d1, st));
+    PB_CUDA(launch_fill((long)N, v2, d2, st));
+    PB_CUDA(launch_fill((long)N, v3, d3, st));
+    PB_CUDA(launch_fill((long)N, dx * dy * dz, cv, st));
+    PB_CUDA(launch_fill((long)N, fmin(v1, fmin(v2, v3)), gl, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    pl->mesh_set = true;
+    return PB_OK;
+  }
+  // curvilinear, mesh.f90:244-358
+  if (pl->p[2] > 1) return fail(PB_ERR_UNSUPPORTED, "curvilinear metrics on a split z axis are not implemented");
+  const char *jn[9] = {"_dxdA", "_dxdB", "_dxdC", "_dydA", "_dydB", "_dydC", "_dzdA", "_dzdB", "_dzdC"};
+  const char *in[9] = {"dAx", "dAy", "dAz", "dBx", "dBy", "dBz", "dCx", "dCy", "dCz"};
+  double *J[9], *I[9], *det;
+  for (int k = 0; k < 9; ++k)
+    if ((rc = new_mesh_arr(pl, jn[k], &J[k])) || (rc = new_mesh_arr(pl, in[k], &I[k]))) return rc;
+  if ((rc = new_mesh_arr(pl, "dtJ", &det))) return rc;
+  const double *xyz[3] = {dxg, dyg, dzg};
+  for (int a = 0; a < 3; ++a) {
+    SweepPlan *sp = &pl->sw[K_D1][a];
+    if (periodic_grid) {  // mesh.f90:251-304: non-periodic first derivative with one-sided ends
+      if (!pl->custom_d1[a].built) {
+        if ((rc = build_sweep(pl, pl->custom_d1[a], K_D1, a, false)) != PB_OK) return rc;
+      }
+      sp = &pl->custom_d1[a];
+    }
+    for (int c = 0; c < 3; ++c) {
+      double *dst = J[c * 3 + a];
+      if (sp->null_op) {
+        // evalx on a null operator returns zeros (compact_d1.f90:51-63); the 2-D special cases
+        // mesh.f90:332-334 then overwrite the diagonal entry with one
+        PB_CUDA(launch_fill((long)N, (pl->n[a] == 1 && c == a) ? 1.0 : 0.0, dst, st));
+      } else if ((rc = apply_dir(pl, *sp, xyz[c], dst, kStore, st)) != PB_OK) {
+        return rc;  // note: the sweep already divides by dA (dv.scale = 1/d)
+      }
+    }
+  }
+  {
+    const double *Jc[9]; double *Ic[9];
+    for (int k = 0; k < 9; ++k) { Jc[k] = J[k]; Ic[k] = I[k]; }
+    PB_CUDA(launch_metrics((long)N, Jc, pl->d[0], pl->d[1], pl->d[2], Ic, det, d1, d2, d3, cv, gl, st));
+  }
+  // filtered cell volumes, mesh.f90:374-383
+  double *cvs, *cvg, *tmp;
+  if ((rc = new_mesh_arr(pl, "CellVolS", &cvs)) || (rc = new_mesh_arr(pl, "CellVolG", &cvg)) || (rc = get_scratch(pl, 0, &tmp)))
+    return rc;
+  for (int which = 0; which < 2; ++which) {
+    const int kind = which == 0 ? K_SF : K_GF;
+    double *dst = which == 0 ? cvs : cvg;
+    if ((rc = apply_dir(pl, pl->sw[kind][0], cv, dst, kStore, st)) != PB_OK) return rc;
+    if ((rc = apply_dir(pl, pl->sw[kind][1], dst, tmp, kStore, st)) != PB_OK) return rc;
+    if ((rc = apply_dir(pl, pl->sw[kind][2], tmp, dst, kStore, st)) != PB_OK) return rc;
+  }
+  PB_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < 9; ++k) {  // the Jacobian itself is not kept (mesh.f90:360-368)
+    cudaFree(J[k]);
+    pl->mesh.erase(jn[k]);
+  }
+  pl->mesh_set = true;
+  return PB_OK;
+}
+
+int pb_getvar_device(const pb_plan *pl, const char *name, const double **dev_ptr) {
+  if (!pl || !name || !dev_ptr) return fail(PB_ERR_ARG, "NULL argument");
+  if (!pl->mesh_set) return fail(PB_ERR_STATE, "mesh arrays requested before pb_plan_set_mesh");
+  double *d = mesh_arr(pl, name);
+  if (!d || name[0] == '_') return fail(PB_ERR_ARG, std::string("unknown mesh variable: ") + name);  // parcop.f90:123-126
+  *dev_ptr = d;
+  return PB_OK;
+}
+
+int pb_getvar(const pb_plan *pl, const char *name, double *host_out) {
+  const double *d;
+  int rc = pb_getvar_device(pl, name, &d);
+  if (rc != PB_OK) return rc;
+  PB_CUDA(cudaMemcpy(host_out, d, sizeof(double) * pl->npts, cudaMemcpyDeviceToHost));
+  return PB_OK;
+}
+
+int pb_apply(pb_plan *pl, int opcode, const double *in, double *out, void *stream) {
+  if (!pl || !in || !out) return fail(PB_ERR_ARG, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long N = (long)pl->npts;
+  int rc;
+  switch (opcode) {
+    case PB_OP_DDX: case PB_OP_DDY: case PB_OP_DDZ:
+      return apply_dir(pl, pl->sw[K_D1][opcode - PB_OP_DDX], in, out, kStore, st);
+    case PB_OP_DD8X: case PB_OP_DD8Y: case PB_OP_DD8Z:
+      return apply_dir(pl, pl->sw[K_D8][opcode - PB_OP_DD8X], in, out, kStore, st);
+    case PB_OP_D2X: case PB_OP_D2Y: case PB_OP_D2Z:
+      return apply_dir(pl, pl->sw[K_D2][opcode - PB_OP_D2X], in, out, kStore, st);
+    case PB_OP_GFILTERX: case PB_OP_GFILTERY: case PB_OP_GFILTERZ:
+      return apply_dir(pl, pl->sw[K_GF][opcode - PB_OP_GFILTERX], in, out, kStore, st);
+    case PB_OP_SFILTERX: case PB_OP_SFILTERY: case PB_OP_SFILTERZ:
+      return apply_dir(pl, pl->sw[K_SF][opcode - PB_OP_SFILTERX], in, out, kStore, st);
+    case PB_OP_LAPLACIAN: {  // operators.f90:523-526
+      if (pl->coordsys != 0) return fail(PB_ERR_UNSUPPORTED, "laplacian has no curvilinear branch in the reference (operators.f90:521-560)");
+      const EpiArgs acc = {EPI_ACC, 0.0, nullptr};
+      if ((rc = apply_dir(pl, pl->sw[K_D2][0], in, out, kStore, st)) != PB_OK) return rc;
+      if ((rc = apply_dir(pl, pl->sw[K_D2][1], in, out, acc, st)) != PB_OK) return rc;
+      return apply_dir(pl, pl->sw[K_D2][2], in, out, acc, st);
+    }
+    case PB_OP_RING: {  // operators.f90:615-643 (L = 2), ringx/y/z :701-753
+      if (!pl->mesh_set) return fail(PB_ERR_STATE, "ring needs the mesh length scales: call pb_plan_set_mesh first");
+      const char *dn[3] = {"d1", "d2", "d3"};
+      bool first = true;
+      for (int d = 0; d < 3; ++d) {
+        if (pl->n[d] == 1 || pl->sw[K_D8][d].null_op) continue;  // contributes max(.,0)
+        EpiArgs e;
+        e.mode = first ? EPI_RING_SET : EPI_RING_MAX;
+        e.field = nullptr; e.s2 = 0.0;
+        if (pl->coordsys == 0) {
+          const double len = (d == 0) ? pl->d[0] : (d == 1 ? pl->d[1] : pl->d[2]);
+          e.s2 = len * len;
+        } else {
+          e.field = mesh_arr(pl, dn[d]);
+        }
+        if ((rc = apply_dir(pl, pl->sw[K_D8][d], in, out, e, st)) != PB_OK) return rc;
+        first = false;
+      }
+      if (first) PB_CUDA(launch_fill(N, 0.0, out, st));
+      return PB_OK;
+    }
+    case PB_OP_GFILTER:  // 'smooth' operators.f90:848-853: no cell-volume weighting
+      return filter3(pl, K_GF, in, out, st);
+    case PB_OP_SFILTER: {  // 'spectral' operators.f90:860-862, 871-893
+      if (pl->coordsys == 0) return filter3(pl, K_SF, in, out, st);
+      if (!pl->mesh_set) return fail(PB_ERR_STATE, "curvilinear filter needs pb_plan_set_mesh");
+      double *tmp, *tmp2;
+      if ((rc = get_scratch(pl, 0, &tmp)) != PB_OK || (rc = get_scratch(pl, 1, &tmp2)) != PB_OK) return rc;
+      PB_CUDA(launch_mul(N, in, mesh_arr(pl, "CellVol"), tmp2, st));
+      if ((rc = apply_dir(pl, pl->sw[K_SF][0], tmp2, out, kStore, st)) != PB_OK) return rc;
+      if ((rc = apply_dir(pl, pl->sw[K_SF][1], out, tmp, kStore, st)) != PB_OK) return rc;
+      if ((rc = apply_dir(pl, pl->sw[K_SF][2], tmp, tmp2, kStore, st)) != PB_OK) return rc;
+      PB_CUDA(launch_div(N, tmp2, mesh_arr(pl, "CellVolS"), out, st));
+      return PB_OK;
+    }
+    default:
+      return fail(PB_ERR_ARG, "unknown opcode");
+  }
+}
+
+int pb_divergence(pb_plan *pl, const double *fx, const double *fy, const double *fz, double *out, void *stream) {
+  if (!pl || !fx || !fy || !fz || !out) return fail(PB_ERR_ARG, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const EpiArgs acc = {EPI_ACC, 0.0, nullptr};
+  int rc;
+  if (pl->coordsys == 0) {  // operators.f90:48-52
+    if ((rc = apply_dir(pl, pl->sw[K_D1][0], fx, out, kStore, st)) != PB_OK) return rc;
+    if ((rc = apply_dir(pl, pl->sw[K_D1][1], fy, out, acc, st)) != PB_OK) return rc;
+    return apply_dir(pl, pl->sw[K_D1][2], fz, out, acc, st);
+  }
+  if (!pl->mesh_set) return fail(PB_ERR_STATE, "curvilinear divergence needs pb_plan_set_mesh");
+  double *fA, *fB, *fC;
+  if ((rc = get_scratch(pl, 1, &fA)) || (rc = get_scratch(pl, 2, &fB)) || (rc = get_scratch(pl, 3, &fC))) return rc;
+  const char *in[9] = {"dAx", "dAy", "dAz", "dBx", "dBy", "dBz", "dCx", "dCy", "dCz"};
+  const double *M[9];
+  for (int k = 0; k < 9; ++k) M[k] = mesh_arr(pl, in[k]);
+  const double *det = mesh_arr(pl, "dtJ");
+  PB_CUDA(launch_contra((long)pl->npts, fx, fy, fz, M, det, fA, fB, fC, st));  // operators.f90:79-81
+  if ((rc = apply_dir(pl, pl->sw[K_D1][0], fA, out, kStore, st)) != PB_OK) return rc;
+  if ((rc = apply_dir(pl, pl->sw[K_D1][1], fB, out, acc, st)) != PB_OK) return rc;
+  if ((rc = apply_dir(pl, pl->sw[K_D1][2], fC, out, acc, st)) != PB_OK) return rc;
+  PB_CUDA(launch_div((long)pl->npts, out, det, out, st));  // operators.f90:90
+  return PB_OK;
+}
+
+int pb_grads(pb_plan *pl, const double *in, double *gx, double *gy, double *gz, void *stream) {
+  if (!pl || !in || !gx || !gy || !gz) return fail(PB_ERR_ARG, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = apply_dir(pl, pl->sw[K_D1][0], in, gx, kStore, st)) != PB_OK) return rc;  // operators.f90:191-193
+  if ((rc = apply_dir(pl, pl->sw[K_D1][1], in, gy, kStore, st)) != PB_OK) return rc;
+  if ((rc = apply_dir(pl, pl->sw[K_D1][2], in, gz, kStore, st)) != PB_OK) return rc;
+  if (pl->coordsys == 3) {
+    if (!pl->mesh_set) return fail(PB_ERR_STATE, "curvilinear gradient needs pb_plan_set_mesh");
+    const char *names[9] = {"dAx", "dAy", "dAz", "dBx", "dBy", "dBz", "dCx", "dCy", "dCz"};
+    const double *M[9];
+    for (int k = 0; k < 9; ++k) M[k] = mesh_arr(pl, names[k]);
+    PB_CUDA(launch_grad_contract((long)pl->npts, M, gx, gy, gz, st));  // operators.f90:204-209
+  }
+  return PB_OK;
+}
+
+int pb_rk4_stage(pb_plan *pl, long n, double dt, double A, double B, const double *F, double *PHI, double *U, void *stream) {
+  if (!pl || !F || !PHI || !U || n < 0) return fail(PB_ERR_ARG, "bad argument");
+  PB_CUDA(launch_rk4_stage(n, dt, A, B, F, PHI, U, (cudaStream_t)stream));
+  return PB_OK;
+}
+
+int pb_reduce(pb_plan *pl, int kind, long n, const double *d_val, double *host_out, void *stream) {
+  if (!pl || !d_val || !host_out || n <= 0 || kind < 0 || kind > 2) return fail(PB_ERR_ARG, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PB_CUDA(launch_reduce(kind, n, d_val, pl->red_partial, 2048, pl->red_result, st));
+  PB_CUDA(cudaMemcpyAsync(pl->red_host, pl->red_result, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  *host_out = *pl->red_host;
+  return PB_OK;
+}
+
+// ---- z-slab pieces -------------------------------------------------------------------------------
+static int zop_kind(int zop) {
+  switch (zop) {
+    case PB_OP_DDZ: return K_D1;
+    case PB_OP_DD8Z: return K_D8;
+    case PB_OP_D2Z: return K_D2;
+    case PB_OP_SFILTERZ: return K_SF;
+    case PB_OP_GFILTERZ: return K_GF;
+    default: return -1;
+  }
+}
+
+int pb_z_pack_halo(pb_plan *pl, int zop, const double *d_val, double *send_lo, double *send_hi, void *stream) {
+  const int k = zop_kind(zop);
+  if (!pl || k < 0 || !d_val || !send_lo || !send_hi) return fail(PB_ERR_ARG, "bad argument");
+  const SweepPlan &sp = pl->sw[k][2];
+  if (sp.null_op) return PB_OK;
+  const long plane = (long)pl->a[0] * pl->a[1];
+  PB_CUDA(launch_pack_planes(d_val, plane, pl->a[2], sp.st.nor, send_lo, send_hi, (cudaStream_t)stream));
+  return PB_OK;
+}
+
+int pb_z_local(pb_plan *pl, int zop, const double *d_val, const double *recv_lo, const double *recv_hi, double *d_out,
+               double *iface_local, void *stream) {
+  const int k = zop_kind(zop);
+  if (!pl || k < 0 || !d_val || !d_out) return fail(PB_ERR_ARG, "bad argument");
+  SweepPlan &sp = pl->sw[k][2];
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sp.null_op || !sp.split) {
+    // not distributed: the whole operator in one call
+    return apply_dir(pl, sp, d_val, d_out, kStore, st);
+  }
+  if ((!sp.dev.phys_lo && !recv_lo) || (!sp.dev.phys_hi && !recv_hi)) return fail(PB_ERR_ARG, "missing halo buffer");
+  SweepDev dv = sp.dev;
+  if (sp.st.implicit) {
+    if (!iface_local) return fail(PB_ERR_ARG, "missing interface buffer");
+    dv.scale = 1.0;  // scale and add-back happen after the rank-level correction (pb_z_finish)
+    dv.add_v = 0;
+  }
+  PB_CUDA(launch_sweep_yz(sp.st.fam, 0, dv, d_val, d_out, recv_lo, recv_hi, sp.st.implicit ? iface_local : nullptr, kStore, st));
+  return PB_OK;
+}
+
+int pb_z_finish(pb_plan *pl, int zop, const double *d_val, const double *iface_all, double *d_out, void *stream) {
+  const int k = zop_kind(zop);
+  if (!pl || k < 0 || !d_out) return fail(PB_ERR_ARG, "bad argument");
+  SweepPlan &sp = pl->sw[k][2];
+  if (sp.null_op || !sp.split || !sp.st.implicit) return PB_OK;  // explicit operators are complete after pb_z_local
+  if (!iface_all || !d_val) return fail(PB_ERR_ARG, "missing interface buffer");
+  const long plane = (long)pl->a[0] * pl->a[1];
+  PB_CUDA(launch_z_finish(d_out, d_val, d_out, plane, pl->a[2], sp.RC, sp.GR, sp.np, iface_all, sp.dev.scale, sp.dev.add_v,
+                          (cudaStream_t)stream));
+  return PB_OK;
+}
+
+// ---- host-array wrappers -------------------------------------------------------------------------
+int pb_host_apply(pb_plan *pl, int opcode, const double *h_val, double *h_out) {
+  if (!pl || !h_val || !h_out) return fail(PB_ERR_ARG, "NULL argument");
+  double *din, *dout;
+  int rc;
+  if ((rc = get_scratch(pl, 4, &din)) || (rc = get_scratch(pl, 5, &dout))) return rc;
+  const size_t bytes = sizeof(double) * pl->npts;
+  PB_CUDA(cudaMemcpyAsync(din, h_val, bytes, cudaMemcpyHostToDevice, 0));
+  if ((rc = pb_apply(pl, opcode, din, dout, nullptr)) != PB_OK) return rc;
+  PB_CUDA(cudaMemcpyAsync(h_out, dout, bytes, cudaMemcpyDeviceToHost, 0));
+  PB_CUDA(cudaStreamSynchronize(0));
+  return PB_OK;
+}
+
+int pb_host_divergence(pb_plan *pl, const double *h_fx, const double *h_fy, const double *h_fz, double *h_out) {
+  if (!pl || !h_fx || !h_fy || !h_fz || !h_out) return fail(PB_ERR_ARG, "NULL argument");
+  double *d[4];
+  int rc;
+  for (int k = 0; k < 4; ++k)
+    if ((rc = get_scratch(pl, 4 + k, &d[k]))) return rc;
+  const size_t bytes = sizeof(double) * pl->npts;
+  PB_CUDA(cudaMemcpyAsync(d[0], h_fx, bytes, cudaMemcpyHostToDevice, 0));
+  PB_CUDA(cudaMemcpyAsync(d[1], h_fy, bytes, cudaMemcpyHostToDevice, 0));
+  PB_CUDA(cudaMemcpyAsync(d[2], h_fz, bytes, cudaMemcpyHostToDevice, 0));
+  if ((rc = pb_divergence(pl, d[0], d[1], d[2], d[3], nullptr)) != PB_OK) return rc;
+  PB_CUDA(cudaMemcpyAsync(h_out, d[3], bytes, cudaMemcpyDeviceToHost, 0));
+  PB_CUDA(cudaStreamSynchronize(0));
+  return PB_OK;
+}
+
+int pb_host_grads(pb_plan *pl, const double *h_val, double *h_gx, double *h_gy, double *h_gz) {
+  if (!pl || !h_val || !h_gx || !h_gy || !h_gz) return fail(PB_ERR_ARG, "NULL argument");
+  double *d[4];
+  int rc;
+  for (int k = 0; k < 4; ++k)
+    if ((rc = get_scratch(pl, 4 + k, &d[k]))) return rc;
+  const size_t bytes = sizeof(double) * pl->npts;
+  PB_CUDA(cudaMemcpyAsync(d[0], h_val, bytes, cudaMemcpyHostToDevice, 0));
+  if ((rc = pb_grads(pl, d[0], d[1], d[2], d[3], nullptr)) != PB_OK) return rc;
+  PB_CUDA(cudaMemcpyAsync(h_gx, d[1], bytes, cudaMemcpyDeviceToHost, 0));
+  PB_CUDA(cudaMemcpyAsync(h_gy, d[2], bytes, cudaMemcpyDeviceToHost, 0));
+  PB_CUDA(cudaMemcpyAsync(h_gz, d[3], bytes, cudaMemcpyDeviceToHost, 0));
+  PB_CUDA(cudaStreamSynchronize(0));
+  return PB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,790 @@
+// Hand-written sm_100a kernels of libparcop_b200.
+//
+// A directional compact operator (reference: eval_compact_op1{x,y,z}_{d1,r3,r4},
+// pyranda/parcop/compact_d1.f90:38-998, compact_r3.f90:37-572, compact_r4.f90:37-877, plus the
+// batched solves pentadiagonal.f90:629-825 and the metric scale compact_operators.f90:41-46) is
+// ONE kernel here: stencil right-hand side, pentadiagonal solve, scale / filter add-back and the
+// composite epilogue are fused so a sweep moves 16 B/point through HBM (read v, write dv).
+//
+// The solve is partitioned: each grid line is cut into P chunks of C rows; a thread owns one
+// (line, chunk), runs the chunk-local LU recurrences sequentially, and the chunks are stitched
+// with a dense pre-inverted interface system (tables.cpp).  The forward-eliminated values live in
+// shared memory (the whole line tile stays on chip between the two substitution sweeps), so the
+// field is read once and written once.
+//
+//   y / z sweeps: a tile is NL consecutive x-lines (one 128-byte segment per row); threads of a
+//   half-warp are adjacent lines, so global loads/stores are fully coalesced and shared-memory
+//   accesses conflict free.  v is streamed from global memory straight into a register window.
+//   x sweep: lines are unit stride; a tile of NLX lines is staged through shared memory with
+//   coalesced loads (row pitch odd => conflict-free column access), solved in place, and written
+//   back coalesced.
+#include "kernels.cuh"
+
+#include <atomic>
+
+#include "tables.hpp"
+
+#ifdef PB_EMULATE
+#define PB_SHARED(S) double *S = emul::t_smem
+#define PB_LAUNCH(kernel, grid, block, smem, st, ...) emul::launch(grid, block, smem, [&] { kernel(__VA_ARGS__); })
+#define PB_EW_GRID(n) dim3(1)
+#define PB_EW_BLOCK dim3(1)
+#else
+#define PB_SHARED(S) extern __shared__ double S[]
+#define PB_LAUNCH(kernel, grid, block, smem, st, ...) kernel<<<grid, block, smem, st>>>(__VA_ARGS__)
+#define PB_EW_GRID(n) dim3(ew_blocks(n))
+#define PB_EW_BLOCK dim3(256)
+#endif
+
+namespace pb {
+
+static std::atomic<long> g_launches{0};
+long launch_count() { return g_launches.load(); }
+static int g_yz_lines = 16;
+static int g_x_lines = 16;
+void set_yz_lines(int nl) { if (nl == 8 || nl == 16 || nl == 32) g_yz_lines = nl; }
+void set_x_lines(int nl) { if (nl == 8 || nl == 16 || nl == 32) g_x_lines = nl; }
+
+__device__ __forceinline__ double4 ldg4(const double4 *p) {
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+template <int FAM>
+struct FT {
+  static constexpr int H = (FAM == F_R4) ? 4 : 3;
+  static constexpr int W = 2 * H + 1;
+};
+
+// ---- right-hand sides ---------------------------------------------------------------------------
+// interior / halo rows.  w = v[i-H .. i+H].
+// D1: compact_d1.f90:156, R3: compact_r3.f90:127-128, R4: compact_r4.f90:148-152
+template <int FAM>
+__device__ __forceinline__ double rhs_center(const double *w, const double *ar) {
+  if (FAM == F_D1) {
+    return ar[4] * (w[4] - w[2]) + ar[5] * (w[5] - w[1]) + ar[6] * (w[6] - w[0]);
+  } else if (FAM == F_R3) {
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < 7; ++l)
+      if (l != 3) s += ar[l] * (w[l] - w[3]);
+    return s;
+  } else {
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < 9; ++l)
+      if (l != 4) s += (w[l] - w[4]) * ar[l];
+    return s;
+  }
+}
+
+// first four rows at a one-sided physical boundary; vv = v[0..8], b = closure rows.
+// D1: compact_d1.f90:134-136 (+ row 4 by :156 with closure weights), R3: compact_r3.f90:118-120,
+// R4: compact_r4.f90:123-126
+template <int FAM>
+__device__ __forceinline__ void rhs_lo4(const double *vv, const double (*b)[9], double *r) {
+  if (FAM == F_D1) {
+    const double v0 = vv[0];
+    r[0] = b[0][4] * (vv[1] - v0) + b[0][5] * (vv[2] - v0) + b[0][6] * (vv[3] - v0);
+    r[1] = b[1][3] * (vv[1] - v0) + b[1][4] * (vv[2] - v0) + b[1][5] * (vv[3] - v0) + b[1][6] * (vv[4] - v0);
+    r[2] = b[2][4] * (vv[3] - vv[1]) + b[2][5] * (vv[4] - v0) + b[2][6] * (vv[5] - v0);
+    r[3] = b[3][4] * (vv[4] - vv[2]) + b[3][5] * (vv[5] - vv[1]) + b[3][6] * (vv[6] - v0);
+  } else if (FAM == F_R3) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < 7; ++l) {
+        const int k = l - 3 + i;
+        if (k >= 0 && k != i) s += b[i][l] * (vv[k] - vv[i]);
+      }
+      r[i] = s;
+    }
+  } else {
+    const double v0 = vv[0];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 5 - i; l < 9; ++l) s += b[i][l] * (vv[l - 4 + i] - v0);
+      r[i] = s;
+    }
+  }
+}
+
+// last four rows; u = v[m-8..m-1], h = closure rows for rows m-4..m-1.
+// D1: compact_d1.f90:176-178, R3: compact_r3.f90:144-146, R4: compact_r4.f90:174-177
+template <int FAM>
+__device__ __forceinline__ void rhs_hi4(const double *u, const double (*h)[9], double *r) {
+  if (FAM == F_D1) {
+    const double vm = u[7];
+    r[0] = h[0][4] * (u[5] - u[3]) + h[0][5] * (u[6] - u[2]) + h[0][6] * (u[7] - u[1]);
+    r[1] = h[1][0] * (u[2] - vm) + h[1][1] * (u[3] - vm) + h[1][2] * (u[4] - u[6]);
+    r[2] = h[2][0] * (u[3] - vm) + h[2][1] * (u[4] - vm) + h[2][2] * (u[5] - vm) + h[2][3] * (u[6] - vm);
+    r[3] = h[3][0] * (u[4] - vm) + h[3][1] * (u[5] - vm) + h[3][2] * (u[6] - vm);
+  } else if (FAM == F_R3) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = 4 + q;  // index of this row in u
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < 7; ++l) {
+        const int k = c - 3 + l;
+        if (k < 8 && k != c) s += h[q][l] * (u[k] - u[c]);
+      }
+      r[q] = s;
+    }
+  } else {
+    const double vm = u[7];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < 7 - q; ++l) s += h[q][l] * (u[q + l] - vm);
+      r[q] = s;
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_store(double *__restrict__ out, long idx, double val, const EpiArgs &epi) {
+  switch (epi.mode) {
+    case EPI_STORE: out[idx] = val; break;
+    case EPI_ACC: out[idx] += val; break;
+    default: {
+      double sc = epi.s2;
+      if (epi.field) { const double f = epi.field[idx]; sc = f * f; }
+      double r = fabs(val) * sc;
+      if (epi.mode == EPI_RING_MAX) r = fmax(r, out[idx]);
+      out[idx] = r;
+    }
+  }
+}
+
+// ---- y / z sweep ---------------------------------------------------------------------------------
+template <int FAM, int NL>
+__global__ void sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
+                                double *__restrict__ out, const double *__restrict__ halo_lo,
+                                const double *__restrict__ halo_hi, double *__restrict__ iface,
+                                const __grid_constant__ EpiArgs epi) {
+  constexpr int H = FT<FAM>::H, W = FT<FAM>::W, D = 4;
+  PB_SHARED(S);  // [m][NL]: forward-eliminated rows, then the chunk-local solution
+  const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
+  const int tiles_i = (a.nfast + NL - 1) / NL;
+  const int ti = blockIdx.x % tiles_i, o = blockIdx.x / tiles_i;
+  int i0 = ti * NL + l;
+  const bool valid = i0 < a.nfast;
+  if (!valid) i0 = a.nfast - 1;
+  const long rs = a.rstride;
+  const long base = (long)i0 + (long)o * a.ostride;
+  const int m = a.m, C = a.C, P = a.P;
+  const int s = p * C, e = s + C;
+  const int type = a.ctype[p];
+  const bool implicit = a.implicit != 0;
+  const bool add_v = a.add_v != 0;
+  const double scale = a.scale;
+
+  auto ld = [&](int r) -> double {
+    if (r >= 0 && r < m) return __ldg(v + base + (long)r * rs);
+    if (r < 0) return a.wrap ? __ldg(v + base + (long)(r + m) * rs) : __ldg(halo_lo + base + (long)(r + H) * rs);
+    return a.wrap ? __ldg(v + base + (long)(r - m) * rs) : __ldg(halo_hi + base + (long)(r - m) * rs);
+  };
+
+  const double2 *luf = a.lu_f + (size_t)type * C;
+  double rm1 = 0.0, rm2 = 0.0;
+  // forward elimination with the chunk-local factors (pentadiagonal.f90:639-642, pull form), or
+  // direct output for explicit operators (compact_r4.f90:209-218)
+  auto emit = [&](int row, double rhs, double vc) {
+    if (implicit) {
+      const double2 c = __ldg(luf + (row - s));
+      double t = fma(-c.x, rm2, rhs);
+      t = fma(-c.y, rm1, t);
+      S[row * NL + l] = t;
+      rm2 = rm1;
+      rm1 = t;
+    } else if (valid) {
+      double val = rhs * scale;
+      if (add_v) val += vc;
+      epi_store(out, base + (long)row * rs, val, epi);
+    }
+  };
+
+  const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
+  int i = s;
+  double w[W];
+  if (lo_sp) {
+    double vv[9], r4[4];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) vv[k] = ld(k);
+    rhs_lo4<FAM>(vv, a.arb_lo, r4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(k, r4[k], vv[k]);
+    i = 4;
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) w[k] = vv[4 - H + k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) w[k] = ld(i - H + k);
+  }
+  const int iend = hi_sp ? e - 4 : e;
+  const int lim = iend + H;
+  double pf[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) pf[d] = (i + H + d < lim) ? ld(i + H + d) : 0.0;
+#pragma unroll 4
+  for (; i < iend; ++i) {
+    w[W - 1] = pf[0];
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d) pf[d] = pf[d + 1];
+    pf[D - 1] = (i + H + D < lim) ? ld(i + H + D) : 0.0;
+    const double rhs = rhs_center<FAM>(w, a.ari);
+    emit(i, rhs, w[H]);
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) w[k] = w[k + 1];
+  }
+  if (hi_sp) {
+    double u[8], r4[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] = ld(m - 8 + k);
+    rhs_hi4<FAM>(u, a.arb_hi, r4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(m - 4 + k, r4[k], u[4 + k]);
+  }
+  if (!implicit) return;
+
+  // back substitution (pentadiagonal.f90:643-647)
+  {
+    const double4 *lub = a.lu_b + (size_t)type * C;
+    double x1 = 0.0, x2 = 0.0;
+#pragma unroll 4
+    for (int r = e - 1; r >= s; --r) {
+      const double4 c = ldg4(lub + (r - s));
+      double t = S[r * NL + l];
+      t = fma(-c.y, x1, t);
+      t = fma(-c.z, x2, t);
+      t *= c.x;
+      S[r * NL + l] = t;
+      x2 = x1;
+      x1 = t;
+    }
+  }
+  __syncthreads();
+
+  // interface unknowns of the neighbouring chunks: g = G_p * d, d = first/last two values of
+  // every chunk-local solution (the in-block analogue of compact_d1.f90:243-279)
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+  if (P > 1 || a.wrap) {
+    const int n4 = 4 * P;
+    const double *Gp = a.G + (size_t)p * 4 * n4;
+    for (int q = 0; q < P; ++q) {
+      const double d0 = S[(q * C) * NL + l], d1 = S[(q * C + 1) * NL + l];
+      const double d2 = S[(q * C + C - 2) * NL + l], d3 = S[(q * C + C - 1) * NL + l];
+      const double *gq = Gp + 4 * q;
+      g0 += __ldg(gq) * d0 + __ldg(gq + 1) * d1 + __ldg(gq + 2) * d2 + __ldg(gq + 3) * d3;
+      g1 += __ldg(gq + n4) * d0 + __ldg(gq + n4 + 1) * d1 + __ldg(gq + n4 + 2) * d2 + __ldg(gq + n4 + 3) * d3;
+      g2 += __ldg(gq + 2 * n4) * d0 + __ldg(gq + 2 * n4 + 1) * d1 + __ldg(gq + 2 * n4 + 2) * d2 + __ldg(gq + 2 * n4 + 3) * d3;
+      g3 += __ldg(gq + 3 * n4) * d0 + __ldg(gq + 3 * n4 + 1) * d1 + __ldg(gq + 3 * n4 + 2) * d2 + __ldg(gq + 3 * n4 + 3) * d3;
+    }
+  }
+
+  // spike correction (compact_d1.f90:285-286), metric scale (compact_operators.f90:43), filter
+  // add-back (compact_r4.f90:226-232) and the composite epilogue, straight to global memory
+  {
+    const double4 *rcp = a.rc + (size_t)type * C;
+#pragma unroll 4
+    for (int r = s; r < e; ++r) {
+      const double4 c = ldg4(rcp + (r - s));
+      double x = S[r * NL + l];
+      x = fma(-c.x, g0, x);
+      x = fma(-c.y, g1, x);
+      x = fma(-c.z, g2, x);
+      x = fma(-c.w, g3, x);
+      if (iface != nullptr) {  // z-slab: publish this rank's 4 interface values (compact_d1.f90:858-878)
+        const long plane = (long)a.nfast * a.nouter;
+        const long li = base;  // i + ax*j for the z sweep
+        if (valid) {
+          if (r < 2) iface[(long)r * plane + li] = a.phys_lo ? 0.0 : x;
+          if (r >= m - 2) iface[(long)(r - (m - 4)) * plane + li] = a.phys_hi ? 0.0 : x;
+        }
+      }
+      double val = x * scale;
+      if (add_v) val += ld(r);
+      if (valid) epi_store(out, base + (long)r * rs, val, epi);
+    }
+  }
+}
+
+// ---- x sweep -------------------------------------------------------------------------------------
+template <int FAM, int NLX>
+__global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
+                               double *__restrict__ out, const __grid_constant__ EpiArgs epi) {
+  constexpr int H = FT<FAM>::H, W = FT<FAM>::W;
+  PB_SHARED(S);  // [NLX][LD]
+  const int m = a.m, LD = m | 1, C = a.C, P = a.P;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+  const long nlines = a.nfast;
+  const long L0 = (long)blockIdx.x * NLX;
+  const bool implicit = a.implicit != 0;
+  const bool add_v = a.add_v != 0;
+
+  // stage the tile, coalesced
+  for (int ll = wid; ll < NLX; ll += nw) {
+    long L = L0 + ll;
+    if (L >= nlines) L = nlines - 1;
+    const double *src = v + L * (long)m;
+    double *dst = S + ll * LD;
+    for (int ii = lane; ii < m; ii += 32) dst[ii] = __ldg(src + ii);
+  }
+  __syncthreads();
+
+  const int l = tid % NLX, p = tid / NLX;
+  const bool active = p < P;  // blockDim may be rounded up to a warp multiple
+  const int s = p * C, e = s + C;
+  double *Sl = S + l * LD;
+  const int type = active ? a.ctype[p] : 0;
+  const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
+
+  // neighbours' rows this thread needs, read before anyone overwrites them
+  double hv[H], tv[H], vv[9], u[8];
+  if (active) {
+    if (lo_sp) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) vv[k] = Sl[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < H; ++k) { int r = s - H + k; if (r < 0) r += m; hv[k] = Sl[r]; }
+    }
+    if (hi_sp) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = Sl[m - 8 + k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < H; ++k) { int r = e + k; if (r >= m) r -= m; tv[k] = Sl[r]; }
+    }
+  }
+  __syncthreads();
+
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+  if (active) {
+    const double2 *luf = a.lu_f + (size_t)type * C;
+    double rm1 = 0.0, rm2 = 0.0;
+    auto emit = [&](int row, double rhs) {
+      if (implicit) {
+        const double2 c = __ldg(luf + (row - s));
+        double t = fma(-c.x, rm2, rhs);
+        t = fma(-c.y, rm1, t);
+        Sl[row] = t;
+        rm2 = rm1;
+        rm1 = t;
+      } else {
+        Sl[row] = rhs;
+      }
+    };
+    int i = s;
+    double w[W];
+    if (lo_sp) {
+      double r4[4];
+      rhs_lo4<FAM>(vv, a.arb_lo, r4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) emit(k, r4[k]);
+      i = 4;
+#pragma unroll
+      for (int k = 0; k < W - 1; ++k) w[k] = vv[4 - H + k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < H; ++k) w[k] = hv[k];
+#pragma unroll
+      for (int k = H; k < W - 1; ++k) w[k] = Sl[s + k - H];
+    }
+    const int imain = hi_sp ? e - 4 : e - H;  // rows whose look-ahead value is still inside the chunk
+#pragma unroll 4
+    for (; i < imain; ++i) {
+      w[W - 1] = Sl[i + H];
+      const double rhs = rhs_center<FAM>(w, a.ari);
+      emit(i, rhs);
+#pragma unroll
+      for (int k = 0; k < W - 1; ++k) w[k] = w[k + 1];
+    }
+    if (hi_sp) {
+      double r4[4];
+      rhs_hi4<FAM>(u, a.arb_hi, r4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) emit(m - 4 + k, r4[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        w[W - 1] = tv[k];
+        const double rhs = rhs_center<FAM>(w, a.ari);
+        emit(e - H + k, rhs);
+#pragma unroll
+        for (int q = 0; q < W - 1; ++q) w[q] = w[q + 1];
+      }
+    }
+    if (implicit) {
+      const double4 *lub = a.lu_b + (size_t)type * C;
+      double x1 = 0.0, x2 = 0.0;
+#pragma unroll 4
+      for (int r = e - 1; r >= s; --r) {
+        const double4 c = ldg4(lub + (r - s));
+        double t = Sl[r];
+        t = fma(-c.y, x1, t);
+        t = fma(-c.z, x2, t);
+        t *= c.x;
+        Sl[r] = t;
+        x2 = x1;
+        x1 = t;
+      }
+    }
+  }
+  if (implicit) {
+    __syncthreads();
+    if (active && (P > 1 || a.wrap)) {
+      const int n4 = 4 * P;
+      const double *Gp = a.G + (size_t)p * 4 * n4;
+      for (int q = 0; q < P; ++q) {
+        const double d0 = Sl[q * C], d1 = Sl[q * C + 1], d2 = Sl[q * C + C - 2], d3 = Sl[q * C + C - 1];
+        const double *gq = Gp + 4 * q;
+        g0 += __ldg(gq) * d0 + __ldg(gq + 1) * d1 + __ldg(gq + 2) * d2 + __ldg(gq + 3) * d3;
+        g1 += __ldg(gq + n4) * d0 + __ldg(gq + n4 + 1) * d1 + __ldg(gq + n4 + 2) * d2 + __ldg(gq + n4 + 3) * d3;
+        g2 += __ldg(gq + 2 * n4) * d0 + __ldg(gq + 2 * n4 + 1) * d1 + __ldg(gq + 2 * n4 + 2) * d2 + __ldg(gq + 2 * n4 + 3) * d3;
+        g3 += __ldg(gq + 3 * n4) * d0 + __ldg(gq + 3 * n4 + 1) * d1 + __ldg(gq + 3 * n4 + 2) * d2 + __ldg(gq + 3 * n4 + 3) * d3;
+      }
+    }
+    __syncthreads();
+    if (active && (P > 1 || a.wrap)) {
+      const double4 *rcp = a.rc + (size_t)type * C;
+#pragma unroll 4
+      for (int r = s; r < e; ++r) {
+        const double4 c = ldg4(rcp + (r - s));
+        double x = Sl[r];
+        x = fma(-c.x, g0, x);
+        x = fma(-c.y, g1, x);
+        x = fma(-c.z, g2, x);
+        x = fma(-c.w, g3, x);
+        Sl[r] = x;
+      }
+    }
+  }
+  __syncthreads();
+
+  // write back, coalesced, with scale / add-back / epilogue
+  const double scale = a.scale;
+  for (int ll = wid; ll < NLX; ll += nw) {
+    const long L = L0 + ll;
+    if (L >= nlines) break;
+    const double *src = S + ll * LD;
+    for (int ii = lane; ii < m; ii += 32) {
+      const long idx = L * (long)m + ii;
+      double val = src[ii] * scale;
+      if (add_v) val += __ldg(v + idx);
+      epi_store(out, idx, val, epi);
+    }
+  }
+}
+
+// ---- launchers -----------------------------------------------------------------------------------
+template <int FAM, int NL>
+static cudaError_t launch_yz_t(const SweepDev &a, const double *v, double *out, const double *hlo,
+                               const double *hhi, double *iface, const EpiArgs &epi, cudaStream_t st) {
+  const size_t smem = a.implicit ? (size_t)a.m * NL * sizeof(double) : 0;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(sweep_yz_kernel<FAM, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
+  const int tiles_i = (a.nfast + NL - 1) / NL;
+  const dim3 grid((unsigned)(tiles_i * a.nouter)), block(NL * a.P);
+  auto kfn = sweep_yz_kernel<FAM, NL>;
+  PB_LAUNCH(kfn, grid, block, smem, st, a, v, out, hlo, hhi, iface, epi);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+template <int FAM>
+static cudaError_t launch_yz_f(int lines, const SweepDev &a, const double *v, double *out, const double *hlo,
+                               const double *hhi, double *iface, const EpiArgs &epi, cudaStream_t st) {
+  switch (lines) {
+    case 8: return launch_yz_t<FAM, 8>(a, v, out, hlo, hhi, iface, epi, st);
+    case 32: return launch_yz_t<FAM, 32>(a, v, out, hlo, hhi, iface, epi, st);
+    default: return launch_yz_t<FAM, 16>(a, v, out, hlo, hhi, iface, epi, st);
+  }
+}
+
+cudaError_t launch_sweep_yz(int fam, int lines, const SweepDev &a, const double *v, double *out,
+                            const double *halo_lo, const double *halo_hi, double *iface,
+                            const EpiArgs &epi, cudaStream_t st) {
+  if (lines <= 0) lines = g_yz_lines;
+  // keep the tile within the shared-memory budget of one SM
+  while (lines > 8 && (size_t)a.m * lines * sizeof(double) > 200 * 1024) lines /= 2;
+  switch (fam) {
+    case F_D1: return launch_yz_f<F_D1>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
+    case F_R3: return launch_yz_f<F_R3>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
+    default: return launch_yz_f<F_R4>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
+  }
+}
+
+template <int FAM, int NLX>
+static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
+  const size_t smem = (size_t)NLX * (a.m | 1) * sizeof(double);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(sweep_x_kernel<FAM, NLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
+  const long ntiles = ((long)a.nfast + NLX - 1) / NLX;
+  int threads = NLX * a.P;
+  threads = (threads + 31) / 32 * 32;
+  auto kfn = sweep_x_kernel<FAM, NLX>;
+  PB_LAUNCH(kfn, dim3((unsigned)ntiles), dim3(threads), smem, st, a, v, out, epi);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+template <int FAM>
+static cudaError_t launch_x_f(int lines, const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
+  switch (lines) {
+    case 8: return launch_x_t<FAM, 8>(a, v, out, epi, st);
+    case 32: return launch_x_t<FAM, 32>(a, v, out, epi, st);
+    default: return launch_x_t<FAM, 16>(a, v, out, epi, st);
+  }
+}
+
+cudaError_t launch_sweep_x(int fam, int lines, const SweepDev &a, const double *v, double *out,
+                           const EpiArgs &epi, cudaStream_t st) {
+  if (lines <= 0) lines = g_x_lines;
+  while (lines > 8 && (size_t)(a.m | 1) * lines * sizeof(double) > 200 * 1024) lines /= 2;
+  switch (fam) {
+    case F_D1: return launch_x_f<F_D1>(lines, a, v, out, epi, st);
+    case F_R3: return launch_x_f<F_R3>(lines, a, v, out, epi, st);
+    default: return launch_x_f<F_R4>(lines, a, v, out, epi, st);
+  }
+}
+
+// ---- z-slab helpers ------------------------------------------------------------------------------
+__global__ void pack_planes_kernel(const double *__restrict__ v, long plane, int m, int h,
+                                   double *__restrict__ send_lo, double *__restrict__ send_hi) {
+  const long n = plane * h;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    send_lo[t] = v[t];                          // first h planes   (compact_d1.f90:723)
+    send_hi[t] = v[(long)(m - h) * plane + t];  // last h planes    (compact_d1.f90:722)
+  }
+}
+cudaError_t launch_pack_planes(const double *v, long plane, int m, int h, double *send_lo, double *send_hi, cudaStream_t st) {
+  const long n = plane * h;
+  PB_LAUNCH(pack_planes_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, v, plane, m, h, send_lo, send_hi);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+// reduced interface solve (dense pre-inverted rows) + rank-level spike correction
+// (compact_d1.f90:892-928, compact_r4.f90:820-...): one thread per line of the xy plane and a slab
+// of rows (blockIdx.y)
+__global__ void z_finish_kernel(const double *__restrict__ z, const double *__restrict__ v, double *__restrict__ out,
+                                long plane, int m, const double4 *__restrict__ RC, const double *__restrict__ GR,
+                                int np, const double *__restrict__ iface_all, double scale, int add_v, int rows_per_block) {
+  const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (li >= plane) return;
+  double g[4] = {0.0, 0.0, 0.0, 0.0};
+  const int n4 = 4 * np;
+  for (int r = 0; r < np; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double d = __ldg(iface_all + ((long)r * 4 + j) * plane + li);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) g[c] += __ldg(GR + c * n4 + 4 * r + j) * d;
+    }
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(m, r0 + rows_per_block);
+  for (int r = r0; r < r1; ++r) {
+    const double4 c = ldg4(RC + r);
+    const long idx = (long)r * plane + li;
+    double x = z[idx];
+    x = fma(-c.x, g[0], x);
+    x = fma(-c.y, g[1], x);
+    x = fma(-c.z, g[2], x);
+    x = fma(-c.w, g[3], x);
+    double val = x * scale;
+    if (add_v) val += __ldg(v + idx);
+    out[idx] = val;
+  }
+}
+cudaError_t launch_z_finish(const double *z, const double *v, double *out, long plane, int m, const double4 *RC,
+                            const double *GR, int np, const double *iface_all, double scale, int add_v, cudaStream_t st) {
+  const int rows_per_block = 32;
+  dim3 grid((unsigned)((plane + 127) / 128), (unsigned)((m + rows_per_block - 1) / rows_per_block));
+  PB_LAUNCH(z_finish_kernel, grid, dim3(128), 0, st, z, v, out, plane, m, RC, GR, np, iface_all, scale, add_v, rows_per_block);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+// ---- pointwise -----------------------------------------------------------------------------------
+static inline int ew_blocks(long n) {
+  long b = (n + 255) / 256;
+  const long cap = 148L * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+#define PB_GRID_STRIDE(t, n) for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < (n); t += (long)gridDim.x * blockDim.x)
+
+// pyranda.py:800-804: PHI = dt*F + A*PHI ; U = U + B*PHI
+__global__ void rk4_stage_kernel(long n, double dt, double A, double B, const double *__restrict__ F,
+                                 double *__restrict__ PHI, double *__restrict__ U) {
+  PB_GRID_STRIDE(t, n) {
+    const double tmp1 = A * PHI[t];
+    const double phi = dt * F[t] + tmp1;
+    PHI[t] = phi;
+    const double tmp2 = B * phi;
+    U[t] = U[t] + tmp2;
+  }
+}
+cudaError_t launch_rk4_stage(long n, double dt, double A, double B, const double *F, double *PHI, double *U, cudaStream_t st) {
+  PB_LAUNCH(rk4_stage_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, dt, A, B, F, PHI, U);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+__global__ void copy_kernel(long n, const double *__restrict__ a, double *__restrict__ o) { PB_GRID_STRIDE(t, n) o[t] = a[t]; }
+__global__ void fill_kernel(long n, double val, double *__restrict__ o) { PB_GRID_STRIDE(t, n) o[t] = val; }
+__global__ void mul_kernel(long n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ o) { PB_GRID_STRIDE(t, n) o[t] = a[t] * b[t]; }
+__global__ void div_kernel(long n, const double *a, const double *b, double *o) { PB_GRID_STRIDE(t, n) o[t] = a[t] / b[t]; }
+cudaError_t launch_copy(long n, const double *a, double *out, cudaStream_t st) { PB_LAUNCH(copy_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, a, out); ++g_launches; return cudaGetLastError(); }
+cudaError_t launch_fill(long n, double val, double *out, cudaStream_t st) { PB_LAUNCH(fill_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, val, out); ++g_launches; return cudaGetLastError(); }
+cudaError_t launch_mul(long n, const double *a, const double *b, double *out, cudaStream_t st) { PB_LAUNCH(mul_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, a, b, out); ++g_launches; return cudaGetLastError(); }
+cudaError_t launch_div(long n, const double *a, const double *b, double *out, cudaStream_t st) { PB_LAUNCH(div_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, a, b, out); ++g_launches; return cudaGetLastError(); }
+
+struct CP9 { const double *p[9]; };
+struct P9 { double *p[9]; };
+
+// operators.f90:79-81
+__global__ void contra_kernel(long n, const double *__restrict__ fx, const double *__restrict__ fy, const double *__restrict__ fz,
+                              CP9 M, const double *__restrict__ det, double *__restrict__ fA, double *__restrict__ fB, double *__restrict__ fC) {
+  PB_GRID_STRIDE(t, n) {
+    const double x = fx[t], y = fy[t], zz = fz[t], d = det[t];
+    fA[t] = (x * M.p[0][t] + y * M.p[1][t] + zz * M.p[2][t]) * d;
+    fB[t] = (x * M.p[3][t] + y * M.p[4][t] + zz * M.p[5][t]) * d;
+    fC[t] = (x * M.p[6][t] + y * M.p[7][t] + zz * M.p[8][t]) * d;
+  }
+}
+cudaError_t launch_contra(long n, const double *fx, const double *fy, const double *fz, const double *const *metric9,
+                          const double *det, double *fA, double *fB, double *fC, cudaStream_t st) {
+  CP9 M;
+  for (int k = 0; k < 9; ++k) M.p[k] = metric9[k];
+  PB_LAUNCH(contra_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, fx, fy, fz, M, det, fA, fB, fC);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+// operators.f90:204-209; metric9 = dAdx dAdy dAdz dBdx dBdy dBdz dCdx dCdy dCdz
+__global__ void grad_contract_kernel(long n, CP9 M, double *__restrict__ gx, double *__restrict__ gy, double *__restrict__ gz) {
+  PB_GRID_STRIDE(t, n) {
+    const double a = gx[t], b = gy[t], c = gz[t];
+    gx[t] = a * M.p[0][t] + b * M.p[3][t] + c * M.p[6][t];
+    gy[t] = a * M.p[1][t] + b * M.p[4][t] + c * M.p[7][t];
+    gz[t] = a * M.p[2][t] + b * M.p[5][t] + c * M.p[8][t];
+  }
+}
+cudaError_t launch_grad_contract(long n, const double *const *metric9, double *gx, double *gy, double *gz, cudaStream_t st) {
+  CP9 M;
+  for (int k = 0; k < 9; ++k) M.p[k] = metric9[k];
+  PB_LAUNCH(grad_contract_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, M, gx, gy, gz);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+// mesh.f90:337-358; J9 = dxdA dxdB dxdC dydA dydB dydC dzdA dzdB dzdC (already divided by dA,dB,dC)
+__global__ void metrics_kernel(long n, CP9 J, double dA, double dB, double dC, P9 I, double *__restrict__ det,
+                               double *__restrict__ d1, double *__restrict__ d2, double *__restrict__ d3,
+                               double *__restrict__ cellvol, double *__restrict__ gridlen) {
+  PB_GRID_STRIDE(t, n) {
+    const double dxdA = J.p[0][t], dxdB = J.p[1][t], dxdC = J.p[2][t];
+    const double dydA = J.p[3][t], dydB = J.p[4][t], dydC = J.p[5][t];
+    const double dzdA = J.p[6][t], dzdB = J.p[7][t], dzdC = J.p[8][t];
+    const double dt = -dxdC * dydB * dzdA + dxdB * dydC * dzdA + dxdC * dydA * dzdB - dxdA * dydC * dzdB - dxdB * dydA * dzdC + dxdA * dydB * dzdC;
+    det[t] = dt;
+    I.p[0][t] = (-dydC * dzdB + dydB * dzdC) / dt;
+    I.p[1][t] = (dxdC * dzdB - dxdB * dzdC) / dt;
+    I.p[2][t] = (-dxdC * dydB + dxdB * dydC) / dt;
+    I.p[3][t] = (dydC * dzdA - dydA * dzdC) / dt;
+    I.p[4][t] = (-dxdC * dzdA + dxdA * dzdC) / dt;
+    I.p[5][t] = (dxdC * dydA - dxdA * dydC) / dt;
+    I.p[6][t] = (-dydB * dzdA + dydA * dzdB) / dt;
+    I.p[7][t] = (dxdB * dzdA - dxdA * dzdB) / dt;
+    I.p[8][t] = (-dxdB * dydA + dxdA * dydB) / dt;
+    const double a = sqrt((dxdA * dA) * (dxdA * dA) + (dydA * dA) * (dydA * dA) + (dzdA * dA) * (dzdA * dA));
+    const double b = sqrt((dxdB * dB) * (dxdB * dB) + (dydB * dB) * (dydB * dB) + (dzdB * dB) * (dzdB * dB));
+    const double c = sqrt((dxdC * dC) * (dxdC * dC) + (dydC * dC) * (dydC * dC) + (dzdC * dC) * (dzdC * dC));
+    d1[t] = a; d2[t] = b; d3[t] = c;
+    cellvol[t] = a * b * c;
+    gridlen[t] = fmin(a, fmin(b, c));
+  }
+}
+cudaError_t launch_metrics(long n, const double *const *J9, double dA, double dB, double dC, double *const *inv9,
+                           double *det, double *d1, double *d2, double *d3, double *cellvol, double *gridlen, cudaStream_t st) {
+  CP9 J; P9 I;
+  for (int k = 0; k < 9; ++k) { J.p[k] = J9[k]; I.p[k] = inv9[k]; }
+  PB_LAUNCH(metrics_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, J, dA, dB, dC, I, det, d1, d2, d3, cellvol, gridlen);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+// ---- reductions (pyrandaMPI.py:307-326, local part) ---------------------------------------------
+template <int KIND>
+__device__ __forceinline__ double red_op(double a, double b) {
+  return KIND == 0 ? a + b : (KIND == 1 ? fmax(a, b) : fmin(a, b));
+}
+#ifdef PB_EMULATE
+template <int KIND>
+__global__ void reduce_kernel(long n, const double *__restrict__ v, double *__restrict__ outp) {
+  double acc = (KIND == 0) ? 0.0 : ((KIND == 1) ? -INFINITY : INFINITY);
+  for (long t = 0; t < n; ++t) acc = red_op<KIND>(acc, v[t]);
+  outp[0] = acc;
+}
+#else
+template <int KIND>
+__global__ void reduce_kernel(long n, const double *__restrict__ v, double *__restrict__ outp) {
+  __shared__ double sm[32];
+  double acc = (KIND == 0) ? 0.0 : ((KIND == 1) ? -INFINITY : INFINITY);
+  PB_GRID_STRIDE(t, n) acc = red_op<KIND>(acc, v[t]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc = red_op<KIND>(acc, __shfl_down_sync(0xffffffffu, acc, off));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = blockDim.x >> 5;
+    acc = (lane < nw) ? sm[lane] : ((KIND == 0) ? 0.0 : ((KIND == 1) ? -INFINITY : INFINITY));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc = red_op<KIND>(acc, __shfl_down_sync(0xffffffffu, acc, off));
+    if (lane == 0) outp[blockIdx.x] = acc;
+  }
+}
+#endif
+
+template <int KIND>
+static void reduce_two_stage(long n, const double *v, double *partial, int blocks, double *result, cudaStream_t st) {
+  auto kfn = reduce_kernel<KIND>;
+#ifdef PB_EMULATE
+  (void)blocks;
+  PB_LAUNCH(kfn, dim3(1), dim3(1), 0, st, n, v, partial);
+  PB_LAUNCH(kfn, dim3(1), dim3(1), 0, st, 1L, partial, result);
+#else
+  PB_LAUNCH(kfn, dim3(blocks), dim3(256), 0, st, n, v, partial);
+  PB_LAUNCH(kfn, dim3(1), dim3(256), 0, st, (long)blocks, partial, result);
+#endif
+}
+
+cudaError_t launch_reduce(int kind, long n, const double *v, double *partial, int nblocks, double *result, cudaStream_t st) {
+  long want = (n + 1023) / 1024;
+  int blocks = (int)(want < nblocks ? (want < 1 ? 1 : want) : nblocks);
+  switch (kind) {
+    case 0: reduce_two_stage<0>(n, v, partial, blocks, result, st); break;
+    case 1: reduce_two_stage<1>(n, v, partial, blocks, result, st); break;
+    default: reduce_two_stage<2>(n, v, partial, blocks, result, st); break;
+  }
+  g_launches += 2;
+  return cudaGetLastError();
+}
+
+}  // namespace pb

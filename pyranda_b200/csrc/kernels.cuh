@@ -1,0 +1,91 @@
+// Device-side declarations shared by kernels.cu and api.cu.
+#pragma once
+#ifdef PB_EMULATE
+#include "cuda_emul.h"  // tests/emul: host emulation of the CUDA sources (test infrastructure)
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace pb {
+
+constexpr int kMaxChunks = 32;
+
+// epilogue applied when a sweep writes its result
+enum Epi {
+  EPI_STORE = 0,     // out = val
+  EPI_ACC = 1,       // out += val                         (div / laplacian accumulation)
+  EPI_RING_SET = 2,  // out = |val| * s^2                  (ring, first direction)
+  EPI_RING_MAX = 3   // out = max(out, |val| * s^2)        (ring, later directions)
+};
+
+// Everything a directional sweep needs; passed by value (kernel parameter / constant bank).
+struct SweepDev {
+  // line geometry --------------------------------------------------------------------------
+  int m;         // rows along the sweep axis on this rank
+  int nfast;     // y/z sweeps: lines along x (ax);            x sweep: number of lines (ay*az)
+  int nouter;    // y sweep: az, z sweep: ay;                   x sweep: unused
+  long rstride;  // stride between consecutive rows (y: ax, z: ax*ay, x: 1)
+  long ostride;  // stride between outer slices (y: ax*ay, z: ax)
+  // partition of a line into chunks --------------------------------------------------------
+  int P, C;
+  int ctype[kMaxChunks];
+  const double2 *lu_f;  // [ntypes][C]  {l2, l1}        forward multipliers (rows i-2, i-1)
+  const double4 *lu_b;  // [ntypes][C]  {1/pivot, u1, u2, 0}
+  const double4 *rc;    // [ntypes][C]  spike columns
+  const double *G;      // [P][4][4P]
+  // right-hand side ------------------------------------------------------------------------
+  double ari[9];
+  double arb_lo[4][9], arb_hi[4][9];
+  int phys_lo, phys_hi;  // one-sided closure rows at the local ends
+  int wrap;              // periodic and not split: halo rows come from the field itself
+  int implicit;          // solve after the stencil
+  int add_v;             // filters: result += input (null_option == 1)
+  double scale;          // 1/d, 1/d^2 or 1
+};
+
+struct EpiArgs {
+  int mode;
+  double s2;           // constant length-scale squared for EPI_RING_* when field == nullptr
+  const double *field; // per-point length scale (curvilinear d1/d2/d3); squared in the kernel
+};
+
+// launches (return cudaError_t of the launch)
+cudaError_t launch_sweep_yz(int fam, int lines, const SweepDev &a, const double *v, double *out,
+                            const double *halo_lo, const double *halo_hi, double *iface,
+                            const EpiArgs &epi, cudaStream_t st);
+cudaError_t launch_sweep_x(int fam, int lines, const SweepDev &a, const double *v, double *out,
+                           const EpiArgs &epi, cudaStream_t st);
+
+// z-slab helpers
+cudaError_t launch_pack_planes(const double *v, long plane, int m, int h, double *send_lo,
+                               double *send_hi, cudaStream_t st);
+cudaError_t launch_z_finish(const double *z, const double *v, double *out, long plane, int m,
+                            const double4 *RC, const double *GR, int np, const double *iface_all,
+                            double scale, int add_v, cudaStream_t st);
+
+// pointwise / reductions
+cudaError_t launch_rk4_stage(long n, double dt, double A, double B, const double *F, double *PHI,
+                             double *U, cudaStream_t st);
+cudaError_t launch_reduce(int kind, long n, const double *v, double *partial, int nblocks,
+                          double *result, cudaStream_t st);
+cudaError_t launch_copy(long n, const double *a, double *out, cudaStream_t st);
+cudaError_t launch_fill(long n, double val, double *out, cudaStream_t st);
+cudaError_t launch_mul(long n, const double *a, const double *b, double *out, cudaStream_t st);
+cudaError_t launch_div(long n, const double *a, const double *b, double *out, cudaStream_t st);
+// curvilinear divergence pre-contraction: fA/fB/fC = (fx*dAdx + fy*dAdy + fz*dAdz)*det ...
+cudaError_t launch_contra(long n, const double *fx, const double *fy, const double *fz,
+                          const double *const *metric9, const double *det, double *fA, double *fB,
+                          double *fC, cudaStream_t st);
+// curvilinear gradient contraction in place on (gx, gy, gz)
+cudaError_t launch_grad_contract(long n, const double *const *metric9, double *gx, double *gy,
+                                 double *gz, cudaStream_t st);
+// metrics from the nine Jacobian entries (mesh.f90:337-358)
+cudaError_t launch_metrics(long n, const double *const *J9, double dA, double dB, double dC,
+                           double *const *inv9, double *det, double *d1, double *d2, double *d3,
+                           double *cellvol, double *gridlen, cudaStream_t st);
+
+long launch_count();
+void set_yz_lines(int nl);
+void set_x_lines(int nl);
+
+}  // namespace pb

@@ -1,0 +1,326 @@
+// See tables.hpp.  Host only.
+#include "tables.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace pb {
+
+namespace {
+
+// lower closure rows are given; the upper ones are their mirror image (sign -1 for the
+// antisymmetric first derivative), as in stencils.f90:243-254 and the analogous lines of each set.
+void mirror_closures(Stencil &s, double rhs_sign) {
+  for (int r = 0; r < 4; ++r) {
+    for (int l = 0; l < s.ncl; ++l) s.alb_hi[r][l] = s.alb_lo[3 - r][s.ncl - 1 - l];
+    for (int l = 0; l < s.ncr; ++l) s.arb_hi[r][l] = rhs_sign * s.arb_lo[3 - r][s.ncr - 1 - l];
+  }
+}
+
+void set_row(double *dst, std::initializer_list<double> v) {
+  int i = 0;
+  for (double x : v) dst[i++] = x;
+}
+
+// filters are evaluated as f + A^-1 (B - A) f: subtract the lhs row from the centre of the rhs row
+// (stencils.f90:831-834 for the compact filter, :1472-1475 for the Gaussian)
+void difference_form(Stencil &s) {
+  const int off = s.nor - s.nol;
+  for (int l = 0; l < s.ncl; ++l) s.ari[off + l] -= s.ali[l];
+  for (int r = 0; r < 4; ++r)
+    for (int l = 0; l < s.ncl; ++l) {
+      s.arb_lo[r][off + l] -= s.alb_lo[r][l];
+      s.arb_hi[r][off + l] -= s.alb_hi[r][l];
+    }
+}
+
+}  // namespace
+
+Stencil make_stencil(Kind k) {
+  Stencil s;
+  switch (k) {
+    case K_D1: {  // 10th-order compact first derivative, stencils.f90:207-254
+      s.nol = 2; s.nor = 3; s.implicit = true; s.null_option = 0; s.post = 1; s.fam = F_D1;
+      s.ncl = 5; s.ncr = 7;
+      set_row(s.ali, {0.45, 4.5, 9.0, 4.5, 0.45});
+      set_row(s.ari, {-0.015, -1.515, -6.375, 0.0, 6.375, 1.515, 0.015});
+      set_row(s.alb_lo[0], {0.0, 0.0, 4.725, 9.45, 0.0});
+      set_row(s.alb_lo[1], {0.0, 1.94578125, 7.783125, 1.94578125, 0.0});
+      set_row(s.alb_lo[2], {0.2964375, 4.743, 10.67175, 4.743, 0.2964375});
+      set_row(s.alb_lo[3], {0.451390625, 4.63271875, 9.38146875, 4.63271875, 0.451390625});
+      set_row(s.arb_lo[0], {0.0, 0.0, 0.0, -11.8125, 9.45, 2.3625, 0.0});
+      set_row(s.arb_lo[1], {0.0, 0.0, -5.83734375, 0.0, 5.83734375, 0.0, 0.0});
+      set_row(s.arb_lo[2], {0.0, -1.23515625, -7.905, 0.0, 7.905, 1.23515625, 0.0});
+      set_row(s.arb_lo[3], {-0.015, -1.53, -6.66984375, 0.0, 6.66984375, 1.53, 0.015});
+      mirror_closures(s, -1.0);
+      break;
+    }
+    case K_D2: {  // 10th-order compact second derivative, stencils.f90:358-405
+      s.nol = 2; s.nor = 3; s.implicit = true; s.null_option = 0; s.post = 2; s.fam = F_R3;
+      s.ncl = 5; s.ncr = 7;
+      set_row(s.ali, {387.0, 6012.0, 16182.0, 6012.0, 387.0});
+      set_row(s.ari, {79.0, 4671.0, 9585.0, -28670.0, 9585.0, 4671.0, 79.0});
+      set_row(s.alb_lo[0], {0.0, 0.0, 1.0, 11.0, 0.0});
+      set_row(s.alb_lo[1], {0.0, 1.0, 10.0, 1.0, 0.0});
+      set_row(s.alb_lo[2], {23.0, 688.0, 2358.0, 688.0, 23.0});
+      set_row(s.alb_lo[3], {387.0, 6012.0, 16182.0, 6012.0, 387.0});
+      set_row(s.arb_lo[0], {0.0, 0.0, 0.0, 13.0, -27.0, 15.0, -1.0});
+      set_row(s.arb_lo[1], {0.0, 0.0, 12.0, -24.0, 12.0, 0.0, 0.0});
+      set_row(s.arb_lo[2], {0.0, 465.0, 1920.0, -4770.0, 1920.0, 465.0, 0.0});
+      set_row(s.arb_lo[3], {79.0, 4671.0, 9585.0, -28670.0, 9585.0, 4671.0, 79.0});
+      mirror_closures(s, 1.0);
+      break;
+    }
+    case K_D8: {  // compact 8th derivative (ringing detector), stencils.f90:515-591
+      const double zeta = 29.0, alpha = 14.0, beta = 1.5;
+      const double aa = 4200.0, bb = -3360.0, cc = 1680.0, dd = -480.0, ee = 60.0;
+      s.nol = 2; s.nor = 4; s.implicit = true; s.null_option = 0; s.post = 0; s.fam = F_R4;
+      s.ncl = 5; s.ncr = 9;
+      set_row(s.ali, {beta, alpha, zeta, alpha, beta});
+      set_row(s.ari, {ee, dd, cc, bb, aa, bb, cc, dd, ee});
+      set_row(s.alb_lo[0], {0.0, 0.0, alpha + zeta, beta + alpha, beta});
+      set_row(s.alb_lo[1], {0.0, beta + alpha, zeta, alpha, beta});
+      set_row(s.alb_lo[2], {beta, alpha, zeta, alpha, beta});
+      set_row(s.alb_lo[3], {beta, alpha, zeta, alpha, beta});
+      set_row(s.arb_lo[0], {0.0, 0.0, 0.0, 0.0, bb + aa, cc + bb, dd + cc, ee + dd, ee});
+      set_row(s.arb_lo[1], {0.0, 0.0, 0.0, cc + bb, dd + aa, ee + bb, cc, dd, ee});
+      set_row(s.arb_lo[2], {0.0, 0.0, dd + cc, ee + bb, aa, bb, cc, dd, ee});
+      set_row(s.arb_lo[3], {0.0, ee + dd, cc, bb, aa, bb, cc, dd, ee});
+      mirror_closures(s, 1.0);
+      break;
+    }
+    case K_SF: {  // 8th-order compact "9/10" filter, telescoped closures, stencils.f90:713-835
+      const double beta = 1.6688e-1, alpha = 6.6624e-1, zeta = 1.0;
+      const double aa = 9.9965e-1, bb = 6.6652e-1, cc = 1.6674e-1, dd = 4.0e-5, ee = -5.0e-6;
+      s.nol = 2; s.nor = 4; s.implicit = true; s.null_option = 1; s.post = 0; s.fam = F_R4;
+      s.ncl = 5; s.ncr = 9;
+      set_row(s.ali, {beta, alpha, zeta, alpha, beta});
+      set_row(s.ari, {ee, dd, cc, bb, aa, bb, cc, dd, ee});
+      set_row(s.alb_lo[0], {0.0, 0.0, 1.0, 0.0, 0.0});
+      set_row(s.alb_lo[1], {0.0, 4.997e-1, 1.0, 4.997e-1, 0.0});
+      set_row(s.alb_lo[2], {1.6688e-1, 6.6624e-1, 1.0, 6.6624e-1, 1.6688e-1});
+      set_row(s.alb_lo[3], {1.6688e-1, 6.6624e-1, 1.0, 6.6624e-1, 1.6688e-1});
+      set_row(s.arb_lo[0], {0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0});
+      set_row(s.arb_lo[1], {0.0, 0.0, 0.0, 4.9985e-1, 9.997e-1, 4.9985e-1, 0.0, 0.0, 0.0});
+      set_row(s.arb_lo[2], {0.0, 0.0, 1.668e-1, 6.6656e-1, 9.9952e-1, 6.6656e-1, 1.668e-1, 0.0, 0.0});
+      set_row(s.arb_lo[3], {0.0, 4.0e-5, 1.6672e-1, 6.6652e-1, 9.9968e-1, 6.6652e-1, 1.6672e-1, 4.0e-5, 0.0});
+      mirror_closures(s, 1.0);
+      difference_form(s);
+      break;
+    }
+    case K_GF: {  // explicit 9-point Gaussian, stencils.f90:1387-1476
+      const double a = 3565.0 / 10368.0, b = 3091.0 / 12960.0, c = 1997.0 / 25920.0,
+                   d = 149.0 / 12960.0, e = 107.0 / 103680.0;
+      s.nol = 0; s.nor = 4; s.implicit = false; s.null_option = 1; s.post = 0; s.fam = F_R4;
+      s.ncl = 1; s.ncr = 9;
+      s.ali[0] = 1.0;
+      set_row(s.ari, {e, d, c, b, a, b, c, d, e});
+      for (int r = 0; r < 4; ++r) s.alb_lo[r][0] = 1.0;
+      set_row(s.arb_lo[0], {0.0, 0.0, 0.0, 0.0, a + b, b + c, c + d, d + e, e});
+      set_row(s.arb_lo[1], {0.0, 0.0, 0.0, b + c, a + d, b + e, c, d, e});
+      set_row(s.arb_lo[2], {0.0, 0.0, c + d, b + e, a, b, c, d, e});
+      set_row(s.arb_lo[3], {0.0, d + e, c, b, a, b, c, d, e});
+      mirror_closures(s, 1.0);
+      difference_form(s);
+      break;
+    }
+    default:
+      throw std::invalid_argument("make_stencil: unknown operator kind");
+  }
+  return s;
+}
+
+std::vector<double> assemble_bands(const Stencil &st, int n, bool periodic) {
+  // compact_basetype.f90:123-133: interior weights on every row, closures patched on the ends
+  std::vector<double> b((size_t)n * 5, 0.0);
+  if (!st.implicit) {
+    for (int i = 0; i < n; ++i) b[(size_t)i * 5 + 2] = 1.0;
+    return b;
+  }
+  for (int i = 0; i < n; ++i)
+    for (int l = 0; l < 5; ++l) b[(size_t)i * 5 + l] = st.ali[l];
+  if (!periodic) {
+    for (int r = 0; r < 4 && r < n; ++r)
+      for (int l = 0; l < 5; ++l) b[(size_t)r * 5 + l] = st.alb_lo[r][l];
+    for (int r = 0; r < 4 && n - 4 + r >= 0; ++r)
+      for (int l = 0; l < 5; ++l) b[(size_t)(n - 4 + r) * 5 + l] = st.alb_hi[r][l];
+  }
+  return b;
+}
+
+int choose_chunks(int m, int chunk_len) {
+  if (chunk_len < 16) chunk_len = 16;
+  int best = 1;
+  // largest P (<= 32) dividing m whose chunk length stays >= chunk_len; otherwise the closest
+  for (int P = 1; P <= 32; ++P) {
+    if (m % P) continue;
+    const int C = m / P;
+    if (C < 16) break;
+    if (C >= chunk_len) best = P;
+  }
+  return best;
+}
+
+namespace {
+
+// LU of a bounded pentadiagonal block without pivoting; the reference's elimination order
+// (pentadiagonal.f90:18-39).  c: C x 5 in place; pivots are stored inverted.
+void lu_block(std::vector<double> &c, int C) {
+  auto at = [&](int i, int l) -> double & { return c[(size_t)i * 5 + l]; };
+  for (int i = 0; i + 2 < C; ++i) {
+    at(i + 1, 1) /= at(i, 2);
+    at(i + 1, 2) -= at(i, 3) * at(i + 1, 1);
+    at(i + 1, 3) -= at(i, 4) * at(i + 1, 1);
+    at(i + 2, 0) /= at(i, 2);
+    at(i + 2, 1) -= at(i, 3) * at(i + 2, 0);
+    at(i + 2, 2) -= at(i, 4) * at(i + 2, 0);
+  }
+  at(C - 1, 1) /= at(C - 2, 2);
+  at(C - 1, 2) -= at(C - 2, 3) * at(C - 1, 1);
+  for (int i = 0; i < C; ++i) at(i, 2) = 1.0 / at(i, 2);
+  // entries that point outside the block are never used by the solve: zero them so the kernels
+  // can run one uniform recurrence over every row
+  at(0, 0) = at(0, 1) = at(1, 0) = 0.0;
+  at(C - 1, 3) = at(C - 1, 4) = at(C - 2, 4) = 0.0;
+}
+
+// solve with the factors above (pentadiagonal.f90:42-61), pull form
+void solve_block(const std::vector<double> &c, int C, double *r) {
+  auto at = [&](int i, int l) { return c[(size_t)i * 5 + l]; };
+  for (int i = 0; i < C; ++i) {
+    double t = r[i];
+    if (i >= 2) t -= at(i, 0) * r[i - 2];
+    if (i >= 1) t -= at(i, 1) * r[i - 1];
+    r[i] = t;
+  }
+  for (int i = C - 1; i >= 0; --i) {
+    double t = r[i];
+    if (i + 1 < C) t -= at(i, 3) * r[i + 1];
+    if (i + 2 < C) t -= at(i, 4) * r[i + 2];
+    r[i] = t * at(i, 2);
+  }
+}
+
+// dense inverse by Gauss-Jordan with partial pivoting, long double
+std::vector<long double> invert_dense(std::vector<long double> a, int n) {
+  std::vector<long double> inv((size_t)n * n, 0.0L);
+  for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0L;
+  for (int col = 0; col < n; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < n; ++r)
+      if (fabsl(a[(size_t)r * n + col]) > fabsl(a[(size_t)piv * n + col])) piv = r;
+    if (a[(size_t)piv * n + col] == 0.0L) throw std::runtime_error("reduced interface system is singular");
+    if (piv != col)
+      for (int c = 0; c < n; ++c) {
+        std::swap(a[(size_t)piv * n + c], a[(size_t)col * n + c]);
+        std::swap(inv[(size_t)piv * n + c], inv[(size_t)col * n + c]);
+      }
+    const long double d = 1.0L / a[(size_t)col * n + col];
+    for (int c = 0; c < n; ++c) { a[(size_t)col * n + c] *= d; inv[(size_t)col * n + c] *= d; }
+    for (int r = 0; r < n; ++r) {
+      if (r == col) continue;
+      const long double f = a[(size_t)r * n + col];
+      if (f == 0.0L) continue;
+      for (int c = 0; c < n; ++c) {
+        a[(size_t)r * n + c] -= f * a[(size_t)col * n + c];
+        inv[(size_t)r * n + c] -= f * inv[(size_t)col * n + c];
+      }
+    }
+  }
+  return inv;
+}
+
+}  // namespace
+
+Partition build_partition(int m, const std::vector<double> &bands, bool cyclic, int P) {
+  if (P < 1 || m % P != 0) throw std::invalid_argument("build_partition: P must divide m");
+  const int C = m / P;
+  if (C < 8) throw std::invalid_argument("build_partition: chunk shorter than 8 rows");
+  Partition part;
+  part.m = m; part.P = P; part.C = C; part.cyclic = cyclic;
+  part.ctype.assign(P, 0);
+  part.G.assign((size_t)P * 4 * 4 * P, 0.0);
+
+  std::vector<std::vector<double>> lu_all(P), rc_all(P);
+  auto band = [&](int i, int l) { return bands[(size_t)i * 5 + l]; };
+  const int nred = 4 * P;
+  std::vector<long double> R((size_t)nred * nred, 0.0L);
+  for (int i = 0; i < nred; ++i) R[(size_t)i * nred + i] = 1.0L;
+  std::vector<int> prev(P), next(P);
+
+  for (int p = 0; p < P; ++p) {
+    const int s = p * C, e = s + C;
+    std::vector<double> c((size_t)C * 5);
+    for (int i = 0; i < C; ++i)
+      for (int l = 0; l < 5; ++l) c[(size_t)i * 5 + l] = band(s + i, l);
+    lu_block(c, C);
+    prev[p] = (p > 0) ? p - 1 : (cyclic ? P - 1 : -1);
+    next[p] = (p + 1 < P) ? p + 1 : (cyclic ? 0 : -1);
+    // spike columns: A_p^-1 applied to the dropped couplings (compact_basetype.f90:151-181)
+    std::vector<double> rc((size_t)C * 4, 0.0), col(C);
+    for (int q = 0; q < 4; ++q) {
+      std::fill(col.begin(), col.end(), 0.0);
+      bool any = false;
+      if (q < 2 && prev[p] >= 0) {
+        if (q == 0) { col[0] = band(s, 0); }
+        else { col[0] = band(s, 1); col[1] = band(s + 1, 0); }
+        any = true;
+      } else if (q >= 2 && next[p] >= 0) {
+        if (q == 2) { col[C - 2] = band(e - 2, 4); col[C - 1] = band(e - 1, 3); }
+        else { col[C - 1] = band(e - 1, 4); }
+        any = true;
+      }
+      if (any) {
+        bool nz = false;
+        for (double x : col) nz = nz || (x != 0.0);
+        if (nz) solve_block(c, C, col.data());
+      }
+      for (int i = 0; i < C; ++i) rc[(size_t)i * 4 + q] = any ? col[i] : 0.0;
+    }
+    // reduced system rows of this chunk: y_p + V^ y_prev(3:4) + W^ y_next(1:2) = d_p
+    const int rows[4] = {0, 1, C - 2, C - 1};
+    for (int r = 0; r < 4; ++r)
+      for (int q = 0; q < 4; ++q) {
+        const int nb = (q < 2) ? prev[p] : next[p];
+        if (nb < 0) continue;
+        const int colidx = (q < 2) ? 4 * nb + 2 + q : 4 * nb + (q - 2);
+        R[(size_t)(4 * p + r) * nred + colidx] += (long double)rc[(size_t)rows[r] * 4 + q];
+      }
+    lu_all[p] = std::move(c);
+    rc_all[p] = std::move(rc);
+  }
+
+  std::vector<long double> Rinv = invert_dense(R, nred);
+  for (int p = 0; p < P; ++p)
+    for (int q = 0; q < 4; ++q) {
+      const int nb = (q < 2) ? prev[p] : next[p];
+      if (nb < 0) continue;
+      const int row = (q < 2) ? 4 * nb + 2 + q : 4 * nb + (q - 2);
+      for (int j = 0; j < nred; ++j)
+        part.G[((size_t)p * 4 + q) * nred + j] = (double)Rinv[(size_t)row * nred + j];
+    }
+
+  // share identical chunk tables
+  std::vector<int> rep;  // representative chunk of each type
+  for (int p = 0; p < P; ++p) {
+    int t = -1;
+    for (size_t k = 0; k < rep.size(); ++k) {
+      const int q = rep[k];
+      if (!memcmp(lu_all[p].data(), lu_all[q].data(), sizeof(double) * C * 5) &&
+          !memcmp(rc_all[p].data(), rc_all[q].data(), sizeof(double) * C * 4)) { t = (int)k; break; }
+    }
+    if (t < 0) { t = (int)rep.size(); rep.push_back(p); }
+    part.ctype[p] = t;
+  }
+  part.ntypes = (int)rep.size();
+  part.lu.resize((size_t)part.ntypes * C * 5);
+  part.rc.resize((size_t)part.ntypes * C * 4);
+  for (int t = 0; t < part.ntypes; ++t) {
+    memcpy(&part.lu[(size_t)t * C * 5], lu_all[rep[t]].data(), sizeof(double) * C * 5);
+    memcpy(&part.rc[(size_t)t * C * 4], rc_all[rep[t]].data(), sizeof(double) * C * 4);
+  }
+  return part;
+}
+
+}  // namespace pb
