@@ -563,11 +563,18 @@ cudaError_t launch_sweep_x(int fam, int lines, const SweepDev &a, const double *
   }
 }
 
+static inline int ew_blocks(long n) {
+  long b = (n + 255) / 256;
+  const long cap = 148L * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+#define PB_GRID_STRIDE(t, n) for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < (n); t += (long)gridDim.x * blockDim.x)
+
 // ---- z-slab helpers ------------------------------------------------------------------------------
 __global__ void pack_planes_kernel(const double *__restrict__ v, long plane, int m, int h,
                                    double *__restrict__ send_lo, double *__restrict__ send_hi) {
   const long n = plane * h;
-  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+  PB_GRID_STRIDE(t, n) {
     send_lo[t] = v[t];                          // first h planes   (compact_d1.f90:723)
     send_hi[t] = v[(long)(m - h) * plane + t];  // last h planes    (compact_d1.f90:722)
   }
@@ -621,12 +628,6 @@ cudaError_t launch_z_finish(const double *z, const double *v, double *out, long 
 }
 
 // ---- pointwise -----------------------------------------------------------------------------------
-static inline int ew_blocks(long n) {
-  long b = (n + 255) / 256;
-  const long cap = 148L * 16;
-  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
-}
-#define PB_GRID_STRIDE(t, n) for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < (n); t += (long)gridDim.x * blockDim.x)
 
 // pyranda.py:800-804: PHI = dt*F + A*PHI ; U = U + B*PHI
 __global__ void rk4_stage_kernel(long n, double dt, double A, double B, const double *__restrict__ F,

@@ -143,6 +143,12 @@ class ParcopPlan:
         check(self.L, self.L.pb_host_apply(self._h, code, a.ctypes.data, out.ctypes.data))
         return out
 
+    def apply_host_into(self, op, a_in, a_out):
+        """Host path into a caller-owned (e.g. pinned) Fortran-ordered output array."""
+        if not (a_in.flags.f_contiguous and a_out.flags.f_contiguous and a_in.shape == self.shape == a_out.shape):
+            raise ParcopError("apply_host_into needs Fortran-ordered float64 arrays of the local extents")
+        check(self.L, self.L.pb_host_apply(self._h, OP[op], a_in.ctypes.data, a_out.ctypes.data))
+
     # parcop.f90:225-368, one method per f2py subroutine (lower-case names as f2py exports them)
     def ddx(self, val): return self.apply("ddx", val)
     def ddy(self, val): return self.apply("ddy", val)

@@ -1,0 +1,158 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerance: 1e-12 relative L-infinity per operator application (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+from conftest import domain, rel_linf, synthetic_field
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+UNARY = ["ddx", "ddy", "ddz", "dd8x", "dd8y", "dd8z", "d2x", "d2y", "d2z", "plaplacian", "pring",
+         "sfilter", "gfilter"]
+
+
+def _pair(n, periodic, oracle_mod, **kw):
+    from pyranda_b200 import ParcopPlan
+    (x1, xn), (y1, yn), (z1, zn) = domain(n, periodic)
+    o = oracle_mod.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3)
+    p = ParcopPlan(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3, **kw)
+    p.set_mesh()
+    f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+    return o, p, f
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("n", [(64, 64, 64), (32, 48, 80), (128, 64, 32)])
+def test_unary_operators_host_arrays(n, periodic, oracle_mod):
+    o, p, f = _pair(n, periodic, oracle_mod)
+    for name in UNARY:
+        ref = getattr(o, name)(f)
+        got = getattr(p, name)(f)
+        assert got.flags.f_contiguous and got.shape == f.shape
+        assert rel_linf(got, ref) < TOL, (name, n, periodic, rel_linf(got, ref))
+    for d in (1, 2, 3):
+        assert rel_linf(p.gfilterdir(f, d), o.gfilterdir(f, d)) < TOL
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_div_grad(periodic, oracle_mod):
+    o, p, f = _pair((48, 64, 32), periodic, oracle_mod)
+    g = np.asfortranarray(np.cos(f) + 0.3 * f)
+    h = np.asfortranarray(f * f)
+    assert rel_linf(p.divergence(f, g, h), o.divergence(f, g, h)) < TOL
+    for a, b in zip(p.grads(f), o.grads(f)):
+        assert rel_linf(a, b) < TOL
+
+
+@pytest.mark.parametrize("chunk", [16, 32, 64])
+@pytest.mark.parametrize("lines", [8, 16, 32])
+def test_tile_shapes(chunk, lines, oracle_mod):
+    """Every chunk length / tile width the launcher can pick gives the same answer."""
+    from pyranda_b200 import _lib
+    L = _lib.load()
+    L.pb_set_tuning(lines, lines, chunk)
+    try:
+        for periodic in (True, False):
+            o, p, f = _pair((128, 64, 64), periodic, oracle_mod)
+            for name in ("ddx", "ddy", "ddz", "sfilter", "dd8x", "d2z"):
+                assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < TOL, (name, chunk, lines, periodic)
+    finally:
+        L.pb_set_tuning(16, 16, 64)
+
+
+def test_device_resident_tensors(oracle_mod):
+    import torch
+    o, p, f = _pair((64, 64, 64), True, oracle_mod)
+    t = p.empty_device()
+    t.copy_(torch.from_numpy(f))
+    for name in ("ddx", "ddy", "ddz", "sfilter", "gfilter", "pring"):
+        out = getattr(p, name)(t)
+        assert out.is_cuda and out.stride() == (1, 64, 64 * 64)
+        assert rel_linf(out.cpu().numpy(), getattr(o, name)(f)) < TOL, name
+    # non-Fortran input is copied, like f2py does
+    c = torch.from_numpy(np.ascontiguousarray(f)).cuda()
+    assert rel_linf(p.ddx(c).cpu().numpy(), o.ddx(f)) < TOL
+    # reductions and the fused RK4 stage update
+    assert abs(p.reduce("sum", t) - f.sum()) < 1e-9 * abs(f).sum()
+    assert p.reduce("max", t) == f.max() and p.reduce("min", t) == f.min()
+    F, PHI, U = (p.empty_device() for _ in range(3))
+    rng = np.random.default_rng(7)
+    hF, hP, hU = (np.asfortranarray(rng.standard_normal(f.shape)) for _ in range(3))
+    for d, h in ((F, hF), (PHI, hP), (U, hU)):
+        d.copy_(torch.from_numpy(h))
+    p.rk4_stage(0.01, -0.48, 0.74, F, PHI, U)
+    phi = 0.01 * hF + (-0.48) * hP
+    assert np.abs(PHI.cpu().numpy() - phi).max() < 1e-15
+    assert np.abs(U.cpu().numpy() - (hU + 0.74 * phi)).max() < 1e-15
+
+
+def test_null_directions_and_2d(oracle_mod):
+    """n < 4 along an axis: derivatives return zero, filters copy (compact.f90:95-97)."""
+    from pyranda_b200 import ParcopPlan
+    n = (64, 48, 1)
+    o = oracle_mod.Oracle(*n, 0, 1, 0, 1, 0, 1)
+    p = ParcopPlan(*n, 0, 1, 0, 1, 0, 1)
+    p.set_mesh()
+    f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+    for name in UNARY:
+        ref, got = getattr(o, name)(f), getattr(p, name)(f)
+        assert rel_linf(got, ref) < TOL, name
+    assert np.all(p.ddz(f) == 0.0)
+
+
+def test_errors_are_loud():
+    from pyranda_b200 import ParcopError, ParcopPlan
+    p = ParcopPlan(32, 32, 32)
+    with pytest.raises(ParcopError):
+        p.ddx(np.zeros((16, 32, 32)))
+    with pytest.raises(ParcopError):
+        p.pring(np.zeros((32, 32, 32)))  # mesh not set
+    with pytest.raises(ParcopError):
+        ParcopPlan(8, 32, 32)  # 4 <= n < 16 is refused, not silently wrong
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_full_size_properties_512(periodic):
+    """At the benchmark size the oracle is too slow to run per test; check size-independent
+    properties instead: exactness on constants / low-order polynomials or the analytic transfer
+    function of a Fourier mode, linearity, and agreement of the three directions."""
+    import torch
+    from pyranda_b200 import ParcopPlan
+    N = 512
+    (x1, xn), (y1, yn), (z1, zn) = domain((N, N, N), periodic)
+    p = ParcopPlan(N, N, N, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3)
+    p.set_mesh()
+    dev = torch.device("cuda")
+    ax = x1 + p.dx * torch.arange(N, dtype=torch.float64, device=dev)
+    X = p.empty_device(); Y = p.empty_device(); Z = p.empty_device()
+    X.copy_(ax.view(N, 1, 1).expand(N, N, N)); Y.copy_(ax.view(1, N, 1).expand(N, N, N)); Z.copy_(ax.view(1, 1, N).expand(N, N, N))
+    ops = (p.ddx, p.ddy, p.ddz)
+    if periodic:
+        # modified wavenumber of c10d1 for mode k = 3 (stencils.f90:236-237)
+        k, h = 3.0, p.dx
+        num = 2 * (6.375 * np.sin(k * h) + 1.515 * np.sin(2 * k * h) + 0.015 * np.sin(3 * k * h))
+        den = 9.0 + 2 * 4.5 * np.cos(k * h) + 2 * 0.45 * np.cos(2 * k * h)
+        kp = num / den / h
+        for C, op in zip((X, Y, Z), ops):
+            err = (op(torch.sin(k * C)) - kp * torch.cos(k * C)).abs().max().item()
+            assert err < 1e-11, err
+        one = torch.ones_like(X)
+        for name in ("sfilter", "gfilter"):
+            assert (getattr(p, name)(one) - 1.0).abs().max().item() < 1e-14
+    else:
+        for C, op in zip((X, Y, Z), ops):
+            assert (op(C * C * C) - 3 * C * C).abs().max().item() < 1e-9
+            assert op(torch.ones_like(C)).abs().max().item() == 0.0
+        assert (p.sfilter(X + 2 * Y - Z) - (X + 2 * Y - Z)).abs().max().item() < 1e-12
+    # linearity and direction symmetry on a random field
+    g = torch.rand((N, N, N), dtype=torch.float64, device=dev).permute(2, 1, 0)
+    a = p.ddx(g)
+    b = p.ddy(g.permute(1, 0, 2)).permute(1, 0, 2)
+    c = p.ddz(g.permute(2, 1, 0)).permute(2, 1, 0)
+    scale = a.abs().max().item()
+    assert (a - b).abs().max().item() < 1e-12 * scale and (a - c).abs().max().item() < 1e-12 * scale
+    assert (p.sfilter(2.5 * g) - 2.5 * p.sfilter(g)).abs().max().item() < 1e-13
