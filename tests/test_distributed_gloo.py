@@ -1,0 +1,68 @@
+"""world_size = 2 (and 4) over gloo on CPU: the z-slab orchestration of pyranda_b200.distributed
+(halo send/recv, interface all-gather, reduced solve + correction) against the one-rank oracle.
+Compute runs through the emulated build of the CUDA sources (tests/emul); on the GPU box the same
+class runs over NCCL."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul")
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+from conftest import domain, rel_linf, synthetic_field
+from oracle import oracle
+from pyranda_b200 import _lib
+from pyranda_b200.distributed import DistributedParcop
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+L = _lib.load(os.path.join({emul!r}, "libparcop_emul.so"))
+L.pb_set_tuning(16, 16, 16)
+n = (32, 32, 32 * world)
+worst = 0.0
+for periodic in (True, False):
+    (x1, xn), (y1, yn), (z1, zn) = domain(n, periodic)
+    o = oracle.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3)
+    f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+    eng = DistributedParcop(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3, lib=L, tensor_device="cpu")
+    az = n[2] // world
+    sl = slice(rank * az, (rank + 1) * az)
+    loc = eng.empty(); loc.copy_(torch.from_numpy(f[:, :, sl].copy()))
+    for name, ref in (("ddx", o.ddx), ("ddy", o.ddy), ("ddz", o.ddz), ("dd8z", o.dd8z), ("d2z", o.d2z),
+                      ("sfilter", o.sfilter), ("gfilter", o.gfilter), ("laplacian", o.plaplacian), ("ring", o.pring)):
+        got = eng.apply(name, loc).numpy()
+        err = rel_linf(got, ref(f)[:, :, sl])
+        worst = max(worst, err)
+        assert err < 1e-12, (name, periodic, rank, err)
+    got = eng.divergence(loc, loc * 2, loc * loc).numpy()
+    assert rel_linf(got, o.divergence(f, 2 * f, f * f)[:, :, sl]) < 1e-12
+    assert abs(eng.sum3D(loc) - f.sum()) < 1e-9 * np.abs(f).sum()
+    assert eng.max3D(loc) == f.max() and eng.min3D(loc) == f.min()
+print("rank", rank, "worst", worst)
+dist.destroy_process_group()
+"""
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_zslab_gloo(world, tmp_path):
+    subprocess.check_call(["make", "-C", EMUL, "-s"])
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, emul=EMUL))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("worst") == world

@@ -1,0 +1,79 @@
+"""The real CUDA kernel sources, compiled for the host against tests/emul/cuda_emul.h (one
+std::thread per CUDA thread, std::barrier for __syncthreads), checked against the oracle.
+
+This is how indexing / barrier placement of kernels.cu and the dispatch logic of api.cu are
+debugged in the GPU-less development container.  The emulated library is test infrastructure: the
+product never loads it (pyranda_b200._lib only knows libparcop_b200.so).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import domain, rel_linf, synthetic_field
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul")
+
+
+@pytest.fixture(scope="module")
+def emul_lib():
+    subprocess.check_call(["make", "-C", EMUL, "-s"])
+    from pyranda_b200 import _lib
+    L = _lib.load(os.path.join(EMUL, "libparcop_emul.so"))
+    L.pb_set_tuning(16, 16, 16)  # short chunks so that small grids still exercise P > 1
+    return L
+
+
+def _pair(n, periodic, oracle_mod, lib):
+    from pyranda_b200 import ParcopPlan
+    (x1, xn), (y1, yn), (z1, zn) = domain(n, periodic)
+    o = oracle_mod.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3)
+    p = ParcopPlan(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3, lib=lib)
+    p.set_mesh()
+    return o, p, synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_emulated_operators_match_oracle(periodic, oracle_mod, emul_lib):
+    o, p, f = _pair((32, 48, 32), periodic, oracle_mod, emul_lib)
+    for name in ("ddx", "ddy", "ddz", "dd8x", "dd8z", "d2y", "sfilter", "gfilter", "plaplacian", "pring"):
+        assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < 1e-13, (name, periodic)
+    assert rel_linf(p.divergence(f, 2 * f, f * f), o.divergence(f, 2 * f, f * f)) < 1e-13
+    for a, b in zip(p.grads(f), o.grads(f)):
+        assert rel_linf(a, b) < 1e-13
+
+
+def test_emulated_partial_tiles_and_single_chunk(oracle_mod, emul_lib):
+    """nx not a multiple of the tile width, line count not a multiple of the x tile, P == 1."""
+    emul_lib.pb_set_tuning(16, 16, 64)
+    try:
+        for periodic in (True, False):
+            o, p, f = _pair((24, 20, 18), periodic, oracle_mod, emul_lib)
+            for name in ("ddx", "ddy", "ddz", "sfilter"):
+                assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < 1e-13, (name, periodic)
+    finally:
+        emul_lib.pb_set_tuning(16, 16, 16)
+
+
+def test_emulated_curvilinear(oracle_mod, emul_lib):
+    """coordsys = 3: metrics, div, grad and the cell-volume weighted filter on a distorted grid."""
+    from pyranda_b200 import ParcopPlan
+    n = (32, 24, 16)
+    xs = [np.linspace(0, 1, k) for k in n]
+    X, Y, Z = np.meshgrid(*xs, indexing="ij")
+    Xd = X + 0.05 * np.sin(2 * np.pi * Y) * np.sin(np.pi * X)
+    Yd = Y + 0.04 * np.sin(2 * np.pi * X) * Z
+    Zd = Z * (1 + 0.1 * X)
+    o = oracle_mod.Oracle(*n, 0, 1, 0, 1, 0, 1, coordsys=3, mesh_xyz=(Xd, Yd, Zd))
+    p = ParcopPlan(*n, 0, 1, 0, 1, 0, 1, coordsys=3, lib=emul_lib)
+    p.set_mesh(Xd, Yd, Zd)
+    for name in ("dtJ", "dAx", "dBy", "dCz", "dAy", "d1", "d2", "d3", "CellVol", "GridLen"):
+        assert rel_linf(p.getvar(name), o.getvar(name)) < 1e-12, name
+    f = synthetic_field(X, Y, Z)
+    assert rel_linf(p.divergence(f, 2 * f, -f), o.divergence(f, 2 * f, -f)) < 1e-12
+    for a, b in zip(p.grads(f), o.grads(f)):
+        assert rel_linf(a, b) < 1e-12
+    assert rel_linf(p.sfilter(f), o.sfilter(f)) < 1e-12
+    assert rel_linf(p.pring(f), o.pring(f)) < 1e-12
