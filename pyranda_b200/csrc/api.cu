@@ -22,7 +22,7 @@ namespace {
 thread_local std::string g_err;
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
-int g_chunk_len = 64;
+int g_chunk_len = 32;
 
 #define PB_CUDA(call)                                                                      \
   do {                                                                                     \
@@ -121,22 +121,30 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
           return fail(PB_ERR_UNSUPPORTED, "r3 closure rows reach outside the domain");
   }
   if (st.implicit) {
-    Partition part;
-    try { part = build_partition(m, local, cyclic_local, P); }
+    LineTables lt;
+    try { lt = build_line_tables(m, local, cyclic_local, P); }
     catch (const std::exception &ex) { return fail(PB_ERR_ARG, ex.what()); }
-    for (int q = 0; q < P; ++q) dv.ctype[q] = part.ctype[q];
-    std::vector<double2> luf((size_t)part.ntypes * dv.C);
-    std::vector<double4> lub((size_t)part.ntypes * dv.C), rc((size_t)part.ntypes * dv.C);
-    for (size_t t = 0; t < luf.size(); ++t) {
-      luf[t] = make_double2(part.lu[t * 5 + 0], part.lu[t * 5 + 1]);
-      lub[t] = make_double4(part.lu[t * 5 + 2], part.lu[t * 5 + 3], part.lu[t * 5 + 4], 0.0);
-      rc[t] = make_double4(part.rc[t * 4 + 0], part.rc[t * 4 + 1], part.rc[t * 4 + 2], part.rc[t * 4 + 3]);
+    for (int q = 0; q < P; ++q) dv.ctype[q] = lt.ctype[q];
+    dv.wmask = lt.wmask;
+    dv.has_const = lt.has_const ? 1 : 0;
+    for (int q = 0; q < 5; ++q) dv.cst[q] = lt.cst[q];
+    for (int q = 0; q < 16; ++q) dv.K[q] = lt.K[q];
+    const size_t nt = (size_t)lt.ntypes * dv.C;
+    std::vector<double2> luf(nt), phi(nt), psi(nt);
+    std::vector<double4> lub(nt), Wc(lt.W.size() / 4);
+    for (size_t t = 0; t < nt; ++t) {
+      luf[t] = make_double2(lt.luf[t * 2], lt.luf[t * 2 + 1]);
+      phi[t] = make_double2(lt.phi[t * 2], lt.phi[t * 2 + 1]);
+      psi[t] = make_double2(lt.psi[t * 2], lt.psi[t * 2 + 1]);
+      lub[t] = make_double4(lt.lub[t * 4], lt.lub[t * 4 + 1], lt.lub[t * 4 + 2], 0.0);
     }
+    for (size_t t = 0; t < Wc.size(); ++t) Wc[t] = make_double4(lt.W[t * 4], lt.W[t * 4 + 1], lt.W[t * 4 + 2], lt.W[t * 4 + 3]);
     int rcv;
-    if ((rcv = upload(sp, luf, &dv.lu_f)) != PB_OK) return rcv;
-    if ((rcv = upload(sp, lub, &dv.lu_b)) != PB_OK) return rcv;
-    if ((rcv = upload(sp, rc, &dv.rc)) != PB_OK) return rcv;
-    if ((rcv = upload(sp, part.G, &dv.G)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, luf, &dv.luf)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, lub, &dv.lub)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, phi, &dv.phi)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, psi, &dv.psi)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, Wc, &dv.W)) != PB_OK) return rcv;
     if (sp.split) {
       // rank level: the same partition algebra with ranks as chunks (compact_basetype.f90:150-198)
       Partition rp;

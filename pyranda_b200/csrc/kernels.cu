@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 
 #include <atomic>
+#include <type_traits>
 
 #include "tables.hpp"
 
@@ -161,14 +162,61 @@ __device__ __forceinline__ void epi_store(double *__restrict__ out, long idx, do
   }
 }
 
-// ---- y / z sweep ---------------------------------------------------------------------------------
-template <int FAM, int NL>
+// rotated window access: logical element j of the window lives in slot (K + j) % W
+template <int FAM, int K>
+__device__ __forceinline__ double rhs_center_rot(const double *w, const double *ar) {
+  constexpr int W = FT<FAM>::W;
+#define WR(j) w[(K + (j)) % W]
+  if (FAM == F_D1) {
+    return ar[4] * (WR(4) - WR(2)) + ar[5] * (WR(5) - WR(1)) + ar[6] * (WR(6) - WR(0));
+  } else if (FAM == F_R3) {
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < 7; ++l)
+      if (l != 3) s += ar[l] * (WR(l) - WR(3));
+    return s;
+  } else {
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < 9; ++l)
+      if (l != 4) s += (WR(l) - WR(4)) * ar[l];
+    return s;
+  }
+#undef WR
+}
+
+template <bool PLAIN>
+__device__ __forceinline__ void put(double *__restrict__ out, long idx, double val, const EpiArgs &epi) {
+  if (PLAIN) out[idx] = val;
+  else epi_store(out, idx, val, epi);
+}
+
+// compile-time loop: F(k) is called with k as a template argument
+template <int K, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (K < N) {
+    f(std::integral_constant<int, K>{});
+    static_for<K + 1, N>(f);
+  }
+}
+
+// ---- y / z sweep (implicit operators) ------------------------------------------------------------
+// Phases per tile:  A  rhs + forward recurrence over the chunk (zero incoming state)  -> S
+//                   F  serial scan over chunks: true forward state entering each chunk -> SF
+//                   B  add phi * state, backward recurrence (zero incoming state)       -> S
+//                   T  serial scan (reverse): true backward state; periodic: y = K z_R  -> TB, YW
+//                   D  add psi * state, Woodbury corner correction, scale / add-back    -> global
+template <int FAM, int NL, bool PLAIN, bool ADDV>
 __global__ void sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
                                 double *__restrict__ out, const double *__restrict__ halo_lo,
                                 const double *__restrict__ halo_hi, double *__restrict__ iface,
                                 const __grid_constant__ EpiArgs epi) {
-  constexpr int H = FT<FAM>::H, W = FT<FAM>::W, D = 4;
-  PB_SHARED(S);  // [m][NL]: forward-eliminated rows, then the chunk-local solution
+  constexpr int H = FT<FAM>::H, W = FT<FAM>::W;
+  PB_SHARED(S);  // [m][NL] recurrence values, then scan states
+  const int m = a.m, C = a.C, P = a.P;
+  double2 *SF = reinterpret_cast<double2 *>(S + (size_t)m * NL);  // [P][NL]
+  double2 *TB = SF + P * NL;                                       // [P][NL]
+  double *YW = reinterpret_cast<double *>(TB + P * NL);            // [4][NL]
   const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
   const int tiles_i = (a.nfast + NL - 1) / NL;
   const int ti = blockIdx.x % tiles_i, o = blockIdx.x / tiles_i;
@@ -177,45 +225,219 @@ __global__ void sweep_yz_kernel(const __grid_constant__ SweepDev a, const double
   if (!valid) i0 = a.nfast - 1;
   const long rs = a.rstride;
   const long base = (long)i0 + (long)o * a.ostride;
-  const int m = a.m, C = a.C, P = a.P;
+  const double *vp = v + base;
   const int s = p * C, e = s + C;
   const int type = a.ctype[p];
-  const bool implicit = a.implicit != 0;
-  const bool add_v = a.add_v != 0;
+  const bool cc = a.has_const && type == 0;
   const double scale = a.scale;
 
-  auto ld = [&](int r) -> double {
-    if (r >= 0 && r < m) return __ldg(v + base + (long)r * rs);
-    if (r < 0) return a.wrap ? __ldg(v + base + (long)(r + m) * rs) : __ldg(halo_lo + base + (long)(r + H) * rs);
-    return a.wrap ? __ldg(v + base + (long)(r - m) * rs) : __ldg(halo_hi + base + (long)(r - m) * rs);
+  auto ldc = [&](int r) -> double {  // row outside [0,m): periodic wrap or neighbour halo planes
+    if (r < 0) return a.wrap ? __ldg(vp + (long)(r + m) * rs) : __ldg(halo_lo + base + (long)(r + H) * rs);
+    if (r >= m) return a.wrap ? __ldg(vp + (long)(r - m) * rs) : __ldg(halo_hi + base + (long)(r - m) * rs);
+    return __ldg(vp + (long)r * rs);
   };
 
-  const double2 *luf = a.lu_f + (size_t)type * C;
-  double rm1 = 0.0, rm2 = 0.0;
-  // forward elimination with the chunk-local factors (pentadiagonal.f90:639-642, pull form), or
-  // direct output for explicit operators (compact_r4.f90:209-218)
-  auto emit = [&](int row, double rhs, double vc) {
-    if (implicit) {
-      const double2 c = __ldg(luf + (row - s));
+  // ---- A ----
+  {
+    const double2 *luf = a.luf + (size_t)type * C - s;
+    const double l2c = a.cst[0], l1c = a.cst[1];
+    double rm1 = 0.0, rm2 = 0.0;
+    auto emit = [&](int row, double rhs) {  // pentadiagonal.f90:639-642 in pull form
+      double2 c;
+      if (cc) c = make_double2(l2c, l1c);
+      else c = __ldg(luf + row);
       double t = fma(-c.x, rm2, rhs);
       t = fma(-c.y, rm1, t);
       S[row * NL + l] = t;
       rm2 = rm1;
       rm1 = t;
-    } else if (valid) {
-      double val = rhs * scale;
-      if (add_v) val += vc;
-      epi_store(out, base + (long)row * rs, val, epi);
+    };
+    const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
+    int i = s;
+    double w[W], pf[W];
+    if (lo_sp) {
+      double vv[9], r4[4];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) vv[k] = __ldg(vp + (long)k * rs);
+      rhs_lo4<FAM>(vv, a.arb_lo, r4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) emit(k, r4[k]);
+      i = 4;
+#pragma unroll
+      for (int k = 0; k < W - 1; ++k) w[k] = vv[4 - H + k];
+    } else if (s - H >= 0) {
+#pragma unroll
+      for (int k = 0; k < W - 1; ++k) w[k] = __ldg(vp + (long)(s - H + k) * rs);
+    } else {
+#pragma unroll
+      for (int k = 0; k < W - 1; ++k) w[k] = ldc(s - H + k);
     }
-  };
+    const int iend = hi_sp ? e - 4 : e;
+    const int lim = iend + H;             // rows >= lim are never needed by this thread
+    const int safe = lim < m ? lim : m;   // rows < safe are inside the field
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      const int r = i + H + k;
+      pf[k] = r < safe ? __ldg(vp + (long)r * rs) : (r < lim ? ldc(r) : 0.0);
+    }
+    int rpre = i + H + W;
+    const double *pl = vp + (long)rpre * rs;
+    for (; i < iend; i += W) {
+      static_for<0, W>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        if (i + k < iend) {
+          w[(k + W - 1) % W] = pf[k];
+          pf[k] = rpre < safe ? __ldg(pl) : (rpre < lim ? ldc(rpre) : 0.0);
+          pl += rs;
+          ++rpre;
+          emit(i + k, rhs_center_rot<FAM, k>(w, a.ari));
+        }
+      });
+    }
+    if (hi_sp) {
+      double u[8], r4[4];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = __ldg(vp + (long)(m - 8 + k) * rs);
+      rhs_hi4<FAM>(u, a.arb_hi, r4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) emit(m - 4 + k, r4[k]);
+    }
+  }
+  __syncthreads();
 
+  // ---- F: r'[s_q - 1], r'[s_q - 2] entering every chunk ----
+  if (tid < NL) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int q = 0; q < P; ++q) {
+      SF[q * NL + tid] = make_double2(s0, s1);
+      const double2 *ph = a.phi + (size_t)a.ctype[q] * C;
+      const double2 f1 = __ldg(ph + C - 1), f2 = __ldg(ph + C - 2);
+      const double r1 = fma(f1.y, s1, fma(f1.x, s0, S[(q * C + C - 1) * NL + tid]));
+      const double r2 = fma(f2.y, s1, fma(f2.x, s0, S[(q * C + C - 2) * NL + tid]));
+      s0 = r1;
+      s1 = r2;
+    }
+  }
+  __syncthreads();
+
+  // ---- B: back substitution (pentadiagonal.f90:643-647) ----
+  {
+    const double2 st = SF[p * NL + l];
+    const double2 *ph = a.phi + (size_t)type * C - s;
+    const double4 *lub = a.lub + (size_t)type * C - s;
+    const double ipc = a.cst[2], u1c = a.cst[3], u2c = a.cst[4];
+    double x1 = 0.0, x2 = 0.0;
+#pragma unroll 4
+    for (int r = e - 1; r >= s; --r) {
+      const double2 f = __ldg(ph + r);
+      double t = S[r * NL + l];
+      t = fma(f.x, st.x, t);
+      t = fma(f.y, st.y, t);
+      double ip, u1, u2;
+      if (cc) { ip = ipc; u1 = u1c; u2 = u2c; }
+      else { const double4 c = ldg4(lub + r); ip = c.x; u1 = c.y; u2 = c.z; }
+      t = fma(-u1, x1, t);
+      t = fma(-u2, x2, t);
+      t *= ip;
+      S[r * NL + l] = t;
+      x2 = x1;
+      x1 = t;
+    }
+  }
+  __syncthreads();
+
+  // ---- T: x[e_q], x[e_q + 1] entering every chunk from above; periodic corner unknowns ----
+  if (tid < NL) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int q = P - 1; q >= 0; --q) {
+      TB[q * NL + tid] = make_double2(t0, t1);
+      const double2 *ps = a.psi + (size_t)a.ctype[q] * C;
+      const double2 g0 = __ldg(ps), g1 = __ldg(ps + 1);
+      const double n0 = fma(g0.y, t1, fma(g0.x, t0, S[(q * C) * NL + tid]));
+      const double n1 = fma(g1.y, t1, fma(g1.x, t0, S[(q * C + 1) * NL + tid]));
+      t0 = n0;
+      t1 = n1;
+    }
+    if (a.wrap) {  // Sherman-Morrison-Woodbury: y = (I + W_R)^-1 z_R
+      const double z2 = S[(m - 2) * NL + tid], z3 = S[(m - 1) * NL + tid];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        YW[c * NL + tid] = a.K[c * 4 + 0] * t0 + a.K[c * 4 + 1] * t1 + a.K[c * 4 + 2] * z2 + a.K[c * 4 + 3] * z3;
+    }
+  }
+  __syncthreads();
+
+  // ---- D ----
+  {
+    const double2 tb = TB[p * NL + l];
+    const double2 *ps = a.psi + (size_t)type * C - s;
+    const bool wf = a.wrap && ((a.wmask >> p) & 1u);
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+    if (wf) { y0 = YW[l]; y1 = YW[NL + l]; y2 = YW[2 * NL + l]; y3 = YW[3 * NL + l]; }
+    const double *pv = vp + (long)s * rs;
+    long oidx = base + (long)s * rs;
+#pragma unroll 4
+    for (int r = s; r < e; ++r) {
+      const double2 g = __ldg(ps + r);
+      double x = S[r * NL + l];
+      x = fma(g.x, tb.x, x);
+      x = fma(g.y, tb.y, x);
+      if (wf) {
+        const double4 c = ldg4(a.W + r);
+        x = fma(-c.x, y0, x);
+        x = fma(-c.y, y1, x);
+        x = fma(-c.z, y2, x);
+        x = fma(-c.w, y3, x);
+      }
+      if (iface != nullptr && valid) {  // z-slab: this rank's 4 interface values (compact_d1.f90:858-878)
+        const long plane = (long)a.nfast * a.nouter;
+        if (r < 2) iface[(long)r * plane + base] = a.phys_lo ? 0.0 : x;
+        if (r >= m - 2) iface[(long)(r - (m - 4)) * plane + base] = a.phys_hi ? 0.0 : x;
+      }
+      double val = x * scale;
+      if (ADDV) val += __ldg(pv);
+      if (valid) put<PLAIN>(out, oidx, val, epi);
+      pv += rs;
+      oidx += rs;
+    }
+  }
+}
+
+// ---- y / z sweep (explicit operators: the Gaussian filter) ---------------------------------------
+template <int FAM, int NL, bool PLAIN, bool ADDV>
+__global__ void explicit_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
+                                   double *__restrict__ out, const double *__restrict__ halo_lo,
+                                   const double *__restrict__ halo_hi, const __grid_constant__ EpiArgs epi) {
+  constexpr int H = FT<FAM>::H, W = FT<FAM>::W;
+  const int m = a.m, C = a.C, P = a.P;
+  const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
+  const int tiles_i = (a.nfast + NL - 1) / NL;
+  const int ti = blockIdx.x % tiles_i, o = blockIdx.x / tiles_i;
+  int i0 = ti * NL + l;
+  const bool valid = i0 < a.nfast;
+  if (!valid) i0 = a.nfast - 1;
+  const long rs = a.rstride;
+  const long base = (long)i0 + (long)o * a.ostride;
+  const double *vp = v + base;
+  const int s = p * C, e = s + C;
+  const double scale = a.scale;
+  auto ldc = [&](int r) -> double {
+    if (r < 0) return a.wrap ? __ldg(vp + (long)(r + m) * rs) : __ldg(halo_lo + base + (long)(r + H) * rs);
+    if (r >= m) return a.wrap ? __ldg(vp + (long)(r - m) * rs) : __ldg(halo_hi + base + (long)(r - m) * rs);
+    return __ldg(vp + (long)r * rs);
+  };
+  auto emit = [&](int row, double rhs, double vc) {  // compact_r4.f90:209-218
+    double val = rhs * scale;
+    if (ADDV) val += vc;
+    if (valid) put<PLAIN>(out, base + (long)row * rs, val, epi);
+  };
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
   int i = s;
-  double w[W];
+  double w[W], pf[W];
   if (lo_sp) {
     double vv[9], r4[4];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) vv[k] = ld(k);
+    for (int k = 0; k < 9; ++k) vv[k] = __ldg(vp + (long)k * rs);
     rhs_lo4<FAM>(vv, a.arb_lo, r4);
 #pragma unroll
     for (int k = 0; k < 4; ++k) emit(k, r4[k], vv[k]);
@@ -224,112 +446,58 @@ __global__ void sweep_yz_kernel(const __grid_constant__ SweepDev a, const double
     for (int k = 0; k < W - 1; ++k) w[k] = vv[4 - H + k];
   } else {
 #pragma unroll
-    for (int k = 0; k < W - 1; ++k) w[k] = ld(i - H + k);
+    for (int k = 0; k < W - 1; ++k) w[k] = ldc(s - H + k);
   }
   const int iend = hi_sp ? e - 4 : e;
   const int lim = iend + H;
-  double pf[D];
+  const int safe = lim < m ? lim : m;
 #pragma unroll
-  for (int d = 0; d < D; ++d) pf[d] = (i + H + d < lim) ? ld(i + H + d) : 0.0;
-#pragma unroll 4
-  for (; i < iend; ++i) {
-    w[W - 1] = pf[0];
-#pragma unroll
-    for (int d = 0; d < D - 1; ++d) pf[d] = pf[d + 1];
-    pf[D - 1] = (i + H + D < lim) ? ld(i + H + D) : 0.0;
-    const double rhs = rhs_center<FAM>(w, a.ari);
-    emit(i, rhs, w[H]);
-#pragma unroll
-    for (int k = 0; k < W - 1; ++k) w[k] = w[k + 1];
+  for (int k = 0; k < W; ++k) {
+    const int r = i + H + k;
+    pf[k] = r < safe ? __ldg(vp + (long)r * rs) : (r < lim ? ldc(r) : 0.0);
+  }
+  int rpre = i + H + W;
+  const double *pl = vp + (long)rpre * rs;
+  for (; i < iend; i += W) {
+    static_for<0, W>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      if (i + k < iend) {
+        w[(k + W - 1) % W] = pf[k];
+        pf[k] = rpre < safe ? __ldg(pl) : (rpre < lim ? ldc(rpre) : 0.0);
+        pl += rs;
+        ++rpre;
+        emit(i + k, rhs_center_rot<FAM, k>(w, a.ari), w[(k + H) % W]);
+      }
+    });
   }
   if (hi_sp) {
     double u[8], r4[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) u[k] = ld(m - 8 + k);
+    for (int k = 0; k < 8; ++k) u[k] = __ldg(vp + (long)(m - 8 + k) * rs);
     rhs_hi4<FAM>(u, a.arb_hi, r4);
 #pragma unroll
     for (int k = 0; k < 4; ++k) emit(m - 4 + k, r4[k], u[4 + k]);
   }
-  if (!implicit) return;
-
-  // back substitution (pentadiagonal.f90:643-647)
-  {
-    const double4 *lub = a.lu_b + (size_t)type * C;
-    double x1 = 0.0, x2 = 0.0;
-#pragma unroll 4
-    for (int r = e - 1; r >= s; --r) {
-      const double4 c = ldg4(lub + (r - s));
-      double t = S[r * NL + l];
-      t = fma(-c.y, x1, t);
-      t = fma(-c.z, x2, t);
-      t *= c.x;
-      S[r * NL + l] = t;
-      x2 = x1;
-      x1 = t;
-    }
-  }
-  __syncthreads();
-
-  // interface unknowns of the neighbouring chunks: g = G_p * d, d = first/last two values of
-  // every chunk-local solution (the in-block analogue of compact_d1.f90:243-279)
-  double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-  if (P > 1 || a.wrap) {
-    const int n4 = 4 * P;
-    const double *Gp = a.G + (size_t)p * 4 * n4;
-    for (int q = 0; q < P; ++q) {
-      const double d0 = S[(q * C) * NL + l], d1 = S[(q * C + 1) * NL + l];
-      const double d2 = S[(q * C + C - 2) * NL + l], d3 = S[(q * C + C - 1) * NL + l];
-      const double *gq = Gp + 4 * q;
-      g0 += __ldg(gq) * d0 + __ldg(gq + 1) * d1 + __ldg(gq + 2) * d2 + __ldg(gq + 3) * d3;
-      g1 += __ldg(gq + n4) * d0 + __ldg(gq + n4 + 1) * d1 + __ldg(gq + n4 + 2) * d2 + __ldg(gq + n4 + 3) * d3;
-      g2 += __ldg(gq + 2 * n4) * d0 + __ldg(gq + 2 * n4 + 1) * d1 + __ldg(gq + 2 * n4 + 2) * d2 + __ldg(gq + 2 * n4 + 3) * d3;
-      g3 += __ldg(gq + 3 * n4) * d0 + __ldg(gq + 3 * n4 + 1) * d1 + __ldg(gq + 3 * n4 + 2) * d2 + __ldg(gq + 3 * n4 + 3) * d3;
-    }
-  }
-
-  // spike correction (compact_d1.f90:285-286), metric scale (compact_operators.f90:43), filter
-  // add-back (compact_r4.f90:226-232) and the composite epilogue, straight to global memory
-  {
-    const double4 *rcp = a.rc + (size_t)type * C;
-#pragma unroll 4
-    for (int r = s; r < e; ++r) {
-      const double4 c = ldg4(rcp + (r - s));
-      double x = S[r * NL + l];
-      x = fma(-c.x, g0, x);
-      x = fma(-c.y, g1, x);
-      x = fma(-c.z, g2, x);
-      x = fma(-c.w, g3, x);
-      if (iface != nullptr) {  // z-slab: publish this rank's 4 interface values (compact_d1.f90:858-878)
-        const long plane = (long)a.nfast * a.nouter;
-        const long li = base;  // i + ax*j for the z sweep
-        if (valid) {
-          if (r < 2) iface[(long)r * plane + li] = a.phys_lo ? 0.0 : x;
-          if (r >= m - 2) iface[(long)(r - (m - 4)) * plane + li] = a.phys_hi ? 0.0 : x;
-        }
-      }
-      double val = x * scale;
-      if (add_v) val += ld(r);
-      if (valid) epi_store(out, base + (long)r * rs, val, epi);
-    }
-  }
 }
 
 // ---- x sweep -------------------------------------------------------------------------------------
-template <int FAM, int NLX>
+// Same algorithm on a tile of NLX unit-stride lines staged through shared memory (row pitch odd).
+template <int FAM, int NLX, bool PLAIN, bool ADDV>
 __global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
                                double *__restrict__ out, const __grid_constant__ EpiArgs epi) {
   constexpr int H = FT<FAM>::H, W = FT<FAM>::W;
-  PB_SHARED(S);  // [NLX][LD]
+  PB_SHARED(S);  // [NLX][LD], then scan states
   const int m = a.m, LD = m | 1, C = a.C, P = a.P;
+  double2 *SF = reinterpret_cast<double2 *>(S + (((size_t)NLX * LD + 1) & ~(size_t)1));  // [P][NLX]
+  double2 *TB = SF + P * NLX;
+  double *YW = reinterpret_cast<double *>(TB + P * NLX);  // [4][NLX]
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
   const long nlines = a.nfast;
   const long L0 = (long)blockIdx.x * NLX;
   const bool implicit = a.implicit != 0;
-  const bool add_v = a.add_v != 0;
 
-  // stage the tile, coalesced
-  for (int ll = wid; ll < NLX; ll += nw) {
+  for (int ll = wid; ll < NLX; ll += nw) {  // stage the tile, coalesced
     long L = L0 + ll;
     if (L >= nlines) L = nlines - 1;
     const double *src = v + L * (long)m;
@@ -339,13 +507,14 @@ __global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double 
   __syncthreads();
 
   const int l = tid % NLX, p = tid / NLX;
-  const bool active = p < P;  // blockDim may be rounded up to a warp multiple
+  const bool active = p < P;  // blockDim is rounded up to a warp multiple
   const int s = p * C, e = s + C;
   double *Sl = S + l * LD;
   const int type = active ? a.ctype[p] : 0;
+  const bool cc = a.has_const && type == 0;
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
 
-  // neighbours' rows this thread needs, read before anyone overwrites them
+  // rows of neighbouring chunks this thread's stencil needs, read before anyone overwrites them
   double hv[H], tv[H], vv[9], u[8];
   if (active) {
     if (lo_sp) {
@@ -365,13 +534,15 @@ __global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double 
   }
   __syncthreads();
 
-  double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-  if (active) {
-    const double2 *luf = a.lu_f + (size_t)type * C;
+  if (active) {  // ---- A ----
+    const double2 *luf = a.luf + (size_t)type * C - s;
+    const double l2c = a.cst[0], l1c = a.cst[1];
     double rm1 = 0.0, rm2 = 0.0;
     auto emit = [&](int row, double rhs) {
       if (implicit) {
-        const double2 c = __ldg(luf + (row - s));
+        double2 c;
+        if (cc) c = make_double2(l2c, l1c);
+        else c = __ldg(luf + row);
         double t = fma(-c.x, rm2, rhs);
         t = fma(-c.y, rm1, t);
         Sl[row] = t;
@@ -398,13 +569,15 @@ __global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double 
       for (int k = H; k < W - 1; ++k) w[k] = Sl[s + k - H];
     }
     const int imain = hi_sp ? e - 4 : e - H;  // rows whose look-ahead value is still inside the chunk
-#pragma unroll 4
-    for (; i < imain; ++i) {
-      w[W - 1] = Sl[i + H];
-      const double rhs = rhs_center<FAM>(w, a.ari);
-      emit(i, rhs);
-#pragma unroll
-      for (int k = 0; k < W - 1; ++k) w[k] = w[k + 1];
+    const int istart = i;
+    for (; i < imain; i += W) {
+      static_for<0, W>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        if (i + k < imain) {
+          w[(k + W - 1) % W] = Sl[i + k + H];
+          emit(i + k, rhs_center_rot<FAM, k>(w, a.ari));
+        }
+      });
     }
     if (hi_sp) {
       double r4[4];
@@ -412,64 +585,112 @@ __global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double 
 #pragma unroll
       for (int k = 0; k < 4; ++k) emit(m - 4 + k, r4[k]);
     } else {
+      // the main loop stopped at row e-H with its window rotated by (rows done) % W: copy it out
+      // in canonical order (rows e-2H .. e-1) for the H rows whose look-ahead is in the next chunk
+      double wl[W];
+      const int rot = (imain - istart) % W;
+      static_for<0, W>([&](auto rc) {
+        constexpr int R = decltype(rc)::value;
+        if (rot == R) {
+#pragma unroll
+          for (int k = 0; k < W - 1; ++k) wl[k] = w[(R + k) % W];
+        }
+      });
 #pragma unroll
       for (int k = 0; k < H; ++k) {
-        w[W - 1] = tv[k];
-        const double rhs = rhs_center<FAM>(w, a.ari);
-        emit(e - H + k, rhs);
+        wl[W - 1] = tv[k];
+        emit(e - H + k, rhs_center<FAM>(wl, a.ari));
 #pragma unroll
-        for (int q = 0; q < W - 1; ++q) w[q] = w[q + 1];
-      }
-    }
-    if (implicit) {
-      const double4 *lub = a.lu_b + (size_t)type * C;
-      double x1 = 0.0, x2 = 0.0;
-#pragma unroll 4
-      for (int r = e - 1; r >= s; --r) {
-        const double4 c = ldg4(lub + (r - s));
-        double t = Sl[r];
-        t = fma(-c.y, x1, t);
-        t = fma(-c.z, x2, t);
-        t *= c.x;
-        Sl[r] = t;
-        x2 = x1;
-        x1 = t;
+        for (int q = 0; q < W - 1; ++q) wl[q] = wl[q + 1];
       }
     }
   }
   if (implicit) {
     __syncthreads();
-    if (active && (P > 1 || a.wrap)) {
-      const int n4 = 4 * P;
-      const double *Gp = a.G + (size_t)p * 4 * n4;
+    if (tid < NLX) {  // ---- F ----
+      const double *Sq = S + tid * LD;
+      double s0 = 0.0, s1 = 0.0;
       for (int q = 0; q < P; ++q) {
-        const double d0 = Sl[q * C], d1 = Sl[q * C + 1], d2 = Sl[q * C + C - 2], d3 = Sl[q * C + C - 1];
-        const double *gq = Gp + 4 * q;
-        g0 += __ldg(gq) * d0 + __ldg(gq + 1) * d1 + __ldg(gq + 2) * d2 + __ldg(gq + 3) * d3;
-        g1 += __ldg(gq + n4) * d0 + __ldg(gq + n4 + 1) * d1 + __ldg(gq + n4 + 2) * d2 + __ldg(gq + n4 + 3) * d3;
-        g2 += __ldg(gq + 2 * n4) * d0 + __ldg(gq + 2 * n4 + 1) * d1 + __ldg(gq + 2 * n4 + 2) * d2 + __ldg(gq + 2 * n4 + 3) * d3;
-        g3 += __ldg(gq + 3 * n4) * d0 + __ldg(gq + 3 * n4 + 1) * d1 + __ldg(gq + 3 * n4 + 2) * d2 + __ldg(gq + 3 * n4 + 3) * d3;
+        SF[q * NLX + tid] = make_double2(s0, s1);
+        const double2 *ph = a.phi + (size_t)a.ctype[q] * C;
+        const double2 f1 = __ldg(ph + C - 1), f2 = __ldg(ph + C - 2);
+        const double r1 = fma(f1.y, s1, fma(f1.x, s0, Sq[q * C + C - 1]));
+        const double r2 = fma(f2.y, s1, fma(f2.x, s0, Sq[q * C + C - 2]));
+        s0 = r1;
+        s1 = r2;
       }
     }
     __syncthreads();
-    if (active && (P > 1 || a.wrap)) {
-      const double4 *rcp = a.rc + (size_t)type * C;
+    if (active) {  // ---- B ----
+      const double2 st = SF[p * NLX + l];
+      const double2 *ph = a.phi + (size_t)type * C - s;
+      const double4 *lub = a.lub + (size_t)type * C - s;
+      const double ipc = a.cst[2], u1c = a.cst[3], u2c = a.cst[4];
+      double x1 = 0.0, x2 = 0.0;
+#pragma unroll 4
+      for (int r = e - 1; r >= s; --r) {
+        const double2 f = __ldg(ph + r);
+        double t = Sl[r];
+        t = fma(f.x, st.x, t);
+        t = fma(f.y, st.y, t);
+        double ip, u1, u2;
+        if (cc) { ip = ipc; u1 = u1c; u2 = u2c; }
+        else { const double4 c = ldg4(lub + r); ip = c.x; u1 = c.y; u2 = c.z; }
+        t = fma(-u1, x1, t);
+        t = fma(-u2, x2, t);
+        t *= ip;
+        Sl[r] = t;
+        x2 = x1;
+        x1 = t;
+      }
+    }
+    __syncthreads();
+    if (tid < NLX) {  // ---- T ----
+      const double *Sq = S + tid * LD;
+      double t0 = 0.0, t1 = 0.0;
+      for (int q = P - 1; q >= 0; --q) {
+        TB[q * NLX + tid] = make_double2(t0, t1);
+        const double2 *ps = a.psi + (size_t)a.ctype[q] * C;
+        const double2 g0 = __ldg(ps), g1 = __ldg(ps + 1);
+        const double n0 = fma(g0.y, t1, fma(g0.x, t0, Sq[q * C]));
+        const double n1 = fma(g1.y, t1, fma(g1.x, t0, Sq[q * C + 1]));
+        t0 = n0;
+        t1 = n1;
+      }
+      if (a.wrap) {
+        const double z2 = Sq[m - 2], z3 = Sq[m - 1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          YW[c * NLX + tid] = a.K[c * 4 + 0] * t0 + a.K[c * 4 + 1] * t1 + a.K[c * 4 + 2] * z2 + a.K[c * 4 + 3] * z3;
+      }
+    }
+    __syncthreads();
+    if (active) {  // ---- D (in place; the coalesced write-back follows) ----
+      const double2 tb = TB[p * NLX + l];
+      const double2 *ps = a.psi + (size_t)type * C - s;
+      const bool wf = a.wrap && ((a.wmask >> p) & 1u);
+      double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+      if (wf) { y0 = YW[l]; y1 = YW[NLX + l]; y2 = YW[2 * NLX + l]; y3 = YW[3 * NLX + l]; }
 #pragma unroll 4
       for (int r = s; r < e; ++r) {
-        const double4 c = ldg4(rcp + (r - s));
+        const double2 g = __ldg(ps + r);
         double x = Sl[r];
-        x = fma(-c.x, g0, x);
-        x = fma(-c.y, g1, x);
-        x = fma(-c.z, g2, x);
-        x = fma(-c.w, g3, x);
+        x = fma(g.x, tb.x, x);
+        x = fma(g.y, tb.y, x);
+        if (wf) {
+          const double4 c = ldg4(a.W + r);
+          x = fma(-c.x, y0, x);
+          x = fma(-c.y, y1, x);
+          x = fma(-c.z, y2, x);
+          x = fma(-c.w, y3, x);
+        }
         Sl[r] = x;
       }
     }
   }
   __syncthreads();
 
-  // write back, coalesced, with scale / add-back / epilogue
-  const double scale = a.scale;
+  const double scale = a.scale;  // write back, coalesced, with scale / add-back / epilogue
   for (int ll = wid; ll < NLX; ll += nw) {
     const long L = L0 + ll;
     if (L >= nlines) break;
@@ -477,89 +698,101 @@ __global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double 
     for (int ii = lane; ii < m; ii += 32) {
       const long idx = L * (long)m + ii;
       double val = src[ii] * scale;
-      if (add_v) val += __ldg(v + idx);
-      epi_store(out, idx, val, epi);
+      if (ADDV) val += __ldg(v + idx);
+      put<PLAIN>(out, idx, val, epi);
     }
   }
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
-template <int FAM, int NL>
+template <int FAM, int NL, bool PLAIN, bool ADDV>
 static cudaError_t launch_yz_t(const SweepDev &a, const double *v, double *out, const double *hlo,
                                const double *hhi, double *iface, const EpiArgs &epi, cudaStream_t st) {
-  const size_t smem = a.implicit ? (size_t)a.m * NL * sizeof(double) : 0;
+  const int tiles_i = (a.nfast + NL - 1) / NL;
+  const dim3 grid((unsigned)(tiles_i * a.nouter)), block(NL * a.P);
+  if (!a.implicit) {
+    auto kfn = explicit_yz_kernel<FAM, NL, PLAIN, ADDV>;
+    PB_LAUNCH(kfn, grid, block, 0, st, a, v, out, hlo, hhi, epi);
+    ++g_launches;
+    return cudaGetLastError();
+  }
+  const size_t smem = ((size_t)a.m * NL + 4 * (size_t)a.P * NL + 4 * NL) * sizeof(double);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t err = cudaFuncSetAttribute(sweep_yz_kernel<FAM, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(sweep_yz_kernel<FAM, NL, PLAIN, ADDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     configured = smem;
   }
-  const int tiles_i = (a.nfast + NL - 1) / NL;
-  const dim3 grid((unsigned)(tiles_i * a.nouter)), block(NL * a.P);
-  auto kfn = sweep_yz_kernel<FAM, NL>;
+  auto kfn = sweep_yz_kernel<FAM, NL, PLAIN, ADDV>;
   PB_LAUNCH(kfn, grid, block, smem, st, a, v, out, hlo, hhi, iface, epi);
   ++g_launches;
   return cudaGetLastError();
 }
 
-template <int FAM>
+template <int FAM, bool ADDV>
 static cudaError_t launch_yz_f(int lines, const SweepDev &a, const double *v, double *out, const double *hlo,
                                const double *hhi, double *iface, const EpiArgs &epi, cudaStream_t st) {
-  switch (lines) {
-    case 8: return launch_yz_t<FAM, 8>(a, v, out, hlo, hhi, iface, epi, st);
-    case 32: return launch_yz_t<FAM, 32>(a, v, out, hlo, hhi, iface, epi, st);
-    default: return launch_yz_t<FAM, 16>(a, v, out, hlo, hhi, iface, epi, st);
-  }
+  const bool plain = epi.mode == EPI_STORE;
+  if (lines == 8)
+    return plain ? launch_yz_t<FAM, 8, true, ADDV>(a, v, out, hlo, hhi, iface, epi, st)
+                 : launch_yz_t<FAM, 8, false, ADDV>(a, v, out, hlo, hhi, iface, epi, st);
+  return plain ? launch_yz_t<FAM, 16, true, ADDV>(a, v, out, hlo, hhi, iface, epi, st)
+               : launch_yz_t<FAM, 16, false, ADDV>(a, v, out, hlo, hhi, iface, epi, st);
 }
 
 cudaError_t launch_sweep_yz(int fam, int lines, const SweepDev &a, const double *v, double *out,
                             const double *halo_lo, const double *halo_hi, double *iface,
                             const EpiArgs &epi, cudaStream_t st) {
   if (lines <= 0) lines = g_yz_lines;
-  // keep the tile within the shared-memory budget of one SM
-  while (lines > 8 && (size_t)a.m * lines * sizeof(double) > 200 * 1024) lines /= 2;
+  if (lines != 8) lines = 16;
+  // keep three tiles resident per SM when the line is long
+  if (lines == 16 && a.implicit && (size_t)a.m * 16 * sizeof(double) > 72 * 1024) lines = 8;
   switch (fam) {
-    case F_D1: return launch_yz_f<F_D1>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
-    case F_R3: return launch_yz_f<F_R3>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
-    default: return launch_yz_f<F_R4>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
+    case F_D1: return launch_yz_f<F_D1, false>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
+    case F_R3: return launch_yz_f<F_R3, false>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
+    default:
+      return a.add_v ? launch_yz_f<F_R4, true>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st)
+                     : launch_yz_f<F_R4, false>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
   }
 }
 
-template <int FAM, int NLX>
+template <int FAM, int NLX, bool PLAIN, bool ADDV>
 static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
-  const size_t smem = (size_t)NLX * (a.m | 1) * sizeof(double);
+  const size_t tile = (((size_t)NLX * (a.m | 1) + 1) & ~(size_t)1);
+  const size_t smem = (tile + 4 * (size_t)a.P * NLX + 4 * NLX) * sizeof(double);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t err = cudaFuncSetAttribute(sweep_x_kernel<FAM, NLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(sweep_x_kernel<FAM, NLX, PLAIN, ADDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     configured = smem;
   }
   const long ntiles = ((long)a.nfast + NLX - 1) / NLX;
   int threads = NLX * a.P;
   threads = (threads + 31) / 32 * 32;
-  auto kfn = sweep_x_kernel<FAM, NLX>;
+  auto kfn = sweep_x_kernel<FAM, NLX, PLAIN, ADDV>;
   PB_LAUNCH(kfn, dim3((unsigned)ntiles), dim3(threads), smem, st, a, v, out, epi);
   ++g_launches;
   return cudaGetLastError();
 }
 
-template <int FAM>
+template <int FAM, bool ADDV>
 static cudaError_t launch_x_f(int lines, const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
-  switch (lines) {
-    case 8: return launch_x_t<FAM, 8>(a, v, out, epi, st);
-    case 32: return launch_x_t<FAM, 32>(a, v, out, epi, st);
-    default: return launch_x_t<FAM, 16>(a, v, out, epi, st);
-  }
+  const bool plain = epi.mode == EPI_STORE;
+  if (lines == 8)
+    return plain ? launch_x_t<FAM, 8, true, ADDV>(a, v, out, epi, st) : launch_x_t<FAM, 8, false, ADDV>(a, v, out, epi, st);
+  return plain ? launch_x_t<FAM, 16, true, ADDV>(a, v, out, epi, st) : launch_x_t<FAM, 16, false, ADDV>(a, v, out, epi, st);
 }
 
 cudaError_t launch_sweep_x(int fam, int lines, const SweepDev &a, const double *v, double *out,
                            const EpiArgs &epi, cudaStream_t st) {
   if (lines <= 0) lines = g_x_lines;
-  while (lines > 8 && (size_t)(a.m | 1) * lines * sizeof(double) > 200 * 1024) lines /= 2;
+  if (lines != 8) lines = 16;
+  if (lines == 16 && (size_t)(a.m | 1) * 16 * sizeof(double) > 72 * 1024) lines = 8;
   switch (fam) {
-    case F_D1: return launch_x_f<F_D1>(lines, a, v, out, epi, st);
-    case F_R3: return launch_x_f<F_R3>(lines, a, v, out, epi, st);
-    default: return launch_x_f<F_R4>(lines, a, v, out, epi, st);
+    case F_D1: return launch_x_f<F_D1, false>(lines, a, v, out, epi, st);
+    case F_R3: return launch_x_f<F_R3, false>(lines, a, v, out, epi, st);
+    default:
+      return a.add_v ? launch_x_f<F_R4, true>(lines, a, v, out, epi, st) : launch_x_f<F_R4, false>(lines, a, v, out, epi, st);
   }
 }
 

@@ -29,10 +29,15 @@ struct SweepDev {
   // partition of a line into chunks --------------------------------------------------------
   int P, C;
   int ctype[kMaxChunks];
-  const double2 *lu_f;  // [ntypes][C]  {l2, l1}        forward multipliers (rows i-2, i-1)
-  const double4 *lu_b;  // [ntypes][C]  {1/pivot, u1, u2, 0}
-  const double4 *rc;    // [ntypes][C]  spike columns
-  const double *G;      // [P][4][4P]
+  unsigned wmask;       // chunks that receive the periodic (Woodbury) corner correction
+  int has_const;        // chunk type 0 has row-independent LU coefficients, kept in cst[]
+  double cst[5];        // l2, l1, 1/pivot, u1, u2 of the converged rows
+  const double2 *luf;   // [ntypes][C]  {l2, l1}   forward multipliers (rows i-2, i-1)
+  const double4 *lub;   // [ntypes][C]  {1/pivot, u1, u2, 0}
+  const double2 *phi;   // [ntypes][C]  forward response to the state entering the chunk
+  const double2 *psi;   // [ntypes][C]  backward response to the state entering the chunk
+  const double4 *W;     // [m]          B^-1 E^ (periodic lines)
+  double K[16];         // (I + W_R)^-1
   // right-hand side ------------------------------------------------------------------------
   double ari[9];
   double arb_lo[4][9], arb_hi[4][9];

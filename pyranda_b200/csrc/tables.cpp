@@ -1,6 +1,7 @@
 // See tables.hpp.  Host only.
 #include "tables.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -321,6 +322,131 @@ Partition build_partition(int m, const std::vector<double> &bands, bool cyclic, 
     memcpy(&part.rc[(size_t)t * C * 4], rc_all[rep[t]].data(), sizeof(double) * C * 4);
   }
   return part;
+}
+
+LineTables build_line_tables(int m, const std::vector<double> &bands, bool cyclic, int P) {
+  if (P < 1 || m % P != 0) throw std::invalid_argument("build_line_tables: P must divide m");
+  const int C = m / P;
+  if (C < 8) throw std::invalid_argument("build_line_tables: chunk shorter than 8 rows");
+  LineTables T;
+  T.m = m; T.P = P; T.C = C; T.cyclic = cyclic;
+  T.ctype.assign(P, 0);
+  auto band = [&](int i, int l) { return bands[(size_t)i * 5 + l]; };
+
+  // one LU of the bounded line (corner couplings of a periodic line are handled below)
+  std::vector<double> c(bands);
+  lu_block(c, m);
+  auto L2 = [&](int i) { return c[(size_t)i * 5 + 0]; };
+  auto L1 = [&](int i) { return c[(size_t)i * 5 + 1]; };
+  auto IP = [&](int i) { return c[(size_t)i * 5 + 2]; };
+  auto U1 = [&](int i) { return c[(size_t)i * 5 + 3]; };
+  auto U2 = [&](int i) { return c[(size_t)i * 5 + 4]; };
+
+  // converged ("Toeplitz limit") coefficients: taken from the middle of the line
+  const int ref = m / 2;
+  auto row_is_const = [&](int i) {
+    for (int k = 0; k < 5; ++k) {
+      const double a = c[(size_t)i * 5 + k], b = c[(size_t)ref * 5 + k];
+      if (std::fabs(a - b) > 8.0 * 2.220446049250313e-16 * std::fabs(b)) return false;
+    }
+    return true;
+  };
+  std::vector<char> chunk_const(P, 0);
+  int nconst = 0;
+  for (int p = 0; p < P; ++p) {
+    bool ok = true;
+    for (int i = p * C; i < (p + 1) * C && ok; ++i) ok = row_is_const(i);
+    chunk_const[p] = ok;
+    nconst += ok;
+  }
+  T.has_const = nconst > 0;
+  for (int k = 0; k < 5; ++k) T.cst[k] = c[(size_t)ref * 5 + k];
+
+  struct ChunkTab { std::vector<double> luf, lub, phi, psi; };
+  auto make_chunk = [&](int p, bool use_const) {
+    ChunkTab t;
+    const int s = p * C;
+    t.luf.resize((size_t)C * 2); t.lub.resize((size_t)C * 4); t.phi.resize((size_t)C * 2); t.psi.resize((size_t)C * 2);
+    std::vector<double> l2(C), l1(C), ip(C), u1(C), u2(C);
+    for (int i = 0; i < C; ++i) {
+      l2[i] = use_const ? T.cst[0] : L2(s + i); l1[i] = use_const ? T.cst[1] : L1(s + i);
+      ip[i] = use_const ? T.cst[2] : IP(s + i); u1[i] = use_const ? T.cst[3] : U1(s + i); u2[i] = use_const ? T.cst[4] : U2(s + i);
+      t.luf[i * 2 + 0] = l2[i]; t.luf[i * 2 + 1] = l1[i];
+      t.lub[i * 4 + 0] = ip[i]; t.lub[i * 4 + 1] = u1[i]; t.lub[i * 4 + 2] = u2[i]; t.lub[i * 4 + 3] = 0.0;
+    }
+    // phi: forward recurrence with zero right-hand side and unit incoming state
+    for (int col = 0; col < 2; ++col) {
+      double rm1 = col == 0 ? 1.0 : 0.0, rm2 = col == 0 ? 0.0 : 1.0;  // r'[s-1], r'[s-2]
+      for (int i = 0; i < C; ++i) {
+        const double v = -l2[i] * rm2 - l1[i] * rm1;
+        t.phi[i * 2 + col] = v;
+        rm2 = rm1; rm1 = v;
+      }
+    }
+    // psi: backward recurrence with zero r' and unit incoming (x[e], x[e+1])
+    for (int col = 0; col < 2; ++col) {
+      double x1 = col == 0 ? 1.0 : 0.0, x2 = col == 0 ? 0.0 : 1.0;  // x[i+1], x[i+2]
+      for (int i = C - 1; i >= 0; --i) {
+        const double v = (-u1[i] * x1 - u2[i] * x2) * ip[i];
+        t.psi[i * 2 + col] = v;
+        x2 = x1; x1 = v;
+      }
+    }
+    return t;
+  };
+
+  std::vector<ChunkTab> types;
+  std::vector<int> rep;
+  if (T.has_const) {
+    int p0 = 0;
+    while (!chunk_const[p0]) ++p0;
+    types.push_back(make_chunk(p0, true));
+    rep.push_back(-1);
+  }
+  for (int p = 0; p < P; ++p) {
+    if (chunk_const[p]) { T.ctype[p] = 0; continue; }
+    ChunkTab t = make_chunk(p, false);
+    int found = -1;
+    for (size_t k = T.has_const ? 1 : 0; k < types.size(); ++k)
+      if (types[k].luf == t.luf && types[k].lub == t.lub && types[k].phi == t.phi && types[k].psi == t.psi) { found = (int)k; break; }
+    if (found < 0) { found = (int)types.size(); types.push_back(std::move(t)); rep.push_back(p); }
+    T.ctype[p] = found;
+  }
+  T.ntypes = (int)types.size();
+  for (auto &t : types) {
+    T.luf.insert(T.luf.end(), t.luf.begin(), t.luf.end());
+    T.lub.insert(T.lub.end(), t.lub.begin(), t.lub.end());
+    T.phi.insert(T.phi.end(), t.phi.begin(), t.phi.end());
+    T.psi.insert(T.psi.end(), t.psi.begin(), t.psi.end());
+  }
+
+  if (cyclic) {
+    // A = B + E with E the two 2x2 corner blocks; E x = E^ y, y = (x0, x1, x[m-2], x[m-1])
+    T.W.assign((size_t)m * 4, 0.0);
+    std::vector<double> col(m);
+    for (int q = 0; q < 4; ++q) {
+      std::fill(col.begin(), col.end(), 0.0);
+      if (q == 0) { col[m - 2] = band(m - 2, 4); col[m - 1] = band(m - 1, 3); }
+      else if (q == 1) { col[m - 1] = band(m - 1, 4); }
+      else if (q == 2) { col[0] = band(0, 0); }
+      else { col[0] = band(0, 1); col[1] = band(1, 0); }
+      solve_block(c, m, col.data());
+      for (int i = 0; i < m; ++i) T.W[(size_t)i * 4 + q] = col[i];
+    }
+    const int rows[4] = {0, 1, m - 2, m - 1};
+    std::vector<long double> M(16);
+    for (int r = 0; r < 4; ++r)
+      for (int q = 0; q < 4; ++q) M[r * 4 + q] = (r == q ? 1.0L : 0.0L) + (long double)T.W[(size_t)rows[r] * 4 + q];
+    std::vector<long double> Minv = invert_dense(M, 4);
+    for (int k = 0; k < 16; ++k) T.K[k] = (double)Minv[k];
+    for (int p = 0; p < P; ++p) {
+      double mx = 0.0;
+      for (int i = p * C; i < (p + 1) * C; ++i)
+        for (int q = 0; q < 4; ++q) mx = std::max(mx, std::fabs(T.W[(size_t)i * 4 + q]));
+      if (mx > 1e-20) T.wmask |= (1u << p);
+    }
+  }
+  return T;
 }
 
 }  // namespace pb

@@ -44,6 +44,28 @@ struct Partition {
   std::vector<double> G;    // [P][4][4P]       g_p = G_p * d_all
 };
 
+// Tables for the in-kernel solve ("chunked Thomas with carried state"): ONE LU factorisation of
+// the whole (bounded) line; a thread runs the forward / backward recurrences over its chunk with a
+// zero incoming state, a short serial scan propagates the true 2-value state from chunk to chunk,
+// and the homogeneous responses phi / psi add the carried state back.  Rows whose LU coefficients
+// have converged to the Toeplitz limit share one "constant" chunk type whose coefficients live in
+// registers.  A periodic line is the bounded line plus a rank-4 corner update, applied with the
+// Sherman-Morrison-Woodbury identity (columns W, 4x4 capacitance inverse K).
+struct LineTables {
+  int m = 0, P = 1, C = 0, ntypes = 0;
+  bool cyclic = false, has_const = false;
+  double cst[5] = {0, 0, 0, 0, 0};  // l2, l1, 1/pivot, u1, u2 of the converged rows
+  std::vector<int> ctype;           // [P]; type 0 is the constant type when has_const
+  unsigned wmask = 0;               // chunks whose rows get the Woodbury correction
+  std::vector<double> luf;          // [ntypes][C][2]  l2, l1
+  std::vector<double> lub;          // [ntypes][C][4]  1/pivot, u1, u2, 0
+  std::vector<double> phi;          // [ntypes][C][2]  forward response to (r'[s-1], r'[s-2])
+  std::vector<double> psi;          // [ntypes][C][2]  backward response to (x[e], x[e+1])
+  std::vector<double> W;            // [m][4]          B^-1 E^, cyclic only
+  double K[16] = {0};               // (I + W_R)^-1, row major
+};
+LineTables build_line_tables(int m, const std::vector<double> &bands, bool cyclic, int P);
+
 // bands: m rows x 5, row i multiplies x[i-2..i+2]; entries that fall outside [0,m) are couplings
 // to the other end when `cyclic`, and are ignored otherwise.
 Partition build_partition(int m, const std::vector<double> &bands, bool cyclic, int P);
