@@ -1,0 +1,326 @@
+"""Device-resident mirror of pyrandaSim's time loop (reference: pyranda/pyranda.py).
+
+What is mirrored, and only that: the mesh mini-language (pyrandaMesh.py:33-56), the EOM / IC string
+interpreter (pyranda.py:231-416,812-869, pyrandaUtils.py:22-66, pyrandaEq.py:16-45), the operator
+forwards (pyranda.py:607-736), the low-storage 5-stage RK4 (pyranda.py:758-810) and the time-step
+package (pyrandaTimestep.py:42-77).  User decks (the strings) are unchanged; what changes is where
+the arrays live: every variable is a float64 CUDA tensor with Fortran strides, operators go through
+the C ABI (ParcopPlan), pointwise expressions run as device tensor ops, and the stage update is the
+fused pb_rk4_stage kernel -- nothing round-trips to the host inside a step except the scalar
+results of max / min / sum reductions (as in the reference, which allreduces them).
+
+The class is generic over a small `backend` object so the SAME driver can be run on numpy arrays
+with another operator provider; tests use that to compare the CUDA path with the CPU oracle after
+many steps.  The product ships only CudaBackend.
+"""
+import math
+import re
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------------------------------
+class CudaBackend:
+    """Fields are CUDA tensors; operators are libparcop_b200 kernels behind a ParcopPlan."""
+
+    def __init__(self, plan):
+        import torch
+        self.torch = torch
+        self.plan = plan
+        self.xp = _TorchNS(torch)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def zeros(self):
+        t = self.plan.empty_device()
+        t.zero_()
+        return t
+
+    def asfield(self, a):
+        t = self.plan.empty_device()
+        t.copy_(self.torch.as_tensor(np.ascontiguousarray(a), device=self.device))
+        return t
+
+    def tohost(self, t):
+        return t.cpu().numpy() if hasattr(t, "cpu") else t
+
+    def isfield(self, a):
+        return isinstance(a, self.torch.Tensor)
+
+    def _f(self, a):
+        """Operators need a full Fortran-strided field; broadcast scalars / fix strides."""
+        if not self.isfield(a):
+            t = self.plan.empty_device()
+            t.fill_(float(a))
+            return t
+        return a
+
+    # operators (pyranda.py:607-736 -> pyrandaMPI.py:664-740)
+    def ddx(self, v): return self.plan.ddx(self._f(v))
+    def ddy(self, v): return self.plan.ddy(self._f(v))
+    def ddz(self, v): return self.plan.ddz(self._f(v))
+    def dd8x(self, v): return self.plan.dd8x(self._f(v))
+    def dd8y(self, v): return self.plan.dd8y(self._f(v))
+    def dd8z(self, v): return self.plan.dd8z(self._f(v))
+    def filter(self, v): return self.plan.sfilter(self._f(v))
+    def gfilter(self, v): return self.plan.gfilter(self._f(v))
+    def gfilterdir(self, v, d): return self.plan.gfilterdir(self._f(v), d)
+    def ring(self, v): return self.plan.pring(self._f(v))
+    def laplacian(self, v): return self.plan.plaplacian(self._f(v))
+    def div(self, a, b, c): return self.plan.divergence(self._f(a), self._f(b), self._f(c))
+    def grad(self, v): return self.plan.grads(self._f(v))
+    def getvar(self, name): return self.asfield(self.plan.getvar(name))
+
+    # reductions (pyrandaMPI.py:307-326)
+    def sum3D(self, a): return self.plan.reduce("sum", self._c(a)) if self.isfield(a) else float(a)
+    def max3D(self, a): return self.plan.reduce("max", self._c(a)) if self.isfield(a) else float(a)
+    def min3D(self, a): return self.plan.reduce("min", self._c(a)) if self.isfield(a) else float(a)
+
+    def _c(self, a):
+        ax, ay, az = self.plan.shape
+        return a if a.stride() == (1, ax, ax * ay) else self._f(a.contiguous()).copy_(a)
+
+    def rk4_stage(self, dt, A, B, F, PHI, U):
+        """pyranda.py:800-804 fused; returns the new U (updated in place)."""
+        F = self._c(self._f(F))
+        U = self._c(U)
+        self.plan.rk4_stage(dt, A, B, F, PHI, U)
+        return U
+
+
+class _TorchNS:
+    """The handful of `numpy.` functions decks and sMap use (pyranda.py:842-858), on tensors or floats."""
+
+    def __init__(self, torch):
+        self.t = torch
+        self.pi = math.pi
+
+    def _u(self, name, a):
+        return getattr(self.t, name)(a) if isinstance(a, self.t.Tensor) else getattr(math, {"abs": "fabs"}.get(name, name))(a)
+
+    def sqrt(self, a): return self._u("sqrt", a)
+    def abs(self, a): return self._u("abs", a)
+    def sin(self, a): return self._u("sin", a)
+    def cos(self, a): return self._u("cos", a)
+    def tanh(self, a): return self._u("tanh", a)
+    def exp(self, a): return self._u("exp", a)
+    def sign(self, a): return self.t.sign(a) if isinstance(a, self.t.Tensor) else float(np.sign(a))
+
+    def _b(self, name, a, b):
+        T = self.t.Tensor
+        if isinstance(a, T) or isinstance(b, T):
+            ref = a if isinstance(a, T) else b
+            a = a if isinstance(a, T) else self.t.full_like(ref, float(a))
+            b = b if isinstance(b, T) else self.t.full_like(ref, float(b))
+            return getattr(self.t, name)(a, b)
+        return getattr(np, name)(a, b)
+
+    def minimum(self, a, b): return self._b("minimum", a, b)
+    def maximum(self, a, b): return self._b("maximum", a, b)
+
+    def where(self, c, a, b):
+        T = self.t.Tensor
+        a = a if isinstance(a, T) else self.t.full_like(c, float(a), dtype=self.t.float64)
+        b = b if isinstance(b, T) else self.t.full_like(c, float(b), dtype=self.t.float64)
+        return self.t.where(c, a, b)
+
+
+# --------------------------------------------------------------------------------------------------
+_FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-858)
+    "ddx": "self.ddx", "ddy": "self.ddy", "ddz": "self.ddz", "div": "self.div", "grad": "self.grad",
+    "fbar": "self.filter", "gbar": "self.gfilter", "gbarx": "self.gfilterx", "gbary": "self.gfiltery",
+    "gbarz": "self.gfilterz", "lap": "self.laplacian", "ring": "self.ring", "dd8x": "self.dd8x",
+    "dd8y": "self.dd8y", "dd8z": "self.dd8z", "sum": "self.B.sum3D", "max": "self.B.max3D", "min": "self.B.min3D",
+    "mean": "self.mean", "sign": "xp.sign", "abs": "xp.abs", "sqrt": "xp.sqrt", "sin": "xp.sin", "cos": "xp.cos",
+    "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar",
+    "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff", "numpy.minimum": "xp.minimum",
+    "numpy.maximum": "xp.maximum", "numpy.sqrt": "xp.sqrt", "numpy.abs": "xp.abs", "numpy.where": "xp.where",
+}
+_NAMES = {"simtime": "self.time", "deltat": "self.deltat", "pi": "xp.pi", "meshx": 'self.variables["meshx"]',
+          "meshy": 'self.variables["meshy"]', "meshz": 'self.variables["meshz"]', "gridLen": "self.GridLen"}
+_VAR = re.compile(r":([A-Za-z_]\w*):")
+_CALL = re.compile(r"(?<![\w.\"])((?:dt\.|numpy\.)?[A-Za-z_3]\w*)\(")
+_WORD = re.compile(r"(?<![\w.\"])([A-Za-z_]\w*)(?![\w(\"])")
+
+
+def translate(expr):
+    """Deck expression -> Python source evaluated with `self` (the sim) and `xp` in scope."""
+    expr = expr.replace(" ", "").strip()
+    expr = _VAR.sub(lambda m: 'self.variables["%s"]' % m.group(1), expr)
+    expr = _CALL.sub(lambda m: (_FUNCS[m.group(1)] + "(") if m.group(1) in _FUNCS else m.group(0), expr)
+    expr = _WORD.sub(lambda m: _NAMES.get(m.group(1), m.group(1)), expr)
+    return expr
+
+
+def _lines(text):
+    out = []
+    for ln in text.split("\n"):
+        ln = ln.strip()
+        if ln and not ln.startswith("#"):
+            out.append(ln)
+    return out
+
+
+class _Equation:
+    def __init__(self, text):
+        self.text = text
+        lhs, rhs = text.split("=", 1) if "=" in text else (None, text)
+        self.lhs = _VAR.findall(lhs) if lhs is not None else None
+        self.kind = "PDE" if "ddt(" in text else "ALG"  # pyrandaEq.py:42-43
+        self.src = translate(rhs)
+        self.code = compile(self.src, "<eom>", "eval")
+
+
+def parse_mesh(text):
+    """`xdom = (x1, xn, n, periodic=True)` lines (pyrandaMesh.py:33-56)."""
+    opt = {"x1": [0.0, 0.0, 0.0], "xn": [1.0, 1.0, 1.0], "nn": [1, 1, 1], "periodic": [False, False, False]}
+
+    def setter(ind):
+        def f(x1, xn, nn, periodic=False):
+            opt["x1"][ind], opt["xn"][ind], opt["nn"][ind], opt["periodic"][ind] = float(x1), float(xn), int(nn), bool(periodic)
+        return f
+    ns = {"xdom": None, "ydom": None, "zdom": None}
+    for ln in _lines(text):
+        ln = ln.replace(" ", "")
+        for k, name in enumerate(("xdom", "ydom", "zdom")):
+            if ln.startswith(name + "=("):
+                eval("f" + ln[len(name) + 1:], {"f": setter(k)})
+    return opt
+
+
+class pyrandaSim:
+    """`ss = pyrandaSim(name, mesh); ss.EOM(eom); ss.setIC(ic); ss.rk4(time, dt)` on the device."""
+
+    def __init__(self, name, mesh, backend=None, device=0):
+        self.name = name
+        opt = parse_mesh(mesh) if isinstance(mesh, str) else mesh
+        self.meshOptions = opt
+        self.nx, self.ny, self.nz = opt["nn"]
+        self.npts = self.nx * self.ny * self.nz
+        if backend is None:
+            from .plan import ParcopPlan
+            plan = ParcopPlan(self.nx, self.ny, self.nz, opt["x1"][0], opt["xn"][0], opt["x1"][1], opt["xn"][1],
+                              opt["x1"][2], opt["xn"][2], periodic=tuple(opt["periodic"]), device=device)
+            plan.set_mesh()
+            backend = CudaBackend(plan)
+        self.B = backend
+        self.xp = backend.xp
+        self.variables = {}
+        self.equations = []
+        self.conserved = []
+        self.time, self.deltat, self.cycle = 0.0, 0.0, 0
+        for k, nm in enumerate(("meshx", "meshy", "meshz")):
+            self.variables[nm] = backend.getvar("xyz"[k])
+        self.d1, self.d2, self.d3 = (backend.getvar(n) for n in ("d1", "d2", "d3"))
+        self.GridLen = backend.getvar("GridLen")
+        self.zero = backend.zeros()
+        self._ns = {"xp": self.xp, "numpy": self.xp, "self": self}
+
+    # ---- operator forwards (pyranda.py:607-736) ----
+    def ddx(self, v): return 0.0 if self.nx <= 1 else self.B.ddx(v)
+    def ddy(self, v): return 0.0 if self.ny <= 1 else self.B.ddy(v)
+    def ddz(self, v): return 0.0 if self.nz <= 1 else self.B.ddz(v)
+    def dd8x(self, v): return self.B.dd8x(v)
+    def dd8y(self, v): return self.B.dd8y(v)
+    def dd8z(self, v): return self.B.dd8z(v)
+    def filter(self, v): return self.B.filter(v)
+    def gfilter(self, v): return self.B.gfilter(v)
+    def gfilterx(self, v): return self.B.gfilterdir(v, 1)
+    def gfiltery(self, v): return self.B.gfilterdir(v, 2)
+    def gfilterz(self, v): return self.B.gfilterdir(v, 3)
+    def ring(self, v): return self.B.ring(v)
+    def laplacian(self, v): return self.B.laplacian(v)
+    def grad(self, v): return self.B.grad(v)
+
+    def div(self, f1, f2=None, f3=None):  # pyranda.py:640-671
+        z = self.zero
+        if f2 is None and f3 is None:
+            if self.nx > 1: return self.B.div(f1, z, z)
+            if self.ny > 1: return self.B.div(z, f1, z)
+            if self.nz > 1: return self.B.div(z, z, f1)
+            return 0.0
+        if f3 is None:
+            if self.nx > 1 and self.ny > 1: return self.B.div(f1, f2, z)
+            if self.nz > 1 and self.ny > 1: return self.B.div(z, f1, f2)
+            if self.nz > 1 and self.nx > 1: return self.B.div(f1, z, f2)
+            if self.nx > 1: return self.B.div(f1, z, z)
+            if self.ny > 1: return self.B.div(z, f1, z)
+            if self.nz > 1: return self.B.div(z, z, f1)
+            return 0.0
+        return self.B.div(f1, f2, f3)
+
+    def emptyScalar(self, val=0.0):
+        return self.B.zeros() + val
+
+    def mean(self, a):
+        return 1.0 / float(self.npts) * self.B.sum3D(a)
+
+    # ---- pyrandaTimestep.py:42-77 (Cartesian branch) ----
+    def dt_courant(self, u, v, w, c):
+        xp = self.xp
+        vrate = xp.abs(u) / self.d1 + xp.abs(v) / self.d2 + xp.abs(w) / self.d3
+        crate = xp.abs(c) / self.GridLen
+        return 1.0 / self.B.max3D(vrate + crate)
+
+    def dt_diff(self, bulk, density):
+        delta = self.GridLen
+        drate = density * delta * delta / self.xp.maximum(1.0e-12, bulk)
+        return self.B.min3D(drate)
+
+    # ---- interpreter (pyranda.py:231-416) ----
+    def EOM(self, eom):
+        for ln in _lines(eom):
+            eq = _Equation(ln)
+            self.equations.append(eq)
+            for nm in _VAR.findall(ln):
+                self.variables.setdefault(nm, self.B.zeros())
+            if eq.kind == "PDE":
+                self.conserved.append(eq.lhs[0])
+
+    def setIC(self, ics):
+        local = {}
+        for ln in _lines(ics):
+            for nm in _VAR.findall(ln):
+                self.variables.setdefault(nm, self.B.zeros())
+            exec(translate(ln), self._ns, local)
+        self.updateVars()
+
+    def updateFlux(self):  # pyranda.py:376-394
+        return {eq.lhs[0]: eval(eq.code, self._ns) for eq in self.equations if eq.kind == "PDE"}
+
+    def updateVars(self):  # pyranda.py:397-416
+        for eq in self.equations:
+            if eq.kind != "ALG":
+                continue
+            rhs = eval(eq.code, self._ns)
+            if not eq.lhs:
+                continue
+            if len(eq.lhs) == 1:
+                self.variables[eq.lhs[0]] = rhs
+            else:
+                for nm, r in zip(eq.lhs, rhs):
+                    self.variables[nm] = r
+
+    def var(self, name):
+        return self.variables[name]
+
+    # ---- pyranda.py:758-810 ----
+    ARK = (0.0, -6234157559845. / 12983515589748., -6194124222391. / 4410992767914.,
+           -31623096876824. / 15682348800105., -12251185447671. / 11596622555746.)
+    BRK = (494393426753. / 4806282396855., 4047970641027. / 5463924506627., 9795748752853. / 13190207949281.,
+           4009051133189. / 8539092990294., 1348533437543. / 7166442652324.)
+    ETA = (494393426753. / 4806282396855., 4702696611523. / 9636871101405., 3614488396635. / 5249666457482.,
+           9766892798963. / 10823461281321., 1.0)
+
+    def rk4(self, time, dt):
+        PHI = {U: self.B.zeros() for U in self.conserved}
+        time_i = time
+        self.deltat = dt
+        for ii in range(5):
+            FLUX = self.updateFlux()
+            for U in self.conserved:
+                self.variables[U] = self.B.rk4_stage(dt, self.ARK[ii], self.BRK[ii], FLUX[U], PHI[U], self.variables[U])
+            time = time_i + self.ETA[ii] * dt
+            self.time = time
+            self.updateVars()
+        self.cycle += 1
+        return time

@@ -1,0 +1,47 @@
+"""The deck interpreter + RK4 driver (pyranda_b200.sim) on the numpy / oracle backend, pinned to the
+reference's golden scalars for whole simulations (tolerance 1e-4, tests/run_tests.py:84)."""
+import numpy as np
+
+from decks import run_tgv, tgv_mesh
+from oracle_backend import make_sim
+
+
+def test_translate():
+    from pyranda_b200.sim import translate
+    s = translate(":mu: = gbar( abs(ring(:S:)) ) * :rho: * 1.0e-4")
+    assert s == 'self.variables["mu"]=self.gfilter(xp.abs(self.ring(self.variables["S"])))*self.variables["rho"]*1.0e-4'
+    assert translate("dt.courant(:u:,:v:,:w:,:cs:)*1.0").startswith("self.dt_courant(")
+    assert translate("numpy.minimum(:dt:,0.2*dt.diff(:beta:,:rho:))") == \
+        'xp.minimum(self.variables["dt"],0.2*self.dt_diff(self.variables["beta"],self.variables["rho"]))'
+    assert translate("sin(meshx)*pi") == 'xp.sin(self.variables["meshx"])*xp.pi'
+    assert translate("gbarx(:a:)+expo") == 'self.gfilterx(self.variables["a"])+expo'
+
+
+def test_taylor_green_golden(oracle_mod):
+    """tests/cases/testTaylorGreen.py:3: enstrophy ratio 1.00106718415 at t = 0.1 on 32^3."""
+    ss = make_sim(oracle_mod, "TGvortex", tgv_mesh(32))
+    enst, time, n = run_tgv(ss, tstop=0.1)
+    assert abs(enst - 1.00106718415) / 1.00106718415 < 1e-4, (enst, time, n)
+
+
+def test_advection_1d_golden(oracle_mod):
+    """tests/cases/test1DAdvection.py:3-4 (examples/advection.py): sum((phi - phi0)^2) after one
+    period of periodic 1-D advection, N = 50 and 100."""
+    from pyranda_b200.sim import pyrandaSim
+    from oracle_backend import NumpyOracleBackend
+    for npts, golden in ((50, 9.65612670412e-09), (100, 7.6111541815e-11)):
+        L = np.pi * 2.0
+        mesh = {"x1": [0.0, 0.0, 0.0], "xn": [L * (npts - 1) / npts, 1.0, 1.0], "nn": [npts, 1, 1], "periodic": [True, False, False]}
+        o = oracle_mod.Oracle(npts, 1, 1, 0.0, mesh["xn"][0], 0, 1, 0, 1, periodic=(True, False, False))
+        ss = pyrandaSim("advection", mesh, backend=NumpyOracleBackend(o))
+        ss.EOM(" ddt(:phi:)  =  -:c: * ddx(:phi:) ")
+        ss.setIC("r   = sqrt( (meshx-pi)**2  )\n:phi: = 1.0 + 0.1 * exp( -(r/(pi/4.0))**2 )\n:phi2: = 1.0*:phi:\n:c:   = 1.0")
+        v = 1.0
+        dt_max = v / npts * L * .90
+        tt = L / v * 1.0
+        dt, time = dt_max, 0.0
+        while tt > time:
+            time = ss.rk4(time, dt)
+            dt = min(dt_max, (tt - time))
+        err = float(np.sum((ss.variables["phi"] - ss.variables["phi2"]) ** 2))
+        assert abs(err - golden) / golden < 1e-3, (npts, err, golden)
