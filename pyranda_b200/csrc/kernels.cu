@@ -162,11 +162,25 @@ __device__ __forceinline__ void epi_store(double *__restrict__ out, long idx, do
   }
 }
 
-// rotated window access: logical element j of the window lives in slot (K + j) % W
+template <bool PLAIN>
+__device__ __forceinline__ void put(double *__restrict__ out, long idx, double val, const EpiArgs &epi) {
+  if (PLAIN) out[idx] = val;
+  else epi_store(out, idx, val, epi);
+}
+
+// compile-time loop: F(k) is called with k as a template argument
+template <int K, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (K < N) {
+    f(std::integral_constant<int, K>{});
+    static_for<K + 1, N>(f);
+  }
+}
+
+// ring access: at step K of a 16-row block the window element j (row - H + j) lives in slot (K+j)&15
 template <int FAM, int K>
-__device__ __forceinline__ double rhs_center_rot(const double *w, const double *ar) {
-  constexpr int W = FT<FAM>::W;
-#define WR(j) w[(K + (j)) % W]
+__device__ __forceinline__ double rhs_ring(const double *g, const double *ar) {
+#define WR(j) g[(K + (j)) & 15]
   if (FAM == F_D1) {
     return ar[4] * (WR(4) - WR(2)) + ar[5] * (WR(5) - WR(1)) + ar[6] * (WR(6) - WR(0));
   } else if (FAM == F_R3) {
@@ -185,18 +199,59 @@ __device__ __forceinline__ double rhs_center_rot(const double *w, const double *
 #undef WR
 }
 
-template <bool PLAIN>
-__device__ __forceinline__ void put(double *__restrict__ out, long idx, double val, const EpiArgs &epi) {
-  if (PLAIN) out[idx] = val;
-  else epi_store(out, idx, val, epi);
-}
-
-// compile-time loop: F(k) is called with k as a template argument
-template <int K, int N, class F>
-__device__ __forceinline__ void static_for(F &&f) {
-  if constexpr (K < N) {
-    f(std::integral_constant<int, K>{});
-    static_for<K + 1, N>(f);
+// Streams one chunk of one grid line through a 16-slot register ring (stencil window + prefetch)
+// and hands every row's right-hand side to `emit(local_row, rhs, centre_value)`.
+//   fast path: interior chunk, C % 16 == 0: no bounds checks, pointer-increment loads
+//   generic path: first / last chunk (closures, periodic wrap, halo planes) or odd chunk lengths
+template <int FAM, class LDC, class EMIT>
+__device__ __forceinline__ void stream_chunk(const SweepDev &a, const double *__restrict__ vp, long rs, int p, LDC &&ldc, EMIT &&emit) {
+  constexpr int H = FT<FAM>::H;
+  const int m = a.m, C = a.C, P = a.P;
+  const int s = p * C;
+  double ring[16];
+  if (p >= 1 && p <= P - 2 && (C & 15) == 0) {
+    const double *pl = vp + (long)(s - H) * rs;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { ring[j] = __ldg(pl); pl += rs; }
+    for (int b = 0; b < C; b += 16) {
+      static_for<0, 16>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        const double rhs = rhs_ring<FAM, k>(ring, a.ari);
+        const double vc = ring[(k + H) & 15];
+        ring[k] = __ldg(pl);
+        pl += rs;
+        emit(b + k, rhs, vc);
+      });
+    }
+    return;
+  }
+  const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) ring[j] = ldc(s - H + j);
+  if (lo_sp) {  // one-sided closure rows 0..3
+    double vv[9], r4[4];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) vv[k] = ring[(k + H) & 15];
+    rhs_lo4<FAM>(vv, a.arb_lo, r4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(k, r4[k], vv[k]);
+  }
+  for (int b = 0; b < C; b += 16) {
+    static_for<0, 16>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      const int lr = b + k, row = s + lr;
+      if (lr < C && !(lo_sp && lr < 4) && !(hi_sp && row >= m - 4))
+        emit(lr, rhs_ring<FAM, k>(ring, a.ari), ring[(k + H) & 15]);
+      ring[k] = ldc(row - H + 16);
+    });
+  }
+  if (hi_sp) {  // one-sided closure rows m-4..m-1
+    double u[8], r4[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] = __ldg(vp + (long)(m - 8 + k) * rs);
+    rhs_hi4<FAM>(u, a.arb_hi, r4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(C - 4 + k, r4[k], u[4 + k]);
   }
 }
 
@@ -207,11 +262,12 @@ __device__ __forceinline__ void static_for(F &&f) {
 //                   T  serial scan (reverse): true backward state; periodic: y = K z_R  -> TB, YW
 //                   D  add psi * state, Woodbury corner correction, scale / add-back    -> global
 template <int FAM, int NL, bool PLAIN, bool ADDV>
-__global__ void sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
-                                double *__restrict__ out, const double *__restrict__ halo_lo,
-                                const double *__restrict__ halo_hi, double *__restrict__ iface,
-                                const __grid_constant__ EpiArgs epi) {
-  constexpr int H = FT<FAM>::H, W = FT<FAM>::W;
+__global__ void __launch_bounds__(NL * kMaxChunks)
+sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
+                double *__restrict__ out, const double *__restrict__ halo_lo,
+                const double *__restrict__ halo_hi, double *__restrict__ iface,
+                const __grid_constant__ EpiArgs epi) {
+  constexpr int H = FT<FAM>::H;
   PB_SHARED(S);  // [m][NL] recurrence values, then scan states
   const int m = a.m, C = a.C, P = a.P;
   double2 *SF = reinterpret_cast<double2 *>(S + (size_t)m * NL);  // [P][NL]
@@ -226,81 +282,46 @@ __global__ void sweep_yz_kernel(const __grid_constant__ SweepDev a, const double
   const long rs = a.rstride;
   const long base = (long)i0 + (long)o * a.ostride;
   const double *vp = v + base;
-  const int s = p * C, e = s + C;
+  const int s = p * C;
   const int type = a.ctype[p];
   const bool cc = a.has_const && type == 0;
   const double scale = a.scale;
 
   auto ldc = [&](int r) -> double {  // row outside [0,m): periodic wrap or neighbour halo planes
-    if (r < 0) return a.wrap ? __ldg(vp + (long)(r + m) * rs) : __ldg(halo_lo + base + (long)(r + H) * rs);
-    if (r >= m) return a.wrap ? __ldg(vp + (long)(r - m) * rs) : __ldg(halo_hi + base + (long)(r - m) * rs);
+    if (r < 0) {
+      if (a.wrap) return __ldg(vp + (long)(r + m) * rs);
+      return halo_lo ? __ldg(halo_lo + base + (long)(r + H) * rs) : 0.0;
+    }
+    if (r >= m) {
+      if (a.wrap) return __ldg(vp + (long)(r - m) * rs);
+      return halo_hi ? __ldg(halo_hi + base + (long)(r - m) * rs) : 0.0;
+    }
     return __ldg(vp + (long)r * rs);
   };
 
-  // ---- A ----
+  // ---- A: forward elimination, pentadiagonal.f90:639-642 in pull form ----
   {
-    const double2 *luf = a.luf + (size_t)type * C - s;
-    const double l2c = a.cst[0], l1c = a.cst[1];
     double rm1 = 0.0, rm2 = 0.0;
-    auto emit = [&](int row, double rhs) {  // pentadiagonal.f90:639-642 in pull form
-      double2 c;
-      if (cc) c = make_double2(l2c, l1c);
-      else c = __ldg(luf + row);
-      double t = fma(-c.x, rm2, rhs);
-      t = fma(-c.y, rm1, t);
-      S[row * NL + l] = t;
-      rm2 = rm1;
-      rm1 = t;
-    };
-    const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
-    int i = s;
-    double w[W], pf[W];
-    if (lo_sp) {
-      double vv[9], r4[4];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) vv[k] = __ldg(vp + (long)k * rs);
-      rhs_lo4<FAM>(vv, a.arb_lo, r4);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) emit(k, r4[k]);
-      i = 4;
-#pragma unroll
-      for (int k = 0; k < W - 1; ++k) w[k] = vv[4 - H + k];
-    } else if (s - H >= 0) {
-#pragma unroll
-      for (int k = 0; k < W - 1; ++k) w[k] = __ldg(vp + (long)(s - H + k) * rs);
-    } else {
-#pragma unroll
-      for (int k = 0; k < W - 1; ++k) w[k] = ldc(s - H + k);
-    }
-    const int iend = hi_sp ? e - 4 : e;
-    const int lim = iend + H;             // rows >= lim are never needed by this thread
-    const int safe = lim < m ? lim : m;   // rows < safe are inside the field
-#pragma unroll
-    for (int k = 0; k < W; ++k) {
-      const int r = i + H + k;
-      pf[k] = r < safe ? __ldg(vp + (long)r * rs) : (r < lim ? ldc(r) : 0.0);
-    }
-    int rpre = i + H + W;
-    const double *pl = vp + (long)rpre * rs;
-    for (; i < iend; i += W) {
-      static_for<0, W>([&](auto kc) {
-        constexpr int k = decltype(kc)::value;
-        if (i + k < iend) {
-          w[(k + W - 1) % W] = pf[k];
-          pf[k] = rpre < safe ? __ldg(pl) : (rpre < lim ? ldc(rpre) : 0.0);
-          pl += rs;
-          ++rpre;
-          emit(i + k, rhs_center_rot<FAM, k>(w, a.ari));
-        }
+    double *sp = S + (size_t)s * NL + l;
+    if (cc) {
+      const double l2c = a.cst[0], l1c = a.cst[1];
+      stream_chunk<FAM>(a, vp, rs, p, ldc, [&](int lr, double rhs, double) {
+        double t = fma(-l2c, rm2, rhs);
+        t = fma(-l1c, rm1, t);
+        sp[lr * NL] = t;
+        rm2 = rm1;
+        rm1 = t;
       });
-    }
-    if (hi_sp) {
-      double u[8], r4[4];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] = __ldg(vp + (long)(m - 8 + k) * rs);
-      rhs_hi4<FAM>(u, a.arb_hi, r4);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) emit(m - 4 + k, r4[k]);
+    } else {
+      const double2 *luf = a.luf + (size_t)type * C;
+      stream_chunk<FAM>(a, vp, rs, p, ldc, [&](int lr, double rhs, double) {
+        const double2 c = __ldg(luf + lr);
+        double t = fma(-c.x, rm2, rhs);
+        t = fma(-c.y, rm1, t);
+        sp[lr * NL] = t;
+        rm2 = rm1;
+        rm1 = t;
+      });
     }
   }
   __syncthreads();
@@ -323,25 +344,40 @@ __global__ void sweep_yz_kernel(const __grid_constant__ SweepDev a, const double
   // ---- B: back substitution (pentadiagonal.f90:643-647) ----
   {
     const double2 st = SF[p * NL + l];
-    const double2 *ph = a.phi + (size_t)type * C - s;
-    const double4 *lub = a.lub + (size_t)type * C - s;
-    const double ipc = a.cst[2], u1c = a.cst[3], u2c = a.cst[4];
+    const double2 *ph = a.phi + (size_t)type * C + (C - 1);
+    double *sp = S + (size_t)(s + C - 1) * NL + l;
     double x1 = 0.0, x2 = 0.0;
+    if (cc) {
+      const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+#pragma unroll 8
+      for (int r = 0; r < C; ++r) {
+        const double2 f = __ldg(ph - r);
+        double t = sp[-(r * NL)];
+        t = fma(f.x, st.x, t);
+        t = fma(f.y, st.y, t);
+        t = fma(-u1, x1, t);
+        t = fma(-u2, x2, t);
+        t *= ip;
+        sp[-(r * NL)] = t;
+        x2 = x1;
+        x1 = t;
+      }
+    } else {
+      const double4 *lub = a.lub + (size_t)type * C + (C - 1);
 #pragma unroll 4
-    for (int r = e - 1; r >= s; --r) {
-      const double2 f = __ldg(ph + r);
-      double t = S[r * NL + l];
-      t = fma(f.x, st.x, t);
-      t = fma(f.y, st.y, t);
-      double ip, u1, u2;
-      if (cc) { ip = ipc; u1 = u1c; u2 = u2c; }
-      else { const double4 c = ldg4(lub + r); ip = c.x; u1 = c.y; u2 = c.z; }
-      t = fma(-u1, x1, t);
-      t = fma(-u2, x2, t);
-      t *= ip;
-      S[r * NL + l] = t;
-      x2 = x1;
-      x1 = t;
+      for (int r = 0; r < C; ++r) {
+        const double2 f = __ldg(ph - r);
+        const double4 c = ldg4(lub - r);
+        double t = sp[-(r * NL)];
+        t = fma(f.x, st.x, t);
+        t = fma(f.y, st.y, t);
+        t = fma(-c.y, x1, t);
+        t = fma(-c.z, x2, t);
+        t *= c.x;
+        sp[-(r * NL)] = t;
+        x2 = x1;
+        x1 = t;
+      }
     }
   }
   __syncthreads();
@@ -367,49 +403,74 @@ __global__ void sweep_yz_kernel(const __grid_constant__ SweepDev a, const double
   }
   __syncthreads();
 
-  // ---- D ----
+  // ---- D: carried state, corner correction, metric scale (compact_operators.f90:43), filter
+  //         add-back (compact_r4.f90:226-232) and the composite epilogue, straight to global ----
   {
     const double2 tb = TB[p * NL + l];
-    const double2 *ps = a.psi + (size_t)type * C - s;
+    const double2 *ps = a.psi + (size_t)type * C;
     const bool wf = a.wrap && ((a.wmask >> p) & 1u);
-    double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-    if (wf) { y0 = YW[l]; y1 = YW[NL + l]; y2 = YW[2 * NL + l]; y3 = YW[3 * NL + l]; }
+    const double *sp = S + (size_t)s * NL + l;
     const double *pv = vp + (long)s * rs;
     long oidx = base + (long)s * rs;
+    if (!wf) {
+#pragma unroll 8
+      for (int r = 0; r < C; ++r) {
+        const double2 g = __ldg(ps + r);
+        double x = sp[r * NL];
+        x = fma(g.x, tb.x, x);
+        x = fma(g.y, tb.y, x);
+        double val = x * scale;
+        if (ADDV) val += __ldg(pv);
+        if (valid) put<PLAIN>(out, oidx, val, epi);
+        pv += rs;
+        oidx += rs;
+      }
+    } else {
+      const double y0 = YW[l], y1 = YW[NL + l], y2 = YW[2 * NL + l], y3 = YW[3 * NL + l];
+      const double4 *Wp = a.W + s;
 #pragma unroll 4
-    for (int r = s; r < e; ++r) {
-      const double2 g = __ldg(ps + r);
-      double x = S[r * NL + l];
-      x = fma(g.x, tb.x, x);
-      x = fma(g.y, tb.y, x);
-      if (wf) {
-        const double4 c = ldg4(a.W + r);
+      for (int r = 0; r < C; ++r) {
+        const double2 g = __ldg(ps + r);
+        const double4 c = ldg4(Wp + r);
+        double x = sp[r * NL];
+        x = fma(g.x, tb.x, x);
+        x = fma(g.y, tb.y, x);
         x = fma(-c.x, y0, x);
         x = fma(-c.y, y1, x);
         x = fma(-c.z, y2, x);
         x = fma(-c.w, y3, x);
+        double val = x * scale;
+        if (ADDV) val += __ldg(pv);
+        if (valid) put<PLAIN>(out, oidx, val, epi);
+        pv += rs;
+        oidx += rs;
       }
-      if (iface != nullptr && valid) {  // z-slab: this rank's 4 interface values (compact_d1.f90:858-878)
-        const long plane = (long)a.nfast * a.nouter;
-        if (r < 2) iface[(long)r * plane + base] = a.phys_lo ? 0.0 : x;
-        if (r >= m - 2) iface[(long)(r - (m - 4)) * plane + base] = a.phys_hi ? 0.0 : x;
+    }
+    if (iface != nullptr && valid && (p == 0 || p == P - 1)) {
+      // z-slab: publish this rank's 4 interface values, unscaled (compact_d1.f90:858-878)
+      const long plane = (long)a.nfast * a.nouter;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int lr = (p == 0) ? q : C - 2 + q;
+        const double2 g = __ldg(ps + lr);
+        double x = sp[lr * NL];
+        x = fma(g.x, tb.x, x);
+        x = fma(g.y, tb.y, x);
+        if (p == 0) iface[(long)q * plane + base] = a.phys_lo ? 0.0 : x;
+        if (p == P - 1) iface[(long)(2 + q) * plane + base] = a.phys_hi ? 0.0 : x;
       }
-      double val = x * scale;
-      if (ADDV) val += __ldg(pv);
-      if (valid) put<PLAIN>(out, oidx, val, epi);
-      pv += rs;
-      oidx += rs;
     }
   }
 }
 
 // ---- y / z sweep (explicit operators: the Gaussian filter) ---------------------------------------
 template <int FAM, int NL, bool PLAIN, bool ADDV>
-__global__ void explicit_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
-                                   double *__restrict__ out, const double *__restrict__ halo_lo,
-                                   const double *__restrict__ halo_hi, const __grid_constant__ EpiArgs epi) {
-  constexpr int H = FT<FAM>::H, W = FT<FAM>::W;
-  const int m = a.m, C = a.C, P = a.P;
+__global__ void __launch_bounds__(NL * kMaxChunks)
+explicit_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
+                   double *__restrict__ out, const double *__restrict__ halo_lo,
+                   const double *__restrict__ halo_hi, const __grid_constant__ EpiArgs epi) {
+  constexpr int H = FT<FAM>::H;
+  const int m = a.m, C = a.C;
   const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
   const int tiles_i = (a.nfast + NL - 1) / NL;
   const int ti = blockIdx.x % tiles_i, o = blockIdx.x / tiles_i;
@@ -419,73 +480,34 @@ __global__ void explicit_yz_kernel(const __grid_constant__ SweepDev a, const dou
   const long rs = a.rstride;
   const long base = (long)i0 + (long)o * a.ostride;
   const double *vp = v + base;
-  const int s = p * C, e = s + C;
   const double scale = a.scale;
   auto ldc = [&](int r) -> double {
-    if (r < 0) return a.wrap ? __ldg(vp + (long)(r + m) * rs) : __ldg(halo_lo + base + (long)(r + H) * rs);
-    if (r >= m) return a.wrap ? __ldg(vp + (long)(r - m) * rs) : __ldg(halo_hi + base + (long)(r - m) * rs);
+    if (r < 0) {
+      if (a.wrap) return __ldg(vp + (long)(r + m) * rs);
+      return halo_lo ? __ldg(halo_lo + base + (long)(r + H) * rs) : 0.0;
+    }
+    if (r >= m) {
+      if (a.wrap) return __ldg(vp + (long)(r - m) * rs);
+      return halo_hi ? __ldg(halo_hi + base + (long)(r - m) * rs) : 0.0;
+    }
     return __ldg(vp + (long)r * rs);
   };
-  auto emit = [&](int row, double rhs, double vc) {  // compact_r4.f90:209-218
+  const long obase = base + (long)(p * C) * rs;
+  stream_chunk<FAM>(a, vp, rs, p, ldc, [&](int lr, double rhs, double vc) {  // compact_r4.f90:209-218
     double val = rhs * scale;
     if (ADDV) val += vc;
-    if (valid) put<PLAIN>(out, base + (long)row * rs, val, epi);
-  };
-  const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
-  int i = s;
-  double w[W], pf[W];
-  if (lo_sp) {
-    double vv[9], r4[4];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) vv[k] = __ldg(vp + (long)k * rs);
-    rhs_lo4<FAM>(vv, a.arb_lo, r4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) emit(k, r4[k], vv[k]);
-    i = 4;
-#pragma unroll
-    for (int k = 0; k < W - 1; ++k) w[k] = vv[4 - H + k];
-  } else {
-#pragma unroll
-    for (int k = 0; k < W - 1; ++k) w[k] = ldc(s - H + k);
-  }
-  const int iend = hi_sp ? e - 4 : e;
-  const int lim = iend + H;
-  const int safe = lim < m ? lim : m;
-#pragma unroll
-  for (int k = 0; k < W; ++k) {
-    const int r = i + H + k;
-    pf[k] = r < safe ? __ldg(vp + (long)r * rs) : (r < lim ? ldc(r) : 0.0);
-  }
-  int rpre = i + H + W;
-  const double *pl = vp + (long)rpre * rs;
-  for (; i < iend; i += W) {
-    static_for<0, W>([&](auto kc) {
-      constexpr int k = decltype(kc)::value;
-      if (i + k < iend) {
-        w[(k + W - 1) % W] = pf[k];
-        pf[k] = rpre < safe ? __ldg(pl) : (rpre < lim ? ldc(rpre) : 0.0);
-        pl += rs;
-        ++rpre;
-        emit(i + k, rhs_center_rot<FAM, k>(w, a.ari), w[(k + H) % W]);
-      }
-    });
-  }
-  if (hi_sp) {
-    double u[8], r4[4];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) u[k] = __ldg(vp + (long)(m - 8 + k) * rs);
-    rhs_hi4<FAM>(u, a.arb_hi, r4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) emit(m - 4 + k, r4[k], u[4 + k]);
-  }
+    if (valid) put<PLAIN>(out, obase + (long)lr * rs, val, epi);
+  });
 }
 
 // ---- x sweep -------------------------------------------------------------------------------------
-// Same algorithm on a tile of NLX unit-stride lines staged through shared memory (row pitch odd).
+// Same algorithm on a tile of NLX unit-stride lines staged through shared memory (row pitch odd):
+// coalesced tile load, in-place recurrences, coalesced write-back.
 template <int FAM, int NLX, bool PLAIN, bool ADDV>
-__global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
-                               double *__restrict__ out, const __grid_constant__ EpiArgs epi) {
-  constexpr int H = FT<FAM>::H, W = FT<FAM>::W;
+__global__ void __launch_bounds__(NLX * kMaxChunks)
+sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
+               double *__restrict__ out, const __grid_constant__ EpiArgs epi) {
+  constexpr int H = FT<FAM>::H;
   PB_SHARED(S);  // [NLX][LD], then scan states
   const int m = a.m, LD = m | 1, C = a.C, P = a.P;
   double2 *SF = reinterpret_cast<double2 *>(S + (((size_t)NLX * LD + 1) & ~(size_t)1));  // [P][NLX]
@@ -508,100 +530,103 @@ __global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double 
 
   const int l = tid % NLX, p = tid / NLX;
   const bool active = p < P;  // blockDim is rounded up to a warp multiple
-  const int s = p * C, e = s + C;
-  double *Sl = S + l * LD;
+  const int s = p * C;
+  double *Sl = S + l * LD + s;  // this thread's chunk
   const int type = active ? a.ctype[p] : 0;
   const bool cc = a.has_const && type == 0;
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
 
-  // rows of neighbouring chunks this thread's stencil needs, read before anyone overwrites them
-  double hv[H], tv[H], vv[9], u[8];
+  // rows of the neighbouring chunks this thread's stencil needs, read before anyone overwrites them
+  double hv[H], tv[H], u[8];
   if (active) {
-    if (lo_sp) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) vv[k] = Sl[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < H; ++k) { int r = s - H + k; if (r < 0) r += m; hv[k] = Sl[r]; }
+    for (int k = 0; k < H; ++k) {
+      int r = s - H + k;
+      if (r < 0) r += m;
+      hv[k] = lo_sp ? 0.0 : S[l * LD + r];
+      r = s + C + k;
+      if (r >= m) r -= m;
+      tv[k] = hi_sp ? 0.0 : S[l * LD + r];
     }
     if (hi_sp) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] = Sl[m - 8 + k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < H; ++k) { int r = e + k; if (r >= m) r -= m; tv[k] = Sl[r]; }
+      for (int k = 0; k < 8; ++k) u[k] = Sl[C - 8 + k];
     }
   }
   __syncthreads();
 
   if (active) {  // ---- A ----
-    const double2 *luf = a.luf + (size_t)type * C - s;
-    const double l2c = a.cst[0], l1c = a.cst[1];
+    double ring[16];
     double rm1 = 0.0, rm2 = 0.0;
-    auto emit = [&](int row, double rhs) {
+    const double2 *luf = a.luf + (size_t)type * C;
+    const double l2c = a.cst[0], l1c = a.cst[1];
+    auto emit = [&](int lr, double rhs) {
       if (implicit) {
         double2 c;
         if (cc) c = make_double2(l2c, l1c);
-        else c = __ldg(luf + row);
+        else c = __ldg(luf + lr);
         double t = fma(-c.x, rm2, rhs);
         t = fma(-c.y, rm1, t);
-        Sl[row] = t;
+        Sl[lr] = t;
         rm2 = rm1;
         rm1 = t;
       } else {
-        Sl[row] = rhs;
+        Sl[lr] = rhs;
       }
     };
-    int i = s;
-    double w[W];
-    if (lo_sp) {
-      double r4[4];
-      rhs_lo4<FAM>(vv, a.arb_lo, r4);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) emit(k, r4[k]);
-      i = 4;
+    for (int j = 0; j < H; ++j) ring[j] = hv[j];
 #pragma unroll
-      for (int k = 0; k < W - 1; ++k) w[k] = vv[4 - H + k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < H; ++k) w[k] = hv[k];
-#pragma unroll
-      for (int k = H; k < W - 1; ++k) w[k] = Sl[s + k - H];
-    }
-    const int imain = hi_sp ? e - 4 : e - H;  // rows whose look-ahead value is still inside the chunk
-    const int istart = i;
-    for (; i < imain; i += W) {
-      static_for<0, W>([&](auto kc) {
+    for (int j = H; j < 16; ++j) ring[j] = Sl[j - H];
+    if (!lo_sp && !hi_sp && (C & 15) == 0) {
+      for (int b = 0; b < C - 16; b += 16) {
+        static_for<0, 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          const double rhs = rhs_ring<FAM, k>(ring, a.ari);
+          ring[k] = Sl[b + k - H + 16];
+          emit(b + k, rhs);
+        });
+      }
+      static_for<0, 16>([&](auto kc) {  // last block: the look-ahead rows come from the next chunk
         constexpr int k = decltype(kc)::value;
-        if (i + k < imain) {
-          w[(k + W - 1) % W] = Sl[i + k + H];
-          emit(i + k, rhs_center_rot<FAM, k>(w, a.ari));
-        }
+        const double rhs = rhs_ring<FAM, k>(ring, a.ari);
+        if (k < H) ring[k] = Sl[C + k - H];
+        else if (k < 2 * H) ring[k] = tv[k - H];
+        emit(C - 16 + k, rhs);
       });
-    }
-    if (hi_sp) {
-      double r4[4];
-      rhs_hi4<FAM>(u, a.arb_hi, r4);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) emit(m - 4 + k, r4[k]);
     } else {
-      // the main loop stopped at row e-H with its window rotated by (rows done) % W: copy it out
-      // in canonical order (rows e-2H .. e-1) for the H rows whose look-ahead is in the next chunk
-      double wl[W];
-      const int rot = (imain - istart) % W;
-      static_for<0, W>([&](auto rc) {
-        constexpr int R = decltype(rc)::value;
-        if (rot == R) {
+      if (lo_sp) {
+        double vv[9], r4[4];
 #pragma unroll
-          for (int k = 0; k < W - 1; ++k) wl[k] = w[(R + k) % W];
-        }
-      });
+        for (int k = 0; k < 9; ++k) vv[k] = ring[(k + H) & 15];
+        rhs_lo4<FAM>(vv, a.arb_lo, r4);
 #pragma unroll
-      for (int k = 0; k < H; ++k) {
-        wl[W - 1] = tv[k];
-        emit(e - H + k, rhs_center<FAM>(wl, a.ari));
+        for (int k = 0; k < 4; ++k) emit(k, r4[k]);
+      }
+      for (int b = 0; b < C; b += 16) {
+        static_for<0, 16>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          const int lr = b + k;
+          double rhs = 0.0;
+          const bool doit = lr < C && !(lo_sp && lr < 4) && !(hi_sp && lr >= C - 4);
+          if (doit) rhs = rhs_ring<FAM, k>(ring, a.ari);
+          const int r2 = lr - H + 16;
+          double nx = 0.0;
+          if (r2 < C) nx = Sl[r2];
+          else {
 #pragma unroll
-        for (int q = 0; q < W - 1; ++q) wl[q] = wl[q + 1];
+            for (int q = 0; q < H; ++q)
+              if (r2 - C == q) nx = tv[q];
+          }
+          ring[k] = nx;
+          if (doit) emit(lr, rhs);
+        });
+      }
+      if (hi_sp) {
+        double r4[4];
+        rhs_hi4<FAM>(u, a.arb_hi, r4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) emit(C - 4 + k, r4[k]);
       }
     }
   }
@@ -623,25 +648,39 @@ __global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double 
     __syncthreads();
     if (active) {  // ---- B ----
       const double2 st = SF[p * NLX + l];
-      const double2 *ph = a.phi + (size_t)type * C - s;
-      const double4 *lub = a.lub + (size_t)type * C - s;
-      const double ipc = a.cst[2], u1c = a.cst[3], u2c = a.cst[4];
+      const double2 *ph = a.phi + (size_t)type * C;
       double x1 = 0.0, x2 = 0.0;
+      if (cc) {
+        const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+#pragma unroll 8
+        for (int r = C - 1; r >= 0; --r) {
+          const double2 f = __ldg(ph + r);
+          double t = Sl[r];
+          t = fma(f.x, st.x, t);
+          t = fma(f.y, st.y, t);
+          t = fma(-u1, x1, t);
+          t = fma(-u2, x2, t);
+          t *= ip;
+          Sl[r] = t;
+          x2 = x1;
+          x1 = t;
+        }
+      } else {
+        const double4 *lub = a.lub + (size_t)type * C;
 #pragma unroll 4
-      for (int r = e - 1; r >= s; --r) {
-        const double2 f = __ldg(ph + r);
-        double t = Sl[r];
-        t = fma(f.x, st.x, t);
-        t = fma(f.y, st.y, t);
-        double ip, u1, u2;
-        if (cc) { ip = ipc; u1 = u1c; u2 = u2c; }
-        else { const double4 c = ldg4(lub + r); ip = c.x; u1 = c.y; u2 = c.z; }
-        t = fma(-u1, x1, t);
-        t = fma(-u2, x2, t);
-        t *= ip;
-        Sl[r] = t;
-        x2 = x1;
-        x1 = t;
+        for (int r = C - 1; r >= 0; --r) {
+          const double2 f = __ldg(ph + r);
+          const double4 c = ldg4(lub + r);
+          double t = Sl[r];
+          t = fma(f.x, st.x, t);
+          t = fma(f.y, st.y, t);
+          t = fma(-c.y, x1, t);
+          t = fma(-c.z, x2, t);
+          t *= c.x;
+          Sl[r] = t;
+          x2 = x1;
+          x1 = t;
+        }
       }
     }
     __syncthreads();
@@ -667,24 +706,33 @@ __global__ void sweep_x_kernel(const __grid_constant__ SweepDev a, const double 
     __syncthreads();
     if (active) {  // ---- D (in place; the coalesced write-back follows) ----
       const double2 tb = TB[p * NLX + l];
-      const double2 *ps = a.psi + (size_t)type * C - s;
+      const double2 *ps = a.psi + (size_t)type * C;
       const bool wf = a.wrap && ((a.wmask >> p) & 1u);
-      double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-      if (wf) { y0 = YW[l]; y1 = YW[NLX + l]; y2 = YW[2 * NLX + l]; y3 = YW[3 * NLX + l]; }
+      if (!wf) {
+#pragma unroll 8
+        for (int r = 0; r < C; ++r) {
+          const double2 g = __ldg(ps + r);
+          double x = Sl[r];
+          x = fma(g.x, tb.x, x);
+          x = fma(g.y, tb.y, x);
+          Sl[r] = x;
+        }
+      } else {
+        const double y0 = YW[l], y1 = YW[NLX + l], y2 = YW[2 * NLX + l], y3 = YW[3 * NLX + l];
+        const double4 *Wp = a.W + s;
 #pragma unroll 4
-      for (int r = s; r < e; ++r) {
-        const double2 g = __ldg(ps + r);
-        double x = Sl[r];
-        x = fma(g.x, tb.x, x);
-        x = fma(g.y, tb.y, x);
-        if (wf) {
-          const double4 c = ldg4(a.W + r);
+        for (int r = 0; r < C; ++r) {
+          const double2 g = __ldg(ps + r);
+          const double4 c = ldg4(Wp + r);
+          double x = Sl[r];
+          x = fma(g.x, tb.x, x);
+          x = fma(g.y, tb.y, x);
           x = fma(-c.x, y0, x);
           x = fma(-c.y, y1, x);
           x = fma(-c.z, y2, x);
           x = fma(-c.w, y3, x);
+          Sl[r] = x;
         }
-        Sl[r] = x;
       }
     }
   }
