@@ -138,6 +138,12 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
       psi[t] = make_double2(lt.psi[t * 2], lt.psi[t * 2 + 1]);
       lub[t] = make_double4(lt.lub[t * 4], lt.lub[t * 4 + 1], lt.lub[t * 4 + 2], 0.0);
     }
+    std::vector<double4> Mf((size_t)P * P), Mb((size_t)P * P);
+    for (size_t t = 0; t < Mf.size(); ++t) {
+      Mf[t] = make_double4(lt.Mf[t * 4], lt.Mf[t * 4 + 1], lt.Mf[t * 4 + 2], lt.Mf[t * 4 + 3]);
+      Mb[t] = make_double4(lt.Mb[t * 4], lt.Mb[t * 4 + 1], lt.Mb[t * 4 + 2], lt.Mb[t * 4 + 3]);
+    }
+    for (int q = 0; q < P; ++q) { dv.nf[q] = (unsigned char)lt.nF[q]; dv.nb[q] = (unsigned char)lt.nB[q]; }
     for (size_t t = 0; t < Wc.size(); ++t) Wc[t] = make_double4(lt.W[t * 4], lt.W[t * 4 + 1], lt.W[t * 4 + 2], lt.W[t * 4 + 3]);
     int rcv;
     if ((rcv = upload(sp, luf, &dv.luf)) != PB_OK) return rcv;
@@ -145,6 +151,8 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
     if ((rcv = upload(sp, phi, &dv.phi)) != PB_OK) return rcv;
     if ((rcv = upload(sp, psi, &dv.psi)) != PB_OK) return rcv;
     if ((rcv = upload(sp, Wc, &dv.W)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, Mf, &dv.Mf)) != PB_OK) return rcv;
+    if ((rcv = upload(sp, Mb, &dv.Mb)) != PB_OK) return rcv;
     if (sp.split) {
       // rank level: the same partition algebra with ranks as chunks (compact_basetype.f90:150-198)
       Partition rp;

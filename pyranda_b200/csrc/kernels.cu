@@ -270,9 +270,9 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
   constexpr int H = FT<FAM>::H;
   PB_SHARED(S);  // [m][NL] recurrence values, then scan states
   const int m = a.m, C = a.C, P = a.P;
-  double2 *SF = reinterpret_cast<double2 *>(S + (size_t)m * NL);  // [P][NL]
-  double2 *TB = SF + P * NL;                                       // [P][NL]
-  double *YW = reinterpret_cast<double *>(TB + P * NL);            // [4][NL]
+  double2 *EN = reinterpret_cast<double2 *>(S + (size_t)m * NL);  // [P][NL] local end values of the forward pass
+  double2 *ST = EN + P * NL;                                       // [P][NL] local start values of the backward pass
+  double2 *LA = ST + P * NL;                                       // [NL]    x[m-2], x[m-1] of the bounded solve
   const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
   const int tiles_i = (a.nfast + NL - 1) / NL;
   const int ti = blockIdx.x % tiles_i, o = blockIdx.x / tiles_i;
@@ -323,27 +323,25 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
         rm1 = t;
       });
     }
-  }
-  __syncthreads();
-
-  // ---- F: r'[s_q - 1], r'[s_q - 2] entering every chunk ----
-  if (tid < NL) {
-    double s0 = 0.0, s1 = 0.0;
-    for (int q = 0; q < P; ++q) {
-      SF[q * NL + tid] = make_double2(s0, s1);
-      const double2 *ph = a.phi + (size_t)a.ctype[q] * C;
-      const double2 f1 = __ldg(ph + C - 1), f2 = __ldg(ph + C - 2);
-      const double r1 = fma(f1.y, s1, fma(f1.x, s0, S[(q * C + C - 1) * NL + tid]));
-      const double r2 = fma(f2.y, s1, fma(f2.x, s0, S[(q * C + C - 2) * NL + tid]));
-      s0 = r1;
-      s1 = r2;
-    }
+    EN[p * NL + l] = make_double2(rm1, rm2);  // r'_loc[e-1], r'_loc[e-2]
   }
   __syncthreads();
 
   // ---- B: back substitution (pentadiagonal.f90:643-647) ----
   {
-    const double2 st = SF[p * NL + l];
+    // true forward state entering this chunk: short weighted sum over the chunks before it
+    double2 st = make_double2(0.0, 0.0);
+    {
+      const int nf = a.nf[p];
+      if (nf >= 1) st = EN[(p - 1) * NL + l];
+      const double4 *Mp = a.Mf + (size_t)p * P;
+      for (int j = 2; j <= nf; ++j) {
+        const double2 en = EN[(p - j) * NL + l];
+        const double4 M = ldg4(Mp + j);
+        st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
+        st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
+      }
+    }
     const double2 *ph = a.phi + (size_t)type * C + (C - 1);
     double *sp = S + (size_t)(s + C - 1) * NL + l;
     double x1 = 0.0, x2 = 0.0;
@@ -379,36 +377,43 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
         x1 = t;
       }
     }
-  }
-  __syncthreads();
-
-  // ---- T: x[e_q], x[e_q + 1] entering every chunk from above; periodic corner unknowns ----
-  if (tid < NL) {
-    double t0 = 0.0, t1 = 0.0;
-    for (int q = P - 1; q >= 0; --q) {
-      TB[q * NL + tid] = make_double2(t0, t1);
-      const double2 *ps = a.psi + (size_t)a.ctype[q] * C;
-      const double2 g0 = __ldg(ps), g1 = __ldg(ps + 1);
-      const double n0 = fma(g0.y, t1, fma(g0.x, t0, S[(q * C) * NL + tid]));
-      const double n1 = fma(g1.y, t1, fma(g1.x, t0, S[(q * C + 1) * NL + tid]));
-      t0 = n0;
-      t1 = n1;
-    }
-    if (a.wrap) {  // Sherman-Morrison-Woodbury: y = (I + W_R)^-1 z_R
-      const double z2 = S[(m - 2) * NL + tid], z3 = S[(m - 1) * NL + tid];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        YW[c * NL + tid] = a.K[c * 4 + 0] * t0 + a.K[c * 4 + 1] * t1 + a.K[c * 4 + 2] * z2 + a.K[c * 4 + 3] * z3;
-    }
+    ST[p * NL + l] = make_double2(x1, x2);  // x_loc[s], x_loc[s+1]
+    if (p == P - 1) LA[l] = make_double2(S[(size_t)(m - 2) * NL + l], S[(size_t)(m - 1) * NL + l]);
   }
   __syncthreads();
 
   // ---- D: carried state, corner correction, metric scale (compact_operators.f90:43), filter
   //         add-back (compact_r4.f90:226-232) and the composite epilogue, straight to global ----
   {
-    const double2 tb = TB[p * NL + l];
+    // true backward state entering chunk q: short weighted sum over the chunks after it
+    auto tin = [&](int q) -> double2 {
+      double2 t = make_double2(0.0, 0.0);
+      const int nb = a.nb[q];
+      if (nb >= 1) t = ST[(q + 1) * NL + l];
+      const double4 *Mp = a.Mb + (size_t)q * P;
+      for (int j = 2; j <= nb; ++j) {
+        const double2 sv = ST[(q + j) * NL + l];
+        const double4 M = ldg4(Mp + j);
+        t.x = fma(M.y, sv.y, fma(M.x, sv.x, t.x));
+        t.y = fma(M.w, sv.y, fma(M.z, sv.x, t.y));
+      }
+      return t;
+    };
+    const double2 tb = tin(p);
     const double2 *ps = a.psi + (size_t)type * C;
     const bool wf = a.wrap && ((a.wmask >> p) & 1u);
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+    if (wf) {  // Sherman-Morrison-Woodbury: y = (I + W_R)^-1 z_R, z = solution of the bounded line
+      const double2 t0 = (p == 0) ? tb : tin(0);
+      const double2 *ps0 = a.psi + (size_t)a.ctype[0] * C;
+      const double2 g0 = __ldg(ps0), g1 = __ldg(ps0 + 1), x01 = ST[l], zl = LA[l];
+      const double z0 = fma(g0.y, t0.y, fma(g0.x, t0.x, x01.x));
+      const double z1 = fma(g1.y, t0.y, fma(g1.x, t0.x, x01.y));
+      y0 = a.K[0] * z0 + a.K[1] * z1 + a.K[2] * zl.x + a.K[3] * zl.y;
+      y1 = a.K[4] * z0 + a.K[5] * z1 + a.K[6] * zl.x + a.K[7] * zl.y;
+      y2 = a.K[8] * z0 + a.K[9] * z1 + a.K[10] * zl.x + a.K[11] * zl.y;
+      y3 = a.K[12] * z0 + a.K[13] * z1 + a.K[14] * zl.x + a.K[15] * zl.y;
+    }
     const double *sp = S + (size_t)s * NL + l;
     const double *pv = vp + (long)s * rs;
     long oidx = base + (long)s * rs;
@@ -426,7 +431,6 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
         oidx += rs;
       }
     } else {
-      const double y0 = YW[l], y1 = YW[NL + l], y2 = YW[2 * NL + l], y3 = YW[3 * NL + l];
       const double4 *Wp = a.W + s;
 #pragma unroll 4
       for (int r = 0; r < C; ++r) {
@@ -510,9 +514,9 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
   constexpr int H = FT<FAM>::H;
   PB_SHARED(S);  // [NLX][LD], then scan states
   const int m = a.m, LD = m | 1, C = a.C, P = a.P;
-  double2 *SF = reinterpret_cast<double2 *>(S + (((size_t)NLX * LD + 1) & ~(size_t)1));  // [P][NLX]
-  double2 *TB = SF + P * NLX;
-  double *YW = reinterpret_cast<double *>(TB + P * NLX);  // [4][NLX]
+  double2 *EN = reinterpret_cast<double2 *>(S + (((size_t)NLX * LD + 1) & ~(size_t)1));  // [P][NLX]
+  double2 *ST = EN + P * NLX;  // [P][NLX]
+  double2 *LA = ST + P * NLX;  // [NLX]
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
   const long nlines = a.nfast;
@@ -629,25 +633,23 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
         for (int k = 0; k < 4; ++k) emit(C - 4 + k, r4[k]);
       }
     }
+    if (implicit) EN[p * NLX + l] = make_double2(rm1, rm2);
   }
   if (implicit) {
     __syncthreads();
-    if (tid < NLX) {  // ---- F ----
-      const double *Sq = S + tid * LD;
-      double s0 = 0.0, s1 = 0.0;
-      for (int q = 0; q < P; ++q) {
-        SF[q * NLX + tid] = make_double2(s0, s1);
-        const double2 *ph = a.phi + (size_t)a.ctype[q] * C;
-        const double2 f1 = __ldg(ph + C - 1), f2 = __ldg(ph + C - 2);
-        const double r1 = fma(f1.y, s1, fma(f1.x, s0, Sq[q * C + C - 1]));
-        const double r2 = fma(f2.y, s1, fma(f2.x, s0, Sq[q * C + C - 2]));
-        s0 = r1;
-        s1 = r2;
-      }
-    }
-    __syncthreads();
     if (active) {  // ---- B ----
-      const double2 st = SF[p * NLX + l];
+      double2 st = make_double2(0.0, 0.0);
+      {
+        const int nf = a.nf[p];
+        if (nf >= 1) st = EN[(p - 1) * NLX + l];
+        const double4 *Mp = a.Mf + (size_t)p * P;
+        for (int j = 2; j <= nf; ++j) {
+          const double2 en = EN[(p - j) * NLX + l];
+          const double4 M = ldg4(Mp + j);
+          st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
+          st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
+        }
+      }
       const double2 *ph = a.phi + (size_t)type * C;
       double x1 = 0.0, x2 = 0.0;
       if (cc) {
@@ -682,30 +684,25 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
           x1 = t;
         }
       }
-    }
-    __syncthreads();
-    if (tid < NLX) {  // ---- T ----
-      const double *Sq = S + tid * LD;
-      double t0 = 0.0, t1 = 0.0;
-      for (int q = P - 1; q >= 0; --q) {
-        TB[q * NLX + tid] = make_double2(t0, t1);
-        const double2 *ps = a.psi + (size_t)a.ctype[q] * C;
-        const double2 g0 = __ldg(ps), g1 = __ldg(ps + 1);
-        const double n0 = fma(g0.y, t1, fma(g0.x, t0, Sq[q * C]));
-        const double n1 = fma(g1.y, t1, fma(g1.x, t0, Sq[q * C + 1]));
-        t0 = n0;
-        t1 = n1;
-      }
-      if (a.wrap) {
-        const double z2 = Sq[m - 2], z3 = Sq[m - 1];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          YW[c * NLX + tid] = a.K[c * 4 + 0] * t0 + a.K[c * 4 + 1] * t1 + a.K[c * 4 + 2] * z2 + a.K[c * 4 + 3] * z3;
-      }
+      ST[p * NLX + l] = make_double2(x1, x2);
+      if (p == P - 1) LA[l] = make_double2(Sl[C - 2], Sl[C - 1]);
     }
     __syncthreads();
     if (active) {  // ---- D (in place; the coalesced write-back follows) ----
-      const double2 tb = TB[p * NLX + l];
+      auto tin = [&](int q) -> double2 {
+        double2 t = make_double2(0.0, 0.0);
+        const int nb = a.nb[q];
+        if (nb >= 1) t = ST[(q + 1) * NLX + l];
+        const double4 *Mp = a.Mb + (size_t)q * P;
+        for (int j = 2; j <= nb; ++j) {
+          const double2 sv = ST[(q + j) * NLX + l];
+          const double4 M = ldg4(Mp + j);
+          t.x = fma(M.y, sv.y, fma(M.x, sv.x, t.x));
+          t.y = fma(M.w, sv.y, fma(M.z, sv.x, t.y));
+        }
+        return t;
+      };
+      const double2 tb = tin(p);
       const double2 *ps = a.psi + (size_t)type * C;
       const bool wf = a.wrap && ((a.wmask >> p) & 1u);
       if (!wf) {
@@ -718,7 +715,15 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
           Sl[r] = x;
         }
       } else {
-        const double y0 = YW[l], y1 = YW[NLX + l], y2 = YW[2 * NLX + l], y3 = YW[3 * NLX + l];
+        const double2 t0 = (p == 0) ? tb : tin(0);
+        const double2 *ps0 = a.psi + (size_t)a.ctype[0] * C;
+        const double2 g0 = __ldg(ps0), g1 = __ldg(ps0 + 1), x01 = ST[l], zl = LA[l];
+        const double z0 = fma(g0.y, t0.y, fma(g0.x, t0.x, x01.x));
+        const double z1 = fma(g1.y, t0.y, fma(g1.x, t0.x, x01.y));
+        const double y0 = a.K[0] * z0 + a.K[1] * z1 + a.K[2] * zl.x + a.K[3] * zl.y;
+        const double y1 = a.K[4] * z0 + a.K[5] * z1 + a.K[6] * zl.x + a.K[7] * zl.y;
+        const double y2 = a.K[8] * z0 + a.K[9] * z1 + a.K[10] * zl.x + a.K[11] * zl.y;
+        const double y3 = a.K[12] * z0 + a.K[13] * z1 + a.K[14] * zl.x + a.K[15] * zl.y;
         const double4 *Wp = a.W + s;
 #pragma unroll 4
         for (int r = 0; r < C; ++r) {

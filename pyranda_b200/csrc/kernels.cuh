@@ -36,6 +36,9 @@ struct SweepDev {
   const double4 *lub;   // [ntypes][C]  {1/pivot, u1, u2, 0}
   const double2 *phi;   // [ntypes][C]  forward response to the state entering the chunk
   const double2 *psi;   // [ntypes][C]  backward response to the state entering the chunk
+  const double4 *Mf;    // [P][P]       2x2 products giving the forward state entering a chunk
+  const double4 *Mb;    // [P][P]       same for the backward state
+  unsigned char nf[kMaxChunks], nb[kMaxChunks];  // terms kept per chunk
   const double4 *W;     // [m]          B^-1 E^ (periodic lines)
   double K[16];         // (I + W_R)^-1
   // right-hand side ------------------------------------------------------------------------

@@ -420,6 +420,44 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
     T.psi.insert(T.psi.end(), t.psi.begin(), t.psi.end());
   }
 
+  // chunk transfer matrices and their truncated products
+  {
+    auto typ = [&](int q) -> const ChunkTab & { return types[T.ctype[q]]; };
+    struct M2 { long double a, b, c, d; };
+    auto mul = [](const M2 &x, const M2 &y) { return M2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d}; };
+    std::vector<M2> Tf(P), Tb(P);
+    for (int q = 0; q < P; ++q) {
+      const ChunkTab &t = typ(q);
+      Tf[q] = M2{t.phi[(C - 1) * 2 + 0], t.phi[(C - 1) * 2 + 1], t.phi[(C - 2) * 2 + 0], t.phi[(C - 2) * 2 + 1]};
+      Tb[q] = M2{t.psi[0], t.psi[1], t.psi[2], t.psi[3]};
+    }
+    T.Mf.assign((size_t)P * P * 4, 0.0); T.Mb.assign((size_t)P * P * 4, 0.0);
+    T.nF.assign(P, 0); T.nB.assign(P, 0);
+    const long double tiny = 1e-22L;
+    for (int p = 0; p < P; ++p) {
+      // forward: s_in[p] = end[p-1] + T[p-1] end[p-2] + T[p-1] T[p-2] end[p-3] + ...
+      M2 acc{1, 0, 0, 1};
+      for (int j = 1; j <= p; ++j) {
+        if (j >= 2) acc = mul(acc, Tf[p - j + 1]);
+        const long double mx = std::max(std::max(fabsl(acc.a), fabsl(acc.b)), std::max(fabsl(acc.c), fabsl(acc.d)));
+        if (j >= 2 && mx < tiny) break;
+        double *dst = &T.Mf[((size_t)p * P + j) * 4];
+        dst[0] = (double)acc.a; dst[1] = (double)acc.b; dst[2] = (double)acc.c; dst[3] = (double)acc.d;
+        T.nF[p] = j;
+      }
+      // backward: t_in[p] = start[p+1] + U[p+1] start[p+2] + U[p+1] U[p+2] start[p+3] + ...
+      acc = M2{1, 0, 0, 1};
+      for (int j = 1; p + j < P; ++j) {
+        if (j >= 2) acc = mul(acc, Tb[p + j - 1]);
+        const long double mx = std::max(std::max(fabsl(acc.a), fabsl(acc.b)), std::max(fabsl(acc.c), fabsl(acc.d)));
+        if (j >= 2 && mx < tiny) break;
+        double *dst = &T.Mb[((size_t)p * P + j) * 4];
+        dst[0] = (double)acc.a; dst[1] = (double)acc.b; dst[2] = (double)acc.c; dst[3] = (double)acc.d;
+        T.nB[p] = j;
+      }
+    }
+  }
+
   if (cyclic) {
     // A = B + E with E the two 2x2 corner blocks; E x = E^ y, y = (x0, x1, x[m-2], x[m-1])
     T.W.assign((size_t)m * 4, 0.0);

@@ -61,6 +61,12 @@ struct LineTables {
   std::vector<double> lub;          // [ntypes][C][4]  1/pivot, u1, u2, 0
   std::vector<double> phi;          // [ntypes][C][2]  forward response to (r'[s-1], r'[s-2])
   std::vector<double> psi;          // [ntypes][C][2]  backward response to (x[e], x[e+1])
+  // carried state without a serial scan: the state entering chunk p is a short sum over the
+  // local end values of the chunks before (after) it, weighted by products of 2x2 chunk transfer
+  // matrices; the products decay like rho^(C*distance) and are truncated below 1e-22.
+  std::vector<double> Mf;           // [P][P][4]  Mf[p][j] applies to the end values of chunk p-j (j >= 2; j = 1 is I)
+  std::vector<double> Mb;           // [P][P][4]  Mb[p][j] applies to the start values of chunk p+j
+  std::vector<int> nF, nB;          // [P] number of terms kept (including the identity term)
   std::vector<double> W;            // [m][4]          B^-1 E^, cyclic only
   double K[16] = {0};               // (I + W_R)^-1, row major
 };
