@@ -201,23 +201,60 @@ __device__ __forceinline__ double rhs_ring(const double *g, const double *ar) {
 
 // Streams one chunk of one grid line through a 16-slot register ring (stencil window + prefetch)
 // and hands every row's right-hand side to `emit(local_row, rhs, centre_value)`.
-//   fast path: interior chunk, C % 16 == 0: no bounds checks, pointer-increment loads
-//   generic path: first / last chunk (closures, periodic wrap, halo planes) or odd chunk lengths
+// When C % 16 == 0 every chunk runs the same branch-free block loop: the first chunk only starts
+// from a different pointer (periodic wrap rows or the lower halo planes), the last chunk switches
+// its load pointer once (wrap rows / upper halo planes), and the one-sided closure rows override
+// the right-hand side of the first / last four rows.  Other chunk lengths use the checked path.
 template <int FAM, class LDC, class EMIT>
-__device__ __forceinline__ void stream_chunk(const SweepDev &a, const double *__restrict__ vp, long rs, int p, LDC &&ldc, EMIT &&emit) {
+__device__ __forceinline__ void stream_chunk(const SweepDev &a, const double *__restrict__ vp, long rs, int p,
+                                             const double *__restrict__ lo_rows, const double *__restrict__ hi_rows,
+                                             LDC &&ldc, EMIT &&emit) {
   constexpr int H = FT<FAM>::H;
   const int m = a.m, C = a.C, P = a.P;
   const int s = p * C;
+  const bool first = p == 0, last = p == P - 1;
+  const bool lo_sp = a.phys_lo && first, hi_sp = a.phys_hi && last;
   double ring[16];
-  if (p >= 1 && p <= P - 2 && (C & 15) == 0) {
-    const double *pl = vp + (long)(s - H) * rs;
+  if ((C & 15) == 0) {
+    // rows s-H .. s-1: previous chunk, periodic wrap, lower halo planes, or (closure) unused
+    const double *pl = first ? (a.wrap ? vp + (long)(m - H) * rs : (lo_rows ? lo_rows : vp)) : vp + (long)(s - H) * rs;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { ring[j] = __ldg(pl); pl += rs; }
+    for (int j = 0; j < H; ++j) { ring[j] = __ldg(pl); pl += rs; }
+    if (first) pl = vp;
+#pragma unroll
+    for (int j = H; j < 16; ++j) { ring[j] = __ldg(pl); pl += rs; }
+    double rlo[4] = {0.0, 0.0, 0.0, 0.0}, rhi[4] = {0.0, 0.0, 0.0, 0.0};
+    if (lo_sp) {
+      double vv[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) vv[q] = ring[(q + H) & 15];
+      rhs_lo4<FAM>(vv, a.arb_lo, rlo);
+    }
+    // rows m .. m+H-1 of the last chunk: periodic wrap / upper halo planes / (closure) unused
+    const double *pend = a.wrap ? vp : (hi_rows ? hi_rows : vp);
     for (int b = 0; b < C; b += 16) {
+      const bool lastblk = last && b == C - 16;
       static_for<0, 16>([&](auto kc) {
         constexpr int k = decltype(kc)::value;
-        const double rhs = rhs_ring<FAM, k>(ring, a.ari);
+        double rhs = rhs_ring<FAM, k>(ring, a.ari);
         const double vc = ring[(k + H) & 15];
+        if (k < 4) {
+          if (lo_sp && b == 0) rhs = rlo[k];
+        }
+        if (k == 12) {
+          if (hi_sp && lastblk) {
+            double u[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) u[q] = ring[(q + H + 8) & 15];
+            rhs_hi4<FAM>(u, a.arb_hi, rhi);
+          }
+        }
+        if (k >= 12) {
+          if (hi_sp && lastblk) rhs = rhi[k - 12];
+        }
+        if (k == H) {
+          if (lastblk) pl = pend;  // the next row to load is row m
+        }
         ring[k] = __ldg(pl);
         pl += rs;
         emit(b + k, rhs, vc);
@@ -225,7 +262,6 @@ __device__ __forceinline__ void stream_chunk(const SweepDev &a, const double *__
     }
     return;
   }
-  const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
 #pragma unroll
   for (int j = 0; j < 16; ++j) ring[j] = ldc(s - H + j);
   if (lo_sp) {  // one-sided closure rows 0..3
@@ -305,7 +341,7 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
     double *sp = S + (size_t)s * NL + l;
     if (cc) {
       const double l2c = a.cst[0], l1c = a.cst[1];
-      stream_chunk<FAM>(a, vp, rs, p, ldc, [&](int lr, double rhs, double) {
+      stream_chunk<FAM>(a, vp, rs, p, halo_lo ? halo_lo + base : nullptr, halo_hi ? halo_hi + base : nullptr, ldc, [&](int lr, double rhs, double) {
         double t = fma(-l2c, rm2, rhs);
         t = fma(-l1c, rm1, t);
         sp[lr * NL] = t;
@@ -314,7 +350,7 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
       });
     } else {
       const double2 *luf = a.luf + (size_t)type * C;
-      stream_chunk<FAM>(a, vp, rs, p, ldc, [&](int lr, double rhs, double) {
+      stream_chunk<FAM>(a, vp, rs, p, halo_lo ? halo_lo + base : nullptr, halo_hi ? halo_hi + base : nullptr, ldc, [&](int lr, double rhs, double) {
         const double2 c = __ldg(luf + lr);
         double t = fma(-c.x, rm2, rhs);
         t = fma(-c.y, rm1, t);
@@ -497,7 +533,7 @@ explicit_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
     return __ldg(vp + (long)r * rs);
   };
   const long obase = base + (long)(p * C) * rs;
-  stream_chunk<FAM>(a, vp, rs, p, ldc, [&](int lr, double rhs, double vc) {  // compact_r4.f90:209-218
+  stream_chunk<FAM>(a, vp, rs, p, halo_lo ? halo_lo + base : nullptr, halo_hi ? halo_hi + base : nullptr, ldc, [&](int lr, double rhs, double vc) {  // compact_r4.f90:209-218
     double val = rhs * scale;
     if (ADDV) val += vc;
     if (valid) put<PLAIN>(out, obase + (long)lr * rs, val, epi);
@@ -582,18 +618,35 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
     for (int j = 0; j < H; ++j) ring[j] = hv[j];
 #pragma unroll
     for (int j = H; j < 16; ++j) ring[j] = Sl[j - H];
-    if (!lo_sp && !hi_sp && (C & 15) == 0) {
+    if ((C & 15) == 0) {
+      double rlo[4] = {0.0, 0.0, 0.0, 0.0}, rhi[4] = {0.0, 0.0, 0.0, 0.0};
+      if (lo_sp) {
+        double vv[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) vv[q] = ring[(q + H) & 15];
+        rhs_lo4<FAM>(vv, a.arb_lo, rlo);
+      }
+      if (hi_sp) rhs_hi4<FAM>(u, a.arb_hi, rhi);
       for (int b = 0; b < C - 16; b += 16) {
         static_for<0, 16>([&](auto kc) {
           constexpr int k = decltype(kc)::value;
-          const double rhs = rhs_ring<FAM, k>(ring, a.ari);
+          double rhs = rhs_ring<FAM, k>(ring, a.ari);
+          if (k < 4) {
+            if (lo_sp && b == 0) rhs = rlo[k];
+          }
           ring[k] = Sl[b + k - H + 16];
           emit(b + k, rhs);
         });
       }
       static_for<0, 16>([&](auto kc) {  // last block: the look-ahead rows come from the next chunk
         constexpr int k = decltype(kc)::value;
-        const double rhs = rhs_ring<FAM, k>(ring, a.ari);
+        double rhs = rhs_ring<FAM, k>(ring, a.ari);
+        if (k < 4) {
+          if (lo_sp && C == 16) rhs = rlo[k];
+        }
+        if (k >= 12) {
+          if (hi_sp) rhs = rhi[k - 12];
+        }
         if (k < H) ring[k] = Sl[C + k - H];
         else if (k < 2 * H) ring[k] = tv[k - H];
         emit(C - 16 + k, rhs);
