@@ -129,6 +129,12 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
     dv.has_const = lt.has_const ? 1 : 0;
     for (int q = 0; q < 5; ++q) dv.cst[q] = lt.cst[q];
     for (int q = 0; q < 16; ++q) dv.K[q] = lt.K[q];
+    dv.cparam = (lt.has_const && dv.C <= kParamRows) ? 1 : 0;
+    if (dv.cparam)
+      for (int q = 0; q < dv.C; ++q) {
+        dv.phi0[q] = make_double2(lt.phi[q * 2], lt.phi[q * 2 + 1]);  // type 0 comes first in the tables
+        dv.psi0[q] = make_double2(lt.psi[q * 2], lt.psi[q * 2 + 1]);
+      }
     const size_t nt = (size_t)lt.ntypes * dv.C;
     std::vector<double2> luf(nt), phi(nt), psi(nt);
     std::vector<double4> lub(nt), Wc(lt.W.size() / 4);

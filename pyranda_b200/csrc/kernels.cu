@@ -41,8 +41,8 @@ namespace pb {
 
 static std::atomic<long> g_launches{0};
 long launch_count() { return g_launches.load(); }
-static int g_yz_lines = 16;
-static int g_x_lines = 16;
+static int g_yz_lines = 32;
+static int g_x_lines = 32;
 void set_yz_lines(int nl) { if (nl == 8 || nl == 16 || nl == 32) g_yz_lines = nl; }
 void set_x_lines(int nl) { if (nl == 8 || nl == 16 || nl == 32) g_x_lines = nl; }
 
@@ -298,7 +298,7 @@ __device__ __forceinline__ void stream_chunk(const SweepDev &a, const double *__
 //                   T  serial scan (reverse): true backward state; periodic: y = K z_R  -> TB, YW
 //                   D  add psi * state, Woodbury corner correction, scale / add-back    -> global
 template <int FAM, int NL, bool PLAIN, bool ADDV>
-__global__ void __launch_bounds__(NL * kMaxChunks)
+__global__ void __launch_bounds__(kBlockThreads, 3)
 sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
                 double *__restrict__ out, const double *__restrict__ halo_lo,
                 const double *__restrict__ halo_hi, double *__restrict__ iface,
@@ -383,18 +383,24 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
     double x1 = 0.0, x2 = 0.0;
     if (cc) {
       const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
-#pragma unroll 8
-      for (int r = 0; r < C; ++r) {
-        const double2 f = __ldg(ph - r);
-        double t = sp[-(r * NL)];
+      auto rowB = [&](double2 f, int j) {
+        double t = sp[-(j * NL)];
         t = fma(f.x, st.x, t);
         t = fma(f.y, st.y, t);
         t = fma(-u1, x1, t);
         t = fma(-u2, x2, t);
         t *= ip;
-        sp[-(r * NL)] = t;
+        sp[-(j * NL)] = t;
         x2 = x1;
         x1 = t;
+      };
+      if (a.cparam && C == 32) {
+        static_for<0, 32>([&](auto jc) { constexpr int j = decltype(jc)::value; rowB(a.phi0[31 - j], j); });
+      } else if (a.cparam && C == 16) {
+        static_for<0, 16>([&](auto jc) { constexpr int j = decltype(jc)::value; rowB(a.phi0[15 - j], j); });
+      } else {
+#pragma unroll 8
+        for (int r = 0; r < C; ++r) rowB(__ldg(ph - r), r);
       }
     } else {
       const double4 *lub = a.lub + (size_t)type * C + (C - 1);
@@ -453,18 +459,30 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
     const double *sp = S + (size_t)s * NL + l;
     const double *pv = vp + (long)s * rs;
     long oidx = base + (long)s * rs;
-    if (!wf) {
-#pragma unroll 8
-      for (int r = 0; r < C; ++r) {
-        const double2 g = __ldg(ps + r);
-        double x = sp[r * NL];
-        x = fma(g.x, tb.x, x);
-        x = fma(g.y, tb.y, x);
-        double val = x * scale;
-        if (ADDV) val += __ldg(pv);
-        if (valid) put<PLAIN>(out, oidx, val, epi);
-        pv += rs;
+    double *po = out + oidx;
+    auto rowD = [&](double2 g, int r) {
+      double x = sp[r * NL];
+      x = fma(g.x, tb.x, x);
+      x = fma(g.y, tb.y, x);
+      double val = x * scale;
+      if (ADDV) val += __ldg(pv);
+      if (PLAIN) {
+        if (valid) *po = val;
+        po += rs;
+      } else {
+        if (valid) epi_store(out, oidx, val, epi);
         oidx += rs;
+      }
+      pv += rs;
+    };
+    if (!wf) {
+      if (cc && a.cparam && C == 32) {
+        static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; rowD(a.psi0[r], r); });
+      } else if (cc && a.cparam && C == 16) {
+        static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; rowD(a.psi0[r], r); });
+      } else {
+#pragma unroll 8
+        for (int r = 0; r < C; ++r) rowD(__ldg(ps + r), r);
       }
     } else {
       const double4 *Wp = a.W + s;
@@ -505,7 +523,7 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
 
 // ---- y / z sweep (explicit operators: the Gaussian filter) ---------------------------------------
 template <int FAM, int NL, bool PLAIN, bool ADDV>
-__global__ void __launch_bounds__(NL * kMaxChunks)
+__global__ void __launch_bounds__(kBlockThreads, 3)
 explicit_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
                    double *__restrict__ out, const double *__restrict__ halo_lo,
                    const double *__restrict__ halo_hi, const __grid_constant__ EpiArgs epi) {
@@ -544,7 +562,7 @@ explicit_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
 // Same algorithm on a tile of NLX unit-stride lines staged through shared memory (row pitch odd):
 // coalesced tile load, in-place recurrences, coalesced write-back.
 template <int FAM, int NLX, bool PLAIN, bool ADDV>
-__global__ void __launch_bounds__(NLX * kMaxChunks)
+__global__ void __launch_bounds__(kBlockThreads, 3)
 sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
                double *__restrict__ out, const __grid_constant__ EpiArgs epi) {
   constexpr int H = FT<FAM>::H;
@@ -839,20 +857,27 @@ template <int FAM, bool ADDV>
 static cudaError_t launch_yz_f(int lines, const SweepDev &a, const double *v, double *out, const double *hlo,
                                const double *hhi, double *iface, const EpiArgs &epi, cudaStream_t st) {
   const bool plain = epi.mode == EPI_STORE;
-  if (lines == 8)
-    return plain ? launch_yz_t<FAM, 8, true, ADDV>(a, v, out, hlo, hhi, iface, epi, st)
-                 : launch_yz_t<FAM, 8, false, ADDV>(a, v, out, hlo, hhi, iface, epi, st);
-  return plain ? launch_yz_t<FAM, 16, true, ADDV>(a, v, out, hlo, hhi, iface, epi, st)
-               : launch_yz_t<FAM, 16, false, ADDV>(a, v, out, hlo, hhi, iface, epi, st);
+#define PB_YZ(NLV)                                                                                   \
+  return plain ? launch_yz_t<FAM, NLV, true, ADDV>(a, v, out, hlo, hhi, iface, epi, st)              \
+               : launch_yz_t<FAM, NLV, false, ADDV>(a, v, out, hlo, hhi, iface, epi, st)
+  if (lines == 8) { PB_YZ(8); }
+  if (lines == 32) { PB_YZ(32); }
+  PB_YZ(16);
+#undef PB_YZ
+}
+
+// lines per tile: as many as fit a 256-thread block (lines * chunks) and ~64 KB of shared memory
+static int pick_lines(int want, int P, size_t row_bytes) {
+  int lines = (want == 8 || want == 16 || want == 32) ? want : 32;
+  while (lines > 8 && (lines * P > kBlockThreads || (size_t)lines * row_bytes > 72 * 1024)) lines /= 2;
+  return lines;
 }
 
 cudaError_t launch_sweep_yz(int fam, int lines, const SweepDev &a, const double *v, double *out,
                             const double *halo_lo, const double *halo_hi, double *iface,
                             const EpiArgs &epi, cudaStream_t st) {
-  if (lines <= 0) lines = g_yz_lines;
-  if (lines != 8) lines = 16;
-  // keep three tiles resident per SM when the line is long
-  if (lines == 16 && a.implicit && (size_t)a.m * 16 * sizeof(double) > 72 * 1024) lines = 8;
+  if (a.P * 8 > kBlockThreads) return cudaErrorInvalidConfiguration;
+  lines = pick_lines(lines > 0 ? lines : g_yz_lines, a.P, a.implicit ? (size_t)a.m * sizeof(double) : 0);
   switch (fam) {
     case F_D1: return launch_yz_f<F_D1, false>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
     case F_R3: return launch_yz_f<F_R3, false>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
@@ -884,16 +909,18 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
 template <int FAM, bool ADDV>
 static cudaError_t launch_x_f(int lines, const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
   const bool plain = epi.mode == EPI_STORE;
-  if (lines == 8)
-    return plain ? launch_x_t<FAM, 8, true, ADDV>(a, v, out, epi, st) : launch_x_t<FAM, 8, false, ADDV>(a, v, out, epi, st);
-  return plain ? launch_x_t<FAM, 16, true, ADDV>(a, v, out, epi, st) : launch_x_t<FAM, 16, false, ADDV>(a, v, out, epi, st);
+#define PB_X(NLV) \
+  return plain ? launch_x_t<FAM, NLV, true, ADDV>(a, v, out, epi, st) : launch_x_t<FAM, NLV, false, ADDV>(a, v, out, epi, st)
+  if (lines == 8) { PB_X(8); }
+  if (lines == 32) { PB_X(32); }
+  PB_X(16);
+#undef PB_X
 }
 
 cudaError_t launch_sweep_x(int fam, int lines, const SweepDev &a, const double *v, double *out,
                            const EpiArgs &epi, cudaStream_t st) {
-  if (lines <= 0) lines = g_x_lines;
-  if (lines != 8) lines = 16;
-  if (lines == 16 && (size_t)(a.m | 1) * 16 * sizeof(double) > 72 * 1024) lines = 8;
+  if (a.P * 8 > kBlockThreads) return cudaErrorInvalidConfiguration;
+  lines = pick_lines(lines > 0 ? lines : g_x_lines, a.P, (size_t)(a.m | 1) * sizeof(double));
   switch (fam) {
     case F_D1: return launch_x_f<F_D1, false>(lines, a, v, out, epi, st);
     case F_R3: return launch_x_f<F_R3, false>(lines, a, v, out, epi, st);

@@ -9,6 +9,8 @@
 namespace pb {
 
 constexpr int kMaxChunks = 32;
+constexpr int kParamRows = 32;   // chunk length up to which the constant-chunk tables ride in the kernel parameters
+constexpr int kBlockThreads = 256; // every sweep block has at most this many threads
 
 // epilogue applied when a sweep writes its result
 enum Epi {
@@ -41,6 +43,8 @@ struct SweepDev {
   unsigned char nf[kMaxChunks], nb[kMaxChunks];  // terms kept per chunk
   const double4 *W;     // [m]          B^-1 E^ (periodic lines)
   double K[16];         // (I + W_R)^-1
+  int cparam;           // phi0 / psi0 below are valid (has_const and C <= kParamRows)
+  double2 phi0[kParamRows], psi0[kParamRows];  // phi / psi of the constant chunk type: constant-bank operands
   // right-hand side ------------------------------------------------------------------------
   double ari[9];
   double arb_lo[4][9], arb_hi[4][9];

@@ -27,8 +27,11 @@ def _is_torch(a):
 class ParcopPlan:
     def __init__(self, nx, ny, nz, x1=0.0, xn=1.0, y1=0.0, yn=1.0, z1=0.0, zn=1.0,
                  periodic=(False, False, False), px=1, py=1, pz=1, coords=(0, 0, 0), coordsys=0,
-                 symmetric=((False, False), (False, False), (False, False)), device=-1, lib=None):
+                 symmetric=((False, False), (False, False), (False, False)), device=-1, lib=None,
+                 tensor_device="cuda"):
         self.L = lib if lib is not None else _lib.load()
+        # where device-resident fields live; "cpu" only makes sense with the emulated library (tests)
+        self.tensor_device = tensor_device
         bcs = []
         for d in range(3):  # pyrandaMPI.py:101-131
             b1 = bn = b"NONE"
@@ -107,24 +110,28 @@ class ParcopPlan:
         """A CUDA field with Fortran strides (pyrandaMPI.emptyScalar, device resident)."""
         import torch
         ax, ay, az = self.shape
-        dev = like.device if like is not None else torch.device("cuda", torch.cuda.current_device())
+        if like is not None:
+            dev = like.device
+        elif self.tensor_device == "cuda":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        else:
+            dev = torch.device(self.tensor_device)
         return torch.empty((az, ay, ax), dtype=torch.float64, device=dev).permute(2, 1, 0)
 
     def _dev_in(self, t):
         import torch
         ax, ay, az = self.shape
-        if tuple(t.shape) != self.shape or t.dtype != torch.float64 or not t.is_cuda:
-            raise ParcopError("operand must be a float64 CUDA tensor of shape %s" % (self.shape,))
+        if tuple(t.shape) != self.shape or t.dtype != torch.float64 or t.device.type != torch.device(self.tensor_device).type:
+            raise ParcopError("operand must be a float64 %s tensor of shape %s" % (self.tensor_device, self.shape))
         if t.stride() != (1, ax, ax * ay):
             f = self.empty_device(t)
             f.copy_(t)
             t = f
         return t
 
-    @staticmethod
-    def _stream():
+    def _stream(self):
         import torch
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream().cuda_stream if self.tensor_device == "cuda" else 0
 
     # ------------------------------------------------------------------ operators
     def apply_ptr(self, op, in_ptr, out_ptr, stream=0):

@@ -28,7 +28,8 @@ class CudaBackend:
         self.torch = torch
         self.plan = plan
         self.xp = _TorchNS(torch)
-        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.device = (torch.device("cuda", torch.cuda.current_device()) if plan.tensor_device == "cuda"
+                       else torch.device(plan.tensor_device))
 
     def zeros(self):
         t = self.plan.empty_device()
