@@ -125,10 +125,8 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
     try { lt = build_line_tables(m, local, cyclic_local, P); }
     catch (const std::exception &ex) { return fail(PB_ERR_ARG, ex.what()); }
     for (int q = 0; q < P; ++q) dv.ctype[q] = lt.ctype[q];
-    dv.wmask = lt.wmask;
     dv.has_const = lt.has_const ? 1 : 0;
     for (int q = 0; q < 5; ++q) dv.cst[q] = lt.cst[q];
-    for (int q = 0; q < 16; ++q) dv.K[q] = lt.K[q];
     dv.cparam = (lt.has_const && dv.C <= kParamRows) ? 1 : 0;
     if (dv.cparam)
       for (int q = 0; q < dv.C; ++q) {
@@ -137,26 +135,24 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
       }
     const size_t nt = (size_t)lt.ntypes * dv.C;
     std::vector<double2> luf(nt), phi(nt), psi(nt);
-    std::vector<double4> lub(nt), Wc(lt.W.size() / 4);
+    std::vector<double4> lub(nt);
     for (size_t t = 0; t < nt; ++t) {
       luf[t] = make_double2(lt.luf[t * 2], lt.luf[t * 2 + 1]);
       phi[t] = make_double2(lt.phi[t * 2], lt.phi[t * 2 + 1]);
       psi[t] = make_double2(lt.psi[t * 2], lt.psi[t * 2 + 1]);
       lub[t] = make_double4(lt.lub[t * 4], lt.lub[t * 4 + 1], lt.lub[t * 4 + 2], 0.0);
     }
-    std::vector<double4> Mf((size_t)P * P), Mb((size_t)P * P);
+    std::vector<double4> Mf((size_t)P * (P + 1)), Mb((size_t)P * (P + 1));
     for (size_t t = 0; t < Mf.size(); ++t) {
       Mf[t] = make_double4(lt.Mf[t * 4], lt.Mf[t * 4 + 1], lt.Mf[t * 4 + 2], lt.Mf[t * 4 + 3]);
       Mb[t] = make_double4(lt.Mb[t * 4], lt.Mb[t * 4 + 1], lt.Mb[t * 4 + 2], lt.Mb[t * 4 + 3]);
     }
     for (int q = 0; q < P; ++q) { dv.nf[q] = (unsigned char)lt.nF[q]; dv.nb[q] = (unsigned char)lt.nB[q]; }
-    for (size_t t = 0; t < Wc.size(); ++t) Wc[t] = make_double4(lt.W[t * 4], lt.W[t * 4 + 1], lt.W[t * 4 + 2], lt.W[t * 4 + 3]);
     int rcv;
     if ((rcv = upload(sp, luf, &dv.luf)) != PB_OK) return rcv;
     if ((rcv = upload(sp, lub, &dv.lub)) != PB_OK) return rcv;
     if ((rcv = upload(sp, phi, &dv.phi)) != PB_OK) return rcv;
     if ((rcv = upload(sp, psi, &dv.psi)) != PB_OK) return rcv;
-    if ((rcv = upload(sp, Wc, &dv.W)) != PB_OK) return rcv;
     if ((rcv = upload(sp, Mf, &dv.Mf)) != PB_OK) return rcv;
     if ((rcv = upload(sp, Mb, &dv.Mb)) != PB_OK) return rcv;
     if (sp.split) {

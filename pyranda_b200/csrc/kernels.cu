@@ -308,7 +308,6 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
   const int m = a.m, C = a.C, P = a.P;
   double2 *EN = reinterpret_cast<double2 *>(S + (size_t)m * NL);  // [P][NL] local end values of the forward pass
   double2 *ST = EN + P * NL;                                       // [P][NL] local start values of the backward pass
-  double2 *LA = ST + P * NL;                                       // [NL]    x[m-2], x[m-1] of the bounded solve
   const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
   const int tiles_i = (a.nfast + NL - 1) / NL;
   const int ti = blockIdx.x % tiles_i, o = blockIdx.x / tiles_i;
@@ -369,10 +368,11 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
     double2 st = make_double2(0.0, 0.0);
     {
       const int nf = a.nf[p];
-      if (nf >= 1) st = EN[(p - 1) * NL + l];
-      const double4 *Mp = a.Mf + (size_t)p * P;
-      for (int j = 2; j <= nf; ++j) {
-        const double2 en = EN[(p - j) * NL + l];
+      const double4 *Mp = a.Mf + (size_t)p * (P + 1);
+      for (int j = 1; j <= nf; ++j) {
+        int q = p - j;
+        if (q < 0) q += P;  // periodic line: the ring of chunks
+        const double2 en = EN[q * NL + l];
         const double4 M = ldg4(Mp + j);
         st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
         st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
@@ -420,7 +420,6 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
       }
     }
     ST[p * NL + l] = make_double2(x1, x2);  // x_loc[s], x_loc[s+1]
-    if (p == P - 1) LA[l] = make_double2(S[(size_t)(m - 2) * NL + l], S[(size_t)(m - 1) * NL + l]);
   }
   __syncthreads();
 
@@ -431,10 +430,11 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
     auto tin = [&](int q) -> double2 {
       double2 t = make_double2(0.0, 0.0);
       const int nb = a.nb[q];
-      if (nb >= 1) t = ST[(q + 1) * NL + l];
-      const double4 *Mp = a.Mb + (size_t)q * P;
-      for (int j = 2; j <= nb; ++j) {
-        const double2 sv = ST[(q + j) * NL + l];
+      const double4 *Mp = a.Mb + (size_t)q * (P + 1);
+      for (int j = 1; j <= nb; ++j) {
+        int qq = q + j;
+        if (qq >= P) qq -= P;
+        const double2 sv = ST[qq * NL + l];
         const double4 M = ldg4(Mp + j);
         t.x = fma(M.y, sv.y, fma(M.x, sv.x, t.x));
         t.y = fma(M.w, sv.y, fma(M.z, sv.x, t.y));
@@ -443,19 +443,6 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
     };
     const double2 tb = tin(p);
     const double2 *ps = a.psi + (size_t)type * C;
-    const bool wf = a.wrap && ((a.wmask >> p) & 1u);
-    double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-    if (wf) {  // Sherman-Morrison-Woodbury: y = (I + W_R)^-1 z_R, z = solution of the bounded line
-      const double2 t0 = (p == 0) ? tb : tin(0);
-      const double2 *ps0 = a.psi + (size_t)a.ctype[0] * C;
-      const double2 g0 = __ldg(ps0), g1 = __ldg(ps0 + 1), x01 = ST[l], zl = LA[l];
-      const double z0 = fma(g0.y, t0.y, fma(g0.x, t0.x, x01.x));
-      const double z1 = fma(g1.y, t0.y, fma(g1.x, t0.x, x01.y));
-      y0 = a.K[0] * z0 + a.K[1] * z1 + a.K[2] * zl.x + a.K[3] * zl.y;
-      y1 = a.K[4] * z0 + a.K[5] * z1 + a.K[6] * zl.x + a.K[7] * zl.y;
-      y2 = a.K[8] * z0 + a.K[9] * z1 + a.K[10] * zl.x + a.K[11] * zl.y;
-      y3 = a.K[12] * z0 + a.K[13] * z1 + a.K[14] * zl.x + a.K[15] * zl.y;
-    }
     const double *sp = S + (size_t)s * NL + l;
     const double *pv = vp + (long)s * rs;
     long oidx = base + (long)s * rs;
@@ -475,34 +462,13 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
       }
       pv += rs;
     };
-    if (!wf) {
-      if (cc && a.cparam && C == 32) {
-        static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; rowD(a.psi0[r], r); });
-      } else if (cc && a.cparam && C == 16) {
-        static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; rowD(a.psi0[r], r); });
-      } else {
-#pragma unroll 8
-        for (int r = 0; r < C; ++r) rowD(__ldg(ps + r), r);
-      }
+    if (cc && a.cparam && C == 32) {
+      static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; rowD(a.psi0[r], r); });
+    } else if (cc && a.cparam && C == 16) {
+      static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; rowD(a.psi0[r], r); });
     } else {
-      const double4 *Wp = a.W + s;
-#pragma unroll 4
-      for (int r = 0; r < C; ++r) {
-        const double2 g = __ldg(ps + r);
-        const double4 c = ldg4(Wp + r);
-        double x = sp[r * NL];
-        x = fma(g.x, tb.x, x);
-        x = fma(g.y, tb.y, x);
-        x = fma(-c.x, y0, x);
-        x = fma(-c.y, y1, x);
-        x = fma(-c.z, y2, x);
-        x = fma(-c.w, y3, x);
-        double val = x * scale;
-        if (ADDV) val += __ldg(pv);
-        if (valid) put<PLAIN>(out, oidx, val, epi);
-        pv += rs;
-        oidx += rs;
-      }
+#pragma unroll 8
+      for (int r = 0; r < C; ++r) rowD(__ldg(ps + r), r);
     }
     if (iface != nullptr && valid && (p == 0 || p == P - 1)) {
       // z-slab: publish this rank's 4 interface values, unscaled (compact_d1.f90:858-878)
@@ -570,7 +536,6 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
   const int m = a.m, LD = m | 1, C = a.C, P = a.P;
   double2 *EN = reinterpret_cast<double2 *>(S + (((size_t)NLX * LD + 1) & ~(size_t)1));  // [P][NLX]
   double2 *ST = EN + P * NLX;  // [P][NLX]
-  double2 *LA = ST + P * NLX;  // [NLX]
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
   const long nlines = a.nfast;
@@ -712,10 +677,11 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
       double2 st = make_double2(0.0, 0.0);
       {
         const int nf = a.nf[p];
-        if (nf >= 1) st = EN[(p - 1) * NLX + l];
-        const double4 *Mp = a.Mf + (size_t)p * P;
-        for (int j = 2; j <= nf; ++j) {
-          const double2 en = EN[(p - j) * NLX + l];
+        const double4 *Mp = a.Mf + (size_t)p * (P + 1);
+        for (int j = 1; j <= nf; ++j) {
+          int q = p - j;
+          if (q < 0) q += P;
+          const double2 en = EN[q * NLX + l];
           const double4 M = ldg4(Mp + j);
           st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
           st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
@@ -756,17 +722,17 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
         }
       }
       ST[p * NLX + l] = make_double2(x1, x2);
-      if (p == P - 1) LA[l] = make_double2(Sl[C - 2], Sl[C - 1]);
     }
     __syncthreads();
     if (active) {  // ---- D (in place; the coalesced write-back follows) ----
       auto tin = [&](int q) -> double2 {
         double2 t = make_double2(0.0, 0.0);
         const int nb = a.nb[q];
-        if (nb >= 1) t = ST[(q + 1) * NLX + l];
-        const double4 *Mp = a.Mb + (size_t)q * P;
-        for (int j = 2; j <= nb; ++j) {
-          const double2 sv = ST[(q + j) * NLX + l];
+        const double4 *Mp = a.Mb + (size_t)q * (P + 1);
+        for (int j = 1; j <= nb; ++j) {
+          int qq = q + j;
+          if (qq >= P) qq -= P;
+          const double2 sv = ST[qq * NLX + l];
           const double4 M = ldg4(Mp + j);
           t.x = fma(M.y, sv.y, fma(M.x, sv.x, t.x));
           t.y = fma(M.w, sv.y, fma(M.z, sv.x, t.y));
@@ -775,40 +741,19 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
       };
       const double2 tb = tin(p);
       const double2 *ps = a.psi + (size_t)type * C;
-      const bool wf = a.wrap && ((a.wmask >> p) & 1u);
-      if (!wf) {
-#pragma unroll 8
-        for (int r = 0; r < C; ++r) {
-          const double2 g = __ldg(ps + r);
-          double x = Sl[r];
-          x = fma(g.x, tb.x, x);
-          x = fma(g.y, tb.y, x);
-          Sl[r] = x;
-        }
+      auto rowDx = [&](double2 g, int r) {
+        double x = Sl[r];
+        x = fma(g.x, tb.x, x);
+        x = fma(g.y, tb.y, x);
+        Sl[r] = x;
+      };
+      if (cc && a.cparam && C == 32) {
+        static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; rowDx(a.psi0[r], r); });
+      } else if (cc && a.cparam && C == 16) {
+        static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; rowDx(a.psi0[r], r); });
       } else {
-        const double2 t0 = (p == 0) ? tb : tin(0);
-        const double2 *ps0 = a.psi + (size_t)a.ctype[0] * C;
-        const double2 g0 = __ldg(ps0), g1 = __ldg(ps0 + 1), x01 = ST[l], zl = LA[l];
-        const double z0 = fma(g0.y, t0.y, fma(g0.x, t0.x, x01.x));
-        const double z1 = fma(g1.y, t0.y, fma(g1.x, t0.x, x01.y));
-        const double y0 = a.K[0] * z0 + a.K[1] * z1 + a.K[2] * zl.x + a.K[3] * zl.y;
-        const double y1 = a.K[4] * z0 + a.K[5] * z1 + a.K[6] * zl.x + a.K[7] * zl.y;
-        const double y2 = a.K[8] * z0 + a.K[9] * z1 + a.K[10] * zl.x + a.K[11] * zl.y;
-        const double y3 = a.K[12] * z0 + a.K[13] * z1 + a.K[14] * zl.x + a.K[15] * zl.y;
-        const double4 *Wp = a.W + s;
-#pragma unroll 4
-        for (int r = 0; r < C; ++r) {
-          const double2 g = __ldg(ps + r);
-          const double4 c = ldg4(Wp + r);
-          double x = Sl[r];
-          x = fma(g.x, tb.x, x);
-          x = fma(g.y, tb.y, x);
-          x = fma(-c.x, y0, x);
-          x = fma(-c.y, y1, x);
-          x = fma(-c.z, y2, x);
-          x = fma(-c.w, y3, x);
-          Sl[r] = x;
-        }
+#pragma unroll 8
+        for (int r = 0; r < C; ++r) rowDx(__ldg(ps + r), r);
       }
     }
   }

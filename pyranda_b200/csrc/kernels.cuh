@@ -31,18 +31,15 @@ struct SweepDev {
   // partition of a line into chunks --------------------------------------------------------
   int P, C;
   int ctype[kMaxChunks];
-  unsigned wmask;       // chunks that receive the periodic (Woodbury) corner correction
   int has_const;        // chunk type 0 has row-independent LU coefficients, kept in cst[]
   double cst[5];        // l2, l1, 1/pivot, u1, u2 of the converged rows
   const double2 *luf;   // [ntypes][C]  {l2, l1}   forward multipliers (rows i-2, i-1)
   const double4 *lub;   // [ntypes][C]  {1/pivot, u1, u2, 0}
   const double2 *phi;   // [ntypes][C]  forward response to the state entering the chunk
   const double2 *psi;   // [ntypes][C]  backward response to the state entering the chunk
-  const double4 *Mf;    // [P][P]       2x2 products giving the forward state entering a chunk
-  const double4 *Mb;    // [P][P]       same for the backward state
+  const double4 *Mf;    // [P][P+1]     2x2 products giving the forward state entering a chunk
+  const double4 *Mb;    // [P][P+1]     same for the backward state
   unsigned char nf[kMaxChunks], nb[kMaxChunks];  // terms kept per chunk
-  const double4 *W;     // [m]          B^-1 E^ (periodic lines)
-  double K[16];         // (I + W_R)^-1
   int cparam;           // phi0 / psi0 below are valid (has_const and C <= kParamRows)
   double2 phi0[kParamRows], psi0[kParamRows];  // phi / psi of the constant chunk type: constant-bank operands
   // right-hand side ------------------------------------------------------------------------

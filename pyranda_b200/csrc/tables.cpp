@@ -342,6 +342,28 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
   auto U1 = [&](int i) { return c[(size_t)i * 5 + 3]; };
   auto U2 = [&](int i) { return c[(size_t)i * 5 + 4]; };
 
+  // Periodic line: A is circulant, A = Lc * Uc with circulant band factors whose entries are the
+  // Toeplitz limit of the LU recurrence (the spectral factorisation of the symbol).  Every chunk
+  // then has the same constant coefficients and the carried state simply wraps around the ring of
+  // chunks (closed geometric series below) -- no corner correction is needed.
+  long double lim[5] = {0, 0, 0, 0, 0};
+  if (cyclic) {
+    const long double a0 = band(m / 2, 0), a1 = band(m / 2, 1), a2 = band(m / 2, 2), a3 = band(m / 2, 3), a4 = band(m / 2, 4);
+    long double pv1 = a2, pv2 = a2, u1m1 = a3, u1m2 = a3, u2 = a4;  // pivots / u1 of rows r-1, r-2
+    long double l2 = 0, l1 = 0, pv = a2, u1 = a3;
+    for (int it = 0; it < 20000; ++it) {
+      const long double nl2 = a0 / pv2;
+      const long double nl1 = (a1 - u1m2 * nl2) / pv1;
+      const long double npv = a2 - u2 * nl2 - u1m1 * nl1;
+      const long double nu1 = a3 - u2 * nl1;
+      const long double d = fabsl(nl2 - l2) + fabsl(nl1 - l1) + fabsl(npv - pv) + fabsl(nu1 - u1);
+      l2 = nl2; l1 = nl1; pv = npv; u1 = nu1;
+      pv2 = pv1; pv1 = pv; u1m2 = u1m1; u1m1 = u1;
+      if (it > 8 && d < 1e-19L * fabsl(pv)) break;
+    }
+    lim[0] = l2; lim[1] = l1; lim[2] = 1.0L / pv; lim[3] = u1; lim[4] = u2;
+  }
+
   // converged ("Toeplitz limit") coefficients: taken from the middle of the line
   const int ref = m / 2;
   auto row_is_const = [&](int i) {
@@ -361,6 +383,11 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
   }
   T.has_const = nconst > 0;
   for (int k = 0; k < 5; ++k) T.cst[k] = c[(size_t)ref * 5 + k];
+  if (cyclic) {
+    T.has_const = true;
+    for (int p = 0; p < P; ++p) chunk_const[p] = 1;
+    for (int k = 0; k < 5; ++k) T.cst[k] = (double)lim[k];
+  }
 
   struct ChunkTab { std::vector<double> luf, lub, phi, psi; };
   auto make_chunk = [&](int p, bool use_const) {
@@ -431,59 +458,56 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
       Tf[q] = M2{t.phi[(C - 1) * 2 + 0], t.phi[(C - 1) * 2 + 1], t.phi[(C - 2) * 2 + 0], t.phi[(C - 2) * 2 + 1]};
       Tb[q] = M2{t.psi[0], t.psi[1], t.psi[2], t.psi[3]};
     }
-    T.Mf.assign((size_t)P * P * 4, 0.0); T.Mb.assign((size_t)P * P * 4, 0.0);
+    T.Mf.assign((size_t)P * (P + 1) * 4, 0.0); T.Mb.assign((size_t)P * (P + 1) * 4, 0.0);
     T.nF.assign(P, 0); T.nB.assign(P, 0);
     const long double tiny = 1e-22L;
-    for (int p = 0; p < P; ++p) {
-      // forward: s_in[p] = end[p-1] + T[p-1] end[p-2] + T[p-1] T[p-2] end[p-3] + ...
-      M2 acc{1, 0, 0, 1};
-      for (int j = 1; j <= p; ++j) {
-        if (j >= 2) acc = mul(acc, Tf[p - j + 1]);
-        const long double mx = std::max(std::max(fabsl(acc.a), fabsl(acc.b)), std::max(fabsl(acc.c), fabsl(acc.d)));
-        if (j >= 2 && mx < tiny) break;
-        double *dst = &T.Mf[((size_t)p * P + j) * 4];
-        dst[0] = (double)acc.a; dst[1] = (double)acc.b; dst[2] = (double)acc.c; dst[3] = (double)acc.d;
-        T.nF[p] = j;
+    auto mxabs = [](const M2 &x) { return std::max(std::max(fabsl(x.a), fabsl(x.b)), std::max(fabsl(x.c), fabsl(x.d))); };
+    auto put4 = [](double *dst, const M2 &x) { dst[0] = (double)x.a; dst[1] = (double)x.b; dst[2] = (double)x.c; dst[3] = (double)x.d; };
+    if (cyclic) {
+      // s_in = (I - T^P)^-1 (end[p-1] + T end[p-2] + ... + T^(P-1) end[p-P]), indices modulo P
+      for (int dir = 0; dir < 2; ++dir) {
+        const M2 Tm = dir == 0 ? Tf[0] : Tb[0];
+        M2 TP{1, 0, 0, 1};
+        for (int q = 0; q < P; ++q) TP = mul(TP, Tm);
+        const M2 ImT{1 - TP.a, -TP.b, -TP.c, 1 - TP.d};
+        const long double det = ImT.a * ImT.d - ImT.b * ImT.c;
+        const M2 G{ImT.d / det, -ImT.b / det, -ImT.c / det, ImT.a / det};
+        M2 acc = G;
+        int nterms = 0;
+        std::vector<double> row((size_t)(P + 1) * 4, 0.0);
+        for (int j = 1; j <= P; ++j) {
+          if (j >= 2) acc = mul(acc, Tm);
+          if (j >= 2 && mxabs(acc) < tiny) break;
+          put4(&row[(size_t)j * 4], acc);
+          nterms = j;
+        }
+        for (int p = 0; p < P; ++p) {
+          std::copy(row.begin(), row.end(), (dir == 0 ? T.Mf : T.Mb).begin() + (size_t)p * (P + 1) * 4);
+          (dir == 0 ? T.nF : T.nB)[p] = nterms;
+        }
       }
-      // backward: t_in[p] = start[p+1] + U[p+1] start[p+2] + U[p+1] U[p+2] start[p+3] + ...
-      acc = M2{1, 0, 0, 1};
-      for (int j = 1; p + j < P; ++j) {
-        if (j >= 2) acc = mul(acc, Tb[p + j - 1]);
-        const long double mx = std::max(std::max(fabsl(acc.a), fabsl(acc.b)), std::max(fabsl(acc.c), fabsl(acc.d)));
-        if (j >= 2 && mx < tiny) break;
-        double *dst = &T.Mb[((size_t)p * P + j) * 4];
-        dst[0] = (double)acc.a; dst[1] = (double)acc.b; dst[2] = (double)acc.c; dst[3] = (double)acc.d;
-        T.nB[p] = j;
+    } else {
+      for (int p = 0; p < P; ++p) {
+        // forward: s_in[p] = end[p-1] + T[p-1] end[p-2] + T[p-1] T[p-2] end[p-3] + ...
+        M2 acc{1, 0, 0, 1};
+        for (int j = 1; j <= p; ++j) {
+          if (j >= 2) acc = mul(acc, Tf[p - j + 1]);
+          if (j >= 2 && mxabs(acc) < tiny) break;
+          put4(&T.Mf[((size_t)p * (P + 1) + j) * 4], acc);
+          T.nF[p] = j;
+        }
+        // backward: t_in[p] = start[p+1] + U[p+1] start[p+2] + U[p+1] U[p+2] start[p+3] + ...
+        acc = M2{1, 0, 0, 1};
+        for (int j = 1; p + j < P; ++j) {
+          if (j >= 2) acc = mul(acc, Tb[p + j - 1]);
+          if (j >= 2 && mxabs(acc) < tiny) break;
+          put4(&T.Mb[((size_t)p * (P + 1) + j) * 4], acc);
+          T.nB[p] = j;
+        }
       }
     }
   }
 
-  if (cyclic) {
-    // A = B + E with E the two 2x2 corner blocks; E x = E^ y, y = (x0, x1, x[m-2], x[m-1])
-    T.W.assign((size_t)m * 4, 0.0);
-    std::vector<double> col(m);
-    for (int q = 0; q < 4; ++q) {
-      std::fill(col.begin(), col.end(), 0.0);
-      if (q == 0) { col[m - 2] = band(m - 2, 4); col[m - 1] = band(m - 1, 3); }
-      else if (q == 1) { col[m - 1] = band(m - 1, 4); }
-      else if (q == 2) { col[0] = band(0, 0); }
-      else { col[0] = band(0, 1); col[1] = band(1, 0); }
-      solve_block(c, m, col.data());
-      for (int i = 0; i < m; ++i) T.W[(size_t)i * 4 + q] = col[i];
-    }
-    const int rows[4] = {0, 1, m - 2, m - 1};
-    std::vector<long double> M(16);
-    for (int r = 0; r < 4; ++r)
-      for (int q = 0; q < 4; ++q) M[r * 4 + q] = (r == q ? 1.0L : 0.0L) + (long double)T.W[(size_t)rows[r] * 4 + q];
-    std::vector<long double> Minv = invert_dense(M, 4);
-    for (int k = 0; k < 16; ++k) T.K[k] = (double)Minv[k];
-    for (int p = 0; p < P; ++p) {
-      double mx = 0.0;
-      for (int i = p * C; i < (p + 1) * C; ++i)
-        for (int q = 0; q < 4; ++q) mx = std::max(mx, std::fabs(T.W[(size_t)i * 4 + q]));
-      if (mx > 1e-20) T.wmask |= (1u << p);
-    }
-  }
   return T;
 }
 

@@ -49,14 +49,14 @@ struct Partition {
 // zero incoming state, a short serial scan propagates the true 2-value state from chunk to chunk,
 // and the homogeneous responses phi / psi add the carried state back.  Rows whose LU coefficients
 // have converged to the Toeplitz limit share one "constant" chunk type whose coefficients live in
-// registers.  A periodic line is the bounded line plus a rank-4 corner update, applied with the
-// Sherman-Morrison-Woodbury identity (columns W, 4x4 capacitance inverse K).
+// registers.  A periodic line is circulant: it is factored into circulant band factors (the Toeplitz
+// limit of the LU recurrence), every chunk is the constant type, and the carried state wraps around
+// the ring of chunks through a closed geometric series of the 2x2 chunk transfer matrix.
 struct LineTables {
   int m = 0, P = 1, C = 0, ntypes = 0;
   bool cyclic = false, has_const = false;
   double cst[5] = {0, 0, 0, 0, 0};  // l2, l1, 1/pivot, u1, u2 of the converged rows
   std::vector<int> ctype;           // [P]; type 0 is the constant type when has_const
-  unsigned wmask = 0;               // chunks whose rows get the Woodbury correction
   std::vector<double> luf;          // [ntypes][C][2]  l2, l1
   std::vector<double> lub;          // [ntypes][C][4]  1/pivot, u1, u2, 0
   std::vector<double> phi;          // [ntypes][C][2]  forward response to (r'[s-1], r'[s-2])
@@ -64,11 +64,9 @@ struct LineTables {
   // carried state without a serial scan: the state entering chunk p is a short sum over the
   // local end values of the chunks before (after) it, weighted by products of 2x2 chunk transfer
   // matrices; the products decay like rho^(C*distance) and are truncated below 1e-22.
-  std::vector<double> Mf;           // [P][P][4]  Mf[p][j] applies to the end values of chunk p-j (j >= 2; j = 1 is I)
-  std::vector<double> Mb;           // [P][P][4]  Mb[p][j] applies to the start values of chunk p+j
+  std::vector<double> Mf;           // [P][P+1][4]  Mf[p][j], j >= 1, applies to the end values of chunk (p-j) mod P
+  std::vector<double> Mb;           // [P][P+1][4]  Mb[p][j] applies to the start values of chunk (p+j) mod P
   std::vector<int> nF, nB;          // [P] number of terms kept (including the identity term)
-  std::vector<double> W;            // [m][4]          B^-1 E^, cyclic only
-  double K[16] = {0};               // (I + W_R)^-1, row major
 };
 LineTables build_line_tables(int m, const std::vector<double> &bands, bool cyclic, int P);
 
