@@ -255,7 +255,8 @@ long pb_launch_count(void) { return launch_count(); }
 int pb_set_tuning(int lines_yz, int lines_x, int chunk_len) {
   if (lines_yz > 0) set_yz_lines(lines_yz);
   if (lines_x > 0) set_x_lines(lines_x);
-  if (chunk_len >= 16) g_chunk_len = chunk_len;
+  if (chunk_len >= 16) g_chunk_len = chunk_len % 1000;
+  if (chunk_len >= 1000) set_reg_kernels(chunk_len / 1000 == 1 ? 0 : 1);  // 1xxx: shared-memory kernels, 2xxx: register kernels
   return PB_OK;
 }
 

@@ -18,798 +18,29 @@
 //   x sweep: lines are unit stride; a tile of NLX lines is staged through shared memory with
 //   coalesced loads (row pitch odd => conflict-free column access), solved in place, and written
 //   back coalesced.
-#include "kernels.cuh"
-
-#include <atomic>
-#include <type_traits>
-
-#include "tables.hpp"
-
-#ifdef PB_EMULATE
-#define PB_SHARED(S) double *S = emul::t_smem
-#define PB_LAUNCH(kernel, grid, block, smem, st, ...) emul::launch(grid, block, smem, [&] { kernel(__VA_ARGS__); })
-#define PB_EW_GRID(n) dim3(1)
-#define PB_EW_BLOCK dim3(1)
-#else
-#define PB_SHARED(S) extern __shared__ double S[]
-#define PB_LAUNCH(kernel, grid, block, smem, st, ...) kernel<<<grid, block, smem, st>>>(__VA_ARGS__)
-#define PB_EW_GRID(n) dim3(ew_blocks(n))
-#define PB_EW_BLOCK dim3(256)
-#endif
+#include "sweeps.cuh"
 
 namespace pb {
 
-static std::atomic<long> g_launches{0};
+std::atomic<long> g_launches{0};
 long launch_count() { return g_launches.load(); }
+int g_reg_kernels = 1;
+void set_reg_kernels(int on) { g_reg_kernels = on; }
 static int g_yz_lines = 32;
 static int g_x_lines = 32;
 void set_yz_lines(int nl) { if (nl == 8 || nl == 16 || nl == 32) g_yz_lines = nl; }
 void set_x_lines(int nl) { if (nl == 8 || nl == 16 || nl == 32) g_x_lines = nl; }
 
-__device__ __forceinline__ double4 ldg4(const double4 *p) {
-  const double2 *q = reinterpret_cast<const double2 *>(p);
-  const double2 a = __ldg(q), b = __ldg(q + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
-}
 
-template <int FAM>
-struct FT {
-  static constexpr int H = (FAM == F_R4) ? 4 : 3;
-  static constexpr int W = 2 * H + 1;
-};
-
-// ---- right-hand sides ---------------------------------------------------------------------------
-// interior / halo rows.  w = v[i-H .. i+H].
-// D1: compact_d1.f90:156, R3: compact_r3.f90:127-128, R4: compact_r4.f90:148-152
-template <int FAM>
-__device__ __forceinline__ double rhs_center(const double *w, const double *ar) {
-  if (FAM == F_D1) {
-    return ar[4] * (w[4] - w[2]) + ar[5] * (w[5] - w[1]) + ar[6] * (w[6] - w[0]);
-  } else if (FAM == F_R3) {
-    double s = 0.0;
-#pragma unroll
-    for (int l = 0; l < 7; ++l)
-      if (l != 3) s += ar[l] * (w[l] - w[3]);
-    return s;
-  } else {
-    double s = 0.0;
-#pragma unroll
-    for (int l = 0; l < 9; ++l)
-      if (l != 4) s += (w[l] - w[4]) * ar[l];
-    return s;
-  }
-}
-
-// first four rows at a one-sided physical boundary; vv = v[0..8], b = closure rows.
-// D1: compact_d1.f90:134-136 (+ row 4 by :156 with closure weights), R3: compact_r3.f90:118-120,
-// R4: compact_r4.f90:123-126
-template <int FAM>
-__device__ __forceinline__ void rhs_lo4(const double *vv, const double (*b)[9], double *r) {
-  if (FAM == F_D1) {
-    const double v0 = vv[0];
-    r[0] = b[0][4] * (vv[1] - v0) + b[0][5] * (vv[2] - v0) + b[0][6] * (vv[3] - v0);
-    r[1] = b[1][3] * (vv[1] - v0) + b[1][4] * (vv[2] - v0) + b[1][5] * (vv[3] - v0) + b[1][6] * (vv[4] - v0);
-    r[2] = b[2][4] * (vv[3] - vv[1]) + b[2][5] * (vv[4] - v0) + b[2][6] * (vv[5] - v0);
-    r[3] = b[3][4] * (vv[4] - vv[2]) + b[3][5] * (vv[5] - vv[1]) + b[3][6] * (vv[6] - v0);
-  } else if (FAM == F_R3) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double s = 0.0;
-#pragma unroll
-      for (int l = 0; l < 7; ++l) {
-        const int k = l - 3 + i;
-        if (k >= 0 && k != i) s += b[i][l] * (vv[k] - vv[i]);
-      }
-      r[i] = s;
-    }
-  } else {
-    const double v0 = vv[0];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double s = 0.0;
-#pragma unroll
-      for (int l = 5 - i; l < 9; ++l) s += b[i][l] * (vv[l - 4 + i] - v0);
-      r[i] = s;
-    }
-  }
-}
-
-// last four rows; u = v[m-8..m-1], h = closure rows for rows m-4..m-1.
-// D1: compact_d1.f90:176-178, R3: compact_r3.f90:144-146, R4: compact_r4.f90:174-177
-template <int FAM>
-__device__ __forceinline__ void rhs_hi4(const double *u, const double (*h)[9], double *r) {
-  if (FAM == F_D1) {
-    const double vm = u[7];
-    r[0] = h[0][4] * (u[5] - u[3]) + h[0][5] * (u[6] - u[2]) + h[0][6] * (u[7] - u[1]);
-    r[1] = h[1][0] * (u[2] - vm) + h[1][1] * (u[3] - vm) + h[1][2] * (u[4] - u[6]);
-    r[2] = h[2][0] * (u[3] - vm) + h[2][1] * (u[4] - vm) + h[2][2] * (u[5] - vm) + h[2][3] * (u[6] - vm);
-    r[3] = h[3][0] * (u[4] - vm) + h[3][1] * (u[5] - vm) + h[3][2] * (u[6] - vm);
-  } else if (FAM == F_R3) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = 4 + q;  // index of this row in u
-      double s = 0.0;
-#pragma unroll
-      for (int l = 0; l < 7; ++l) {
-        const int k = c - 3 + l;
-        if (k < 8 && k != c) s += h[q][l] * (u[k] - u[c]);
-      }
-      r[q] = s;
-    }
-  } else {
-    const double vm = u[7];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      double s = 0.0;
-#pragma unroll
-      for (int l = 0; l < 7 - q; ++l) s += h[q][l] * (u[q + l] - vm);
-      r[q] = s;
-    }
-  }
-}
-
-__device__ __forceinline__ void epi_store(double *__restrict__ out, long idx, double val, const EpiArgs &epi) {
-  switch (epi.mode) {
-    case EPI_STORE: out[idx] = val; break;
-    case EPI_ACC: out[idx] += val; break;
-    default: {
-      double sc = epi.s2;
-      if (epi.field) { const double f = epi.field[idx]; sc = f * f; }
-      double r = fabs(val) * sc;
-      if (epi.mode == EPI_RING_MAX) r = fmax(r, out[idx]);
-      out[idx] = r;
-    }
-  }
-}
-
-template <bool PLAIN>
-__device__ __forceinline__ void put(double *__restrict__ out, long idx, double val, const EpiArgs &epi) {
-  if (PLAIN) out[idx] = val;
-  else epi_store(out, idx, val, epi);
-}
-
-// compile-time loop: F(k) is called with k as a template argument
-template <int K, int N, class F>
-__device__ __forceinline__ void static_for(F &&f) {
-  if constexpr (K < N) {
-    f(std::integral_constant<int, K>{});
-    static_for<K + 1, N>(f);
-  }
-}
-
-// ring access: at step K of a 16-row block the window element j (row - H + j) lives in slot (K+j)&15
-template <int FAM, int K>
-__device__ __forceinline__ double rhs_ring(const double *g, const double *ar) {
-#define WR(j) g[(K + (j)) & 15]
-  if (FAM == F_D1) {
-    return ar[4] * (WR(4) - WR(2)) + ar[5] * (WR(5) - WR(1)) + ar[6] * (WR(6) - WR(0));
-  } else if (FAM == F_R3) {
-    double s = 0.0;
-#pragma unroll
-    for (int l = 0; l < 7; ++l)
-      if (l != 3) s += ar[l] * (WR(l) - WR(3));
-    return s;
-  } else {
-    double s = 0.0;
-#pragma unroll
-    for (int l = 0; l < 9; ++l)
-      if (l != 4) s += (WR(l) - WR(4)) * ar[l];
-    return s;
-  }
-#undef WR
-}
-
-// Streams one chunk of one grid line through a 16-slot register ring (stencil window + prefetch)
-// and hands every row's right-hand side to `emit(local_row, rhs, centre_value)`.
-// When C % 16 == 0 every chunk runs the same branch-free block loop: the first chunk only starts
-// from a different pointer (periodic wrap rows or the lower halo planes), the last chunk switches
-// its load pointer once (wrap rows / upper halo planes), and the one-sided closure rows override
-// the right-hand side of the first / last four rows.  Other chunk lengths use the checked path.
-template <int FAM, class LDC, class EMIT>
-__device__ __forceinline__ void stream_chunk(const SweepDev &a, const double *__restrict__ vp, long rs, int p,
-                                             const double *__restrict__ lo_rows, const double *__restrict__ hi_rows,
-                                             LDC &&ldc, EMIT &&emit) {
-  constexpr int H = FT<FAM>::H;
-  const int m = a.m, C = a.C, P = a.P;
-  const int s = p * C;
-  const bool first = p == 0, last = p == P - 1;
-  const bool lo_sp = a.phys_lo && first, hi_sp = a.phys_hi && last;
-  double ring[16];
-  if ((C & 15) == 0) {
-    // rows s-H .. s-1: previous chunk, periodic wrap, lower halo planes, or (closure) unused
-    const double *pl = first ? (a.wrap ? vp + (long)(m - H) * rs : (lo_rows ? lo_rows : vp)) : vp + (long)(s - H) * rs;
-#pragma unroll
-    for (int j = 0; j < H; ++j) { ring[j] = __ldg(pl); pl += rs; }
-    if (first) pl = vp;
-#pragma unroll
-    for (int j = H; j < 16; ++j) { ring[j] = __ldg(pl); pl += rs; }
-    double rlo[4] = {0.0, 0.0, 0.0, 0.0}, rhi[4] = {0.0, 0.0, 0.0, 0.0};
-    if (lo_sp) {
-      double vv[9];
-#pragma unroll
-      for (int q = 0; q < 9; ++q) vv[q] = ring[(q + H) & 15];
-      rhs_lo4<FAM>(vv, a.arb_lo, rlo);
-    }
-    // rows m .. m+H-1 of the last chunk: periodic wrap / upper halo planes / (closure) unused
-    const double *pend = a.wrap ? vp : (hi_rows ? hi_rows : vp);
-    for (int b = 0; b < C; b += 16) {
-      const bool lastblk = last && b == C - 16;
-      static_for<0, 16>([&](auto kc) {
-        constexpr int k = decltype(kc)::value;
-        double rhs = rhs_ring<FAM, k>(ring, a.ari);
-        const double vc = ring[(k + H) & 15];
-        if (k < 4) {
-          if (lo_sp && b == 0) rhs = rlo[k];
-        }
-        if (k == 12) {
-          if (hi_sp && lastblk) {
-            double u[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) u[q] = ring[(q + H + 8) & 15];
-            rhs_hi4<FAM>(u, a.arb_hi, rhi);
-          }
-        }
-        if (k >= 12) {
-          if (hi_sp && lastblk) rhs = rhi[k - 12];
-        }
-        if (k == H) {
-          if (lastblk) pl = pend;  // the next row to load is row m
-        }
-        ring[k] = __ldg(pl);
-        pl += rs;
-        emit(b + k, rhs, vc);
-      });
-    }
-    return;
-  }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) ring[j] = ldc(s - H + j);
-  if (lo_sp) {  // one-sided closure rows 0..3
-    double vv[9], r4[4];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) vv[k] = ring[(k + H) & 15];
-    rhs_lo4<FAM>(vv, a.arb_lo, r4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) emit(k, r4[k], vv[k]);
-  }
-  for (int b = 0; b < C; b += 16) {
-    static_for<0, 16>([&](auto kc) {
-      constexpr int k = decltype(kc)::value;
-      const int lr = b + k, row = s + lr;
-      if (lr < C && !(lo_sp && lr < 4) && !(hi_sp && row >= m - 4))
-        emit(lr, rhs_ring<FAM, k>(ring, a.ari), ring[(k + H) & 15]);
-      ring[k] = ldc(row - H + 16);
-    });
-  }
-  if (hi_sp) {  // one-sided closure rows m-4..m-1
-    double u[8], r4[4];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) u[k] = __ldg(vp + (long)(m - 8 + k) * rs);
-    rhs_hi4<FAM>(u, a.arb_hi, r4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) emit(C - 4 + k, r4[k], u[4 + k]);
-  }
-}
-
-// ---- y / z sweep (implicit operators) ------------------------------------------------------------
-// Phases per tile:  A  rhs + forward recurrence over the chunk (zero incoming state)  -> S
-//                   F  serial scan over chunks: true forward state entering each chunk -> SF
-//                   B  add phi * state, backward recurrence (zero incoming state)       -> S
-//                   T  serial scan (reverse): true backward state; periodic: y = K z_R  -> TB, YW
-//                   D  add psi * state, Woodbury corner correction, scale / add-back    -> global
-template <int FAM, int NL, bool PLAIN, bool ADDV>
-__global__ void __launch_bounds__(kBlockThreads, 3)
-sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
-                double *__restrict__ out, const double *__restrict__ halo_lo,
-                const double *__restrict__ halo_hi, double *__restrict__ iface,
-                const __grid_constant__ EpiArgs epi) {
-  constexpr int H = FT<FAM>::H;
-  PB_SHARED(S);  // [m][NL] recurrence values, then scan states
-  const int m = a.m, C = a.C, P = a.P;
-  double2 *EN = reinterpret_cast<double2 *>(S + (size_t)m * NL);  // [P][NL] local end values of the forward pass
-  double2 *ST = EN + P * NL;                                       // [P][NL] local start values of the backward pass
-  const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
-  const int tiles_i = (a.nfast + NL - 1) / NL;
-  const int ti = blockIdx.x % tiles_i, o = blockIdx.x / tiles_i;
-  int i0 = ti * NL + l;
-  const bool valid = i0 < a.nfast;
-  if (!valid) i0 = a.nfast - 1;
-  const long rs = a.rstride;
-  const long base = (long)i0 + (long)o * a.ostride;
-  const double *vp = v + base;
-  const int s = p * C;
-  const int type = a.ctype[p];
-  const bool cc = a.has_const && type == 0;
-  const double scale = a.scale;
-
-  auto ldc = [&](int r) -> double {  // row outside [0,m): periodic wrap or neighbour halo planes
-    if (r < 0) {
-      if (a.wrap) return __ldg(vp + (long)(r + m) * rs);
-      return halo_lo ? __ldg(halo_lo + base + (long)(r + H) * rs) : 0.0;
-    }
-    if (r >= m) {
-      if (a.wrap) return __ldg(vp + (long)(r - m) * rs);
-      return halo_hi ? __ldg(halo_hi + base + (long)(r - m) * rs) : 0.0;
-    }
-    return __ldg(vp + (long)r * rs);
-  };
-
-  // ---- A: forward elimination, pentadiagonal.f90:639-642 in pull form ----
-  {
-    double rm1 = 0.0, rm2 = 0.0;
-    double *sp = S + (size_t)s * NL + l;
-    if (cc) {
-      const double l2c = a.cst[0], l1c = a.cst[1];
-      stream_chunk<FAM>(a, vp, rs, p, halo_lo ? halo_lo + base : nullptr, halo_hi ? halo_hi + base : nullptr, ldc, [&](int lr, double rhs, double) {
-        double t = fma(-l2c, rm2, rhs);
-        t = fma(-l1c, rm1, t);
-        sp[lr * NL] = t;
-        rm2 = rm1;
-        rm1 = t;
-      });
-    } else {
-      const double2 *luf = a.luf + (size_t)type * C;
-      stream_chunk<FAM>(a, vp, rs, p, halo_lo ? halo_lo + base : nullptr, halo_hi ? halo_hi + base : nullptr, ldc, [&](int lr, double rhs, double) {
-        const double2 c = __ldg(luf + lr);
-        double t = fma(-c.x, rm2, rhs);
-        t = fma(-c.y, rm1, t);
-        sp[lr * NL] = t;
-        rm2 = rm1;
-        rm1 = t;
-      });
-    }
-    EN[p * NL + l] = make_double2(rm1, rm2);  // r'_loc[e-1], r'_loc[e-2]
-  }
-  __syncthreads();
-
-  // ---- B: back substitution (pentadiagonal.f90:643-647) ----
-  {
-    // true forward state entering this chunk: short weighted sum over the chunks before it
-    double2 st = make_double2(0.0, 0.0);
-    {
-      const int nf = a.nf[p];
-      const double4 *Mp = a.Mf + (size_t)p * (P + 1);
-      for (int j = 1; j <= nf; ++j) {
-        int q = p - j;
-        if (q < 0) q += P;  // periodic line: the ring of chunks
-        const double2 en = EN[q * NL + l];
-        const double4 M = ldg4(Mp + j);
-        st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
-        st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
-      }
-    }
-    const double2 *ph = a.phi + (size_t)type * C + (C - 1);
-    double *sp = S + (size_t)(s + C - 1) * NL + l;
-    double x1 = 0.0, x2 = 0.0;
-    if (cc) {
-      const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
-      auto rowB = [&](double2 f, int j) {
-        double t = sp[-(j * NL)];
-        t = fma(f.x, st.x, t);
-        t = fma(f.y, st.y, t);
-        t = fma(-u1, x1, t);
-        t = fma(-u2, x2, t);
-        t *= ip;
-        sp[-(j * NL)] = t;
-        x2 = x1;
-        x1 = t;
-      };
-      if (a.cparam && C == 32) {
-        static_for<0, 32>([&](auto jc) { constexpr int j = decltype(jc)::value; rowB(a.phi0[31 - j], j); });
-      } else if (a.cparam && C == 16) {
-        static_for<0, 16>([&](auto jc) { constexpr int j = decltype(jc)::value; rowB(a.phi0[15 - j], j); });
-      } else {
-#pragma unroll 8
-        for (int r = 0; r < C; ++r) rowB(__ldg(ph - r), r);
-      }
-    } else {
-      const double4 *lub = a.lub + (size_t)type * C + (C - 1);
-#pragma unroll 4
-      for (int r = 0; r < C; ++r) {
-        const double2 f = __ldg(ph - r);
-        const double4 c = ldg4(lub - r);
-        double t = sp[-(r * NL)];
-        t = fma(f.x, st.x, t);
-        t = fma(f.y, st.y, t);
-        t = fma(-c.y, x1, t);
-        t = fma(-c.z, x2, t);
-        t *= c.x;
-        sp[-(r * NL)] = t;
-        x2 = x1;
-        x1 = t;
-      }
-    }
-    ST[p * NL + l] = make_double2(x1, x2);  // x_loc[s], x_loc[s+1]
-  }
-  __syncthreads();
-
-  // ---- D: carried state, corner correction, metric scale (compact_operators.f90:43), filter
-  //         add-back (compact_r4.f90:226-232) and the composite epilogue, straight to global ----
-  {
-    // true backward state entering chunk q: short weighted sum over the chunks after it
-    auto tin = [&](int q) -> double2 {
-      double2 t = make_double2(0.0, 0.0);
-      const int nb = a.nb[q];
-      const double4 *Mp = a.Mb + (size_t)q * (P + 1);
-      for (int j = 1; j <= nb; ++j) {
-        int qq = q + j;
-        if (qq >= P) qq -= P;
-        const double2 sv = ST[qq * NL + l];
-        const double4 M = ldg4(Mp + j);
-        t.x = fma(M.y, sv.y, fma(M.x, sv.x, t.x));
-        t.y = fma(M.w, sv.y, fma(M.z, sv.x, t.y));
-      }
-      return t;
-    };
-    const double2 tb = tin(p);
-    const double2 *ps = a.psi + (size_t)type * C;
-    const double *sp = S + (size_t)s * NL + l;
-    const double *pv = vp + (long)s * rs;
-    long oidx = base + (long)s * rs;
-    double *po = out + oidx;
-    auto rowD = [&](double2 g, int r) {
-      double x = sp[r * NL];
-      x = fma(g.x, tb.x, x);
-      x = fma(g.y, tb.y, x);
-      double val = x * scale;
-      if (ADDV) val += __ldg(pv);
-      if (PLAIN) {
-        if (valid) *po = val;
-        po += rs;
-      } else {
-        if (valid) epi_store(out, oidx, val, epi);
-        oidx += rs;
-      }
-      pv += rs;
-    };
-    if (cc && a.cparam && C == 32) {
-      static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; rowD(a.psi0[r], r); });
-    } else if (cc && a.cparam && C == 16) {
-      static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; rowD(a.psi0[r], r); });
-    } else {
-#pragma unroll 8
-      for (int r = 0; r < C; ++r) rowD(__ldg(ps + r), r);
-    }
-    if (iface != nullptr && valid && (p == 0 || p == P - 1)) {
-      // z-slab: publish this rank's 4 interface values, unscaled (compact_d1.f90:858-878)
-      const long plane = (long)a.nfast * a.nouter;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int lr = (p == 0) ? q : C - 2 + q;
-        const double2 g = __ldg(ps + lr);
-        double x = sp[lr * NL];
-        x = fma(g.x, tb.x, x);
-        x = fma(g.y, tb.y, x);
-        if (p == 0) iface[(long)q * plane + base] = a.phys_lo ? 0.0 : x;
-        if (p == P - 1) iface[(long)(2 + q) * plane + base] = a.phys_hi ? 0.0 : x;
-      }
-    }
-  }
-}
-
-// ---- y / z sweep (explicit operators: the Gaussian filter) ---------------------------------------
-template <int FAM, int NL, bool PLAIN, bool ADDV>
-__global__ void __launch_bounds__(kBlockThreads, 3)
-explicit_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
-                   double *__restrict__ out, const double *__restrict__ halo_lo,
-                   const double *__restrict__ halo_hi, const __grid_constant__ EpiArgs epi) {
-  constexpr int H = FT<FAM>::H;
-  const int m = a.m, C = a.C;
-  const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
-  const int tiles_i = (a.nfast + NL - 1) / NL;
-  const int ti = blockIdx.x % tiles_i, o = blockIdx.x / tiles_i;
-  int i0 = ti * NL + l;
-  const bool valid = i0 < a.nfast;
-  if (!valid) i0 = a.nfast - 1;
-  const long rs = a.rstride;
-  const long base = (long)i0 + (long)o * a.ostride;
-  const double *vp = v + base;
-  const double scale = a.scale;
-  auto ldc = [&](int r) -> double {
-    if (r < 0) {
-      if (a.wrap) return __ldg(vp + (long)(r + m) * rs);
-      return halo_lo ? __ldg(halo_lo + base + (long)(r + H) * rs) : 0.0;
-    }
-    if (r >= m) {
-      if (a.wrap) return __ldg(vp + (long)(r - m) * rs);
-      return halo_hi ? __ldg(halo_hi + base + (long)(r - m) * rs) : 0.0;
-    }
-    return __ldg(vp + (long)r * rs);
-  };
-  const long obase = base + (long)(p * C) * rs;
-  stream_chunk<FAM>(a, vp, rs, p, halo_lo ? halo_lo + base : nullptr, halo_hi ? halo_hi + base : nullptr, ldc, [&](int lr, double rhs, double vc) {  // compact_r4.f90:209-218
-    double val = rhs * scale;
-    if (ADDV) val += vc;
-    if (valid) put<PLAIN>(out, obase + (long)lr * rs, val, epi);
-  });
-}
-
-// ---- x sweep -------------------------------------------------------------------------------------
-// Same algorithm on a tile of NLX unit-stride lines staged through shared memory (row pitch odd):
-// coalesced tile load, in-place recurrences, coalesced write-back.
-template <int FAM, int NLX, bool PLAIN, bool ADDV>
-__global__ void __launch_bounds__(kBlockThreads, 3)
-sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
-               double *__restrict__ out, const __grid_constant__ EpiArgs epi) {
-  constexpr int H = FT<FAM>::H;
-  PB_SHARED(S);  // [NLX][LD], then scan states
-  const int m = a.m, LD = m | 1, C = a.C, P = a.P;
-  double2 *EN = reinterpret_cast<double2 *>(S + (((size_t)NLX * LD + 1) & ~(size_t)1));  // [P][NLX]
-  double2 *ST = EN + P * NLX;  // [P][NLX]
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
-  const long nlines = a.nfast;
-  const long L0 = (long)blockIdx.x * NLX;
-  const bool implicit = a.implicit != 0;
-
-  for (int ll = wid; ll < NLX; ll += nw) {  // stage the tile, coalesced
-    long L = L0 + ll;
-    if (L >= nlines) L = nlines - 1;
-    const double *src = v + L * (long)m;
-    double *dst = S + ll * LD;
-    for (int ii = lane; ii < m; ii += 32) dst[ii] = __ldg(src + ii);
-  }
-  __syncthreads();
-
-  const int l = tid % NLX, p = tid / NLX;
-  const bool active = p < P;  // blockDim is rounded up to a warp multiple
-  const int s = p * C;
-  double *Sl = S + l * LD + s;  // this thread's chunk
-  const int type = active ? a.ctype[p] : 0;
-  const bool cc = a.has_const && type == 0;
-  const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
-
-  // rows of the neighbouring chunks this thread's stencil needs, read before anyone overwrites them
-  double hv[H], tv[H], u[8];
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-      int r = s - H + k;
-      if (r < 0) r += m;
-      hv[k] = lo_sp ? 0.0 : S[l * LD + r];
-      r = s + C + k;
-      if (r >= m) r -= m;
-      tv[k] = hi_sp ? 0.0 : S[l * LD + r];
-    }
-    if (hi_sp) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] = Sl[C - 8 + k];
-    }
-  }
-  __syncthreads();
-
-  if (active) {  // ---- A ----
-    double ring[16];
-    double rm1 = 0.0, rm2 = 0.0;
-    const double2 *luf = a.luf + (size_t)type * C;
-    const double l2c = a.cst[0], l1c = a.cst[1];
-    auto emit = [&](int lr, double rhs) {
-      if (implicit) {
-        double2 c;
-        if (cc) c = make_double2(l2c, l1c);
-        else c = __ldg(luf + lr);
-        double t = fma(-c.x, rm2, rhs);
-        t = fma(-c.y, rm1, t);
-        Sl[lr] = t;
-        rm2 = rm1;
-        rm1 = t;
-      } else {
-        Sl[lr] = rhs;
-      }
-    };
-#pragma unroll
-    for (int j = 0; j < H; ++j) ring[j] = hv[j];
-#pragma unroll
-    for (int j = H; j < 16; ++j) ring[j] = Sl[j - H];
-    if ((C & 15) == 0) {
-      double rlo[4] = {0.0, 0.0, 0.0, 0.0}, rhi[4] = {0.0, 0.0, 0.0, 0.0};
-      if (lo_sp) {
-        double vv[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) vv[q] = ring[(q + H) & 15];
-        rhs_lo4<FAM>(vv, a.arb_lo, rlo);
-      }
-      if (hi_sp) rhs_hi4<FAM>(u, a.arb_hi, rhi);
-      for (int b = 0; b < C - 16; b += 16) {
-        static_for<0, 16>([&](auto kc) {
-          constexpr int k = decltype(kc)::value;
-          double rhs = rhs_ring<FAM, k>(ring, a.ari);
-          if (k < 4) {
-            if (lo_sp && b == 0) rhs = rlo[k];
-          }
-          ring[k] = Sl[b + k - H + 16];
-          emit(b + k, rhs);
-        });
-      }
-      static_for<0, 16>([&](auto kc) {  // last block: the look-ahead rows come from the next chunk
-        constexpr int k = decltype(kc)::value;
-        double rhs = rhs_ring<FAM, k>(ring, a.ari);
-        if (k < 4) {
-          if (lo_sp && C == 16) rhs = rlo[k];
-        }
-        if (k >= 12) {
-          if (hi_sp) rhs = rhi[k - 12];
-        }
-        if (k < H) ring[k] = Sl[C + k - H];
-        else if (k < 2 * H) ring[k] = tv[k - H];
-        emit(C - 16 + k, rhs);
-      });
-    } else {
-      if (lo_sp) {
-        double vv[9], r4[4];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) vv[k] = ring[(k + H) & 15];
-        rhs_lo4<FAM>(vv, a.arb_lo, r4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) emit(k, r4[k]);
-      }
-      for (int b = 0; b < C; b += 16) {
-        static_for<0, 16>([&](auto kc) {
-          constexpr int k = decltype(kc)::value;
-          const int lr = b + k;
-          double rhs = 0.0;
-          const bool doit = lr < C && !(lo_sp && lr < 4) && !(hi_sp && lr >= C - 4);
-          if (doit) rhs = rhs_ring<FAM, k>(ring, a.ari);
-          const int r2 = lr - H + 16;
-          double nx = 0.0;
-          if (r2 < C) nx = Sl[r2];
-          else {
-#pragma unroll
-            for (int q = 0; q < H; ++q)
-              if (r2 - C == q) nx = tv[q];
-          }
-          ring[k] = nx;
-          if (doit) emit(lr, rhs);
-        });
-      }
-      if (hi_sp) {
-        double r4[4];
-        rhs_hi4<FAM>(u, a.arb_hi, r4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) emit(C - 4 + k, r4[k]);
-      }
-    }
-    if (implicit) EN[p * NLX + l] = make_double2(rm1, rm2);
-  }
-  if (implicit) {
-    __syncthreads();
-    if (active) {  // ---- B ----
-      double2 st = make_double2(0.0, 0.0);
-      {
-        const int nf = a.nf[p];
-        const double4 *Mp = a.Mf + (size_t)p * (P + 1);
-        for (int j = 1; j <= nf; ++j) {
-          int q = p - j;
-          if (q < 0) q += P;
-          const double2 en = EN[q * NLX + l];
-          const double4 M = ldg4(Mp + j);
-          st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
-          st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
-        }
-      }
-      const double2 *ph = a.phi + (size_t)type * C;
-      double x1 = 0.0, x2 = 0.0;
-      if (cc) {
-        const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
-#pragma unroll 8
-        for (int r = C - 1; r >= 0; --r) {
-          const double2 f = __ldg(ph + r);
-          double t = Sl[r];
-          t = fma(f.x, st.x, t);
-          t = fma(f.y, st.y, t);
-          t = fma(-u1, x1, t);
-          t = fma(-u2, x2, t);
-          t *= ip;
-          Sl[r] = t;
-          x2 = x1;
-          x1 = t;
-        }
-      } else {
-        const double4 *lub = a.lub + (size_t)type * C;
-#pragma unroll 4
-        for (int r = C - 1; r >= 0; --r) {
-          const double2 f = __ldg(ph + r);
-          const double4 c = ldg4(lub + r);
-          double t = Sl[r];
-          t = fma(f.x, st.x, t);
-          t = fma(f.y, st.y, t);
-          t = fma(-c.y, x1, t);
-          t = fma(-c.z, x2, t);
-          t *= c.x;
-          Sl[r] = t;
-          x2 = x1;
-          x1 = t;
-        }
-      }
-      ST[p * NLX + l] = make_double2(x1, x2);
-    }
-    __syncthreads();
-    if (active) {  // ---- D (in place; the coalesced write-back follows) ----
-      auto tin = [&](int q) -> double2 {
-        double2 t = make_double2(0.0, 0.0);
-        const int nb = a.nb[q];
-        const double4 *Mp = a.Mb + (size_t)q * (P + 1);
-        for (int j = 1; j <= nb; ++j) {
-          int qq = q + j;
-          if (qq >= P) qq -= P;
-          const double2 sv = ST[qq * NLX + l];
-          const double4 M = ldg4(Mp + j);
-          t.x = fma(M.y, sv.y, fma(M.x, sv.x, t.x));
-          t.y = fma(M.w, sv.y, fma(M.z, sv.x, t.y));
-        }
-        return t;
-      };
-      const double2 tb = tin(p);
-      const double2 *ps = a.psi + (size_t)type * C;
-      auto rowDx = [&](double2 g, int r) {
-        double x = Sl[r];
-        x = fma(g.x, tb.x, x);
-        x = fma(g.y, tb.y, x);
-        Sl[r] = x;
-      };
-      if (cc && a.cparam && C == 32) {
-        static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; rowDx(a.psi0[r], r); });
-      } else if (cc && a.cparam && C == 16) {
-        static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; rowDx(a.psi0[r], r); });
-      } else {
-#pragma unroll 8
-        for (int r = 0; r < C; ++r) rowDx(__ldg(ps + r), r);
-      }
-    }
-  }
-  __syncthreads();
-
-  const double scale = a.scale;  // write back, coalesced, with scale / add-back / epilogue
-  for (int ll = wid; ll < NLX; ll += nw) {
-    const long L = L0 + ll;
-    if (L >= nlines) break;
-    const double *src = S + ll * LD;
-    for (int ii = lane; ii < m; ii += 32) {
-      const long idx = L * (long)m + ii;
-      double val = src[ii] * scale;
-      if (ADDV) val += __ldg(v + idx);
-      put<PLAIN>(out, idx, val, epi);
-    }
-  }
-}
-
-// ---- launchers -----------------------------------------------------------------------------------
-template <int FAM, int NL, bool PLAIN, bool ADDV>
-static cudaError_t launch_yz_t(const SweepDev &a, const double *v, double *out, const double *hlo,
-                               const double *hhi, double *iface, const EpiArgs &epi, cudaStream_t st) {
-  const int tiles_i = (a.nfast + NL - 1) / NL;
-  const dim3 grid((unsigned)(tiles_i * a.nouter)), block(NL * a.P);
-  if (!a.implicit) {
-    auto kfn = explicit_yz_kernel<FAM, NL, PLAIN, ADDV>;
-    PB_LAUNCH(kfn, grid, block, 0, st, a, v, out, hlo, hhi, epi);
-    ++g_launches;
-    return cudaGetLastError();
-  }
-  const size_t smem = ((size_t)a.m * NL + 4 * (size_t)a.P * NL + 4 * NL) * sizeof(double);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t err = cudaFuncSetAttribute(sweep_yz_kernel<FAM, NL, PLAIN, ADDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    configured = smem;
-  }
-  auto kfn = sweep_yz_kernel<FAM, NL, PLAIN, ADDV>;
-  PB_LAUNCH(kfn, grid, block, smem, st, a, v, out, hlo, hhi, iface, epi);
-  ++g_launches;
-  return cudaGetLastError();
-}
-
-template <int FAM, bool ADDV>
-static cudaError_t launch_yz_f(int lines, const SweepDev &a, const double *v, double *out, const double *hlo,
-                               const double *hhi, double *iface, const EpiArgs &epi, cudaStream_t st) {
-  const bool plain = epi.mode == EPI_STORE;
-#define PB_YZ(NLV)                                                                                   \
-  return plain ? launch_yz_t<FAM, NLV, true, ADDV>(a, v, out, hlo, hhi, iface, epi, st)              \
-               : launch_yz_t<FAM, NLV, false, ADDV>(a, v, out, hlo, hhi, iface, epi, st)
-  if (lines == 8) { PB_YZ(8); }
-  if (lines == 32) { PB_YZ(32); }
-  PB_YZ(16);
-#undef PB_YZ
-}
+// instantiated in sweeps_d1.cu / sweeps_r3.cu / sweeps_r4.cu / sweeps_r4v.cu
+extern template cudaError_t launch_yz_f<F_D1, false>(int, const SweepDev &, const double *, double *, const double *, const double *, double *, const EpiArgs &, cudaStream_t);
+extern template cudaError_t launch_yz_f<F_R3, false>(int, const SweepDev &, const double *, double *, const double *, const double *, double *, const EpiArgs &, cudaStream_t);
+extern template cudaError_t launch_yz_f<F_R4, false>(int, const SweepDev &, const double *, double *, const double *, const double *, double *, const EpiArgs &, cudaStream_t);
+extern template cudaError_t launch_yz_f<F_R4, true>(int, const SweepDev &, const double *, double *, const double *, const double *, double *, const EpiArgs &, cudaStream_t);
+extern template cudaError_t launch_x_f<F_D1, false>(int, const SweepDev &, const double *, double *, const EpiArgs &, cudaStream_t);
+extern template cudaError_t launch_x_f<F_R3, false>(int, const SweepDev &, const double *, double *, const EpiArgs &, cudaStream_t);
+extern template cudaError_t launch_x_f<F_R4, false>(int, const SweepDev &, const double *, double *, const EpiArgs &, cudaStream_t);
+extern template cudaError_t launch_x_f<F_R4, true>(int, const SweepDev &, const double *, double *, const EpiArgs &, cudaStream_t);
 
 // lines per tile: as many as fit a 256-thread block (lines * chunks) and ~64 KB of shared memory
 static int pick_lines(int want, int P, size_t row_bytes) {
@@ -830,36 +61,6 @@ cudaError_t launch_sweep_yz(int fam, int lines, const SweepDev &a, const double 
       return a.add_v ? launch_yz_f<F_R4, true>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st)
                      : launch_yz_f<F_R4, false>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);
   }
-}
-
-template <int FAM, int NLX, bool PLAIN, bool ADDV>
-static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
-  const size_t tile = (((size_t)NLX * (a.m | 1) + 1) & ~(size_t)1);
-  const size_t smem = (tile + 4 * (size_t)a.P * NLX + 4 * NLX) * sizeof(double);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t err = cudaFuncSetAttribute(sweep_x_kernel<FAM, NLX, PLAIN, ADDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    configured = smem;
-  }
-  const long ntiles = ((long)a.nfast + NLX - 1) / NLX;
-  int threads = NLX * a.P;
-  threads = (threads + 31) / 32 * 32;
-  auto kfn = sweep_x_kernel<FAM, NLX, PLAIN, ADDV>;
-  PB_LAUNCH(kfn, dim3((unsigned)ntiles), dim3(threads), smem, st, a, v, out, epi);
-  ++g_launches;
-  return cudaGetLastError();
-}
-
-template <int FAM, bool ADDV>
-static cudaError_t launch_x_f(int lines, const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
-  const bool plain = epi.mode == EPI_STORE;
-#define PB_X(NLV) \
-  return plain ? launch_x_t<FAM, NLV, true, ADDV>(a, v, out, epi, st) : launch_x_t<FAM, NLV, false, ADDV>(a, v, out, epi, st)
-  if (lines == 8) { PB_X(8); }
-  if (lines == 32) { PB_X(32); }
-  PB_X(16);
-#undef PB_X
 }
 
 cudaError_t launch_sweep_x(int fam, int lines, const SweepDev &a, const double *v, double *out,

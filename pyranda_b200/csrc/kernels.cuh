@@ -95,6 +95,7 @@ cudaError_t launch_metrics(long n, const double *const *J9, double dA, double dB
 
 long launch_count();
 void set_yz_lines(int nl);
+void set_reg_kernels(int on);
 void set_x_lines(int nl);
 
 }  // namespace pb
