@@ -105,6 +105,35 @@ def cpu_sample(n=256, reps=1):
             "seconds_per_step": dt}
 
 
+def tgv_step_time(n, warm=2, steps=3):
+    """BASELINE.json configs[1]: Taylor-Green vortex (examples/TaylorGreen.py deck, verbatim) at n^3,
+    device-resident RK4 steps through pyranda_b200.sim; returns seconds per RK4 step."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from decks import TGV_EOM, TGV_IC, tgv_mesh
+    from pyranda_b200.sim import pyrandaSim
+    ss = pyrandaSim("TGvortex", tgv_mesh(n))
+    ss.EOM(TGV_EOM)
+    ss.setIC(TGV_IC)
+    time_, dt = 0.0, ss.variables["dt"] * 0.5
+    l0 = ss.B.plan.launch_count()
+    for _ in range(warm):
+        time_ = ss.rk4(time_, dt)
+        dt = ss.variables["dt"] * 0.5
+    torch.cuda.synchronize()
+    l0 = ss.B.plan.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        time_ = ss.rk4(time_, dt)
+        dt = ss.variables["dt"] * 0.5
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / steps
+    return {"config": "Taylor-Green vortex %d^3 periodic fp64, CFL 0.5, deck of examples/TaylorGreen.py" % n,
+            "ms_per_rk4_step": sec * 1e3, "steps": steps, "sweeps_per_step": 255,
+            "library_launches_per_step": (ss.B.plan.launch_count() - l0) / steps,
+            "gpoints_per_s": n ** 3 / sec / 1e9}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -137,6 +166,8 @@ def main():
     ap.add_argument("--n", type=int, default=NPER, help="points per side per GPU (default 512)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tgv", action="store_true")
+    ap.add_argument("--tgv-n", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -277,6 +308,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": "sweep_yz_kernel<D1> (%s, one launch per application)" % dom, "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": 16 * npts}
+    tgv = None
+    if world == 1 and not args.no_tgv:
+        tgv = tgv_step_time(args.tgv_n)
     cpu = None if args.no_cpu else cpu_sample(256, 1)
     if cpu:
         cpu.pop("seconds_per_step", None)
@@ -286,8 +320,8 @@ def main():
             "config": {"workload": "operator microbench: ddx, ddy, ddz, filter, gfilter once each per step on a periodic fp64 field",
                        "global_grid": [nx, ny, nz], "per_gpu_grid": [ax, ay, az], "partition": "z-slab x%d" % world,
                        "l2": "input 1.07 GB per field, larger than the 126 MB L2; no explicit flush",
-                       "chunk_len": 64},
-            "per_op": per_op, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                       "chunk_len": 32},
+            "per_op": per_op, "tgv": tgv, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
