@@ -29,6 +29,15 @@ SWEEPS = {"ddx": 1, "ddy": 1, "ddz": 1, "sfilter": 3, "gfilter": 3}
 BYTES_PER_POINT = {"ddx": 16, "ddy": 16, "ddz": 16, "sfilter": 48, "gfilter": 48}
 METRIC = "fp64 Gpoints/s (operator applications x points / s), compact ddx+ddy+ddz+filter+gfilter"
 NPER = 512  # points per side per GPU
+# ncu --set full, 512^3 ddz launch: 1.074613 GB read + 1.051958 GB written (profiles/r1_v5_register_kernels_ncu_full.txt)
+NCU_TRAFFIC_DDZ_512 = 2126571000
+
+
+def bench_config(world, n):
+    """The workload both arms are quoted on (BASELINE.json configs[1]: 512^3 fp64 per GPU)."""
+    return {"workload": "operator microbench: ddx, ddy, ddz, filter, gfilter once each per step on a periodic fp64 field",
+            "global_grid": [n, n, n * world], "per_gpu_grid": [n, n, n], "partition": "z-slab x%d" % world,
+            "l2": "input 1.07 GB per field, larger than the 126 MB L2; no explicit flush", "chunk_len": 32}
 
 
 def peaks():
@@ -149,9 +158,9 @@ def run_reference(args):
     cb = dict(res[0]); cb["value"] = value; cb.pop("seconds_per_step", None)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": "ddx,ddy,ddz,filter,gfilter on a periodic fp64 field; CPU sample %d^3" % n,
-                                                            "note": "the Fortran/MPI reference cannot be built in this image (no Fortran compiler, no MPI); "
-                                                                    "this is the oracle port of its algorithm on all host threads"},
+            "dtype": "f64", "data": "synthetic", "config": bench_config(args.gpus, args.n),
+            "note": "the Fortran/MPI reference cannot be built in this image (no Fortran compiler, no MPI); this is the oracle "
+                    "port of its algorithm on all host threads, each step a %d^3 sample of the workload" % n,
             "cpu_baseline": cb, "e2e": {"value": value, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
     print(json.dumps(line), flush=True)
@@ -305,8 +314,10 @@ def main():
     # dominant kernel: the fused y/z sweep (6 of the 9 sweeps of a step); one launch == ddz
     dom = "ddz" if world == 1 else "ddy"
     ach = 16.0 * npts / (per_op_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "sweep_yz_kernel<D1> (%s, one launch per application)" % dom, "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "sweep_yz_reg_kernel<D1,32,16> (%s, one launch per application)" % dom, "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_DDZ_512 if (n == 512 and world == 1) else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the ddz launch in profiles/r1_v5_register_kernels_ncu_full.txt",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": 16 * npts}
     tgv = None
     if world == 1 and not args.no_tgv:
@@ -317,10 +328,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": K, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "operator microbench: ddx, ddy, ddz, filter, gfilter once each per step on a periodic fp64 field",
-                       "global_grid": [nx, ny, nz], "per_gpu_grid": [ax, ay, az], "partition": "z-slab x%d" % world,
-                       "l2": "input 1.07 GB per field, larger than the 126 MB L2; no explicit flush",
-                       "chunk_len": 32},
+            "config": bench_config(world, n),
             "per_op": per_op, "tgv": tgv, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:
