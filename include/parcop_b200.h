@@ -124,6 +124,8 @@ int pb_host_grads(pb_plan *plan, const double *h_val, double *h_gx, double *h_gy
 /* ---- introspection for tests / benchmarks ----------------------------------------------------- */
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long pb_launch_count(void);
+/* of those, launches of the TMA-pipelined persistent sweep kernels (tests assert the fast path ran) */
+long pb_pipe_launch_count(void);
 /* tuning knobs (lines per tile, chunk length); 0 keeps the default.  Affects plans created later. */
 int pb_set_tuning(int lines_yz, int lines_x, int chunk_len);
 

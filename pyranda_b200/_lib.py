@@ -23,7 +23,7 @@ EXPORTS = [
     "pb_plan_spacing", "pb_plan_set_mesh", "pb_getvar", "pb_getvar_device", "pb_apply",
     "pb_divergence", "pb_grads", "pb_rk4_stage", "pb_reduce", "pb_z_pack_halo", "pb_z_local",
     "pb_z_finish", "pb_host_apply", "pb_host_divergence", "pb_host_grads", "pb_launch_count",
-    "pb_set_tuning",
+    "pb_pipe_launch_count", "pb_set_tuning",
 ]
 
 
@@ -55,6 +55,7 @@ def declare(L):
     L.pb_host_divergence.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.pb_host_grads.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.pb_launch_count.restype = ctypes.c_long
+    L.pb_pipe_launch_count.restype = ctypes.c_long
     L.pb_set_tuning.argtypes = [i, i, i]
     return L
 

@@ -251,12 +251,13 @@ extern "C" {
 const char *pb_last_error(void) { return g_err.c_str(); }
 const char *pb_version(void) { return "parcop_b200 0.1 (sm_100a)"; }
 long pb_launch_count(void) { return launch_count(); }
+long pb_pipe_launch_count(void) { return pipe_launch_count(); }
 
 int pb_set_tuning(int lines_yz, int lines_x, int chunk_len) {
   if (lines_yz > 0) set_yz_lines(lines_yz);
   if (lines_x > 0) set_x_lines(lines_x);
   if (chunk_len >= 16) g_chunk_len = chunk_len % 1000;
-  if (chunk_len >= 1000) set_reg_kernels(chunk_len / 1000 == 1 ? 0 : 1);  // 1xxx: shared-memory kernels, 2xxx: register kernels
+  if (chunk_len >= 1000) set_reg_kernels(chunk_len / 1000 - 1);  // 1xxx: shared-memory kernels, 2xxx: register kernels, 3xxx: + pipelined
   return PB_OK;
 }
 

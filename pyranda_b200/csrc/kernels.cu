@@ -24,8 +24,24 @@ namespace pb {
 
 std::atomic<long> g_launches{0};
 long launch_count() { return g_launches.load(); }
+std::atomic<long> g_pipe_launches{0};
+long pipe_launch_count() { return g_pipe_launches.load(); }
 int g_reg_kernels = 1;
-void set_reg_kernels(int on) { g_reg_kernels = on; }
+int g_pipe_kernels = 1;
+// 0: shared-memory kernels, 1: register kernels, 2: register kernels + TMA-pipelined persistent kernels
+void set_reg_kernels(int on) { g_reg_kernels = on >= 1; g_pipe_kernels = on >= 2; }
+int sm_count() {
+#ifdef PB_EMULATE
+  return 1;  // two persistent CTAs: the tile loop and the prefetch hand-over are exercised
+#else
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    return v;
+  }();
+  return n;
+#endif
+}
 static int g_yz_lines = 32;
 static int g_x_lines = 32;
 void set_yz_lines(int nl) { if (nl == 8 || nl == 16 || nl == 32) g_yz_lines = nl; }

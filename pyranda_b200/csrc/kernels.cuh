@@ -94,6 +94,7 @@ cudaError_t launch_metrics(long n, const double *const *J9, double dA, double dB
                            double *cellvol, double *gridlen, cudaStream_t st);
 
 long launch_count();
+long pipe_launch_count();
 void set_yz_lines(int nl);
 void set_reg_kernels(int on);
 void set_x_lines(int nl);

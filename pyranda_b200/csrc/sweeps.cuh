@@ -6,6 +6,7 @@
 
 #include "kernels.cuh"
 #include "tables.hpp"
+#include "tma.cuh"
 
 #ifdef PB_EMULATE
 #define PB_SHARED(S) double *S = emul::t_smem
@@ -13,7 +14,7 @@
 #define PB_EW_GRID(n) dim3(1)
 #define PB_EW_BLOCK dim3(1)
 #else
-#define PB_SHARED(S) extern __shared__ double S[]
+#define PB_SHARED(S) extern __shared__ __align__(128) double S[]
 #define PB_LAUNCH(kernel, grid, block, smem, st, ...) kernel<<<grid, block, smem, st>>>(__VA_ARGS__)
 #define PB_EW_GRID(n) dim3(ew_blocks(n))
 #define PB_EW_BLOCK dim3(256)
@@ -22,7 +23,10 @@
 namespace pb {
 
 extern std::atomic<long> g_launches;
+extern std::atomic<long> g_pipe_launches;
 extern int g_reg_kernels;
+extern int g_pipe_kernels;
+int sm_count();
 
 __device__ __forceinline__ double4 ldg4(const double4 *p) {
   const double2 *q = reinterpret_cast<const double2 *>(p);
@@ -1167,6 +1171,305 @@ sweep_x_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
   }
 }
 
+
+// ---- pipelined sweeps: persistent CTAs, next tile prefetched by TMA --------------------------------
+// The register kernels above only have loads in flight during their forward phase.  Here a CTA
+// walks over tiles; as soon as every thread has pulled its chunk of the current tile out of shared
+// memory (forward phase), one thread asks the TMA unit for the whole next tile, which lands while
+// the CTA runs the backward recurrence and the store phase.  The tile buffer holds rows -4 .. m+3
+// (periodic wrap rows or z-slab halo planes are extra boxes), so every chunk runs the same code with
+// compile-time shared-memory offsets.
+
+struct PipeGeo {
+  int rowdim;          // tensor-map dimension the sweep runs along (1: y, 2: z)
+  int nbox, box_rows;  // main boxes per tile
+  int halo;            // 0: none (one-sided closures), 1: extra boxes for rows -4..-1 and m..m+3
+  int lo_row, hi_row;  // row coordinates of those boxes in their maps
+};
+
+template <int FAM, int CT, int NL, class EMIT>
+__device__ __forceinline__ void stream_chunk_tile(const SweepDev &a, const double *__restrict__ tw, bool lo_sp, bool hi_sp,
+                                                  EMIT &&emit) {
+  // tw points at row s-H of this thread's line inside the tile (row pitch NL)
+  constexpr int H = FT<FAM>::H;
+  double ring[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) ring[j] = tw[j * NL];
+  double rlo[4] = {0.0, 0.0, 0.0, 0.0}, rhi[4] = {0.0, 0.0, 0.0, 0.0};
+  if (lo_sp) {
+    double vv[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) vv[q] = ring[(q + H) & 15];
+    rhs_lo4<FAM>(vv, a.arb_lo, rlo);
+  }
+  static_for<0, CT / 16>([&](auto bc) {
+    constexpr int b = decltype(bc)::value * 16;
+    constexpr bool lastblk = b == CT - 16;
+    static_for<0, 16>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      double rhs = rhs_ring<FAM, k>(ring, a.ari);
+      const double vc = ring[(k + H) & 15];
+      if (b == 0 && k < 4) {
+        if (lo_sp) rhs = rlo[k];
+      }
+      if (lastblk && k == 12) {
+        if (hi_sp) {
+          double u[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) u[q] = ring[(q + H + 8) & 15];
+          rhs_hi4<FAM>(u, a.arb_hi, rhi);
+        }
+      }
+      if (lastblk && k >= 12) {
+        if (hi_sp) rhs = rhi[k - 12];
+      }
+      if (!(lastblk && k >= 2 * H)) ring[k] = tw[(b + k + 16) * NL];  // rows past s + CT + H - 1 are never used
+      emit(std::integral_constant<int, b + k>{}, rhs, vc);
+    });
+  });
+}
+
+template <int FAM, int NL, bool PLAIN, bool ADDV>
+__global__ void __launch_bounds__(kBlockThreads, 2)
+sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tmain,
+                     const __grid_constant__ TileMap tlo, const __grid_constant__ TileMap thi,
+                     const __grid_constant__ PipeGeo g, const double *__restrict__ v, double *__restrict__ out,
+                     double *__restrict__ iface, const __grid_constant__ EpiArgs epi) {
+  constexpr int CT = 32, H = FT<FAM>::H, HP = 4;
+  PB_SHARED(S);
+  const int P = a.P, m = a.m;
+  double *tile = S;                                                         // [m + 2 HP][NL]
+  double2 *EN = reinterpret_cast<double2 *>(S + (size_t)(m + 2 * HP) * NL);  // [P][NL]
+  double2 *ST = EN + P * NL;                                                // [P][NL]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(ST + P * NL);
+  const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
+  const int tiles_i = (a.nfast + NL - 1) / NL;
+  const long ntiles = (long)tiles_i * a.nouter;
+  const long rs = a.rstride;
+  const int s = p * CT;
+  const int type = a.ctype[p];
+  const bool cc = a.has_const && type == 0;
+  const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
+  const double scale = a.scale;
+  const uint32_t tx_bytes = (uint32_t)((m + (g.halo ? 2 * HP : 0)) * NL * sizeof(double));
+
+  auto issue = [&](long t) {  // one thread: arm the barrier, describe the tile to the TMA unit
+    const int x0 = (int)(t % tiles_i) * NL, o = (int)(t / tiles_i);
+    mbar_expect_tx(bar, tx_bytes);
+    for (int b = 0; b < g.nbox; ++b) {
+      const int row = b * g.box_rows;
+      tma_load_3d(tile + (size_t)(HP + row) * NL, &tmain, x0, g.rowdim == 1 ? row : o, g.rowdim == 1 ? o : row, bar);
+    }
+    if (g.halo) {
+      tma_load_3d(tile, &tlo, x0, g.rowdim == 1 ? g.lo_row : o, g.rowdim == 1 ? o : g.lo_row, bar);
+      tma_load_3d(tile + (size_t)(HP + m) * NL, &thi, x0, g.rowdim == 1 ? g.hi_row : o, g.rowdim == 1 ? o : g.hi_row, bar);
+    }
+  };
+
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  long t = blockIdx.x;
+  if (tid == 0 && t < ntiles) issue(t);
+#ifdef PB_EMULATE
+  __syncthreads();
+#endif
+  uint32_t parity = 0;
+  const double *tw = tile + (size_t)(s + HP - H) * NL + l;
+
+  for (; t < ntiles; t += gridDim.x) {
+    const int ti = (int)(t % tiles_i), o = (int)(t / tiles_i);
+    int i0 = ti * NL + l;
+    const bool valid = i0 < a.nfast;
+    if (!valid) i0 = a.nfast - 1;
+    const long base = (long)i0 + (long)o * a.ostride;
+    double rl[CT];
+
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    {  // ---- A: rhs + forward recurrence (zero incoming state), chunk pulled out of the tile ----
+      const double2 *luf = a.luf + (size_t)type * CT;
+      const double l2c = a.cst[0], l1c = a.cst[1];
+      double rm1 = 0.0, rm2 = 0.0;
+      stream_chunk_tile<FAM, CT, NL>(a, tw, lo_sp, hi_sp, [&](auto lrc, double rhs, double) {
+        constexpr int lr = decltype(lrc)::value;
+        double2 c;
+        if (cc) c = make_double2(l2c, l1c);
+        else c = __ldg(luf + lr);
+        double x = fma(-c.x, rm2, rhs);
+        x = fma(-c.y, rm1, x);
+        rl[lr] = x;
+        rm2 = rm1;
+        rm1 = x;
+      });
+      EN[p * NL + l] = make_double2(rm1, rm2);
+    }
+    __syncthreads();  // the tile buffer is free, EN is visible
+    if (tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
+
+    {  // ---- B: add the carried forward state, backward recurrence (zero incoming state) ----
+      double2 st = make_double2(0.0, 0.0);
+      {
+        const int nf = a.nf[p];
+        const double4 *Mp = a.Mf + (size_t)p * (P + 1);
+        for (int j = 1; j <= nf; ++j) {
+          int q = p - j;
+          if (q < 0) q += P;
+          const double2 en = EN[q * NL + l];
+          const double4 M = ldg4(Mp + j);
+          st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
+          st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
+        }
+      }
+      double x1 = 0.0, x2 = 0.0;
+      if (cc) {
+        const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+        static_for<0, CT>([&](auto jc) {
+          constexpr int r = CT - 1 - decltype(jc)::value;
+          double x = rl[r];
+          x = fma(a.phi0[r].x, st.x, x);
+          x = fma(a.phi0[r].y, st.y, x);
+          x = fma(-u1, x1, x);
+          x = fma(-u2, x2, x);
+          x *= ip;
+          rl[r] = x;
+          x2 = x1;
+          x1 = x;
+        });
+      } else {
+        const double2 *ph = a.phi + (size_t)type * CT;
+        const double4 *lub = a.lub + (size_t)type * CT;
+        static_for<0, CT>([&](auto jc) {
+          constexpr int r = CT - 1 - decltype(jc)::value;
+          const double2 f = __ldg(ph + r);
+          const double4 c = ldg4(lub + r);
+          double x = rl[r];
+          x = fma(f.x, st.x, x);
+          x = fma(f.y, st.y, x);
+          x = fma(-c.y, x1, x);
+          x = fma(-c.z, x2, x);
+          x *= c.x;
+          rl[r] = x;
+          x2 = x1;
+          x1 = x;
+        });
+      }
+      ST[p * NL + l] = make_double2(x1, x2);
+    }
+    __syncthreads();
+
+    {  // ---- D: add the carried backward state, scale / add-back / epilogue, store ----
+      double2 tb = make_double2(0.0, 0.0);
+      {
+        const int nb = a.nb[p];
+        const double4 *Mp = a.Mb + (size_t)p * (P + 1);
+        for (int j = 1; j <= nb; ++j) {
+          int q = p + j;
+          if (q >= P) q -= P;
+          const double2 sv = ST[q * NL + l];
+          const double4 M = ldg4(Mp + j);
+          tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
+          tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
+        }
+      }
+      const double *pv = v + base + (long)s * rs;
+      long oidx = base + (long)s * rs;
+      double *po = out + oidx;
+      auto rowD = [&](double gx, double gy, double xl) -> double {
+        double x = fma(gx, tb.x, xl);
+        x = fma(gy, tb.y, x);
+        double val = x * scale;
+        if (ADDV) val += __ldg(pv);
+        if (PLAIN) {
+          if (valid) *po = val;
+          po += rs;
+        } else {
+          if (valid) epi_store(out, oidx, val, epi);
+          oidx += rs;
+        }
+        pv += rs;
+        return x;
+      };
+      double xi[4] = {0.0, 0.0, 0.0, 0.0};  // first / last two solved values (z-slab interface)
+      if (cc) {
+        static_for<0, CT>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          const double x = rowD(a.psi0[r].x, a.psi0[r].y, rl[r]);
+          if (r < 2) xi[r] = x;
+          if (r >= CT - 2) xi[r - (CT - 4)] = x;
+        });
+      } else {
+        const double2 *ps = a.psi + (size_t)type * CT;
+        static_for<0, CT>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          const double2 gq = __ldg(ps + r);
+          const double x = rowD(gq.x, gq.y, rl[r]);
+          if (r < 2) xi[r] = x;
+          if (r >= CT - 2) xi[r - (CT - 4)] = x;
+        });
+      }
+      if (iface != nullptr && valid) {  // z-slab: this rank's 4 interface values, unscaled (compact_d1.f90:858-878)
+        const long plane = (long)a.nfast * a.nouter;
+        if (p == 0) {
+          iface[base] = a.phys_lo ? 0.0 : xi[0];
+          iface[plane + base] = a.phys_lo ? 0.0 : xi[1];
+        }
+        if (p == P - 1) {
+          iface[2 * plane + base] = a.phys_hi ? 0.0 : xi[2];
+          iface[3 * plane + base] = a.phys_hi ? 0.0 : xi[3];
+        }
+      }
+    }
+  }
+}
+
+// Builds the tensor maps of one y/z sweep and launches the persistent kernel.  Returns
+// cudaErrorNotSupported when the geometry does not fit (the caller then uses the register kernels).
+template <int FAM, int NL, bool PLAIN, bool ADDV>
+static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *out, const double *hlo, const double *hhi,
+                                  double *iface, const EpiArgs &epi, cudaStream_t st) {
+  constexpr int H = FT<FAM>::H;
+  const int m = a.m;
+  if (a.C != 32 || NL * a.P != kBlockThreads || m % 256 != 0 || (hlo == nullptr) != (hhi == nullptr)) return cudaErrorNotSupported;
+  // the field as {ax, ay, az}: y sweeps run along dimension 1, z sweeps along dimension 2
+  const bool ysweep = a.rstride < a.ostride;
+  const uint64_t ax = (uint64_t)a.nfast;
+  const uint64_t d1 = ysweep ? (uint64_t)m : (uint64_t)a.nouter, d2 = ysweep ? (uint64_t)a.nouter : (uint64_t)m;
+  const uint64_t s1 = (uint64_t)(ysweep ? a.rstride : a.ostride) * 8, s2 = (uint64_t)(ysweep ? a.ostride : a.rstride) * 8;
+  PipeGeo g;
+  g.rowdim = ysweep ? 1 : 2;
+  g.box_rows = 256;
+  g.nbox = m / 256;
+  g.halo = 0; g.lo_row = 0; g.hi_row = 0;
+  TileMap tmain, tlo, thi;
+  if (!encode_tile_map(&tmain, v, ax, d1, d2, s1, s2, NL, ysweep ? 256 : 1, ysweep ? 1 : 256)) return cudaErrorNotSupported;
+  tlo = tmain; thi = tmain;
+  if (hlo != nullptr) {  // z-slab halo planes received from the neighbours: {ax, ay, H} each
+    if (ysweep) return cudaErrorNotSupported;
+    if (!encode_tile_map(&tlo, hlo, ax, d1, H, s1, s2, NL, 1, 4) || !encode_tile_map(&thi, hhi, ax, d1, H, s1, s2, NL, 1, 4))
+      return cudaErrorNotSupported;
+    g.halo = 1; g.lo_row = H - 4; g.hi_row = 0;
+  } else if (a.wrap) {  // periodic: rows m-4..m-1 and 0..3 of the field itself
+    if (!encode_tile_map(&tlo, v, ax, d1, d2, s1, s2, NL, ysweep ? 4 : 1, ysweep ? 1 : 4)) return cudaErrorNotSupported;
+    thi = tlo;
+    g.halo = 1; g.lo_row = m - 4; g.hi_row = 0;
+  }
+  const size_t smem = ((size_t)(m + 8) * NL + 4 * (size_t)a.P * NL) * sizeof(double) + 16;
+  auto kfn = sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured = true;
+  }
+  const long ntiles = (long)((a.nfast + NL - 1) / NL) * a.nouter;
+  const long want = 2L * sm_count();
+  const dim3 grid((unsigned)(ntiles < want ? ntiles : want)), block(kBlockThreads);
+  PB_LAUNCH(kfn, grid, block, smem, st, a, tmain, tlo, thi, g, v, out, iface, epi);
+  ++g_launches;
+  ++g_pipe_launches;
+  return cudaGetLastError();
+}
+
 // ---- launchers -----------------------------------------------------------------------------------
 template <int FAM, int NL, bool PLAIN, bool ADDV>
 static cudaError_t launch_yz_t(const SweepDev &a, const double *v, double *out, const double *hlo,
@@ -1178,6 +1481,13 @@ static cudaError_t launch_yz_t(const SweepDev &a, const double *v, double *out, 
     PB_LAUNCH(kfn, grid, block, 0, st, a, v, out, hlo, hhi, epi);
     ++g_launches;
     return cudaGetLastError();
+  }
+  if constexpr (NL == 16 || NL == 32) {
+    if (g_pipe_kernels && a.C == 32) {
+      constexpr bool PL = PLAIN && NL == 16;
+      const cudaError_t err = launch_yz_pipe<FAM, NL, PL, ADDV>(a, v, out, hlo, hhi, iface, epi, st);
+      if (err != cudaErrorNotSupported) return err;
+    }
   }
   if (g_reg_kernels && (a.C == 32 || (a.C == 16 && NL == 16))) {
     // register-resident kernels; the plain-store specialisation exists for the common 16-line tile only

@@ -174,6 +174,9 @@ class ParcopPlan:
     def gfilterdir(self, val, direction):
         return self.apply(("gfilterx", "gfiltery", "gfilterz")[int(direction) - 1], val)
 
+    def sfilterdir(self, val, direction):
+        return self.apply(("sfilterx", "sfiltery", "sfilterz")[int(direction) - 1], val)
+
     def divergence(self, fx, fy, fz):
         if _is_torch(fx):
             a, b, c = self._dev_in(fx), self._dev_in(fy), self._dev_in(fz)

@@ -34,7 +34,7 @@ struct dim3 {
 
 typedef void *cudaStream_t;
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidConfiguration = 9 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidConfiguration = 9, cudaErrorNotSupported = 801 };
 enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }

@@ -1,0 +1,70 @@
+"""z-slab operators over NCCL on 2+ GPUs of one box against the one-rank oracle (same worker as the
+gloo test, real library, CUDA tensors). Skipped on a single-GPU box."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+from conftest import domain, rel_linf, synthetic_field
+from oracle import oracle
+from pyranda_b200.distributed import DistributedParcop
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+worst = 0.0
+for n in ((32, 48, 32 * world), (64, 64, 64 * world)):
+    for periodic in (True, False):
+        (x1, xn), (y1, yn), (z1, zn) = domain(n, periodic)
+        o = oracle.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3)
+        f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+        eng = DistributedParcop(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3, device=local)
+        az = n[2] // world
+        sl = slice(rank * az, (rank + 1) * az)
+        loc = eng.empty(); loc.copy_(torch.from_numpy(f[:, :, sl].copy()))
+        for name, ref in (("ddx", o.ddx), ("ddy", o.ddy), ("ddz", o.ddz), ("dd8z", o.dd8z), ("d2z", o.d2z),
+                          ("sfilter", o.sfilter), ("gfilter", o.gfilter), ("laplacian", o.plaplacian), ("ring", o.pring)):
+            got = eng.apply(name, loc).cpu().numpy()
+            err = rel_linf(got, ref(f)[:, :, sl])
+            worst = max(worst, err)
+            assert err < 1e-12, (name, n, periodic, rank, err)
+        got = eng.divergence(loc, loc * 2, loc * loc).cpu().numpy()
+        assert rel_linf(got, o.divergence(f, 2 * f, f * f)[:, :, sl]) < 1e-12
+        assert abs(eng.sum3D(loc) - f.sum()) < 1e-9 * np.abs(f).sum()
+        assert eng.max3D(loc) == f.max() and eng.min3D(loc) == f.min()
+        # host-array entry point (pinned staging inside the engine)
+        hin = np.asfortranarray(f[:, :, sl]); hout = np.empty_like(hin, order="F")
+        eng.apply_host_into("ddz", hin, hout)
+        assert rel_linf(hout, o.ddz(f)[:, :, sl]) < 1e-12
+print("rank", rank, "worst", worst)
+dist.destroy_process_group()
+"""
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.gpu
+def test_zslab_nccl(tmp_path):
+    import torch
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if world < 4 else (4 if world < 8 else 8)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    r = subprocess.run(cmd, env=dict(os.environ, OMP_NUM_THREADS="4"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("worst") == world
