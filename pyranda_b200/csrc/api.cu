@@ -109,7 +109,7 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
   dv.phys_hi = (!periodic && sp.rank == np - 1) ? 1 : 0;
   dv.wrap = cyclic_local ? 1 : 0;
   dv.implicit = st.implicit ? 1 : 0;
-  dv.add_v = (st.null_option == 1) ? 1 : 0;
+  dv.add_v = st.add_back ? 1 : 0;
   const double dd = pl->d[dir];
   dv.scale = st.post == 1 ? 1.0 / dd : (st.post == 2 ? 1.0 / (dd * dd) : 1.0);  // compact_operators.f90:43,152
 

@@ -2,6 +2,7 @@
 // sweeps_*.cu, which instantiate launch_yz_f / launch_x_f, so the families compile in parallel.
 #pragma once
 #include <atomic>
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -54,7 +55,7 @@ __device__ __forceinline__ double rhs_center(const double *w, const double *ar) 
       if (l != 3) s += ar[l] * (w[l] - w[3]);
     return s;
   } else {
-    double s = 0.0;
+    double s = ar[4] * w[4];
 #pragma unroll
     for (int l = 0; l < 9; ++l)
       if (l != 4) s += (w[l] - w[4]) * ar[l];
@@ -88,7 +89,7 @@ __device__ __forceinline__ void rhs_lo4(const double *vv, const double (*b)[9], 
     const double v0 = vv[0];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double s = 0.0;
+      double s = b[i][4 - i] * v0;
 #pragma unroll
       for (int l = 5 - i; l < 9; ++l) s += b[i][l] * (vv[l - 4 + i] - v0);
       r[i] = s;
@@ -122,7 +123,7 @@ __device__ __forceinline__ void rhs_hi4(const double *u, const double (*h)[9], d
     const double vm = u[7];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      double s = 0.0;
+      double s = h[q][7 - q] * vm;
 #pragma unroll
       for (int l = 0; l < 7 - q; ++l) s += h[q][l] * (u[q + l] - vm);
       r[q] = s;
@@ -172,7 +173,7 @@ __device__ __forceinline__ double rhs_ring(const double *g, const double *ar) {
       if (l != 3) s += ar[l] * (WR(l) - WR(3));
     return s;
   } else {
-    double s = 0.0;
+    double s = ar[4] * WR(4);
 #pragma unroll
     for (int l = 0; l < 9; ++l)
       if (l != 4) s += (WR(l) - WR(4)) * ar[l];
@@ -1229,7 +1230,7 @@ __device__ __forceinline__ void stream_chunk_tile(const SweepDev &a, const doubl
   });
 }
 
-template <int FAM, int NL, bool PLAIN, bool ADDV>
+template <int FAM, int NL, bool PLAIN, bool ADDV, bool LATE>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tmain,
                      const __grid_constant__ TileMap tlo, const __grid_constant__ TileMap thi,
@@ -1286,6 +1287,9 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
 
     mbar_wait(bar, parity);
     parity ^= 1;
+#ifdef PB_EMULATE
+    __syncthreads();  // the emulated load is a synchronous copy by thread 0
+#endif
     {  // ---- A: rhs + forward recurrence (zero incoming state), chunk pulled out of the tile ----
       const double2 *luf = a.luf + (size_t)type * CT;
       const double l2c = a.cst[0], l1c = a.cst[1];
@@ -1303,8 +1307,8 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       });
       EN[p * NL + l] = make_double2(rm1, rm2);
     }
-    __syncthreads();  // the tile buffer is free, EN is visible
-    if (tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
+    __syncthreads();  // the tile buffer is free (unless the add-back still reads it), EN is visible
+    if (!(ADDV && LATE) && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
     {  // ---- B: add the carried forward state, backward recurrence (zero incoming state) ----
       double2 st = make_double2(0.0, 0.0);
@@ -1331,7 +1335,7 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           x = fma(-u1, x1, x);
           x = fma(-u2, x2, x);
           x *= ip;
-          rl[r] = x;
+          rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
           x2 = x1;
           x1 = x;
         });
@@ -1348,14 +1352,23 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           x = fma(-c.y, x1, x);
           x = fma(-c.z, x2, x);
           x *= c.x;
-          rl[r] = x;
+          rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
           x2 = x1;
           x1 = x;
         });
       }
       ST[p * NL + l] = make_double2(x1, x2);
     }
+    // filters add the input back: it left the tile when the prefetch started, so it is re-read from
+    // L2 through a 16-row register window whose first half is requested before the barrier
+    const double *pv = v + base + (long)s * rs;
+    double vr[16];
+    if (ADDV && !LATE) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) vr[k] = __ldg(pv + k * rs);
+    }
     __syncthreads();
+    if (ADDV && LATE && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
     {  // ---- D: add the carried backward state, scale / add-back / epilogue, store ----
       double2 tb = make_double2(0.0, 0.0);
@@ -1371,14 +1384,21 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
         }
       }
-      const double *pv = v + base + (long)s * rs;
       long oidx = base + (long)s * rs;
       double *po = out + oidx;
-      auto rowD = [&](double gx, double gy, double xl) -> double {
+      auto rowD = [&](auto rc, double gx, double gy, double xl) -> double {
+        constexpr int r = decltype(rc)::value;
         double x = fma(gx, tb.x, xl);
         x = fma(gy, tb.y, x);
         double val = x * scale;
-        if (ADDV) val += __ldg(pv);
+        if (ADDV && LATE) {  // xl already holds scale * x_local + v
+          val = fma(gx * scale, tb.x, xl);
+          val = fma(gy * scale, tb.y, val);
+        }
+        if (ADDV && !LATE) {
+          val += vr[r & 15];
+          if (r < CT - 16) vr[r & 15] = __ldg(pv + (long)(r + 16) * rs);
+        }
         if (PLAIN) {
           if (valid) *po = val;
           po += rs;
@@ -1386,14 +1406,13 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           if (valid) epi_store(out, oidx, val, epi);
           oidx += rs;
         }
-        pv += rs;
         return x;
       };
       double xi[4] = {0.0, 0.0, 0.0, 0.0};  // first / last two solved values (z-slab interface)
       if (cc) {
         static_for<0, CT>([&](auto rc) {
           constexpr int r = decltype(rc)::value;
-          const double x = rowD(a.psi0[r].x, a.psi0[r].y, rl[r]);
+          const double x = rowD(rc, a.psi0[r].x, a.psi0[r].y, rl[r]);
           if (r < 2) xi[r] = x;
           if (r >= CT - 2) xi[r - (CT - 4)] = x;
         });
@@ -1402,7 +1421,7 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         static_for<0, CT>([&](auto rc) {
           constexpr int r = decltype(rc)::value;
           const double2 gq = __ldg(ps + r);
-          const double x = rowD(gq.x, gq.y, rl[r]);
+          const double x = rowD(rc, gq.x, gq.y, rl[r]);
           if (r < 2) xi[r] = x;
           if (r >= CT - 2) xi[r - (CT - 4)] = x;
         });
@@ -1454,10 +1473,13 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
     g.halo = 1; g.lo_row = m - 4; g.hi_row = 0;
   }
   const size_t smem = ((size_t)(m + 8) * NL + 4 * (size_t)a.P * NL) * sizeof(double) + 16;
-  auto kfn = sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV>;
+  static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
+  auto kfn = (ADDV && late) ? sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, true> : sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, false>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     configured = true;
   }
@@ -1465,6 +1487,265 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
   const long want = 2L * sm_count();
   const dim3 grid((unsigned)(ntiles < want ? ntiles : want)), block(kBlockThreads);
   PB_LAUNCH(kfn, grid, block, smem, st, a, tmain, tlo, thi, g, v, out, iface, epi);
+  ++g_launches;
+  ++g_pipe_launches;
+  return cudaGetLastError();
+}
+
+
+// x sweep, pipelined.  Lines are unit stride, so the tile is staged with 16-byte asynchronous
+// copies (coalesced in global memory) into rows of pitch LT with LT/2 odd: a thread then reads its
+// chunk with conflict-free 128-bit shared loads at compile-time offsets.  The solution leaves
+// through a small transposing stage, 16 rows of every chunk at a time, as coalesced 128-bit stores.
+// Column c of a tile row holds x = c - 4 (periodic wrap values in columns 0..3 and m+4..m+7).
+template <int FAM, int NLX, bool PLAIN, bool ADDV, bool LATE>
+__global__ void __launch_bounds__(kBlockThreads, 2)
+sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v, double *__restrict__ out,
+                    const __grid_constant__ EpiArgs epi) {
+  constexpr int CT = 32, H = FT<FAM>::H, G = 16;
+  constexpr int PC = kBlockThreads / NLX, M = PC * CT;              // chunks per line, line length
+  constexpr int LT = (((M + 8) / 2) & 1) ? M + 8 : M + 10;          // tile pitch, LT/2 odd
+  constexpr int LS = PC * G + 2;                                    // stage pitch, LS/2 odd
+  PB_SHARED(S);
+  constexpr int m = M, P = PC;
+  double *tile = S;                                      // [NLX][LT]
+  double *stage = tile + (size_t)NLX * LT;               // [NLX][LS]
+  double2 *EN = reinterpret_cast<double2 *>(stage + (size_t)NLX * LS);  // [P][NLX]
+  double2 *ST = EN + P * NLX;
+  const int tid = threadIdx.x, l = tid % NLX, p = tid / NLX;
+  const long nlines = a.nfast;
+  const long ntiles = (nlines + NLX - 1) / NLX;
+  const int s = p * CT;
+  const int type = a.ctype[p];
+  const bool cc = a.has_const && type == 0;
+  const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
+  const double scale = a.scale;
+  constexpr int half = M / 2;  // 16-byte pieces per line
+
+  auto issue = [&](long t) {  // every thread copies its share of tile t
+    const long L0 = t * NLX;
+#pragma unroll 4
+    for (int q = tid; q < NLX * half; q += kBlockThreads) {
+      const int line = q / half, j = q % half;
+      long L = L0 + line;
+      if (L >= nlines) L = nlines - 1;
+      cp_async16(tile + (size_t)line * LT + 4 + 2 * j, v + L * (long)m + 2 * j);
+    }
+    if (a.wrap && tid < NLX * 4) {
+      const int line = tid >> 2, w = tid & 3;
+      long L = L0 + line;
+      if (L >= nlines) L = nlines - 1;
+      const int xs = (w < 2) ? m - 4 + 2 * w : 2 * (w - 2);   // source x
+      const int cd = (w < 2) ? 2 * w : m + 4 + 2 * (w - 2);   // destination column
+      cp_async16(tile + (size_t)line * LT + cd, v + L * (long)m + xs);
+    }
+    cp_async_commit();
+  };
+
+  long t = blockIdx.x;
+  if (t < ntiles) issue(t);
+  const double2 *tw = reinterpret_cast<const double2 *>(tile + (size_t)l * LT + s);  // columns s .. s+39 of this line
+
+  for (; t < ntiles; t += gridDim.x) {
+    const long L0 = t * NLX;
+    double rl[CT];
+    cp_async_wait_all();
+    __syncthreads();
+
+    {  // ---- A: rhs + forward recurrence; ring slot = column & 15 ----
+      const double2 *luf = a.luf + (size_t)type * CT;
+      const double l2c = a.cst[0], l1c = a.cst[1];
+      double rm1 = 0.0, rm2 = 0.0;
+      double ring[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double2 w2 = tw[j];
+        ring[2 * j] = w2.x;
+        ring[2 * j + 1] = w2.y;
+      }
+      double rlo[4] = {0.0, 0.0, 0.0, 0.0}, rhi[4] = {0.0, 0.0, 0.0, 0.0};
+      if (lo_sp) {
+        double vv[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) vv[q] = ring[(q + 4) & 15];
+        rhs_lo4<FAM>(vv, a.arb_lo, rlo);
+      }
+      static_for<0, CT>([&](auto lrc) {
+        constexpr int lr = decltype(lrc)::value;
+        double rhs = rhs_ring<FAM, (lr + 4 - H) & 15>(ring, a.ari);
+        if (lr < 4) {
+          if (lo_sp) rhs = rlo[lr];
+        }
+        if (lr == CT - 4) {
+          if (hi_sp) {
+            double u[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) u[q] = ring[(CT - 4 + q) & 15];
+            rhs_hi4<FAM>(u, a.arb_hi, rhi);
+          }
+        }
+        if (lr >= CT - 4) {
+          if (hi_sp) rhs = rhi[lr - (CT - 4)];
+        }
+        if ((lr & 1) && lr + 16 < CT + 8) {  // columns lr+15, lr+16 replace the two just retired
+          const double2 w2 = tw[(lr + 15) / 2];
+          ring[(lr - 1) & 15] = w2.x;
+          ring[lr & 15] = w2.y;
+        }
+        double2 c;
+        if (cc) c = make_double2(l2c, l1c);
+        else c = __ldg(luf + lr);
+        double x = fma(-c.x, rm2, rhs);
+        x = fma(-c.y, rm1, x);
+        rl[lr] = x;
+        rm2 = rm1;
+        rm1 = x;
+      });
+      EN[p * NLX + l] = make_double2(rm1, rm2);
+    }
+    __syncthreads();  // tile consumed (unless the add-back still reads it), EN visible
+    if (!(ADDV && LATE) && t + gridDim.x < ntiles) issue(t + gridDim.x);
+
+    {  // ---- B ----
+      double2 st = make_double2(0.0, 0.0);
+      {
+        const int nf = a.nf[p];
+        const double4 *Mp = a.Mf + (size_t)p * (P + 1);
+        for (int j = 1; j <= nf; ++j) {
+          int q = p - j;
+          if (q < 0) q += P;
+          const double2 en = EN[q * NLX + l];
+          const double4 M = ldg4(Mp + j);
+          st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
+          st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
+        }
+      }
+      double x1 = 0.0, x2 = 0.0;
+      if (cc) {
+        const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+        static_for<0, CT>([&](auto jc) {
+          constexpr int r = CT - 1 - decltype(jc)::value;
+          double x = rl[r];
+          x = fma(a.phi0[r].x, st.x, x);
+          x = fma(a.phi0[r].y, st.y, x);
+          x = fma(-u1, x1, x);
+          x = fma(-u2, x2, x);
+          x *= ip;
+          rl[r] = (ADDV && LATE) ? fma(x, scale, reinterpret_cast<const double *>(tw)[4 + r]) : x;
+          x2 = x1;
+          x1 = x;
+        });
+      } else {
+        const double2 *ph = a.phi + (size_t)type * CT;
+        const double4 *lub = a.lub + (size_t)type * CT;
+        static_for<0, CT>([&](auto jc) {
+          constexpr int r = CT - 1 - decltype(jc)::value;
+          const double2 f = __ldg(ph + r);
+          const double4 c = ldg4(lub + r);
+          double x = rl[r];
+          x = fma(f.x, st.x, x);
+          x = fma(f.y, st.y, x);
+          x = fma(-c.y, x1, x);
+          x = fma(-c.z, x2, x);
+          x *= c.x;
+          rl[r] = (ADDV && LATE) ? fma(x, scale, reinterpret_cast<const double *>(tw)[4 + r]) : x;
+          x2 = x1;
+          x1 = x;
+        });
+      }
+      ST[p * NLX + l] = make_double2(x1, x2);
+    }
+    __syncthreads();
+    if (ADDV && LATE && t + gridDim.x < ntiles) issue(t + gridDim.x);
+
+    {  // ---- D: carried backward state, then 16 rows of every chunk at a time through the stage ----
+      double2 tb = make_double2(0.0, 0.0);
+      {
+        const int nb = a.nb[p];
+        const double4 *Mp = a.Mb + (size_t)p * (P + 1);
+        for (int j = 1; j <= nb; ++j) {
+          int q = p + j;
+          if (q >= P) q -= P;
+          const double2 sv = ST[q * NLX + l];
+          const double4 M = ldg4(Mp + j);
+          tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
+          tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
+        }
+      }
+      const double2 *ps = a.psi + (size_t)type * CT;
+      double2 *sw = reinterpret_cast<double2 *>(stage + (size_t)l * LS + p * G);
+      constexpr int per_line = PC * (G / 2);  // 16-byte pieces of one line in a group
+      static_for<0, CT / G>([&](auto gc) {
+        constexpr int g = decltype(gc)::value;
+        if (g > 0) __syncthreads();  // the previous group has left the stage
+        static_for<0, G / 2>([&](auto kc) {
+          constexpr int r = g * G + 2 * decltype(kc)::value;
+          double2 q0, q1;
+          if (cc) { q0 = a.psi0[r]; q1 = a.psi0[r + 1]; }
+          else { q0 = __ldg(ps + r); q1 = __ldg(ps + r + 1); }
+          const double sc = (ADDV && LATE) ? scale : 1.0;  // late add-back: rl already holds scale * x + v
+          double xa = fma(q0.x * sc, tb.x, rl[r]);
+          xa = fma(q0.y * sc, tb.y, xa);
+          double xb = fma(q1.x * sc, tb.x, rl[r + 1]);
+          xb = fma(q1.y * sc, tb.y, xb);
+          sw[decltype(kc)::value] = (ADDV && LATE) ? make_double2(xa, xb) : make_double2(xa * scale, xb * scale);
+        });
+        __syncthreads();
+        constexpr int PIECES = NLX * PC * (G / 2);  // 16-byte pieces of a group
+        double2 vadd[PIECES / kBlockThreads];
+        if (ADDV && !LATE) {
+#pragma unroll
+          for (int it = 0; it < PIECES / kBlockThreads; ++it) {
+            const int q = it * kBlockThreads + tid;
+            const int line = q / per_line, rr = q - line * per_line;
+            const long L = L0 + line;
+            const long idx = (L < nlines ? L : nlines - 1) * (long)m + (rr >> 3) * CT + g * G + 2 * (rr & 7);
+            vadd[it] = __ldg(reinterpret_cast<const double2 *>(v + idx));
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < PIECES / kBlockThreads; ++it) {
+          const int q = it * kBlockThreads + tid;
+          const int line = q / per_line, rr = q - line * per_line;
+          const long L = L0 + line;
+          const int chunk = rr >> 3, piece = rr & 7;
+          double2 val = *reinterpret_cast<const double2 *>(stage + (size_t)line * LS + chunk * G + 2 * piece);
+          if (ADDV && !LATE) { val.x += vadd[it].x; val.y += vadd[it].y; }
+          if (L < nlines) {
+            const long idx = L * (long)m + chunk * CT + g * G + 2 * piece;
+            if (PLAIN) {
+              *reinterpret_cast<double2 *>(out + idx) = val;
+            } else {
+              epi_store(out, idx, val.x, epi);
+              epi_store(out, idx + 1, val.y, epi);
+            }
+          }
+        }
+      });
+    }
+  }
+}
+
+template <int FAM, int NLX, bool PLAIN, bool ADDV>
+static cudaError_t launch_x_pipe(const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
+  const int m = a.m;
+  if (a.C != 32 || NLX * a.P != kBlockThreads || m != 32 * a.P || !a.implicit) return cudaErrorNotSupported;
+  if ((reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return cudaErrorNotSupported;
+  const int LT = (((m + 8) / 2) & 1) ? m + 8 : m + 10, LS = a.P * 16 + 2;
+  const size_t smem = ((size_t)NLX * LT + (size_t)NLX * LS + 4 * (size_t)a.P * NLX) * sizeof(double);
+  static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
+  auto kfn = (ADDV && late) ? sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, true> : sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, false>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured = true;
+  }
+  const long ntiles = ((long)a.nfast + NLX - 1) / NLX;
+  const long want = 2L * sm_count();
+  PB_LAUNCH(kfn, dim3((unsigned)(ntiles < want ? ntiles : want)), dim3(kBlockThreads), smem, st, a, v, out, epi);
   ++g_launches;
   ++g_pipe_launches;
   return cudaGetLastError();
@@ -1542,6 +1823,13 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
   const long ntiles = ((long)a.nfast + NLX - 1) / NLX;
   int threads = NLX * a.P;
   threads = (threads + 31) / 32 * 32;
+  if constexpr (NLX == 16 || NLX == 32) {
+    if (g_pipe_kernels && a.implicit && a.C == 32) {
+      constexpr bool PL = PLAIN && NLX == 16;
+      const cudaError_t err = launch_x_pipe<FAM, NLX, PL, ADDV>(a, v, out, epi, st);
+      if (err != cudaErrorNotSupported) return err;
+    }
+  }
   if (g_reg_kernels && a.implicit && (a.C == 32 || (a.C == 16 && NLX == 16))) {
     static size_t configured_r = 0;
     constexpr bool PL = PLAIN && NLX == 16;

@@ -36,6 +36,22 @@ void difference_form(Stencil &s) {
     }
 }
 
+// The R4 right-hand side is evaluated as sum_l w_l (v_l - v_ref) + sigma v_ref with v_ref the row's
+// own point (interior) or the boundary point (closure rows, compact_r4.f90:123-126,174-177).  The
+// slot of the reference column carries sigma, the row sum of the weights: zero for the 8th
+// derivative and for both filters in the reference's difference form  v + A^-1 (B - A) v.
+// (direct = true gives  A out = B v  without an add-back; it is NOT used for the compact filter:
+// its matrix is nearly singular at the Nyquist wavenumber, cond ~ 2e3, and the direct form loses
+// three digits against the reference -- measured 3e-13 instead of 2e-15 per application.)
+void set_reference_slots(Stencil &s, bool direct) {
+  auto rowsum = [](const double *w) { double t = 0.0; for (int l = 0; l < 9; ++l) t += w[l]; return t; };
+  s.ari[4] = direct ? rowsum(s.ari) : 0.0;
+  for (int i = 0; i < 4; ++i) {
+    s.arb_lo[i][4 - i] = direct ? rowsum(s.arb_lo[i]) : 0.0;
+    s.arb_hi[i][7 - i] = direct ? rowsum(s.arb_hi[i]) : 0.0;
+  }
+}
+
 }  // namespace
 
 Stencil make_stencil(Kind k) {
@@ -89,6 +105,7 @@ Stencil make_stencil(Kind k) {
       set_row(s.arb_lo[2], {0.0, 0.0, dd + cc, ee + bb, aa, bb, cc, dd, ee});
       set_row(s.arb_lo[3], {0.0, ee + dd, cc, bb, aa, bb, cc, dd, ee});
       mirror_closures(s, 1.0);
+      set_reference_slots(s, false);
       break;
     }
     case K_SF: {  // 8th-order compact "9/10" filter, telescoped closures, stencils.f90:713-835
@@ -108,6 +125,8 @@ Stencil make_stencil(Kind k) {
       set_row(s.arb_lo[3], {0.0, 4.0e-5, 1.6672e-1, 6.6652e-1, 9.9968e-1, 6.6652e-1, 1.6672e-1, 4.0e-5, 0.0});
       mirror_closures(s, 1.0);
       difference_form(s);
+      set_reference_slots(s, false);
+      s.add_back = true;
       break;
     }
     case K_GF: {  // explicit 9-point Gaussian, stencils.f90:1387-1476
@@ -124,6 +143,8 @@ Stencil make_stencil(Kind k) {
       set_row(s.arb_lo[3], {0.0, d + e, c, b, a, b, c, d, e});
       mirror_closures(s, 1.0);
       difference_form(s);
+      set_reference_slots(s, false);
+      s.add_back = true;
       break;
     }
     default:

@@ -22,6 +22,7 @@ struct Stencil {
   bool implicit = false;
   int null_option = 0;  // 0: zero when the direction is a null-op, 1: copy   (stencils.f90:28)
   int post = 0;         // metric scale after the solve: 0 none, 1 /d, 2 /d^2  (compact_operators.f90)
+  bool add_back = false;  // result = input + stencil (the explicit Gaussian in difference form)
   int fam = F_D1;
   double ali[5] = {0, 0, 0, 0, 0};
   double ari[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};

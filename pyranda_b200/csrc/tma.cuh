@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 
 namespace pb {
 
@@ -55,6 +56,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const TileMap *map, int c
       : "memory");
 }
 
+// Ampere-style asynchronous 16-byte copies global -> shared (LDGSTS): used by the x sweep, whose
+// padded tile layout a tensor map cannot express.
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Encodes {d0, d1, d2} doubles with byte strides {8, s1, s2} and a box {b0, b1, b2}.
 // Returns false when the driver entry point is missing or the geometry is not expressible
 // (strides must be multiples of 16 bytes, the base 16-byte aligned): the caller falls back to the
@@ -77,21 +86,27 @@ inline bool encode_tile_map(TileMap *map, const double *base, uint64_t d0, uint6
   const cuuint64_t strides[2] = {s1_bytes, s2_bytes};
   const cuuint32_t box[3] = {b0, b1, b2};
   const cuuint32_t estr[3] = {1, 1, 1};
+  static const int promo = getenv("PB_TMA_PROMO") ? atoi(getenv("PB_TMA_PROMO")) : 2;
+  const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace pb
 #else
 // Host emulation: a "tensor map" is the plain geometry and a load is a synchronous strided copy.
 #include <cstdint>
+#include <cstring>
 namespace pb {
 struct TileMap {
   const double *base;
   uint64_t d0, d1, d2, s1, s2;  // strides in doubles
   uint32_t b0, b1, b2;
 };
+inline void cp_async16(void *dst, const void *src) { std::memcpy(dst, src, 16); }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
 inline void mbar_init(uint64_t *, uint32_t) {}
 inline void mbar_expect_tx(uint64_t *, uint32_t) {}
 inline void mbar_wait(uint64_t *, uint32_t) {}

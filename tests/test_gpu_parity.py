@@ -61,22 +61,23 @@ def test_tile_shapes(chunk, lines, oracle_mod):
             for name in ("ddx", "ddy", "ddz", "sfilter", "dd8x", "d2z"):
                 assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < TOL, (name, chunk, lines, periodic)
     finally:
-        L.pb_set_tuning(16, 16, 64)
+        L.pb_set_tuning(32, 32, 32)
 
 
 @pytest.mark.parametrize("periodic", [True, False])
-@pytest.mark.parametrize("n", [(40, 256, 16), (72, 16, 256), (48, 512, 16), (36, 16, 512), (256, 256, 256)])
+@pytest.mark.parametrize("n", [(40, 256, 16), (72, 16, 256), (48, 512, 16), (36, 16, 512), (256, 18, 20), (512, 17, 16),
+                               (256, 256, 256)])
 def test_pipelined_kernels(n, periodic, oracle_mod):
     """Line lengths of 256 / 512 take the TMA-pipelined persistent kernels (asserted through the
-    launch counter): y and z sweeps, partial x tiles, more tiles than CTAs, every family."""
+    launch counter): x, y and z sweeps, partial tiles, more tiles than CTAs, every family."""
     from pyranda_b200 import _lib
     L = _lib.load()
     o, p, f = _pair(n, periodic, oracle_mod)
-    names = [k for k in ("ddy", "ddz", "dd8y", "dd8z", "d2y", "d2z") if n["xyz".index(k[-1])] >= 256]
+    names = [k for k in ("ddx", "ddy", "ddz", "dd8x", "dd8y", "dd8z", "d2x", "d2y", "d2z") if n["xyz".index(k[-1])] >= 256]
     c0 = L.pb_pipe_launch_count()
     for name in names:
         assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < TOL, (name, n, periodic)
-    for d in (2, 3):
+    for d in (1, 2, 3):
         if n[d - 1] >= 256:
             assert rel_linf(p.sfilterdir(f, d), o.dir_op("sf", d - 1, f)) < TOL, ("sfilter", d, n, periodic)
             names.append("sf")
