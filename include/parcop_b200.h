@@ -99,10 +99,13 @@ int pb_rk4_stage(pb_plan *plan, long n, double dt, double A, double B, const dou
 int pb_reduce(pb_plan *plan, int kind, long n, const double *d_val, double *host_out, void *stream);
 
 /* ---- z-slab multi-GPU pieces (compact_d1.f90:719-746,858-928; compact_r4.f90:640-656,...) ------
- * A distributed z operator is: pb_z_pack_halo -> exchange (ncclSend/Recv by the caller) ->
- * pb_z_local (rhs with halos + local bounded solve, writes the 4 interface unknowns per line) ->
- * all-gather of the interface buffer by the caller -> pb_z_finish (reduced block-tridiagonal
- * solve + spike correction + scale / add-back).  Buffers are device pointers:
+ * A distributed z operator is: halo exchange (ncclSend/Recv by the caller, planes sent straight
+ * from the field or packed with pb_z_pack_halo) -> pb_z_local (rhs with halos + local bounded
+ * solve + scale / add-back; also writes the 4 interface unknowns per line) -> exchange of the
+ * interface buffers by the caller (mpi_allgather in the reference; pb_z_exchange_ranks tells which
+ * ranks' values actually matter, normally the two neighbours) -> pb_z_finish (reduced
+ * block-tridiagonal solve + spike correction, applied only to the rows near the slab faces that
+ * it can change).  Buffers are device pointers:
  *   send_lo/send_hi, recv_lo/recv_hi : 4*ax*ay doubles each (first / last planes, 3 or 4 used)
  *   iface_local : 4*ax*ay doubles,  iface_all : pz*4*ax*ay doubles (rank-major, as mpi_allgather)
  * zop in {PB_OP_DDZ, PB_OP_DD8Z, PB_OP_D2Z, PB_OP_SFILTERZ, PB_OP_GFILTERZ}. */
@@ -112,6 +115,9 @@ int pb_z_local(pb_plan *plan, int zop, const double *d_val, const double *d_recv
                const double *d_recv_hi, double *d_out, double *d_iface_local, void *stream);
 int pb_z_finish(pb_plan *plan, int zop, const double *d_val, const double *d_iface_all,
                 double *d_out, void *stream);
+/* bit r of *mask is set when rank r's interface values enter this rank's correction (0: the
+ * operator needs no exchange); slots of d_iface_all belonging to other ranks are never read */
+int pb_z_exchange_ranks(pb_plan *plan, int zop, unsigned long long *mask);
 
 /* ---- host-array convenience wrappers: the exact f2py call shapes ------------------------------
  * `dval = parcop.parcop.ddx(val)`  ==  pb_host_apply(plan, PB_OP_DDX, val, dval)

@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <cmath>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -38,6 +40,8 @@ struct SweepPlan {
   SweepDev dev;
   double4 *RC = nullptr;  // rank-level spike columns [m]
   double *GR = nullptr;   // rank-level reduced-system rows [4][4np]
+  int zone_lo = 0, zone_hi = 0;     // rows from either end of the slab the rank-level correction reaches
+  unsigned long long rank_mask = 0; // ranks whose interface values enter this rank's correction
   std::vector<void *> owned;
 };
 
@@ -55,6 +59,9 @@ struct pb_plan {
   double *red_partial = nullptr, *red_result = nullptr, *red_host = nullptr;
   std::map<std::string, double *> mesh;  // device mesh arrays
   bool mesh_set = false;
+  // host-array entry points: copy / compute / copy-back pipeline over slabs
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};  // H2D, compute, D2H
+  std::vector<cudaEvent_t> hev;
 };
 
 namespace {
@@ -167,6 +174,24 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
         RC[i] = make_double4(q[0], q[1], q[2], q[3]);
       }
       std::vector<double> GR(rp.G.begin() + (size_t)sp.rank * 16 * np, rp.G.begin() + (size_t)(sp.rank + 1) * 16 * np);
+      // The spike columns decay like rho^row away from the slab faces and the reduced-system rows
+      // like rho^(az * distance in ranks): keep only what can change a double (1e-17 / 1e-19 relative).
+      {
+        double cmax = 0.0, gmax = 0.0;
+        for (int i = 0; i < m; ++i)
+          cmax = std::max({cmax, std::fabs(RC[i].x), std::fabs(RC[i].y), std::fabs(RC[i].z), std::fabs(RC[i].w)});
+        sp.zone_lo = sp.zone_hi = 0;
+        for (int i = 0; i < m; ++i) {
+          if (std::max(std::fabs(RC[i].x), std::fabs(RC[i].y)) > 1e-17 * cmax) sp.zone_lo = i + 1;
+          if (std::max(std::fabs(RC[m - 1 - i].z), std::fabs(RC[m - 1 - i].w)) > 1e-17 * cmax) sp.zone_hi = i + 1;
+        }
+        for (double gv : GR) gmax = std::max(gmax, std::fabs(gv));
+        sp.rank_mask = 0;
+        for (int r = 0; r < np; ++r)
+          for (int c = 0; c < 4; ++c)
+            for (int j = 0; j < 4; ++j)
+              if (std::fabs(GR[(size_t)c * 4 * np + 4 * r + j]) > 1e-19 * gmax) sp.rank_mask |= 1ull << r;
+      }
       const double4 *dRC; const double *dGR;
       if ((rcv = upload(sp, RC, &dRC)) != PB_OK) return rcv;
       if ((rcv = upload(sp, GR, &dGR)) != PB_OK) return rcv;
@@ -216,6 +241,20 @@ int apply_dir(pb_plan *pl, SweepPlan &sp, const double *in, double *out, const E
     return fail(PB_ERR_STATE, "this axis is split across ranks: use pb_z_pack_halo / pb_z_local / pb_z_finish");
   if (sp.dir == 0) PB_CUDA(launch_sweep_x(sp.st.fam, 0, sp.dev, in, out, epi, st));
   else PB_CUDA(launch_sweep_yz(sp.st.fam, 0, sp.dev, in, out, nullptr, nullptr, nullptr, epi, st));
+  return PB_OK;
+}
+
+// the same sweep restricted to `cnt` outer slices starting at `first`: z-planes for x / y sweeps,
+// y-rows for z sweeps.  Used by the host-array pipeline, which works slab by slab.
+int apply_dir_slab(pb_plan *pl, SweepPlan &sp, const double *in, double *out, int first, int cnt, cudaStream_t st) {
+  if (!sp.built || sp.null_op || sp.split) return fail(PB_ERR_STATE, "slab sweeps need a local, non-null direction");
+  SweepDev dv = sp.dev;
+  long off;
+  if (sp.dir == 0) { off = (long)first * pl->a[0] * pl->a[1]; dv.nfast = cnt * pl->a[1]; }
+  else if (sp.dir == 1) { off = (long)first * pl->a[0] * pl->a[1]; dv.nouter = cnt; }
+  else { off = (long)first * pl->a[0]; dv.nouter = cnt; }
+  if (sp.dir == 0) PB_CUDA(launch_sweep_x(sp.st.fam, 0, dv, in + off, out + off, kStore, st));
+  else PB_CUDA(launch_sweep_yz(sp.st.fam, 0, dv, in + off, out + off, nullptr, nullptr, nullptr, kStore, st));
   return PB_OK;
 }
 
@@ -322,6 +361,9 @@ int pb_plan_destroy(pb_plan *pl) {
   if (pl->red_partial) cudaFree(pl->red_partial);
   if (pl->red_result) cudaFree(pl->red_result);
   if (pl->red_host) cudaFreeHost(pl->red_host);
+  for (cudaEvent_t e : pl->hev) cudaEventDestroy(e);
+  for (int k = 0; k < 3; ++k)
+    if (pl->hs[k]) cudaStreamDestroy(pl->hs[k]);
   delete pl;
   return PB_OK;
 }
@@ -611,13 +653,9 @@ int pb_z_local(pb_plan *pl, int zop, const double *d_val, const double *recv_lo,
     return apply_dir(pl, sp, d_val, d_out, kStore, st);
   }
   if ((!sp.dev.phys_lo && !recv_lo) || (!sp.dev.phys_hi && !recv_hi)) return fail(PB_ERR_ARG, "missing halo buffer");
-  SweepDev dv = sp.dev;
-  if (sp.st.implicit) {
-    if (!iface_local) return fail(PB_ERR_ARG, "missing interface buffer");
-    dv.scale = 1.0;  // scale and add-back happen after the rank-level correction (pb_z_finish)
-    dv.add_v = 0;
-  }
-  PB_CUDA(launch_sweep_yz(sp.st.fam, 0, dv, d_val, d_out, recv_lo, recv_hi, sp.st.implicit ? iface_local : nullptr, kStore, st));
+  // the local pass already scales and adds back: pb_z_finish only adds the rank-level correction
+  if (sp.st.implicit && !iface_local) return fail(PB_ERR_ARG, "missing interface buffer");
+  PB_CUDA(launch_sweep_yz(sp.st.fam, 0, sp.dev, d_val, d_out, recv_lo, recv_hi, sp.st.implicit ? iface_local : nullptr, kStore, st));
   return PB_OK;
 }
 
@@ -626,18 +664,130 @@ int pb_z_finish(pb_plan *pl, int zop, const double *d_val, const double *iface_a
   if (!pl || k < 0 || !d_out) return fail(PB_ERR_ARG, "bad argument");
   SweepPlan &sp = pl->sw[k][2];
   if (sp.null_op || !sp.split || !sp.st.implicit) return PB_OK;  // explicit operators are complete after pb_z_local
-  if (!iface_all || !d_val) return fail(PB_ERR_ARG, "missing interface buffer");
+  if (!iface_all) return fail(PB_ERR_ARG, "missing interface buffer");
+  (void)d_val;
   const long plane = (long)pl->a[0] * pl->a[1];
-  PB_CUDA(launch_z_finish(d_out, d_val, d_out, plane, pl->a[2], sp.RC, sp.GR, sp.np, iface_all, sp.dev.scale, sp.dev.add_v,
-                          (cudaStream_t)stream));
+  PB_CUDA(launch_z_finish(d_out, plane, pl->a[2], sp.RC, sp.GR, sp.np, sp.rank_mask, sp.zone_lo, sp.zone_hi, iface_all,
+                          sp.dev.scale, (cudaStream_t)stream));
+  return PB_OK;
+}
+
+int pb_z_exchange_ranks(pb_plan *pl, int zop, unsigned long long *mask) {
+  const int k = zop_kind(zop);
+  if (!pl || k < 0 || !mask) return fail(PB_ERR_ARG, "bad argument");
+  const SweepPlan &sp = pl->sw[k][2];
+  *mask = (sp.null_op || !sp.split || !sp.st.implicit) ? 0ull : sp.rank_mask;
   return PB_OK;
 }
 
 // ---- host-array wrappers -------------------------------------------------------------------------
+// Host arrays in / out.  PCIe dominates (2 x 8 bytes per point against 16-48 bytes of HBM traffic
+// at ~100x the bandwidth), so the field moves in slabs and the three engines overlap:
+//   one-direction operators: slab s is copied in while slab s-1 is swept and slab s-2 copied out
+//     (slabs of z-planes for x / y sweeps, slabs of y-rows for z sweeps);
+//   filter / gfilter (x -> y -> z): x and y sweeps run per z-slab as the slabs arrive, the z sweep
+//     runs per y-slab and each finished slab leaves while the next is swept.
+// Anything else (composites, curvilinear weighting, null or split directions) takes the plain path.
+static int host_pipeline_ready(pb_plan *pl, size_t nev) {
+  for (int k = 0; k < 3; ++k)
+    if (!pl->hs[k]) PB_CUDA(cudaStreamCreateWithFlags(&pl->hs[k], cudaStreamNonBlocking));
+  while (pl->hev.size() < nev) {
+    cudaEvent_t e;
+    PB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    pl->hev.push_back(e);
+  }
+  return PB_OK;
+}
+
+// copies `cnt` slices (z-planes when along_z, else y-rows of every plane) between host and device
+static int copy_slab(pb_plan *pl, void *dst, const void *src, bool along_z, int first, int cnt, cudaMemcpyKind kind, cudaStream_t st) {
+  const size_t ax = pl->a[0], ay = pl->a[1], az = pl->a[2];
+  if (along_z) {
+    const size_t off = (size_t)first * ax * ay * sizeof(double);
+    PB_CUDA(cudaMemcpyAsync((char *)dst + off, (const char *)src + off, (size_t)cnt * ax * ay * sizeof(double), kind, st));
+  } else {
+    const size_t off = (size_t)first * ax * sizeof(double), pitch = ax * ay * sizeof(double);
+    PB_CUDA(cudaMemcpy2DAsync((char *)dst + off, pitch, (const char *)src + off, pitch, (size_t)cnt * ax * sizeof(double), az, kind, st));
+  }
+  return PB_OK;
+}
+
+static int host_apply_pipelined(pb_plan *pl, SweepPlan *sx, SweepPlan *sy, SweepPlan *sz, const double *h_val, double *h_out,
+                                bool *done) {
+  *done = false;
+  SweepPlan *all[3] = {sx, sy, sz};
+  int nsw = 0;
+  for (SweepPlan *s : all)
+    if (s) { if (!s->built || s->null_op || s->split) return PB_OK; ++nsw; }
+  const int az = pl->a[2], ay = pl->a[1];
+  const int NS = 8;
+  if (nsw == 0 || az < 2 * NS || ay < 2 * NS) return PB_OK;
+  int rc;
+  double *d0, *d1, *d2;
+  if ((rc = get_scratch(pl, 4, &d0)) || (rc = get_scratch(pl, 5, &d1)) || (rc = get_scratch(pl, 6, &d2))) return rc;
+  if ((rc = host_pipeline_ready(pl, 2 * NS + 2)) != PB_OK) return rc;
+  cudaStream_t sIn = pl->hs[0], sC = pl->hs[1], sOut = pl->hs[2];
+  auto slab = [&](int n, int s, int *first, int *cnt) { *first = (int)((long)n * s / NS); *cnt = (int)((long)n * (s + 1) / NS) - *first; };
+  PB_CUDA(cudaStreamSynchronize(0));  // earlier work of the caller on the default stream
+  const bool zin = sx || sy;           // the input arrives in z-slabs unless only z is swept
+  for (int s = 0; s < NS; ++s) {
+    int f, c;
+    slab(zin ? az : ay, s, &f, &c);
+    if ((rc = copy_slab(pl, d0, h_val, zin, f, c, cudaMemcpyHostToDevice, sIn)) != PB_OK) return rc;
+    PB_CUDA(cudaEventRecord(pl->hev[s], sIn));
+    PB_CUDA(cudaStreamWaitEvent(sC, pl->hev[s], 0));
+    const double *cur = d0;
+    double *nxt = d1;
+    if (sx) { if ((rc = apply_dir_slab(pl, *sx, cur, nxt, f, c, sC)) != PB_OK) return rc; cur = nxt; nxt = (nxt == d1) ? d2 : d1; }
+    if (sy) { if ((rc = apply_dir_slab(pl, *sy, cur, nxt, f, c, sC)) != PB_OK) return rc; cur = nxt; nxt = (nxt == d1) ? d2 : d1; }
+    if (sz && !zin) { if ((rc = apply_dir_slab(pl, *sz, cur, nxt, f, c, sC)) != PB_OK) return rc; cur = nxt; }
+    if (!(sz && zin)) {  // this slab is final: send it back
+      PB_CUDA(cudaEventRecord(pl->hev[NS + s], sC));
+      PB_CUDA(cudaStreamWaitEvent(sOut, pl->hev[NS + s], 0));
+      if ((rc = copy_slab(pl, h_out, cur, zin, f, c, cudaMemcpyDeviceToHost, sOut)) != PB_OK) return rc;
+    }
+  }
+  if (sz && zin) {  // the z sweep needs whole lines: it runs per y-slab once every z-slab has passed x / y
+    const double *cur = (sx && sy) ? d2 : d1;
+    double *fin = (cur == d1) ? d2 : d1;
+    for (int s = 0; s < NS; ++s) {
+      int f, c;
+      slab(ay, s, &f, &c);
+      if ((rc = apply_dir_slab(pl, *sz, cur, fin, f, c, sC)) != PB_OK) return rc;
+      PB_CUDA(cudaEventRecord(pl->hev[NS + s], sC));
+      PB_CUDA(cudaStreamWaitEvent(sOut, pl->hev[NS + s], 0));
+      if ((rc = copy_slab(pl, h_out, fin, false, f, c, cudaMemcpyDeviceToHost, sOut)) != PB_OK) return rc;
+    }
+  }
+  PB_CUDA(cudaStreamSynchronize(sOut));
+  PB_CUDA(cudaStreamSynchronize(sC));
+  *done = true;
+  return PB_OK;
+}
+
 int pb_host_apply(pb_plan *pl, int opcode, const double *h_val, double *h_out) {
   if (!pl || !h_val || !h_out) return fail(PB_ERR_ARG, "NULL argument");
-  double *din, *dout;
   int rc;
+  {
+    SweepPlan *sx = nullptr, *sy = nullptr, *sz = nullptr;
+    int kind = -1, dir = -1;
+    if (opcode >= PB_OP_DDX && opcode <= PB_OP_DDZ) { kind = K_D1; dir = opcode - PB_OP_DDX; }
+    else if (opcode >= PB_OP_DD8X && opcode <= PB_OP_DD8Z) { kind = K_D8; dir = opcode - PB_OP_DD8X; }
+    else if (opcode >= PB_OP_D2X && opcode <= PB_OP_D2Z) { kind = K_D2; dir = opcode - PB_OP_D2X; }
+    else if (opcode >= PB_OP_GFILTERX && opcode <= PB_OP_GFILTERZ) { kind = K_GF; dir = opcode - PB_OP_GFILTERX; }
+    else if (opcode >= PB_OP_SFILTERX && opcode <= PB_OP_SFILTERZ) { kind = K_SF; dir = opcode - PB_OP_SFILTERX; }
+    else if (opcode == PB_OP_GFILTER) kind = K_GF;
+    else if (opcode == PB_OP_SFILTER && pl->coordsys == 0) kind = K_SF;
+    if (kind >= 0) {
+      if (dir == 0 || dir < 0) sx = &pl->sw[kind][0];
+      if (dir == 1 || dir < 0) sy = &pl->sw[kind][1];
+      if (dir == 2 || dir < 0) sz = &pl->sw[kind][2];
+      bool done = false;
+      if ((rc = host_apply_pipelined(pl, sx, sy, sz, h_val, h_out, &done)) != PB_OK) return rc;
+      if (done) return PB_OK;
+    }
+  }
+  double *din, *dout;
   if ((rc = get_scratch(pl, 4, &din)) || (rc = get_scratch(pl, 5, &dout))) return rc;
   const size_t bytes = sizeof(double) * pl->npts;
   PB_CUDA(cudaMemcpyAsync(din, h_val, bytes, cudaMemcpyHostToDevice, 0));

@@ -115,42 +115,52 @@ cudaError_t launch_pack_planes(const double *v, long plane, int m, int h, double
 }
 
 // reduced interface solve (dense pre-inverted rows) + rank-level spike correction
-// (compact_d1.f90:892-928, compact_r4.f90:820-...): one thread per line of the xy plane and a slab
-// of rows (blockIdx.y)
-__global__ void z_finish_kernel(const double *__restrict__ z, const double *__restrict__ v, double *__restrict__ out,
-                                long plane, int m, const double4 *__restrict__ RC, const double *__restrict__ GR,
-                                int np, const double *__restrict__ iface_all, double scale, int add_v, int rows_per_block) {
+// (compact_d1.f90:892-928, compact_r4.f90:820-...).  The local pass has already written
+// scale * x_local (+ v); this adds  -scale * RC[row] . g  on the rows near the two slab faces where
+// the spike columns are not negligible (zone_lo rows from the bottom, zone_hi from the top).
+// One thread per line of the xy plane and a block of zone rows (blockIdx.y).
+__global__ void z_finish_kernel(double *__restrict__ out, long plane, int m, const double4 *__restrict__ RC,
+                                const double *__restrict__ GR, int np, unsigned long long rank_mask, int zone_lo,
+                                int zone_hi, const double *__restrict__ iface_all, double scale, int rows_per_block) {
   const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (li >= plane) return;
   double g[4] = {0.0, 0.0, 0.0, 0.0};
   const int n4 = 4 * np;
-  for (int r = 0; r < np; ++r)
+  for (int r = 0; r < np; ++r) {
+    if (!((rank_mask >> r) & 1ull)) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const double d = __ldg(iface_all + ((long)r * 4 + j) * plane + li);
 #pragma unroll
       for (int c = 0; c < 4; ++c) g[c] += __ldg(GR + c * n4 + 4 * r + j) * d;
     }
-  const int r0 = blockIdx.y * rows_per_block;
-  const int r1 = min(m, r0 + rows_per_block);
-  for (int r = r0; r < r1; ++r) {
+  }
+  // zone rows are numbered 0 .. nz-1: first the bottom zone, then the top zone
+  const int lo = min(zone_lo, m), hi = min(zone_hi, m - lo);
+  const int nz = lo + hi;
+  const int q0 = blockIdx.y * rows_per_block;
+  const int q1 = min(nz, q0 + rows_per_block);
+  for (int q = q0; q < q1; ++q) {
+    const int r = q < lo ? q : m - hi + (q - lo);
     const double4 c = ldg4(RC + r);
     const long idx = (long)r * plane + li;
-    double x = z[idx];
-    x = fma(-c.x, g[0], x);
-    x = fma(-c.y, g[1], x);
-    x = fma(-c.z, g[2], x);
-    x = fma(-c.w, g[3], x);
-    double val = x * scale;
-    if (add_v) val += __ldg(v + idx);
-    out[idx] = val;
+    double corr = c.x * g[0];
+    corr = fma(c.y, g[1], corr);
+    corr = fma(c.z, g[2], corr);
+    corr = fma(c.w, g[3], corr);
+    out[idx] = fma(-scale, corr, out[idx]);
   }
 }
-cudaError_t launch_z_finish(const double *z, const double *v, double *out, long plane, int m, const double4 *RC,
-                            const double *GR, int np, const double *iface_all, double scale, int add_v, cudaStream_t st) {
+cudaError_t launch_z_finish(double *out, long plane, int m, const double4 *RC, const double *GR, int np,
+                            unsigned long long rank_mask, int zone_lo, int zone_hi, const double *iface_all, double scale,
+                            cudaStream_t st) {
   const int rows_per_block = 32;
-  dim3 grid((unsigned)((plane + 127) / 128), (unsigned)((m + rows_per_block - 1) / rows_per_block));
-  PB_LAUNCH(z_finish_kernel, grid, dim3(128), 0, st, z, v, out, plane, m, RC, GR, np, iface_all, scale, add_v, rows_per_block);
+  const int lo = zone_lo < m ? zone_lo : m, hi = zone_hi < m - lo ? zone_hi : m - lo;
+  const int nz = lo + hi;
+  if (nz <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((plane + 127) / 128), (unsigned)((nz + rows_per_block - 1) / rows_per_block));
+  PB_LAUNCH(z_finish_kernel, grid, dim3(128), 0, st, out, plane, m, RC, GR, np, rank_mask, zone_lo, zone_hi, iface_all, scale,
+            rows_per_block);
   ++g_launches;
   return cudaGetLastError();
 }

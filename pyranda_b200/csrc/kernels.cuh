@@ -68,9 +68,9 @@ cudaError_t launch_sweep_x(int fam, int lines, const SweepDev &a, const double *
 // z-slab helpers
 cudaError_t launch_pack_planes(const double *v, long plane, int m, int h, double *send_lo,
                                double *send_hi, cudaStream_t st);
-cudaError_t launch_z_finish(const double *z, const double *v, double *out, long plane, int m,
-                            const double4 *RC, const double *GR, int np, const double *iface_all,
-                            double scale, int add_v, cudaStream_t st);
+cudaError_t launch_z_finish(double *out, long plane, int m, const double4 *RC, const double *GR, int np,
+                            unsigned long long rank_mask, int zone_lo, int zone_hi, const double *iface_all,
+                            double scale, cudaStream_t st);
 
 // pointwise / reductions
 cudaError_t launch_rk4_stage(long n, double dt, double A, double B, const double *F, double *PHI,

@@ -507,6 +507,91 @@ explicit_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
   });
 }
 
+// ---- x sweep (explicit operators) ----------------------------------------------------------------
+// Unit-stride lines need no tile: a thread produces two neighbouring points from five aligned
+// 16-byte loads (v[x-4 .. x+5]; the overlap between threads is served by L1), so loads and stores are
+// 128-bit and fully coalesced.  Line ends: periodic wrap or the one-sided closure rows.
+constexpr int kExplicitXLines = 8;  // 32 KB in flight per block at m = 512
+
+template <int FAM, bool PLAIN, bool ADDV>
+__global__ void __launch_bounds__(256, 3)
+explicit_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v, double *__restrict__ out,
+                  const __grid_constant__ EpiArgs epi) {
+  constexpr int H = FT<FAM>::H, NLB = kExplicitXLines;  // lines per block iteration
+  PB_SHARED(S);  // 2 x [NLB][m + 8]: column c holds x = c - 4; the two halves alternate (prefetch)
+  const int m = a.m, half = m >> 1, LP = m + 8;
+  const double scale = a.scale;
+  auto stage = [&](long L0, double *buf) {  // asynchronous 16-byte copies: the whole group of lines in flight at once
+#pragma unroll
+    for (int ll = 0; ll < NLB; ++ll) {
+      long L = L0 + ll;
+      if (L >= a.nfast) L = a.nfast - 1;
+      const double *lp = v + L * (long)m;
+      for (int j = threadIdx.x; j < half + 4; j += blockDim.x) {
+        int xs = 2 * j - 4;  // source x of this piece; the first / last two pieces are the wrap halo
+        if (xs < 0) xs = a.wrap ? xs + m : 0;
+        if (xs >= m) xs = a.wrap ? xs - m : m - 2;
+        cp_async16(buf + ll * LP + 2 * j, lp + xs);
+      }
+    }
+    cp_async_commit();
+  };
+  const long step = (long)gridDim.x * NLB;
+  long L0 = (long)blockIdx.x * NLB;
+  int b = 0;
+  if (L0 < a.nfast) stage(L0, S);
+  for (; L0 < a.nfast; L0 += step, b ^= 1) {
+    const double *cur = S + (size_t)b * NLB * LP;
+    if (L0 + step < a.nfast) {
+      stage(L0 + step, S + (size_t)(b ^ 1) * NLB * LP);
+      cp_async_wait_but_one();
+    } else {
+      cp_async_wait_all();
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int q = threadIdx.x; q < NLB * half; q += blockDim.x) {
+      const int ll = q / half, j = q - ll * half, x = 2 * j;
+      const long L = L0 + ll;
+      const double *sl = cur + ll * LP;
+      double w[10];  // v[x-4 .. x+5]
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        const double2 p2 = *reinterpret_cast<const double2 *>(sl + x + 2 * t);
+        w[2 * t] = p2.x;
+        w[2 * t + 1] = p2.y;
+      }
+      double r0 = rhs_center<FAM>(w + (4 - H), a.ari), r1 = rhs_center<FAM>(w + (5 - H), a.ari);
+      if (j < 2 || j >= half - 2) {
+        if (a.phys_lo && x < 4) {  // rows 0..3: closure weights on v[0..8]
+          double r4[4];
+          rhs_lo4<FAM>(sl + 4, a.arb_lo, r4);
+          r0 = x == 0 ? r4[0] : r4[2];
+          r1 = x == 0 ? r4[1] : r4[3];
+        }
+        if (a.phys_hi && x >= m - 4) {  // rows m-4..m-1: closure weights on v[m-8..m-1]
+          double r4[4];
+          rhs_hi4<FAM>(sl + 4 + m - 8, a.arb_hi, r4);
+          r0 = x == m - 4 ? r4[0] : r4[2];
+          r1 = x == m - 4 ? r4[1] : r4[3];
+        }
+      }
+      double2 val = make_double2(r0 * scale, r1 * scale);
+      if (ADDV) { val.x += w[4]; val.y += w[5]; }
+      if (L < a.nfast) {
+        const long idx = L * (long)m + x;
+        if (PLAIN) {
+          *reinterpret_cast<double2 *>(out + idx) = val;
+        } else {
+          epi_store(out, idx, val.x, epi);
+          epi_store(out, idx + 1, val.y, epi);
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with `cur` before it is staged again
+  }
+}
+
 // ---- x sweep -------------------------------------------------------------------------------------
 // Same algorithm on a tile of NLX unit-stride lines staged through shared memory (row pitch odd):
 // coalesced tile load, in-place recurrences, coalesced write-back.
@@ -1310,6 +1395,7 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
     __syncthreads();  // the tile buffer is free (unless the add-back still reads it), EN is visible
     if (!(ADDV && LATE) && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
+    double xloc[4] = {0.0, 0.0, 0.0, 0.0};  // late add-back: local solution of the four interface rows
     {  // ---- B: add the carried forward state, backward recurrence (zero incoming state) ----
       double2 st = make_double2(0.0, 0.0);
       {
@@ -1336,6 +1422,10 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           x = fma(-u2, x2, x);
           x *= ip;
           rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
+          if (ADDV && LATE) {
+            if (r < 2) xloc[r] = x;
+            if (r >= CT - 2) xloc[r - (CT - 4)] = x;
+          }
           x2 = x1;
           x1 = x;
         });
@@ -1353,6 +1443,10 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           x = fma(-c.z, x2, x);
           x *= c.x;
           rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
+          if (ADDV && LATE) {
+            if (r < 2) xloc[r] = x;
+            if (r >= CT - 2) xloc[r - (CT - 4)] = x;
+          }
           x2 = x1;
           x1 = x;
         });
@@ -1394,6 +1488,10 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         if (ADDV && LATE) {  // xl already holds scale * x_local + v
           val = fma(gx * scale, tb.x, xl);
           val = fma(gy * scale, tb.y, val);
+          if (r < 2 || r >= CT - 2) {
+            const double xq = xloc[r < 2 ? r : r - (CT - 4)];
+            x = fma(gy, tb.y, fma(gx, tb.x, xq));
+          }
         }
         if (ADDV && !LATE) {
           val += vr[r & 15];
@@ -1855,6 +1953,22 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
 template <int FAM, bool ADDV>
 cudaError_t launch_x_f(int lines, const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
   const bool plain = epi.mode == EPI_STORE;
+  if (!a.implicit && a.m % 2 == 0 && a.m >= 16 && a.m <= 1024 && !((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+    const long nblk = (a.nfast + kExplicitXLines - 1) / kExplicitXLines, cap = 3L * sm_count();
+    const dim3 grid((unsigned)(nblk < cap ? nblk : cap));
+    const size_t smem = 2 * kExplicitXLines * (size_t)(a.m + 8) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t err = cudaFuncSetAttribute(explicit_x_kernel<FAM, true, ADDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err == cudaSuccess) err = cudaFuncSetAttribute(explicit_x_kernel<FAM, false, ADDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err != cudaSuccess) return err;
+      configured = smem;
+    }
+    if (plain) { auto kfn = explicit_x_kernel<FAM, true, ADDV>; PB_LAUNCH(kfn, grid, dim3(256), smem, st, a, v, out, epi); }
+    else { auto kfn = explicit_x_kernel<FAM, false, ADDV>; PB_LAUNCH(kfn, grid, dim3(256), smem, st, a, v, out, epi); }
+    ++g_launches;
+    return cudaGetLastError();
+  }
 #define PB_X(NLV) \
   return plain ? launch_x_t<FAM, NLV, true, ADDV>(a, v, out, epi, st) : launch_x_t<FAM, NLV, false, ADDV>(a, v, out, epi, st)
   if (lines == 8) { PB_X(8); }

@@ -63,6 +63,7 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // Encodes {d0, d1, d2} doubles with byte strides {8, s1, s2} and a box {b0, b1, b2}.
 // Returns false when the driver entry point is missing or the geometry is not expressible
@@ -107,6 +108,7 @@ struct TileMap {
 inline void cp_async16(void *dst, const void *src) { std::memcpy(dst, src, 16); }
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
+inline void cp_async_wait_but_one() {}
 inline void mbar_init(uint64_t *, uint32_t) {}
 inline void mbar_expect_tx(uint64_t *, uint32_t) {}
 inline void mbar_wait(uint64_t *, uint32_t) {}

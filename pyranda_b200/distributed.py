@@ -11,6 +11,8 @@ scale / add-back are one kernel (pb_z_finish).
 Works with NCCL on GPUs and, for host-logic tests, with gloo on CPU tensors when the plan is bound
 to the emulated library (tests/emul).
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -21,6 +23,50 @@ from .plan import ParcopPlan
 # z operator behind each distributed call and its halo width (nor of the stencil)
 _ZOPS = {"ddz": ("ddz", 3), "dd8z": ("dd8z", 4), "d2z": ("d2z", 3), "sfilterz": ("sfilterz", 4), "gfilterz": ("gfilterz", 4)}
 _IMPLICIT = {"ddz": True, "dd8z": True, "d2z": True, "sfilterz": True, "gfilterz": False}
+
+
+class _PeerBuffers:
+    """Halo planes and interface values written straight into the neighbours' memory over NVLink.
+
+    One symmetric allocation per engine (torch.distributed._symmetric_memory: CUDA IPC mapping of
+    every rank's buffer plus a signal pad), holding two sets of {lower halo, upper halo, gathered
+    interface values}.  An exchange is: copy my planes into the peer's buffer, raise the peer's
+    signal, wait for mine -- all enqueued on the compute stream, no host synchronisation and no
+    NCCL kernel.  The sets alternate per operator, so a rank never overwrites planes its neighbour
+    may still be reading (the neighbour's next signal is ordered after that read)."""
+
+    TIMEOUT_MS = 20000
+
+    def __init__(self, group, rank, world, plane, dev):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.n = rank, world, 4 * plane
+        self.set_len = (2 + world) * self.n
+        self.buf = symm.empty(2 * self.set_len, dtype=torch.float64, device=dev)
+        self.buf.zero_()
+        self.h = symm.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+        self.k = 0
+        self._views = {}
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def view(self, peer, what, slot=0):
+        key = (self.k % 2, peer, what, slot)
+        t = self._views.get(key)
+        if t is None:
+            off = key[0] * self.set_len + {"lo": 0, "hi": self.n, "iface": 2 * self.n}[what] + slot * self.n
+            t = self.buf[off:off + self.n] if peer == self.rank else self.h.get_buffer(peer, (self.n,), torch.float64, off)
+            self._views[key] = t
+        return t
+
+    def iface_all(self):
+        off = (self.k % 2) * self.set_len + 2 * self.n
+        return self.buf[off:off + self.world * self.n]
+
+    def sync(self, peers, channel):
+        for p in peers:
+            self.h.put_signal(p, channel, self.TIMEOUT_MS)
+        for p in peers:
+            self.h.wait_signal(p, channel, self.TIMEOUT_MS)
 
 
 class DistributedParcop:
@@ -39,11 +85,32 @@ class DistributedParcop:
         self.dev = torch.device(tensor_device)
         mk = lambda n: torch.zeros(n, dtype=torch.float64, device=self.dev)
         self.recv_lo, self.recv_hi = mk(4 * self.plane), mk(4 * self.plane)
-        self.iface_local, self.iface_all = mk(4 * self.plane), mk(self.world * 4 * self.plane)
+        self.iface_all = mk(self.world * 4 * self.plane)
+        # this rank's slot of the gathered buffer: the local pass writes its interface values there
+        self.iface_local = self.iface_all[self.rank * 4 * self.plane:(self.rank + 1) * 4 * self.plane]
+        self._xmask = {}
+        self._peers = sorted({r for r in (self.lo_rank(), self.hi_rank()) if r is not None and r != self.rank})
+        self._pb = None
+        if self.dev.type == "cuda" and self.world > 1 and os.environ.get("PB_NO_PEER_MEMORY", "0") != "1":
+            try:
+                self._pb = _PeerBuffers(group, self.rank, self.world, self.plane, self.dev)
+            except Exception as exc:  # no IPC / symmetric-memory support: NCCL send/recv instead
+                import warnings
+                warnings.warn("peer-memory exchange unavailable (%s); using NCCL send/recv" % exc)
+        ok = torch.tensor([1 if self._pb is not None else 0], dtype=torch.int32, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # all ranks or none
+        if not ok.item():
+            self._pb = None
         self._tmp = None
         # MPI_CART_SHIFT (comm.f90:186)
-        self.lo = self.rank - 1 if self.rank > 0 else (self.world - 1 if self.periodic_z else None)
-        self.hi = self.rank + 1 if self.rank < self.world - 1 else (0 if self.periodic_z else None)
+        self.lo, self.hi = self.lo_rank(), self.hi_rank()
+
+    def lo_rank(self):
+        return self.rank - 1 if self.rank > 0 else (self.world - 1 if self.periodic_z else None)
+
+    def hi_rank(self):
+        return self.rank + 1 if self.rank < self.world - 1 else (0 if self.periodic_z else None)
 
     # ---------------------------------------------------------------- helpers
     def empty(self):
@@ -67,6 +134,13 @@ class DistributedParcop:
         neighbour's upper halo.  Sent straight from the field (no pack)."""
         pl = self._planes(f)
         n = h * self.plane
+        if self._pb is not None:
+            if self.hi is not None:
+                self._pb.view(self.hi, "lo")[:n].copy_(pl[pl.shape[0] - h:].reshape(-1))
+            if self.lo is not None:
+                self._pb.view(self.lo, "hi")[:n].copy_(pl[:h].reshape(-1))
+            self._pb.sync(self._peers, 0)
+            return
         ops = []
         if self.hi is not None:
             ops.append(dist.P2POp(dist.isend, pl[pl.shape[0] - h:].reshape(-1), self._global_rank(self.hi), self.group, tag=0))
@@ -86,15 +160,56 @@ class DistributedParcop:
         opname, h = _ZOPS[name]
         code = OP[opname]
         P, L = self.plan, self.plan.L
+        if self._pb is not None:  # this operator's set of peer-visible buffers
+            self._pb.k += 1
+            recv_lo, recv_hi = self._pb.view(self.rank, "lo"), self._pb.view(self.rank, "hi")
+            iface_all = self._pb.iface_all()
+            iface_local = self._pb.view(self.rank, "iface", self.rank)
+        else:
+            recv_lo, recv_hi, iface_all, iface_local = self.recv_lo, self.recv_hi, self.iface_all, self.iface_local
         if self.world > 1:
             self._halo_exchange(f, h)
         st = self._stream()
-        check(L, L.pb_z_local(P._h, code, f.data_ptr(), self.recv_lo.data_ptr(), self.recv_hi.data_ptr(), out.data_ptr(),
-                              self.iface_local.data_ptr(), st))
+        check(L, L.pb_z_local(P._h, code, f.data_ptr(), recv_lo.data_ptr(), recv_hi.data_ptr(), out.data_ptr(),
+                              iface_local.data_ptr(), st))
         if self.world > 1 and _IMPLICIT[name]:
-            dist.all_gather_into_tensor(self.iface_all, self.iface_local, group=self.group)  # compact_d1.f90:890
-            check(L, L.pb_z_finish(P._h, code, f.data_ptr(), self.iface_all.data_ptr(), out.data_ptr(), st))
+            self._iface_exchange(code, iface_all, iface_local)
+            check(L, L.pb_z_finish(P._h, code, f.data_ptr(), iface_all.data_ptr(), out.data_ptr(), st))
         return out
+
+    def _iface_exchange(self, code, iface_all, iface_local):
+        """compact_d1.f90:890 gathers every rank's interface values; the reduced system's inverse
+        decays like rho^(az * rank distance), so normally only the two neighbours' values can change
+        the result and a pair of sends replaces the all-gather (pb_z_exchange_ranks decides)."""
+        if code not in self._xmask:
+            import ctypes
+            m = ctypes.c_ulonglong()
+            check(self.plan.L, self.plan.L.pb_z_exchange_ranks(self.plan._h, code, ctypes.byref(m)))
+            need = {r for r in range(self.world) if (m.value >> r) & 1} - {self.rank}
+            nbrs = {r for r in (self.lo, self.hi) if r is not None}
+            # the decision must be the same on every rank (a collective or none at all)
+            flag = torch.tensor([0 if need <= nbrs else 1], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            self._xmask[code] = "gather" if flag.item() else "neighbours"
+        if self._xmask[code] == "gather":
+            dist.all_gather_into_tensor(iface_all, iface_local.clone(), group=self.group)
+            if self._pb is not None:
+                self._pb.sync(self._peers, 1)  # keeps the per-operator pairing of the buffer sets
+            return
+        n = 4 * self.plane
+        if self._pb is not None:
+            for peer in self._peers:
+                self._pb.view(peer, "iface", self.rank).copy_(iface_local)
+            self._pb.sync(self._peers, 1)
+            return
+        ops = []
+        for peer in self._peers:
+            g = self._global_rank(peer)
+            ops.append(dist.P2POp(dist.isend, iface_local, g, self.group))
+            ops.append(dist.P2POp(dist.irecv, iface_all[peer * n:(peer + 1) * n], g, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
 
     def _local_into(self, opname, f, out):
         check(self.plan.L, self.plan.L.pb_apply(self.plan._h, OP[opname], f.data_ptr(), out.data_ptr(), self._stream()))

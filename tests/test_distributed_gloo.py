@@ -45,6 +45,23 @@ for periodic in (True, False):
     assert rel_linf(got, o.divergence(f, 2 * f, f * f)[:, :, sl]) < 1e-12
     assert abs(eng.sum3D(loc) - f.sum()) < 1e-9 * np.abs(f).sum()
     assert eng.max3D(loc) == f.max() and eng.min3D(loc) == f.min()
+# long slabs: the reduced system couples only neighbouring ranks and the all-gather is replaced by
+# a pair of sends; the correction touches only the rows near the slab faces
+from pyranda_b200._lib import OP
+n = (16, 16, 96 * world)
+for periodic in (True, False):
+    (x1, xn), (y1, yn), (z1, zn) = domain(n, periodic)
+    o = oracle.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3)
+    f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+    eng = DistributedParcop(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3, lib=L, tensor_device="cpu")
+    az = n[2] // world
+    sl = slice(rank * az, (rank + 1) * az)
+    loc = eng.empty(); loc.copy_(torch.from_numpy(f[:, :, sl].copy()))
+    for name, ref in (("ddz", o.ddz), ("d2z", o.d2z)):
+        err = rel_linf(eng.apply(name, loc).numpy(), ref(f)[:, :, sl])
+        worst = max(worst, err)
+        assert err < 1e-12, (name, periodic, rank, err)
+        assert eng._xmask[OP[name]] == "neighbours", eng._xmask
 print("rank", rank, "worst", worst)
 dist.destroy_process_group()
 """

@@ -44,6 +44,22 @@ for n in ((32, 48, 32 * world), (64, 64, 64 * world)):
         hin = np.asfortranarray(f[:, :, sl]); hout = np.empty_like(hin, order="F")
         eng.apply_host_into("ddz", hin, hout)
         assert rel_linf(hout, o.ddz(f)[:, :, sl]) < 1e-12
+# long slabs: neighbour-only interface exchange and the pipelined kernels with halo planes
+from pyranda_b200._lib import OP
+for n in ((32, 32, 128 * world), (48, 32, 256 * world)):
+    for periodic in (True, False):
+        (x1, xn), (y1, yn), (z1, zn) = domain(n, periodic)
+        o = oracle.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3)
+        f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+        eng = DistributedParcop(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3, device=local)
+        az = n[2] // world
+        sl = slice(rank * az, (rank + 1) * az)
+        loc = eng.empty(); loc.copy_(torch.from_numpy(f[:, :, sl].copy()))
+        for name, ref in (("ddz", o.ddz), ("d2z", o.d2z), ("dd8z", o.dd8z), ("sfilter", o.sfilter), ("gfilter", o.gfilter)):
+            err = rel_linf(eng.apply(name, loc).cpu().numpy(), ref(f)[:, :, sl])
+            worst = max(worst, err)
+            assert err < 1e-12, (name, n, periodic, rank, err)
+        assert eng._xmask[OP["ddz"]] == "neighbours", eng._xmask
 print("rank", rank, "worst", worst)
 dist.destroy_process_group()
 """
