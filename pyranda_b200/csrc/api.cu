@@ -104,6 +104,7 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
   SweepDev &dv = sp.dev;
   memset(&dv, 0, sizeof(dv));
   dv.m = m; dv.P = P; dv.C = m / P;
+  for (int q = 0; q < kMaxChunks; ++q) dv.perm[q] = (unsigned char)q;
   const int ax = pl->a[0], ay = pl->a[1], az = pl->a[2];
   if (dir == 0) { dv.nfast = ay * az; dv.nouter = 1; dv.rstride = 1; dv.ostride = 0; }
   else if (dir == 1) { dv.nfast = ax; dv.nouter = az; dv.rstride = ax; dv.ostride = (long)ax * ay; }
@@ -155,6 +156,13 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
       Mb[t] = make_double4(lt.Mb[t * 4], lt.Mb[t * 4 + 1], lt.Mb[t * 4 + 2], lt.Mb[t * 4 + 3]);
     }
     for (int q = 0; q < P; ++q) { dv.nf[q] = (unsigned char)lt.nF[q]; dv.nb[q] = (unsigned char)lt.nB[q]; }
+    {
+      int k = 0;
+      for (int q = 0; q < P; ++q)
+        if (!(dv.has_const && dv.ctype[q] == 0)) dv.perm[k++] = (unsigned char)q;
+      for (int q = 0; q < P; ++q)
+        if (dv.has_const && dv.ctype[q] == 0) dv.perm[k++] = (unsigned char)q;
+    }
     int rcv;
     if ((rcv = upload(sp, luf, &dv.luf)) != PB_OK) return rcv;
     if ((rcv = upload(sp, lub, &dv.lub)) != PB_OK) return rcv;

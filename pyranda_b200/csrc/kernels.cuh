@@ -40,6 +40,8 @@ struct SweepDev {
   const double4 *Mf;    // [P][P+1]     2x2 products giving the forward state entering a chunk
   const double4 *Mb;    // [P][P+1]     same for the backward state
   unsigned char nf[kMaxChunks], nb[kMaxChunks];  // terms kept per chunk
+  unsigned char perm[kMaxChunks];  // thread slot -> chunk: chunks that read coefficient tables come first, so the
+                                   // two chunks sharing a warp (16-line tiles) take the same code path
   int cparam;           // phi0 / psi0 below are valid (has_const and C <= kParamRows)
   double2 phi0[kParamRows], psi0[kParamRows];  // phi / psi of the constant chunk type: constant-bank operands
   // right-hand side ------------------------------------------------------------------------

@@ -145,6 +145,21 @@ __device__ __forceinline__ void epi_store(double *__restrict__ out, long idx, do
   }
 }
 
+// epilogue on a value whose previous output `old` was fetched ahead of time (pipelined kernels)
+__device__ __forceinline__ bool epi_needs_old(const EpiArgs &epi) { return epi.mode == EPI_ACC || epi.mode == EPI_RING_MAX; }
+__device__ __forceinline__ double epi_value(double val, double old, long idx, const EpiArgs &epi) {
+  switch (epi.mode) {
+    case EPI_STORE: return val;
+    case EPI_ACC: return old + val;
+    default: {
+      double sc = epi.s2;
+      if (epi.field) { const double f = __ldg(epi.field + idx); sc = f * f; }
+      const double r = fabs(val) * sc;
+      return epi.mode == EPI_RING_MAX ? fmax(r, old) : r;
+    }
+  }
+}
+
 template <bool PLAIN>
 __device__ __forceinline__ void put(double *__restrict__ out, long idx, double val, const EpiArgs &epi) {
   if (PLAIN) out[idx] = val;
@@ -915,7 +930,7 @@ sweep_yz_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict
   const int P = a.P;
   double2 *EN = reinterpret_cast<double2 *>(S);  // [P][NL] local end values of the forward pass
   double2 *ST = EN + P * NL;                      // [P][NL] local start values of the backward pass
-  const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
+  const int tid = threadIdx.x, l = tid % NL, slot = tid / NL, p = slot < a.P ? a.perm[slot] : slot;
   const int tiles_i = (a.nfast + NL - 1) / NL;
   const int ti = blockIdx.x % tiles_i, o = blockIdx.x / tiles_i;
   int i0 = ti * NL + l;
@@ -1089,7 +1104,7 @@ sweep_x_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
   }
   __syncthreads();
 
-  const int l = tid % NLX, p = tid / NLX;
+  const int l = tid % NLX, slot = tid / NLX, p = slot < a.P ? a.perm[slot] : slot;
   const bool active = p < P;
   const int s = p * CT;
   double *Sl = S + l * LD;  // this thread's line
@@ -1328,7 +1343,7 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   double2 *EN = reinterpret_cast<double2 *>(S + (size_t)(m + 2 * HP) * NL);  // [P][NL]
   double2 *ST = EN + P * NL;                                                // [P][NL]
   uint64_t *bar = reinterpret_cast<uint64_t *>(ST + P * NL);
-  const int tid = threadIdx.x, l = tid % NL, p = tid / NL;
+  const int tid = threadIdx.x, l = tid % NL, p = a.perm[tid / NL];
   const int tiles_i = (a.nfast + NL - 1) / NL;
   const long ntiles = (long)tiles_i * a.nouter;
   const long rs = a.rstride;
@@ -1461,6 +1476,14 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < 16; ++k) vr[k] = __ldg(pv + k * rs);
     }
+    // accumulating epilogues (div, laplacian, ring) read the previous output: same 16-row window
+    const double *pold = out + base + (long)s * rs;
+    const bool need_old = !PLAIN && epi_needs_old(epi);
+    double ow[16];
+    if (!PLAIN) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) ow[k] = need_old ? pold[k * rs] : 0.0;
+    }
     __syncthreads();
     if (ADDV && LATE && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
@@ -1501,7 +1524,11 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           if (valid) *po = val;
           po += rs;
         } else {
-          if (valid) epi_store(out, oidx, val, epi);
+          const double o = epi_value(val, ow[r & 15], oidx, epi);
+          if (r < CT - 16) {
+            if (need_old) ow[r & 15] = pold[(long)(r + 16) * rs];
+          }
+          if (valid) out[oidx] = o;
           oidx += rs;
         }
         return x;
@@ -1610,7 +1637,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict
   double *stage = tile + (size_t)NLX * LT;               // [NLX][LS]
   double2 *EN = reinterpret_cast<double2 *>(stage + (size_t)NLX * LS);  // [P][NLX]
   double2 *ST = EN + P * NLX;
-  const int tid = threadIdx.x, l = tid % NLX, p = tid / NLX;
+  const int tid = threadIdx.x, l = tid % NLX, p = a.perm[tid / NLX];
   const long nlines = a.nfast;
   const long ntiles = (nlines + NLX - 1) / NLX;
   const int s = p * CT;
@@ -1801,6 +1828,18 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict
             vadd[it] = __ldg(reinterpret_cast<const double2 *>(v + idx));
           }
         }
+        double2 oadd[PIECES / kBlockThreads];
+        const bool need_old = !PLAIN && epi_needs_old(epi);
+        if (!PLAIN) {  // accumulating epilogues: fetch the previous output of the whole group first
+#pragma unroll
+          for (int it = 0; it < PIECES / kBlockThreads; ++it) {
+            const int q = it * kBlockThreads + tid;
+            const int line = q / per_line, rr = q - line * per_line;
+            const long L = L0 + line;
+            const long idx = (L < nlines ? L : nlines - 1) * (long)m + (rr >> 3) * CT + g * G + 2 * (rr & 7);
+            oadd[it] = need_old ? *reinterpret_cast<const double2 *>(out + idx) : make_double2(0.0, 0.0);
+          }
+        }
 #pragma unroll
         for (int it = 0; it < PIECES / kBlockThreads; ++it) {
           const int q = it * kBlockThreads + tid;
@@ -1814,8 +1853,8 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict
             if (PLAIN) {
               *reinterpret_cast<double2 *>(out + idx) = val;
             } else {
-              epi_store(out, idx, val.x, epi);
-              epi_store(out, idx + 1, val.y, epi);
+              *reinterpret_cast<double2 *>(out + idx) =
+                  make_double2(epi_value(val.x, oadd[it].x, idx, epi), epi_value(val.y, oadd[it].y, idx + 1, epi));
             }
           }
         }
@@ -1863,7 +1902,7 @@ static cudaError_t launch_yz_t(const SweepDev &a, const double *v, double *out, 
   }
   if constexpr (NL == 16 || NL == 32) {
     if (g_pipe_kernels && a.C == 32) {
-      constexpr bool PL = PLAIN && NL == 16;
+      constexpr bool PL = PLAIN;
       const cudaError_t err = launch_yz_pipe<FAM, NL, PL, ADDV>(a, v, out, hlo, hhi, iface, epi, st);
       if (err != cudaErrorNotSupported) return err;
     }
@@ -1923,7 +1962,7 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
   threads = (threads + 31) / 32 * 32;
   if constexpr (NLX == 16 || NLX == 32) {
     if (g_pipe_kernels && a.implicit && a.C == 32) {
-      constexpr bool PL = PLAIN && NLX == 16;
+      constexpr bool PL = PLAIN;
       const cudaError_t err = launch_x_pipe<FAM, NLX, PL, ADDV>(a, v, out, epi, st);
       if (err != cudaErrorNotSupported) return err;
     }
