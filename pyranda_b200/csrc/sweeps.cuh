@@ -15,7 +15,7 @@
 #define PB_EW_GRID(n) dim3(1)
 #define PB_EW_BLOCK dim3(1)
 #else
-#define PB_SHARED(S) extern __shared__ __align__(128) double S[]
+#define PB_SHARED(S) extern __shared__ __align__(1024) double S[]
 #define PB_LAUNCH(kernel, grid, block, smem, st, ...) kernel<<<grid, block, smem, st>>>(__VA_ARGS__)
 #define PB_EW_GRID(n) dim3(ew_blocks(n))
 #define PB_EW_BLOCK dim3(256)
@@ -472,14 +472,14 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
       // z-slab: publish this rank's 4 interface values, unscaled (compact_d1.f90:858-878)
       const long plane = (long)a.nfast * a.nouter;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int lr = (p == 0) ? q : C - 2 + q;
+      for (int q = 0; q < 4; ++q) {  // q = 0, 1: first two rows (chunk 0); q = 2, 3: last two rows (chunk P-1)
+        if (q < 2 ? p != 0 : p != P - 1) continue;
+        const int lr = q < 2 ? q : C - 4 + q;
         const double2 g = __ldg(ps + lr);
         double x = sp[lr * NL];
         x = fma(g.x, tb.x, x);
         x = fma(g.y, tb.y, x);
-        if (p == 0) iface[(long)q * plane + base] = a.phys_lo ? 0.0 : x;
-        if (p == P - 1) iface[(long)(2 + q) * plane + base] = a.phys_hi ? 0.0 : x;
+        iface[(long)q * plane + base] = (q < 2 ? a.phys_lo : a.phys_hi) ? 0.0 : x;
       }
     }
   }
@@ -1618,76 +1618,86 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
 }
 
 
-// x sweep, pipelined.  Lines are unit stride, so the tile is staged with 16-byte asynchronous
-// copies (coalesced in global memory) into rows of pitch LT with LT/2 odd: a thread then reads its
-// chunk with conflict-free 128-bit shared loads at compile-time offsets.  The solution leaves
-// through a small transposing stage, 16 rows of every chunk at a time, as coalesced 128-bit stores.
-// Column c of a tile row holds x = c - 4 (periodic wrap values in columns 0..3 and m+4..m+7).
+// x sweep, pipelined.  Lines are unit stride, so a tile of NLX lines is described to the TMA unit as
+// boxes of 16 points x NLX lines (128-byte rows) with the hardware 128-byte swizzle: the 16-byte
+// piece c of row r lands at piece c ^ (r & 7), so the eight lanes of a quarter warp -- eight lines,
+// same x -- hit eight different bank groups and a thread reads its chunk with conflict-free 128-bit
+// shared loads without any padding.  Box slot b of the tile holds x = 16 (b - 1) .. 16 b - 1 (slot 0
+// and the last slot are the periodic wrap).  The solution leaves the same way: 16 rows of every
+// chunk at a time are written, swizzled, into a stage of P boxes and one thread hands them to the
+// TMA unit as stores; composite epilogues read the stage back and store with the old output.
 template <int FAM, int NLX, bool PLAIN, bool ADDV, bool LATE>
 __global__ void __launch_bounds__(kBlockThreads, 2)
-sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v, double *__restrict__ out,
+sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tin,
+                    const __grid_constant__ TileMap tout, const double *__restrict__ v, double *__restrict__ out,
                     const __grid_constant__ EpiArgs epi) {
   constexpr int CT = 32, H = FT<FAM>::H, G = 16;
-  constexpr int PC = kBlockThreads / NLX, M = PC * CT;              // chunks per line, line length
-  constexpr int LT = (((M + 8) / 2) & 1) ? M + 8 : M + 10;          // tile pitch, LT/2 odd
-  constexpr int LS = PC * G + 2;                                    // stage pitch, LS/2 odd
+  constexpr int PC = kBlockThreads / NLX, M = PC * CT;  // chunks per line, line length
+  constexpr int BOXB = NLX * 128;                       // bytes of one box
+  constexpr int NBOX = M / 16;
   PB_SHARED(S);
   constexpr int m = M, P = PC;
-  double *tile = S;                                      // [NLX][LT]
-  double *stage = tile + (size_t)NLX * LT;               // [NLX][LS]
-  double2 *EN = reinterpret_cast<double2 *>(stage + (size_t)NLX * LS);  // [P][NLX]
+  char *tile = reinterpret_cast<char *>(S);                                   // [NBOX + 2] boxes
+  char *stage = tile + (size_t)(NBOX + 2) * BOXB;                            // [P] boxes
+  double2 *EN = reinterpret_cast<double2 *>(stage + (size_t)P * BOXB);       // [P][NLX]
   double2 *ST = EN + P * NLX;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(ST + P * NLX);
   const int tid = threadIdx.x, l = tid % NLX, p = a.perm[tid / NLX];
   const long nlines = a.nfast;
   const long ntiles = (nlines + NLX - 1) / NLX;
-  const int s = p * CT;
   const int type = a.ctype[p];
   const bool cc = a.has_const && type == 0;
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
   const double scale = a.scale;
-  constexpr int half = M / 2;  // 16-byte pieces per line
+  const uint32_t tx_bytes = (uint32_t)((NBOX + (a.wrap ? 2 : 0)) * BOXB);
 
-  auto issue = [&](long t) {  // every thread copies its share of tile t
-    const long L0 = t * NLX;
-#pragma unroll 4
-    for (int q = tid; q < NLX * half; q += kBlockThreads) {
-      const int line = q / half, j = q % half;
-      long L = L0 + line;
-      if (L >= nlines) L = nlines - 1;
-      cp_async16(tile + (size_t)line * LT + 4 + 2 * j, v + L * (long)m + 2 * j);
+  auto issue = [&](long t) {  // one thread: the whole tile as boxes
+    const int L0 = (int)(t * NLX);
+    mbar_expect_tx(bar, tx_bytes);
+    for (int b = 0; b < NBOX; ++b) tma_load_3d(tile + (size_t)(b + 1) * BOXB, &tin, 16 * b, L0, 0, bar);
+    if (a.wrap) {
+      tma_load_3d(tile, &tin, m - 16, L0, 0, bar);
+      tma_load_3d(tile + (size_t)(NBOX + 1) * BOXB, &tin, 0, L0, 0, bar);
     }
-    if (a.wrap && tid < NLX * 4) {
-      const int line = tid >> 2, w = tid & 3;
-      long L = L0 + line;
-      if (L >= nlines) L = nlines - 1;
-      const int xs = (w < 2) ? m - 4 + 2 * w : 2 * (w - 2);   // source x
-      const int cd = (w < 2) ? 2 * w : m + 4 + 2 * (w - 2);   // destination column
-      cp_async16(tile + (size_t)line * LT + cd, v + L * (long)m + xs);
-    }
-    cp_async_commit();
+  };
+  // this thread's row inside a box and the swizzled offsets of the eight 16-byte pieces of that row
+  const int rowoff = l * 128, swz = (l & 7) << 4;
+  const char *tb = tile + (size_t)(2 * p) * BOXB + rowoff;  // slot 2p: x = 32 p - 16 ..
+  // pair j holds x = 32 p - 4 + 2 j, 32 p - 3 + 2 j  (columns 12 + 2 j of the window starting at slot 2p)
+  auto pair = [&](auto jc) -> double2 {
+    constexpr int col = 12 + 2 * decltype(jc)::value;
+    return *reinterpret_cast<const double2 *>(tb + (col >> 4) * BOXB + ((((col & 15) >> 1) << 4) ^ swz));
   };
 
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
   long t = blockIdx.x;
-  if (t < ntiles) issue(t);
-  const double2 *tw = reinterpret_cast<const double2 *>(tile + (size_t)l * LT + s);  // columns s .. s+39 of this line
+  if (tid == 0 && t < ntiles) issue(t);
+#ifdef PB_EMULATE
+  __syncthreads();
+#endif
+  uint32_t parity = 0;
 
   for (; t < ntiles; t += gridDim.x) {
     const long L0 = t * NLX;
     double rl[CT];
-    cp_async_wait_all();
+    mbar_wait(bar, parity);
+    parity ^= 1;
+#ifdef PB_EMULATE
     __syncthreads();
+#endif
 
-    {  // ---- A: rhs + forward recurrence; ring slot = column & 15 ----
+    {  // ---- A: rhs + forward recurrence; ring slot = (x - 32 p + 4) & 15 ----
       const double2 *luf = a.luf + (size_t)type * CT;
       const double l2c = a.cst[0], l1c = a.cst[1];
       double rm1 = 0.0, rm2 = 0.0;
       double ring[16];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double2 w2 = tw[j];
+      static_for<0, 8>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const double2 w2 = pair(jc);
         ring[2 * j] = w2.x;
         ring[2 * j + 1] = w2.y;
-      }
+      });
       double rlo[4] = {0.0, 0.0, 0.0, 0.0}, rhi[4] = {0.0, 0.0, 0.0, 0.0};
       if (lo_sp) {
         double vv[9];
@@ -1712,8 +1722,8 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict
         if (lr >= CT - 4) {
           if (hi_sp) rhs = rhi[lr - (CT - 4)];
         }
-        if ((lr & 1) && lr + 16 < CT + 8) {  // columns lr+15, lr+16 replace the two just retired
-          const double2 w2 = tw[(lr + 15) / 2];
+        if constexpr ((lr & 1) && lr + 16 < CT + 8) {  // window columns lr+15, lr+16 replace the two just retired
+          const double2 w2 = pair(std::integral_constant<int, (lr + 15) / 2>{});
           ring[(lr - 1) & 15] = w2.x;
           ring[lr & 15] = w2.y;
         }
@@ -1729,7 +1739,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict
       EN[p * NLX + l] = make_double2(rm1, rm2);
     }
     __syncthreads();  // tile consumed (unless the add-back still reads it), EN visible
-    if (!(ADDV && LATE) && t + gridDim.x < ntiles) issue(t + gridDim.x);
+    if (!(ADDV && LATE) && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
     {  // ---- B ----
       double2 st = make_double2(0.0, 0.0);
@@ -1746,19 +1756,29 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict
         }
       }
       double x1 = 0.0, x2 = 0.0;
+      double2 vv2 = make_double2(0.0, 0.0);  // late add-back: v[r - 1], v[r] of the tile (r odd)
+      auto rowB = [&](auto rc, double f0, double f1, double ip, double u1, double u2) {
+        constexpr int r = decltype(rc)::value;
+        double x = rl[r];
+        x = fma(f0, st.x, x);
+        x = fma(f1, st.y, x);
+        x = fma(-u1, x1, x);
+        x = fma(-u2, x2, x);
+        x *= ip;
+        if constexpr (ADDV && LATE) {
+          if constexpr (r & 1) vv2 = pair(std::integral_constant<int, (r + 3) / 2>{});  // x = 32 p + r - 1, 32 p + r
+          rl[r] = fma(x, scale, (r & 1) ? vv2.y : vv2.x);
+        } else {
+          rl[r] = x;
+        }
+        x2 = x1;
+        x1 = x;
+      };
       if (cc) {
         const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
         static_for<0, CT>([&](auto jc) {
           constexpr int r = CT - 1 - decltype(jc)::value;
-          double x = rl[r];
-          x = fma(a.phi0[r].x, st.x, x);
-          x = fma(a.phi0[r].y, st.y, x);
-          x = fma(-u1, x1, x);
-          x = fma(-u2, x2, x);
-          x *= ip;
-          rl[r] = (ADDV && LATE) ? fma(x, scale, reinterpret_cast<const double *>(tw)[4 + r]) : x;
-          x2 = x1;
-          x1 = x;
+          rowB(std::integral_constant<int, r>{}, a.phi0[r].x, a.phi0[r].y, ip, u1, u2);
         });
       } else {
         const double2 *ph = a.phi + (size_t)type * CT;
@@ -1767,24 +1787,17 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict
           constexpr int r = CT - 1 - decltype(jc)::value;
           const double2 f = __ldg(ph + r);
           const double4 c = ldg4(lub + r);
-          double x = rl[r];
-          x = fma(f.x, st.x, x);
-          x = fma(f.y, st.y, x);
-          x = fma(-c.y, x1, x);
-          x = fma(-c.z, x2, x);
-          x *= c.x;
-          rl[r] = (ADDV && LATE) ? fma(x, scale, reinterpret_cast<const double *>(tw)[4 + r]) : x;
-          x2 = x1;
-          x1 = x;
+          rowB(std::integral_constant<int, r>{}, f.x, f.y, c.x, c.y, c.z);
         });
       }
       ST[p * NLX + l] = make_double2(x1, x2);
     }
+    if (PLAIN && tid == 0) tma_store_wait_read();  // the stage of the previous tile has been read
     __syncthreads();
-    if (ADDV && LATE && t + gridDim.x < ntiles) issue(t + gridDim.x);
+    if (ADDV && LATE && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
     {  // ---- D: carried backward state, then 16 rows of every chunk at a time through the stage ----
-      double2 tb = make_double2(0.0, 0.0);
+      double2 tbk = make_double2(0.0, 0.0);
       {
         const int nb = a.nb[p];
         const double4 *Mp = a.Mb + (size_t)p * (P + 1);
@@ -1793,66 +1806,63 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict
           if (q >= P) q -= P;
           const double2 sv = ST[q * NLX + l];
           const double4 M = ldg4(Mp + j);
-          tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
-          tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
+          tbk.x = fma(M.y, sv.y, fma(M.x, sv.x, tbk.x));
+          tbk.y = fma(M.w, sv.y, fma(M.z, sv.x, tbk.y));
         }
       }
       const double2 *ps = a.psi + (size_t)type * CT;
-      double2 *sw = reinterpret_cast<double2 *>(stage + (size_t)l * LS + p * G);
-      constexpr int per_line = PC * (G / 2);  // 16-byte pieces of one line in a group
+      char *sb = stage + (size_t)p * BOXB + rowoff;
       static_for<0, CT / G>([&](auto gc) {
         constexpr int g = decltype(gc)::value;
-        if (g > 0) __syncthreads();  // the previous group has left the stage
+        if (g > 0) {  // the previous group has left the stage
+          if (PLAIN && tid == 0) tma_store_wait_read();
+          __syncthreads();
+        }
         static_for<0, G / 2>([&](auto kc) {
-          constexpr int r = g * G + 2 * decltype(kc)::value;
+          constexpr int kq = decltype(kc)::value, r = g * G + 2 * kq;
           double2 q0, q1;
           if (cc) { q0 = a.psi0[r]; q1 = a.psi0[r + 1]; }
           else { q0 = __ldg(ps + r); q1 = __ldg(ps + r + 1); }
           const double sc = (ADDV && LATE) ? scale : 1.0;  // late add-back: rl already holds scale * x + v
-          double xa = fma(q0.x * sc, tb.x, rl[r]);
-          xa = fma(q0.y * sc, tb.y, xa);
-          double xb = fma(q1.x * sc, tb.x, rl[r + 1]);
-          xb = fma(q1.y * sc, tb.y, xb);
-          sw[decltype(kc)::value] = (ADDV && LATE) ? make_double2(xa, xb) : make_double2(xa * scale, xb * scale);
+          double xa = fma(q0.x * sc, tbk.x, rl[r]);
+          xa = fma(q0.y * sc, tbk.y, xa);
+          double xb = fma(q1.x * sc, tbk.x, rl[r + 1]);
+          xb = fma(q1.y * sc, tbk.y, xb);
+          *reinterpret_cast<double2 *>(sb + ((kq << 4) ^ swz)) =
+              (ADDV && LATE) ? make_double2(xa, xb) : make_double2(xa * scale, xb * scale);
         });
-        __syncthreads();
-        constexpr int PIECES = NLX * PC * (G / 2);  // 16-byte pieces of a group
-        double2 vadd[PIECES / kBlockThreads];
-        if (ADDV && !LATE) {
-#pragma unroll
-          for (int it = 0; it < PIECES / kBlockThreads; ++it) {
-            const int q = it * kBlockThreads + tid;
-            const int line = q / per_line, rr = q - line * per_line;
-            const long L = L0 + line;
-            const long idx = (L < nlines ? L : nlines - 1) * (long)m + (rr >> 3) * CT + g * G + 2 * (rr & 7);
-            vadd[it] = __ldg(reinterpret_cast<const double2 *>(v + idx));
+        if (PLAIN) {
+          fence_async_smem();
+          __syncthreads();
+          if (tid == 0) {
+            for (int q = 0; q < P; ++q) tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+            tma_store_commit();
           }
-        }
-        double2 oadd[PIECES / kBlockThreads];
-        const bool need_old = !PLAIN && epi_needs_old(epi);
-        if (!PLAIN) {  // accumulating epilogues: fetch the previous output of the whole group first
+        } else {
+          __syncthreads();
+          constexpr int PIECES = NLX * PC * (G / 2);  // 16-byte pieces of a group
+          constexpr int per_line = PC * (G / 2);
+          const bool need_old = epi_needs_old(epi);
+          double2 vadd[PIECES / kBlockThreads], oadd[PIECES / kBlockThreads];
 #pragma unroll
-          for (int it = 0; it < PIECES / kBlockThreads; ++it) {
+          for (int it = 0; it < PIECES / kBlockThreads; ++it) {  // fetch add-back / previous output of the whole group first
             const int q = it * kBlockThreads + tid;
             const int line = q / per_line, rr = q - line * per_line;
             const long L = L0 + line;
             const long idx = (L < nlines ? L : nlines - 1) * (long)m + (rr >> 3) * CT + g * G + 2 * (rr & 7);
+            if (ADDV && !LATE) vadd[it] = __ldg(reinterpret_cast<const double2 *>(v + idx));
             oadd[it] = need_old ? *reinterpret_cast<const double2 *>(out + idx) : make_double2(0.0, 0.0);
           }
-        }
 #pragma unroll
-        for (int it = 0; it < PIECES / kBlockThreads; ++it) {
-          const int q = it * kBlockThreads + tid;
-          const int line = q / per_line, rr = q - line * per_line;
-          const long L = L0 + line;
-          const int chunk = rr >> 3, piece = rr & 7;
-          double2 val = *reinterpret_cast<const double2 *>(stage + (size_t)line * LS + chunk * G + 2 * piece);
-          if (ADDV && !LATE) { val.x += vadd[it].x; val.y += vadd[it].y; }
-          if (L < nlines) {
-            const long idx = L * (long)m + chunk * CT + g * G + 2 * piece;
-            if (PLAIN) {
-              *reinterpret_cast<double2 *>(out + idx) = val;
-            } else {
+          for (int it = 0; it < PIECES / kBlockThreads; ++it) {
+            const int q = it * kBlockThreads + tid;
+            const int line = q / per_line, rr = q - line * per_line;
+            const long L = L0 + line;
+            const int chunk = rr >> 3, piece = rr & 7;
+            double2 val = *reinterpret_cast<const double2 *>(stage + (size_t)chunk * BOXB + line * 128 + ((piece ^ (line & 7)) << 4));
+            if (ADDV && !LATE) { val.x += vadd[it].x; val.y += vadd[it].y; }
+            if (L < nlines) {
+              const long idx = L * (long)m + chunk * CT + g * G + 2 * piece;
               *reinterpret_cast<double2 *>(out + idx) =
                   make_double2(epi_value(val.x, oadd[it].x, idx, epi), epi_value(val.y, oadd[it].y, idx + 1, epi));
             }
@@ -1861,15 +1871,19 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const double *__restrict
       });
     }
   }
+  if (PLAIN && tid == 0) tma_store_wait_read();
 }
 
 template <int FAM, int NLX, bool PLAIN, bool ADDV>
 static cudaError_t launch_x_pipe(const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
   const int m = a.m;
   if (a.C != 32 || NLX * a.P != kBlockThreads || m != 32 * a.P || !a.implicit) return cudaErrorNotSupported;
-  if ((reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return cudaErrorNotSupported;
-  const int LT = (((m + 8) / 2) & 1) ? m + 8 : m + 10, LS = a.P * 16 + 2;
-  const size_t smem = ((size_t)NLX * LT + (size_t)NLX * LS + 4 * (size_t)a.P * NLX) * sizeof(double);
+  TileMap tin, tout;
+  const uint64_t rowb = (uint64_t)m * 8;
+  if (!encode_tile_map(&tin, v, (uint64_t)m, (uint64_t)a.nfast, 1, rowb, rowb * (uint64_t)a.nfast, 16, NLX, 1, true) ||
+      !encode_tile_map(&tout, out, (uint64_t)m, (uint64_t)a.nfast, 1, rowb, rowb * (uint64_t)a.nfast, 16, NLX, 1, true))
+    return cudaErrorNotSupported;
+  const size_t smem = (size_t)(m / 16 + 2 + a.P) * NLX * 128 + 4 * (size_t)a.P * NLX * sizeof(double) + 16;
   static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
   auto kfn = (ADDV && late) ? sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, true> : sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, false>;
   static bool configured = false;
@@ -1882,7 +1896,7 @@ static cudaError_t launch_x_pipe(const SweepDev &a, const double *v, double *out
   }
   const long ntiles = ((long)a.nfast + NLX - 1) / NLX;
   const long want = 2L * sm_count();
-  PB_LAUNCH(kfn, dim3((unsigned)(ntiles < want ? ntiles : want)), dim3(kBlockThreads), smem, st, a, v, out, epi);
+  PB_LAUNCH(kfn, dim3((unsigned)(ntiles < want ? ntiles : want)), dim3(kBlockThreads), smem, st, a, tin, tout, v, out, epi);
   ++g_launches;
   ++g_pipe_launches;
   return cudaGetLastError();

@@ -56,6 +56,18 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const TileMap *map, int c
       : "memory");
 }
 
+// one box shared memory -> global (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_3d(const TileMap *map, int c0, int c1, int c2, const void *src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until the stores of this thread have finished READING shared memory (the buffer may be reused)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// makes shared-memory writes of this thread visible to the async proxy (before a TMA store reads them)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Ampere-style asynchronous 16-byte copies global -> shared (LDGSTS): used by the x sweep, whose
 // padded tile layout a tensor map cannot express.
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
@@ -70,7 +82,7 @@ __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async
 // (strides must be multiples of 16 bytes, the base 16-byte aligned): the caller falls back to the
 // register kernels.
 inline bool encode_tile_map(TileMap *map, const double *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
-                            uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+                            uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle128 = false) {
   typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -91,7 +103,8 @@ inline bool encode_tile_map(TileMap *map, const double *base, uint64_t d0, uint6
   const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, pr,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace pb
@@ -104,7 +117,16 @@ struct TileMap {
   const double *base;
   uint64_t d0, d1, d2, s1, s2;  // strides in doubles
   uint32_t b0, b1, b2;
+  bool swz;  // 128-byte swizzle: the 16-byte chunk index of a 128-byte row is XORed with (row & 7)
 };
+inline size_t emul_box_index(const TileMap *map, uint32_t i, uint32_t j, uint32_t k) {
+  size_t e = ((size_t)k * map->b1 + j) * map->b0 + i;
+  if (map->swz) {
+    const size_t row = e / 16, col = e % 16;  // b0 == 16 doubles
+    e = row * 16 + ((((col / 2) ^ (row & 7)) * 2) + (col & 1));
+  }
+  return e;
+}
 inline void cp_async16(void *dst, const void *src) { std::memcpy(dst, src, 16); }
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
@@ -119,13 +141,27 @@ inline void tma_load_3d(void *dst, const TileMap *map, int c0, int c1, int c2, u
       for (uint32_t i = 0; i < map->b0; ++i) {
         const long x = (long)c0 + i, y = (long)c1 + j, z = (long)c2 + k;
         const bool in = x >= 0 && y >= 0 && z >= 0 && x < (long)map->d0 && y < (long)map->d1 && z < (long)map->d2;
-        d[((size_t)k * map->b1 + j) * map->b0 + i] = in ? map->base[x + y * (long)map->s1 + z * (long)map->s2] : 0.0;
+        d[emul_box_index(map, i, j, k)] = in ? map->base[x + y * (long)map->s1 + z * (long)map->s2] : 0.0;
       }
 }
+inline void tma_store_3d(const TileMap *map, int c0, int c1, int c2, const void *src) {
+  const double *s = static_cast<const double *>(src);
+  double *base = const_cast<double *>(map->base);
+  for (uint32_t k = 0; k < map->b2; ++k)
+    for (uint32_t j = 0; j < map->b1; ++j)
+      for (uint32_t i = 0; i < map->b0; ++i) {
+        const long x = (long)c0 + i, y = (long)c1 + j, z = (long)c2 + k;
+        const bool in = x >= 0 && y >= 0 && z >= 0 && x < (long)map->d0 && y < (long)map->d1 && z < (long)map->d2;
+        if (in) base[x + y * (long)map->s1 + z * (long)map->s2] = s[emul_box_index(map, i, j, k)];
+      }
+}
+inline void tma_store_commit() {}
+inline void tma_store_wait_read() {}
+inline void fence_async_smem() {}
 inline bool encode_tile_map(TileMap *map, const double *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
-                            uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
-  if ((s1_bytes & 15) || (s2_bytes & 15) || b0 > 256 || b1 > 256 || b2 > 256) return false;
-  *map = TileMap{base, d0, d1, d2, s1_bytes / 8, s2_bytes / 8, b0, b1, b2};
+                            uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle128 = false) {
+  if ((s1_bytes & 15) || (s2_bytes & 15) || b0 > 256 || b1 > 256 || b2 > 256 || (swizzle128 && b0 != 16)) return false;
+  *map = TileMap{base, d0, d1, d2, s1_bytes / 8, s2_bytes / 8, b0, b1, b2, swizzle128};
   return true;
 }
 }  // namespace pb
