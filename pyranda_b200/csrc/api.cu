@@ -5,6 +5,7 @@
 // (null-op rule, metric scale) and the Cartesian / curvilinear branches of operators.f90.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <cmath>
@@ -105,6 +106,10 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
   memset(&dv, 0, sizeof(dv));
   dv.m = m; dv.P = P; dv.C = m / P;
   for (int q = 0; q < kMaxChunks; ++q) dv.perm[q] = (unsigned char)q;
+  {
+    static const int wstore = getenv("PB_WARP_STORE") ? atoi(getenv("PB_WARP_STORE")) : 1;
+    dv.wstore = wstore;
+  }
   const int ax = pl->a[0], ay = pl->a[1], az = pl->a[2];
   if (dir == 0) { dv.nfast = ay * az; dv.nouter = 1; dv.rstride = 1; dv.ostride = 0; }
   else if (dir == 1) { dv.nfast = ax; dv.nouter = az; dv.rstride = ax; dv.ostride = (long)ax * ay; }

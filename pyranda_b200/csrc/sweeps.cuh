@@ -1334,13 +1334,14 @@ template <int FAM, int NL, bool PLAIN, bool ADDV, bool LATE>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tmain,
                      const __grid_constant__ TileMap tlo, const __grid_constant__ TileMap thi,
-                     const __grid_constant__ PipeGeo g, const double *__restrict__ v, double *__restrict__ out,
+                     const __grid_constant__ TileMap tout, const __grid_constant__ PipeGeo g, const double *__restrict__ v, double *__restrict__ out,
                      double *__restrict__ iface, const __grid_constant__ EpiArgs epi) {
   constexpr int CT = 32, H = FT<FAM>::H, HP = 4;
   PB_SHARED(S);
   const int P = a.P, m = a.m;
   double *tile = S;                                                         // [m + 2 HP][NL]
-  double2 *EN = reinterpret_cast<double2 *>(S + (size_t)(m + 2 * HP) * NL);  // [P][NL]
+  double *stage = S + (size_t)(m + 2 * HP) * NL;                            // [P][16][NL]: 16 rows of every chunk on their way out
+  double2 *EN = reinterpret_cast<double2 *>(stage + (size_t)P * 16 * NL);    // [P][NL]
   double2 *ST = EN + P * NL;                                                // [P][NL]
   uint64_t *bar = reinterpret_cast<uint64_t *>(ST + P * NL);
   const int tid = threadIdx.x, l = tid % NL, p = a.perm[tid / NL];
@@ -1427,15 +1428,15 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       }
       double x1 = 0.0, x2 = 0.0;
       if (cc) {
-        const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+        // x = ip (t - u1 x1 - u2 x2) with only one fma on the chain through x1
+        const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
         static_for<0, CT>([&](auto jc) {
           constexpr int r = CT - 1 - decltype(jc)::value;
           double x = rl[r];
           x = fma(a.phi0[r].x, st.x, x);
           x = fma(a.phi0[r].y, st.y, x);
+          x = fma(-u2, x2, x * ip);
           x = fma(-u1, x1, x);
-          x = fma(-u2, x2, x);
-          x *= ip;
           rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
           if (ADDV && LATE) {
             if (r < 2) xloc[r] = x;
@@ -1502,7 +1503,6 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         }
       }
       long oidx = base + (long)s * rs;
-      double *po = out + oidx;
       auto rowD = [&](auto rc, double gx, double gy, double xl) -> double {
         constexpr int r = decltype(rc)::value;
         double x = fma(gx, tb.x, xl);
@@ -1520,9 +1520,8 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           val += vr[r & 15];
           if (r < CT - 16) vr[r & 15] = __ldg(pv + (long)(r + 16) * rs);
         }
-        if (PLAIN) {
-          if (valid) *po = val;
-          po += rs;
+        if (PLAIN) {  // plain stores leave through the stage and the TMA unit, 16 rows of every chunk at a time
+          stage[(size_t)(p * 16 + (r & 15)) * NL + l] = val;
         } else {
           const double o = epi_value(val, ow[r & 15], oidx, epi);
           if (r < CT - 16) {
@@ -1534,23 +1533,60 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         return x;
       };
       double xi[4] = {0.0, 0.0, 0.0, 0.0};  // first / last two solved values (z-slab interface)
-      if (cc) {
-        static_for<0, CT>([&](auto rc) {
-          constexpr int r = decltype(rc)::value;
-          const double x = rowD(rc, a.psi0[r].x, a.psi0[r].y, rl[r]);
-          if (r < 2) xi[r] = x;
-          if (r >= CT - 2) xi[r - (CT - 4)] = x;
-        });
-      } else {
-        const double2 *ps = a.psi + (size_t)type * CT;
-        static_for<0, CT>([&](auto rc) {
-          constexpr int r = decltype(rc)::value;
-          const double2 gq = __ldg(ps + r);
-          const double x = rowD(rc, gq.x, gq.y, rl[r]);
-          if (r < 2) xi[r] = x;
-          if (r >= CT - 2) xi[r - (CT - 4)] = x;
-        });
-      }
+      const double2 *ps = a.psi + (size_t)type * CT;
+      static_for<0, CT / 16>([&](auto gc) {
+        constexpr int r0 = decltype(gc)::value * 16;
+        if (PLAIN) {  // the previous stores have left the stage (this warp's part, or all of it)
+          if (a.wstore) {
+            if ((tid & 31) == 0) tma_store_wait_read();
+            __syncwarp();
+          } else {
+            if (tid == 0) tma_store_wait_read();
+            __syncthreads();
+          }
+        }
+        if (cc) {
+          static_for<r0, r0 + 16>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            const double x = rowD(rc, a.psi0[r].x, a.psi0[r].y, rl[r]);
+            if (r < 2) xi[r] = x;
+            if (r >= CT - 2) xi[r - (CT - 4)] = x;
+          });
+        } else {
+          static_for<r0, r0 + 16>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            const double2 gq = __ldg(ps + r);
+            const double x = rowD(rc, gq.x, gq.y, rl[r]);
+            if (r < 2) xi[r] = x;
+            if (r >= CT - 2) xi[r - (CT - 4)] = x;
+          });
+        }
+        if (PLAIN) {
+          fence_async_smem();
+          const int x0 = ti * NL;
+          if (a.wstore) {  // every warp hands the rows of its own chunks to the TMA unit: no block-wide barrier
+            __syncwarp();
+            if ((tid & 31) == 0) {
+#pragma unroll
+              for (int w = 0; w < 32 / NL; ++w) {
+                const int q = a.perm[tid / NL + w];
+                const int row = q * CT + r0;
+                tma_store_3d(&tout, x0, g.rowdim == 1 ? row : o, g.rowdim == 1 ? o : row, stage + (size_t)q * 16 * NL);
+              }
+              tma_store_commit();
+            }
+          } else {
+            __syncthreads();
+            if (tid == 0) {
+              for (int q = 0; q < P; ++q) {
+                const int row = q * CT + r0;
+                tma_store_3d(&tout, x0, g.rowdim == 1 ? row : o, g.rowdim == 1 ? o : row, stage + (size_t)q * 16 * NL);
+              }
+              tma_store_commit();
+            }
+          }
+        }
+      });
       if (iface != nullptr && valid) {  // z-slab: this rank's 4 interface values, unscaled (compact_d1.f90:858-878)
         const long plane = (long)a.nfast * a.nouter;
         if (p == 0) {
@@ -1564,6 +1600,7 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       }
     }
   }
+  if (PLAIN && ((tid & 31) == 0)) tma_store_wait_read();  // covers both store modes (thread 0 is a lane 0)
 }
 
 // Builds the tensor maps of one y/z sweep and launches the persistent kernel.  Returns
@@ -1584,9 +1621,10 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
   g.box_rows = 256;
   g.nbox = m / 256;
   g.halo = 0; g.lo_row = 0; g.hi_row = 0;
-  TileMap tmain, tlo, thi;
+  TileMap tmain, tlo, thi, tout;
   if (!encode_tile_map(&tmain, v, ax, d1, d2, s1, s2, NL, ysweep ? 256 : 1, ysweep ? 1 : 256)) return cudaErrorNotSupported;
-  tlo = tmain; thi = tmain;
+  tlo = tmain; thi = tmain; tout = tmain;
+  if (PLAIN && !encode_tile_map(&tout, out, ax, d1, d2, s1, s2, NL, ysweep ? 16 : 1, ysweep ? 1 : 16)) return cudaErrorNotSupported;
   if (hlo != nullptr) {  // z-slab halo planes received from the neighbours: {ax, ay, H} each
     if (ysweep) return cudaErrorNotSupported;
     if (!encode_tile_map(&tlo, hlo, ax, d1, H, s1, s2, NL, 1, 4) || !encode_tile_map(&thi, hhi, ax, d1, H, s1, s2, NL, 1, 4))
@@ -1597,7 +1635,7 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
     thi = tlo;
     g.halo = 1; g.lo_row = m - 4; g.hi_row = 0;
   }
-  const size_t smem = ((size_t)(m + 8) * NL + 4 * (size_t)a.P * NL) * sizeof(double) + 16;
+  const size_t smem = ((size_t)(m + 8) * NL + 16 * (size_t)a.P * NL + 4 * (size_t)a.P * NL) * sizeof(double) + 16;
   static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
   auto kfn = (ADDV && late) ? sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, true> : sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, false>;
   static bool configured = false;
@@ -1611,7 +1649,7 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
   const long ntiles = (long)((a.nfast + NL - 1) / NL) * a.nouter;
   const long want = 2L * sm_count();
   const dim3 grid((unsigned)(ntiles < want ? ntiles : want)), block(kBlockThreads);
-  PB_LAUNCH(kfn, grid, block, smem, st, a, tmain, tlo, thi, g, v, out, iface, epi);
+  PB_LAUNCH(kfn, grid, block, smem, st, a, tmain, tlo, thi, tout, g, v, out, iface, epi);
   ++g_launches;
   ++g_pipe_launches;
   return cudaGetLastError();
@@ -1626,7 +1664,8 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
 // and the last slot are the periodic wrap).  The solution leaves the same way: 16 rows of every
 // chunk at a time are written, swizzled, into a stage of P boxes and one thread hands them to the
 // TMA unit as stores; composite epilogues read the stage back and store with the old output.
-template <int FAM, int NLX, bool PLAIN, bool ADDV, bool LATE>
+// MODE 0: implicit operator; 1: implicit with the late add-back (filters); 2: explicit operator (stencil only)
+template <int FAM, int NLX, bool PLAIN, bool ADDV, int MODE>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tin,
                     const __grid_constant__ TileMap tout, const double *__restrict__ v, double *__restrict__ out,
@@ -1649,6 +1688,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
   const bool cc = a.has_const && type == 0;
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
   const double scale = a.scale;
+  constexpr bool LATE = MODE == 1, implicit = MODE != 2;
   const uint32_t tx_bytes = (uint32_t)((NBOX + (a.wrap ? 2 : 0)) * BOXB);
 
   auto issue = [&](long t) {  // one thread: the whole tile as boxes
@@ -1727,21 +1767,26 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
           ring[(lr - 1) & 15] = w2.x;
           ring[lr & 15] = w2.y;
         }
-        double2 c;
-        if (cc) c = make_double2(l2c, l1c);
-        else c = __ldg(luf + lr);
-        double x = fma(-c.x, rm2, rhs);
-        x = fma(-c.y, rm1, x);
-        rl[lr] = x;
-        rm2 = rm1;
-        rm1 = x;
+        if (!implicit) {  // explicit operators (the Gaussian filter) are complete after the stencil
+          const double vc = ring[(lr + 4) & 15];
+          rl[lr] = ADDV ? fma(rhs, scale, vc) : rhs * scale;
+        } else {
+          double2 c;
+          if (cc) c = make_double2(l2c, l1c);
+          else c = __ldg(luf + lr);
+          double x = fma(-c.x, rm2, rhs);
+          x = fma(-c.y, rm1, x);
+          rl[lr] = x;
+          rm2 = rm1;
+          rm1 = x;
+        }
       });
-      EN[p * NLX + l] = make_double2(rm1, rm2);
+      if (implicit) EN[p * NLX + l] = make_double2(rm1, rm2);
     }
     __syncthreads();  // tile consumed (unless the add-back still reads it), EN visible
     if (!(ADDV && LATE) && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
-    {  // ---- B ----
+    if (implicit) {  // ---- B ----
       double2 st = make_double2(0.0, 0.0);
       {
         const int nf = a.nf[p];
@@ -1762,9 +1807,8 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
         double x = rl[r];
         x = fma(f0, st.x, x);
         x = fma(f1, st.y, x);
-        x = fma(-u1, x1, x);
-        x = fma(-u2, x2, x);
-        x *= ip;
+        x = fma(-(ip * u2), x2, x * ip);  // only one fma on the chain through x1
+        x = fma(-(ip * u1), x1, x);
         if constexpr (ADDV && LATE) {
           if constexpr (r & 1) vv2 = pair(std::integral_constant<int, (r + 3) / 2>{});  // x = 32 p + r - 1, 32 p + r
           rl[r] = fma(x, scale, (r & 1) ? vv2.y : vv2.x);
@@ -1792,13 +1836,12 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
       }
       ST[p * NLX + l] = make_double2(x1, x2);
     }
-    if (PLAIN && tid == 0) tma_store_wait_read();  // the stage of the previous tile has been read
     __syncthreads();
     if (ADDV && LATE && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
     {  // ---- D: carried backward state, then 16 rows of every chunk at a time through the stage ----
       double2 tbk = make_double2(0.0, 0.0);
-      {
+      if (implicit) {
         const int nb = a.nb[p];
         const double4 *Mp = a.Mb + (size_t)p * (P + 1);
         for (int j = 1; j <= nb; ++j) {
@@ -1814,29 +1857,50 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
       char *sb = stage + (size_t)p * BOXB + rowoff;
       static_for<0, CT / G>([&](auto gc) {
         constexpr int g = decltype(gc)::value;
-        if (g > 0) {  // the previous group has left the stage
-          if (PLAIN && tid == 0) tma_store_wait_read();
+        if (PLAIN) {  // the previous stores have left the stage (this warp's part, or all of it)
+          if (a.wstore) {
+            if ((tid & 31) == 0) tma_store_wait_read();
+            __syncwarp();
+          } else {
+            if (tid == 0) tma_store_wait_read();
+            __syncthreads();
+          }
+        } else if (g > 0) {
           __syncthreads();
         }
         static_for<0, G / 2>([&](auto kc) {
           constexpr int kq = decltype(kc)::value, r = g * G + 2 * kq;
-          double2 q0, q1;
-          if (cc) { q0 = a.psi0[r]; q1 = a.psi0[r + 1]; }
-          else { q0 = __ldg(ps + r); q1 = __ldg(ps + r + 1); }
+          double2 q0 = make_double2(0.0, 0.0), q1 = q0;
+          if (implicit) {
+            if (cc) { q0 = a.psi0[r]; q1 = a.psi0[r + 1]; }
+            else { q0 = __ldg(ps + r); q1 = __ldg(ps + r + 1); }
+          }
           const double sc = (ADDV && LATE) ? scale : 1.0;  // late add-back: rl already holds scale * x + v
           double xa = fma(q0.x * sc, tbk.x, rl[r]);
           xa = fma(q0.y * sc, tbk.y, xa);
           double xb = fma(q1.x * sc, tbk.x, rl[r + 1]);
           xb = fma(q1.y * sc, tbk.y, xb);
           *reinterpret_cast<double2 *>(sb + ((kq << 4) ^ swz)) =
-              (ADDV && LATE) ? make_double2(xa, xb) : make_double2(xa * scale, xb * scale);
+              ((ADDV && LATE) || !implicit) ? make_double2(xa, xb) : make_double2(xa * scale, xb * scale);
         });
         if (PLAIN) {
           fence_async_smem();
-          __syncthreads();
-          if (tid == 0) {
-            for (int q = 0; q < P; ++q) tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
-            tma_store_commit();
+          if (a.wstore) {  // every warp hands the boxes of its own chunks to the TMA unit: no block-wide barrier
+            __syncwarp();
+            if ((tid & 31) == 0) {
+#pragma unroll
+              for (int w = 0; w < 32 / NLX; ++w) {
+                const int q = a.perm[tid / NLX + w];
+                tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+              }
+              tma_store_commit();
+            }
+          } else {
+            __syncthreads();
+            if (tid == 0) {
+              for (int q = 0; q < P; ++q) tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+              tma_store_commit();
+            }
           }
         } else {
           __syncthreads();
@@ -1850,7 +1914,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
             const int line = q / per_line, rr = q - line * per_line;
             const long L = L0 + line;
             const long idx = (L < nlines ? L : nlines - 1) * (long)m + (rr >> 3) * CT + g * G + 2 * (rr & 7);
-            if (ADDV && !LATE) vadd[it] = __ldg(reinterpret_cast<const double2 *>(v + idx));
+            if (ADDV && !LATE && implicit) vadd[it] = __ldg(reinterpret_cast<const double2 *>(v + idx));
             oadd[it] = need_old ? *reinterpret_cast<const double2 *>(out + idx) : make_double2(0.0, 0.0);
           }
 #pragma unroll
@@ -1860,7 +1924,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
             const long L = L0 + line;
             const int chunk = rr >> 3, piece = rr & 7;
             double2 val = *reinterpret_cast<const double2 *>(stage + (size_t)chunk * BOXB + line * 128 + ((piece ^ (line & 7)) << 4));
-            if (ADDV && !LATE) { val.x += vadd[it].x; val.y += vadd[it].y; }
+            if (ADDV && !LATE && implicit) { val.x += vadd[it].x; val.y += vadd[it].y; }
             if (L < nlines) {
               const long idx = L * (long)m + chunk * CT + g * G + 2 * piece;
               *reinterpret_cast<double2 *>(out + idx) =
@@ -1871,13 +1935,13 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
       });
     }
   }
-  if (PLAIN && tid == 0) tma_store_wait_read();
+  if (PLAIN && ((tid & 31) == 0)) tma_store_wait_read();  // covers both store modes (thread 0 is a lane 0)
 }
 
 template <int FAM, int NLX, bool PLAIN, bool ADDV>
 static cudaError_t launch_x_pipe(const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
   const int m = a.m;
-  if (a.C != 32 || NLX * a.P != kBlockThreads || m != 32 * a.P || !a.implicit) return cudaErrorNotSupported;
+  if (a.C != 32 || NLX * a.P != kBlockThreads || m != 32 * a.P) return cudaErrorNotSupported;
   TileMap tin, tout;
   const uint64_t rowb = (uint64_t)m * 8;
   if (!encode_tile_map(&tin, v, (uint64_t)m, (uint64_t)a.nfast, 1, rowb, rowb * (uint64_t)a.nfast, 16, NLX, 1, true) ||
@@ -1885,14 +1949,21 @@ static cudaError_t launch_x_pipe(const SweepDev &a, const double *v, double *out
     return cudaErrorNotSupported;
   const size_t smem = (size_t)(m / 16 + 2 + a.P) * NLX * 128 + 4 * (size_t)a.P * NLX * sizeof(double) + 16;
   static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
-  auto kfn = (ADDV && late) ? sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, true> : sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, false>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  void (*kfn)(SweepDev, TileMap, TileMap, const double *, double *, EpiArgs) = nullptr;
+  if (!a.implicit) {
+    if constexpr (FAM == F_R4 && ADDV) kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 2>;
+    else return cudaErrorNotSupported;
+  } else if (ADDV && late) {
+    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 1>;
+  } else {
+    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0>;
+  }
+  static bool configured[3] = {false, false, false};
+  const int slot = !a.implicit ? 2 : ((ADDV && late) ? 1 : 0);
+  if (!configured[slot]) {
+    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    configured = true;
+    configured[slot] = true;
   }
   const long ntiles = ((long)a.nfast + NLX - 1) / NLX;
   const long want = 2L * sm_count();
@@ -1975,7 +2046,7 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
   int threads = NLX * a.P;
   threads = (threads + 31) / 32 * 32;
   if constexpr (NLX == 16 || NLX == 32) {
-    if (g_pipe_kernels && a.implicit && a.C == 32) {
+    if (g_pipe_kernels && a.C == 32) {
       constexpr bool PL = PLAIN;
       const cudaError_t err = launch_x_pipe<FAM, NLX, PL, ADDV>(a, v, out, epi, st);
       if (err != cudaErrorNotSupported) return err;
@@ -2006,6 +2077,12 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
 template <int FAM, bool ADDV>
 cudaError_t launch_x_f(int lines, const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
   const bool plain = epi.mode == EPI_STORE;
+  if (!a.implicit && g_pipe_kernels && a.C == 32 && (lines == 16 || lines == 32)) {  // the TMA-pipelined kernel without its solve phases
+    cudaError_t err;
+    if (lines == 16) err = plain ? launch_x_pipe<FAM, 16, true, ADDV>(a, v, out, epi, st) : launch_x_pipe<FAM, 16, false, ADDV>(a, v, out, epi, st);
+    else err = plain ? launch_x_pipe<FAM, 32, true, ADDV>(a, v, out, epi, st) : launch_x_pipe<FAM, 32, false, ADDV>(a, v, out, epi, st);
+    if (err != cudaErrorNotSupported) return err;
+  }
   if (!a.implicit && a.m % 2 == 0 && a.m >= 16 && a.m <= 1024 && !((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15)) {
     const long nblk = (a.nfast + kExplicitXLines - 1) / kExplicitXLines, cap = 3L * sm_count();
     const dim3 grid((unsigned)(nblk < cap ? nblk : cap));

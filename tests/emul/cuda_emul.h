@@ -103,6 +103,9 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
 #define blockDim (emul::t_blockDim)
 #define gridDim (emul::t_gridDim)
 inline void __syncthreads() { emul::t_barrier->arrive_and_wait(); }
+// every warp of a block executes the same sequence of warp barriers in these kernels, so a block
+// barrier is a valid (over-synchronising) stand-in
+inline void __syncwarp() { emul::t_barrier->arrive_and_wait(); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 using std::fabs;
 using std::fma;
