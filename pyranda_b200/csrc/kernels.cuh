@@ -52,6 +52,7 @@ struct SweepDev {
   int implicit;          // solve after the stencil
   int add_v;             // filters: result += input (null_option == 1)
   double scale;          // 1/d, 1/d^2 or 1
+  int acc;               // pipelined kernels: the stores accumulate (EPI_ACC through the plain-store path, TMA reduce-add)
   int wstore;            // pipelined kernels: every warp issues the TMA stores of its own chunks (else one thread per block)
 };
 

@@ -1273,6 +1273,16 @@ sweep_x_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
 }
 
 
+// chunk of the other half of a warp (tiles of 16 lines put two chunks into one warp)
+template <int NLT>
+__device__ __forceinline__ int warp_other_chunk(const SweepDev &a, int tid, int p) {
+#ifdef PB_EMULATE
+  return NLT == 16 ? a.perm[((tid / NLT) & ~1) + 1] : p;
+#else
+  return NLT == 16 ? __shfl_sync(0xffffffffu, p, 16) : p;
+#endif
+}
+
 // ---- pipelined sweeps: persistent CTAs, next tile prefetched by TMA --------------------------------
 // The register kernels above only have loads in flight during their forward phase.  Here a CTA
 // walks over tiles; as soon as every thread has pulled its chunk of the current tile out of shared
@@ -1536,14 +1546,9 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       const double2 *ps = a.psi + (size_t)type * CT;
       static_for<0, CT / 16>([&](auto gc) {
         constexpr int r0 = decltype(gc)::value * 16;
-        if (PLAIN) {  // the previous stores have left the stage (this warp's part, or all of it)
-          if (a.wstore) {
-            if ((tid & 31) == 0) tma_store_wait_read();
-            __syncwarp();
-          } else {
-            if (tid == 0) tma_store_wait_read();
-            __syncthreads();
-          }
+        if (PLAIN) {  // this warp's previous stores have left its part of the stage
+          if ((tid & 31) == 0) tma_store_wait_read();
+          __syncwarp();
         }
         if (cc) {
           static_for<r0, r0 + 16>([&](auto rc) {
@@ -1561,29 +1566,20 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
             if (r >= CT - 2) xi[r - (CT - 4)] = x;
           });
         }
-        if (PLAIN) {
+        if (PLAIN) {  // every warp hands the rows of its own chunks to the TMA unit: no block-wide barrier
           fence_async_smem();
-          const int x0 = ti * NL;
-          if (a.wstore) {  // every warp hands the rows of its own chunks to the TMA unit: no block-wide barrier
-            __syncwarp();
-            if ((tid & 31) == 0) {
+          __syncwarp();
+          if ((tid & 31) == 0) {
+            const int x0 = ti * NL;
 #pragma unroll
-              for (int w = 0; w < 32 / NL; ++w) {
-                const int q = a.perm[tid / NL + w];
-                const int row = q * CT + r0;
-                tma_store_3d(&tout, x0, g.rowdim == 1 ? row : o, g.rowdim == 1 ? o : row, stage + (size_t)q * 16 * NL);
-              }
-              tma_store_commit();
+            for (int w = 0; w < 32 / NL; ++w) {
+              const int q = a.perm[tid / NL + w];
+              const int row = q * CT + r0;
+              const int c1 = g.rowdim == 1 ? row : o, c2 = g.rowdim == 1 ? o : row;
+              if (a.acc) tma_reduce_add_3d(&tout, x0, c1, c2, stage + (size_t)q * 16 * NL);
+              else tma_store_3d(&tout, x0, c1, c2, stage + (size_t)q * 16 * NL);
             }
-          } else {
-            __syncthreads();
-            if (tid == 0) {
-              for (int q = 0; q < P; ++q) {
-                const int row = q * CT + r0;
-                tma_store_3d(&tout, x0, g.rowdim == 1 ? row : o, g.rowdim == 1 ? o : row, stage + (size_t)q * 16 * NL);
-              }
-              tma_store_commit();
-            }
+            tma_store_commit();
           }
         }
       });
@@ -1665,12 +1661,16 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
 // chunk at a time are written, swizzled, into a stage of P boxes and one thread hands them to the
 // TMA unit as stores; composite epilogues read the stage back and store with the old output.
 // MODE 0: implicit operator; 1: implicit with the late add-back (filters); 2: explicit operator (stencil only)
-template <int FAM, int NLX, bool PLAIN, bool ADDV, int MODE>
+template <int FAM, int NLX, bool PLAIN, bool ADDV, int MODE, bool ACC>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tin,
                     const __grid_constant__ TileMap tout, const double *__restrict__ v, double *__restrict__ out,
                     const __grid_constant__ EpiArgs epi) {
   constexpr int CT = 32, H = FT<FAM>::H, G = 16;
+  constexpr bool LATE = MODE == 1, implicit = MODE != 2;
+  // who issues the TMA stores: lane 0 of every warp for its own chunks (no block-wide barrier in the
+  // store phase; measured faster), or one thread for the whole block
+  constexpr bool WSTORE = true;
   constexpr int PC = kBlockThreads / NLX, M = PC * CT;  // chunks per line, line length
   constexpr int BOXB = NLX * 128;                       // bytes of one box
   constexpr int NBOX = M / 16;
@@ -1688,7 +1688,6 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
   const bool cc = a.has_const && type == 0;
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
   const double scale = a.scale;
-  constexpr bool LATE = MODE == 1, implicit = MODE != 2;
   const uint32_t tx_bytes = (uint32_t)((NBOX + (a.wrap ? 2 : 0)) * BOXB);
 
   auto issue = [&](long t) {  // one thread: the whole tile as boxes
@@ -1767,7 +1766,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
           ring[(lr - 1) & 15] = w2.x;
           ring[lr & 15] = w2.y;
         }
-        if (!implicit) {  // explicit operators (the Gaussian filter) are complete after the stencil
+        if constexpr (!implicit) {  // explicit operators (the Gaussian filter) are complete after the stencil
           const double vc = ring[(lr + 4) & 15];
           rl[lr] = ADDV ? fma(rhs, scale, vc) : rhs * scale;
         } else {
@@ -1781,12 +1780,12 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
           rm1 = x;
         }
       });
-      if (implicit) EN[p * NLX + l] = make_double2(rm1, rm2);
+      if constexpr (implicit) EN[p * NLX + l] = make_double2(rm1, rm2);
     }
     __syncthreads();  // tile consumed (unless the add-back still reads it), EN visible
     if (!(ADDV && LATE) && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
-    if (implicit) {  // ---- B ----
+    if constexpr (implicit) {  // ---- B ----
       double2 st = make_double2(0.0, 0.0);
       {
         const int nf = a.nf[p];
@@ -1807,8 +1806,9 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
         double x = rl[r];
         x = fma(f0, st.x, x);
         x = fma(f1, st.y, x);
-        x = fma(-(ip * u2), x2, x * ip);  // only one fma on the chain through x1
-        x = fma(-(ip * u1), x1, x);
+        x = fma(-u1, x1, x);
+        x = fma(-u2, x2, x);
+        x *= ip;
         if constexpr (ADDV && LATE) {
           if constexpr (r & 1) vv2 = pair(std::integral_constant<int, (r + 3) / 2>{});  // x = 32 p + r - 1, 32 p + r
           rl[r] = fma(x, scale, (r & 1) ? vv2.y : vv2.x);
@@ -1836,12 +1836,13 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
       }
       ST[p * NLX + l] = make_double2(x1, x2);
     }
+    if (PLAIN && !WSTORE && tid == 0) tma_store_wait_read();  // the stage of the previous tile has been read
     __syncthreads();
     if (ADDV && LATE && tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
 
     {  // ---- D: carried backward state, then 16 rows of every chunk at a time through the stage ----
       double2 tbk = make_double2(0.0, 0.0);
-      if (implicit) {
+      if constexpr (implicit) {
         const int nb = a.nb[p];
         const double4 *Mp = a.Mb + (size_t)p * (P + 1);
         for (int j = 1; j <= nb; ++j) {
@@ -1857,23 +1858,21 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
       char *sb = stage + (size_t)p * BOXB + rowoff;
       static_for<0, CT / G>([&](auto gc) {
         constexpr int g = decltype(gc)::value;
-        if (PLAIN) {  // the previous stores have left the stage (this warp's part, or all of it)
-          if (a.wstore) {
-            if ((tid & 31) == 0) tma_store_wait_read();
-            __syncwarp();
-          } else {
-            if (tid == 0) tma_store_wait_read();
-            __syncthreads();
-          }
+        if (PLAIN && WSTORE) {  // this warp's previous stores have left its part of the stage
+          if ((tid & 31) == 0) tma_store_wait_read();
+          __syncwarp();
         } else if (g > 0) {
+          if (PLAIN && tid == 0) tma_store_wait_read();
           __syncthreads();
         }
         static_for<0, G / 2>([&](auto kc) {
           constexpr int kq = decltype(kc)::value, r = g * G + 2 * kq;
-          double2 q0 = make_double2(0.0, 0.0), q1 = q0;
-          if (implicit) {
+          double2 q0, q1;
+          if constexpr (implicit) {
             if (cc) { q0 = a.psi0[r]; q1 = a.psi0[r + 1]; }
             else { q0 = __ldg(ps + r); q1 = __ldg(ps + r + 1); }
+          } else {
+            q0 = make_double2(0.0, 0.0); q1 = q0;
           }
           const double sc = (ADDV && LATE) ? scale : 1.0;  // late add-back: rl already holds scale * x + v
           double xa = fma(q0.x * sc, tbk.x, rl[r]);
@@ -1885,20 +1884,27 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
         });
         if (PLAIN) {
           fence_async_smem();
-          if (a.wstore) {  // every warp hands the boxes of its own chunks to the TMA unit: no block-wide barrier
+          if constexpr (WSTORE) {
             __syncwarp();
+            // every warp hands the boxes of its own chunks (lane 0's and, with 16-line tiles, lane 16's)
+            // to the TMA unit
+            const int q1 = warp_other_chunk<NLX>(a, tid, p);
             if ((tid & 31) == 0) {
-#pragma unroll
-              for (int w = 0; w < 32 / NLX; ++w) {
-                const int q = a.perm[tid / NLX + w];
-                tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+              if constexpr (ACC) tma_reduce_add_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
+              else tma_store_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
+              if (NLX == 16) {
+                if constexpr (ACC) tma_reduce_add_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
+                else tma_store_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
               }
               tma_store_commit();
             }
           } else {
             __syncthreads();
             if (tid == 0) {
-              for (int q = 0; q < P; ++q) tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+              for (int q = 0; q < P; ++q) {
+                if constexpr (ACC) tma_reduce_add_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+                else tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+              }
               tma_store_commit();
             }
           }
@@ -1935,7 +1941,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
       });
     }
   }
-  if (PLAIN && ((tid & 31) == 0)) tma_store_wait_read();  // covers both store modes (thread 0 is a lane 0)
+  if (PLAIN && (tid & 31) == 0) tma_store_wait_read();
 }
 
 template <int FAM, int NLX, bool PLAIN, bool ADDV>
@@ -1950,16 +1956,20 @@ static cudaError_t launch_x_pipe(const SweepDev &a, const double *v, double *out
   const size_t smem = (size_t)(m / 16 + 2 + a.P) * NLX * 128 + 4 * (size_t)a.P * NLX * sizeof(double) + 16;
   static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
   void (*kfn)(SweepDev, TileMap, TileMap, const double *, double *, EpiArgs) = nullptr;
+  int slot;
   if (!a.implicit) {
-    if constexpr (FAM == F_R4 && ADDV) kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 2>;
+    if constexpr (FAM == F_R4 && ADDV) { kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 2, false>; slot = 2; }
     else return cudaErrorNotSupported;
   } else if (ADDV && late) {
-    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 1>;
+    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 1, false>; slot = 1;
+  } else if (PLAIN && !ADDV && a.acc) {
+    if constexpr (PLAIN && !ADDV) kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0, true>;
+    slot = 3;
   } else {
-    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0>;
+    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0, false>; slot = 0;
   }
-  static bool configured[3] = {false, false, false};
-  const int slot = !a.implicit ? 2 : ((ADDV && late) ? 1 : 0);
+  if (kfn == nullptr) return cudaErrorNotSupported;
+  static bool configured[4] = {false, false, false, false};
   if (!configured[slot]) {
     cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -1987,8 +1997,14 @@ static cudaError_t launch_yz_t(const SweepDev &a, const double *v, double *out, 
   }
   if constexpr (NL == 16 || NL == 32) {
     if (g_pipe_kernels && a.C == 32) {
-      constexpr bool PL = PLAIN;
-      const cudaError_t err = launch_yz_pipe<FAM, NL, PL, ADDV>(a, v, out, hlo, hhi, iface, epi, st);
+      cudaError_t err;
+      if (!PLAIN && epi.mode == EPI_ACC) {  // out += val: the plain-store kernel with TMA reduce-add stores
+        SweepDev b = a;
+        b.acc = 1;
+        err = launch_yz_pipe<FAM, NL, true, ADDV>(b, v, out, hlo, hhi, iface, epi, st);
+      } else {
+        err = launch_yz_pipe<FAM, NL, PLAIN, ADDV>(a, v, out, hlo, hhi, iface, epi, st);
+      }
       if (err != cudaErrorNotSupported) return err;
     }
   }
@@ -2047,8 +2063,14 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
   threads = (threads + 31) / 32 * 32;
   if constexpr (NLX == 16 || NLX == 32) {
     if (g_pipe_kernels && a.C == 32) {
-      constexpr bool PL = PLAIN;
-      const cudaError_t err = launch_x_pipe<FAM, NLX, PL, ADDV>(a, v, out, epi, st);
+      cudaError_t err;
+      if (!PLAIN && epi.mode == EPI_ACC) {  // out += val: the plain-store kernel with TMA reduce-add stores
+        SweepDev b = a;
+        b.acc = 1;
+        err = launch_x_pipe<FAM, NLX, true, ADDV>(b, v, out, epi, st);
+      } else {
+        err = launch_x_pipe<FAM, NLX, PLAIN, ADDV>(a, v, out, epi, st);
+      }
       if (err != cudaErrorNotSupported) return err;
     }
   }

@@ -62,6 +62,12 @@ __device__ __forceinline__ void tma_store_3d(const TileMap *map, int c0, int c1,
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(src))
                : "memory");
 }
+// the same box added to global memory (fp64 add performed by the memory system): accumulating epilogues
+__device__ __forceinline__ void tma_reduce_add_3d(const TileMap *map, int c0, int c1, int c2, const void *src) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(src))
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // waits until the stores of this thread have finished READING shared memory (the buffer may be reused)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -153,6 +159,17 @@ inline void tma_store_3d(const TileMap *map, int c0, int c1, int c2, const void 
         const long x = (long)c0 + i, y = (long)c1 + j, z = (long)c2 + k;
         const bool in = x >= 0 && y >= 0 && z >= 0 && x < (long)map->d0 && y < (long)map->d1 && z < (long)map->d2;
         if (in) base[x + y * (long)map->s1 + z * (long)map->s2] = s[emul_box_index(map, i, j, k)];
+      }
+}
+inline void tma_reduce_add_3d(const TileMap *map, int c0, int c1, int c2, const void *src) {
+  const double *s = static_cast<const double *>(src);
+  double *base = const_cast<double *>(map->base);
+  for (uint32_t k = 0; k < map->b2; ++k)
+    for (uint32_t j = 0; j < map->b1; ++j)
+      for (uint32_t i = 0; i < map->b0; ++i) {
+        const long x = (long)c0 + i, y = (long)c1 + j, z = (long)c2 + k;
+        const bool in = x >= 0 && y >= 0 && z >= 0 && x < (long)map->d0 && y < (long)map->d1 && z < (long)map->d2;
+        if (in) base[x + y * (long)map->s1 + z * (long)map->s2] += s[emul_box_index(map, i, j, k)];
       }
 }
 inline void tma_store_commit() {}

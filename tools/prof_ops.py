@@ -8,6 +8,9 @@ import torch
 
 from pyranda_b200 import ParcopPlan, _lib
 
+if os.environ.get("PB_LIB"):  # A/B experiments: another build of the library
+    _lib.LIB_PATH = os.environ["PB_LIB"]
+
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 ops = sys.argv[2:] or ["ddx", "ddy", "ddz", "sfilter", "gfilter"]
 periodic = os.environ.get("PB_BOUNDED", "0") != "1"
