@@ -19,6 +19,8 @@
 #ifndef PARCOP_B200_H
 #define PARCOP_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -115,6 +117,15 @@ int pb_z_local(pb_plan *plan, int zop, const double *d_val, const double *d_recv
                const double *d_recv_hi, double *d_out, double *d_iface_local, void *stream);
 int pb_z_finish(pb_plan *plan, int zop, const double *d_val, const double *d_iface_all,
                 double *d_out, void *stream);
+/* The exchange itself, over NVLink peer memory (replaces MPI_Sendrecv / mpi_allgather of
+ * compact_d1.f90:719-735,890): ONE launch that copies up to four local buffers into peer-mapped
+ * destinations, publishes `epoch` in the flag word of each of up to two neighbours and waits until
+ * the neighbours have published the same epoch in this rank's flag words.  All addresses are
+ * device addresses valid on this GPU (peer memory mapped through CUDA IPC / symmetric memory);
+ * `counter` is a zero-initialised 4-byte scratch word in local memory. */
+int pb_peer_exchange(int ncopies, void *const *d_dst, const void *const *d_src, const size_t *bytes,
+                     int npeers, void *const *d_remote_flags, void *const *d_local_flags,
+                     unsigned long long epoch, void *d_counter, void *stream);
 /* bit r of *mask is set when rank r's interface values enter this rank's correction (0: the
  * operator needs no exchange); slots of d_iface_all belonging to other ranks are never read */
 int pb_z_exchange_ranks(pb_plan *plan, int zop, unsigned long long *mask);

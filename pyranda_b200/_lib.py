@@ -22,7 +22,7 @@ EXPORTS = [
     "pb_last_error", "pb_version", "pb_plan_create", "pb_plan_destroy", "pb_plan_extents",
     "pb_plan_spacing", "pb_plan_set_mesh", "pb_getvar", "pb_getvar_device", "pb_apply",
     "pb_divergence", "pb_grads", "pb_rk4_stage", "pb_reduce", "pb_z_pack_halo", "pb_z_local",
-    "pb_z_finish", "pb_z_exchange_ranks", "pb_host_apply", "pb_host_divergence", "pb_host_grads", "pb_launch_count",
+    "pb_z_finish", "pb_z_exchange_ranks", "pb_peer_exchange", "pb_host_apply", "pb_host_divergence", "pb_host_grads", "pb_launch_count",
     "pb_pipe_launch_count", "pb_set_tuning",
 ]
 
@@ -51,6 +51,7 @@ def declare(L):
     L.pb_z_pack_halo.argtypes = [_vp, i, _vp, _vp, _vp, _vp]
     L.pb_z_local.argtypes = [_vp, i, _vp, _vp, _vp, _vp, _vp, _vp]
     L.pb_z_finish.argtypes = [_vp, i, _vp, _vp, _vp, _vp]
+    L.pb_peer_exchange.argtypes = [i, _vp, _vp, _vp, i, _vp, _vp, ctypes.c_ulonglong, _vp, _vp]
     L.pb_z_exchange_ranks.argtypes = [_vp, i, ctypes.POINTER(ctypes.c_ulonglong)]
     L.pb_host_apply.argtypes = [_vp, i, _vp, _vp]
     L.pb_host_divergence.argtypes = [_vp, _vp, _vp, _vp, _vp]

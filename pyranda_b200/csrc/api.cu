@@ -5,6 +5,7 @@
 // (null-op rule, metric scale) and the Cartesian / curvilinear branches of operators.f90.
 #include <cmath>
 #include <cstdio>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
@@ -188,15 +189,15 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
       }
       std::vector<double> GR(rp.G.begin() + (size_t)sp.rank * 16 * np, rp.G.begin() + (size_t)(sp.rank + 1) * 16 * np);
       // The spike columns decay like rho^row away from the slab faces and the reduced-system rows
-      // like rho^(az * distance in ranks): keep only what can change a double (1e-17 / 1e-19 relative).
+      // like rho^(az * distance in ranks): keep only what can change a double (1e-16 / 1e-19 relative).
       {
         double cmax = 0.0, gmax = 0.0;
         for (int i = 0; i < m; ++i)
           cmax = std::max({cmax, std::fabs(RC[i].x), std::fabs(RC[i].y), std::fabs(RC[i].z), std::fabs(RC[i].w)});
         sp.zone_lo = sp.zone_hi = 0;
         for (int i = 0; i < m; ++i) {
-          if (std::max(std::fabs(RC[i].x), std::fabs(RC[i].y)) > 1e-17 * cmax) sp.zone_lo = i + 1;
-          if (std::max(std::fabs(RC[m - 1 - i].z), std::fabs(RC[m - 1 - i].w)) > 1e-17 * cmax) sp.zone_hi = i + 1;
+          if (std::max(std::fabs(RC[i].x), std::fabs(RC[i].y)) > 1e-16 * cmax) sp.zone_lo = i + 1;
+          if (std::max(std::fabs(RC[m - 1 - i].z), std::fabs(RC[m - 1 - i].w)) > 1e-16 * cmax) sp.zone_hi = i + 1;
         }
         for (double gv : GR) gmax = std::max(gmax, std::fabs(gv));
         sp.rank_mask = 0;
@@ -682,6 +683,29 @@ int pb_z_finish(pb_plan *pl, int zop, const double *d_val, const double *iface_a
   const long plane = (long)pl->a[0] * pl->a[1];
   PB_CUDA(launch_z_finish(d_out, plane, pl->a[2], sp.RC, sp.GR, sp.np, sp.rank_mask, sp.zone_lo, sp.zone_hi, iface_all,
                           sp.dev.scale, (cudaStream_t)stream));
+  return PB_OK;
+}
+
+int pb_peer_exchange(int ncopies, void *const *dst, const void *const *src, const size_t *bytes, int npeers,
+                     void *const *remote_flags, void *const *local_flags, unsigned long long epoch, void *counter,
+                     void *stream) {
+  if (ncopies < 0 || ncopies > 4 || npeers < 0 || npeers > 2 || !counter) return fail(PB_ERR_ARG, "bad peer exchange");
+  PeerExchange x;
+  memset(&x, 0, sizeof(x));
+  x.ncopies = ncopies; x.npeers = npeers; x.epoch = epoch; x.counter = (unsigned int *)counter;
+  for (int c = 0; c < ncopies; ++c) {
+    if (!dst[c] || !src[c] || (bytes[c] & 15) || ((uintptr_t)dst[c] & 15) || ((uintptr_t)src[c] & 15))
+      return fail(PB_ERR_ARG, "peer copies must be 16-byte aligned");
+    x.dst[c] = dst[c]; x.src[c] = src[c]; x.bytes[c] = bytes[c];
+  }
+  for (int p = 0; p < npeers; ++p) {
+    if (!remote_flags[p] || !local_flags[p]) return fail(PB_ERR_ARG, "missing flag address");
+    x.remote_flag[p] = (unsigned long long *)remote_flags[p];
+    x.local_flag[p] = (const volatile unsigned long long *)local_flags[p];
+  }
+  const cudaError_t err = launch_peer_exchange(x, (cudaStream_t)stream);
+  if (err == cudaErrorNotSupported) return fail(PB_ERR_UNSUPPORTED, "peer exchange needs the CUDA build");
+  PB_CUDA(err);
   return PB_OK;
 }
 

@@ -140,15 +140,27 @@ __global__ void z_finish_kernel(double *__restrict__ out, long plane, int m, con
   const int nz = lo + hi;
   const int q0 = blockIdx.y * rows_per_block;
   const int q1 = min(nz, q0 + rows_per_block);
-  for (int q = q0; q < q1; ++q) {
-    const int r = q < lo ? q : m - hi + (q - lo);
-    const double4 c = ldg4(RC + r);
-    const long idx = (long)r * plane + li;
-    double corr = c.x * g[0];
-    corr = fma(c.y, g[1], corr);
-    corr = fma(c.z, g[2], corr);
-    corr = fma(c.w, g[3], corr);
-    out[idx] = fma(-scale, corr, out[idx]);
+  for (int qb = q0; qb < q1; qb += 8) {  // eight rows at a time: all loads first, then the stores
+    double old[8];
+    long idx[8];
+    double4 c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int q = min(qb + k, q1 - 1);
+      const int r = q < lo ? q : m - hi + (q - lo);
+      idx[k] = (long)r * plane + li;
+      c[k] = ldg4(RC + r);
+      old[k] = out[idx[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (qb + k >= q1) break;
+      double corr = c[k].x * g[0];
+      corr = fma(c[k].y, g[1], corr);
+      corr = fma(c[k].z, g[2], corr);
+      corr = fma(c[k].w, g[3], corr);
+      out[idx[k]] = fma(-scale, corr, old[k]);
+    }
   }
 }
 cudaError_t launch_z_finish(double *out, long plane, int m, const double4 *RC, const double *GR, int np,
@@ -163,6 +175,56 @@ cudaError_t launch_z_finish(double *out, long plane, int m, const double4 *RC, c
             rows_per_block);
   ++g_launches;
   return cudaGetLastError();
+}
+
+// ---- peer exchange --------------------------------------------------------------------------------
+// One launch that writes this rank's halo planes / interface values straight into the neighbours'
+// memory over NVLink, raises the neighbours' flags and waits for its own: the whole MPI_Sendrecv /
+// mpi_allgather step of compact_d1.f90:719-735,890 without a library call.  Every thread fences its
+// peer stores at system scope; the last block to finish publishes `epoch` in each neighbour's flag
+// word and then spins (bounded) until every neighbour has published the same epoch here, so kernels
+// queued behind this one see the neighbours' data.
+#ifndef PB_EMULATE
+__global__ void __launch_bounds__(256) peer_exchange_kernel(const __grid_constant__ PeerExchange x) {
+  for (int c = 0; c < x.ncopies; ++c) {
+    const double2 *s = reinterpret_cast<const double2 *>(x.src[c]);
+    double2 *d = reinterpret_cast<double2 *>(x.dst[c]);
+    const long n2 = (long)(x.bytes[c] / sizeof(double2));
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n2; t += (long)gridDim.x * blockDim.x) d[t] = s[t];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(x.counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) {
+    *x.counter = 0;
+    __threadfence_system();
+    for (int p = 0; p < x.npeers; ++p) *reinterpret_cast<volatile unsigned long long *>(x.remote_flag[p]) = x.epoch;
+  }
+  if ((int)threadIdx.x < x.npeers) {
+    const volatile unsigned long long *f = x.local_flag[threadIdx.x];
+    unsigned long long spin = 0;
+    while (*f < x.epoch)
+      if (++spin > (1ull << 31)) __trap();  // a neighbour that never arrives must not hang the GPU
+    __threadfence_system();
+  }
+}
+#endif
+cudaError_t launch_peer_exchange(const PeerExchange &x, cudaStream_t st) {
+#ifdef PB_EMULATE
+  (void)x; (void)st;
+  return cudaErrorNotSupported;
+#else
+  long most = 0;
+  for (int c = 0; c < x.ncopies; ++c) most = x.bytes[c] > (size_t)most ? (long)x.bytes[c] : most;
+  long blocks = (most / 16 + 255) / 256 / 8;
+  blocks = blocks < 1 ? 1 : (blocks > 2L * sm_count() ? 2L * sm_count() : blocks);
+  peer_exchange_kernel<<<(unsigned)blocks, 256, 0, st>>>(x);
+  ++g_launches;
+  return cudaGetLastError();
+#endif
 }
 
 // ---- pointwise -----------------------------------------------------------------------------------

@@ -76,6 +76,19 @@ cudaError_t launch_z_finish(double *out, long plane, int m, const double4 *RC, c
                             unsigned long long rank_mask, int zone_lo, int zone_hi, const double *iface_all,
                             double scale, cudaStream_t st);
 
+// peer exchange: copies into the neighbours' memory + flag handshake in one launch
+struct PeerExchange {
+  int ncopies, npeers;
+  void *dst[4];
+  const void *src[4];
+  size_t bytes[4];                              // multiples of 16
+  unsigned long long *remote_flag[2];           // in each neighbour's memory: the word this rank sets
+  const volatile unsigned long long *local_flag[2];  // in this rank's memory: the word each neighbour sets
+  unsigned long long epoch;
+  unsigned int *counter;                        // zero-initialised scratch word in local memory
+};
+cudaError_t launch_peer_exchange(const PeerExchange &x, cudaStream_t st);
+
 // pointwise / reductions
 cudaError_t launch_rk4_stage(long n, double dt, double A, double B, const double *F, double *PHI,
                              double *U, cudaStream_t st);

@@ -1273,6 +1273,20 @@ sweep_x_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
 }
 
 
+// true when every chunk handled by this warp has constant coefficients: a warp that mixes a table
+// chunk and a constant chunk (16-line tiles, odd number of table chunks) runs the table path for
+// both halves instead of the two paths one after the other
+template <int NLT>
+__device__ __forceinline__ bool warp_all_const(const SweepDev &a, int tid, bool cc) {
+#ifdef PB_EMULATE
+  if (NLT != 16) return cc;
+  const int s0 = (tid / NLT) & ~1;
+  return a.has_const && a.ctype[a.perm[s0]] == 0 && a.ctype[a.perm[s0 + 1]] == 0;
+#else
+  return NLT == 16 ? __all_sync(0xffffffffu, cc) : cc;
+#endif
+}
+
 // chunk of the other half of a warp (tiles of 16 lines put two chunks into one warp)
 template <int NLT>
 __device__ __forceinline__ int warp_other_chunk(const SweepDev &a, int tid, int p) {
@@ -1360,7 +1374,7 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   const long rs = a.rstride;
   const int s = p * CT;
   const int type = a.ctype[p];
-  const bool cc = a.has_const && type == 0;
+  const bool cc = warp_all_const<NL>(a, tid, a.has_const && type == 0);
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
   const double scale = a.scale;
   const uint32_t tx_bytes = (uint32_t)((m + (g.halo ? 2 * HP : 0)) * NL * sizeof(double));
@@ -1685,7 +1699,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
   const long nlines = a.nfast;
   const long ntiles = (nlines + NLX - 1) / NLX;
   const int type = a.ctype[p];
-  const bool cc = a.has_const && type == 0;
+  const bool cc = warp_all_const<NLX>(a, tid, a.has_const && type == 0);
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
   const double scale = a.scale;
   const uint32_t tx_bytes = (uint32_t)((NBOX + (a.wrap ? 2 : 0)) * BOXB);

@@ -28,45 +28,56 @@ _IMPLICIT = {"ddz": True, "dd8z": True, "d2z": True, "sfilterz": True, "gfilterz
 class _PeerBuffers:
     """Halo planes and interface values written straight into the neighbours' memory over NVLink.
 
-    One symmetric allocation per engine (torch.distributed._symmetric_memory: CUDA IPC mapping of
-    every rank's buffer plus a signal pad), holding two sets of {lower halo, upper halo, gathered
-    interface values}.  An exchange is: copy my planes into the peer's buffer, raise the peer's
-    signal, wait for mine -- all enqueued on the compute stream, no host synchronisation and no
-    NCCL kernel.  The sets alternate per operator, so a rank never overwrites planes its neighbour
-    may still be reading (the neighbour's next signal is ordered after that read)."""
+    One symmetric allocation per engine (torch.distributed._symmetric_memory provides the CUDA-IPC
+    mapping of every rank's buffer), holding two sets of {lower halo, upper halo, gathered interface
+    values} and a row of flag words.  An exchange is ONE kernel of this library (pb_peer_exchange):
+    it stores this rank's planes into the neighbours' buffers, publishes a new epoch in their flag
+    words and waits for theirs -- enqueued on the compute stream, no host synchronisation, no NCCL.
+    The sets alternate per operator, so a rank never overwrites planes its neighbour may still be
+    reading (the neighbour's next epoch is ordered after that read)."""
 
-    TIMEOUT_MS = 20000
-
-    def __init__(self, group, rank, world, plane, dev):
+    def __init__(self, lib, group, rank, world, plane, dev):
         import torch.distributed._symmetric_memory as symm
+        self.L = lib
         self.rank, self.world, self.n = rank, world, 4 * plane
         self.set_len = (2 + world) * self.n
-        self.buf = symm.empty(2 * self.set_len, dtype=torch.float64, device=dev)
+        self.flag_off = 2 * self.set_len          # [world] uint64 flags + scratch counter, in doubles
+        self.buf = symm.empty(2 * self.set_len + world + 2, dtype=torch.float64, device=dev)
         self.buf.zero_()
         self.h = symm.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+        self.base = [int(p) for p in self.h.buffer_ptrs]
+        assert self.base[rank] == self.buf.data_ptr()
         self.k = 0
+        self.epoch = 0
         self._views = {}
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
-    def view(self, peer, what, slot=0):
-        key = (self.k % 2, peer, what, slot)
-        t = self._views.get(key)
-        if t is None:
-            off = key[0] * self.set_len + {"lo": 0, "hi": self.n, "iface": 2 * self.n}[what] + slot * self.n
-            t = self.buf[off:off + self.n] if peer == self.rank else self.h.get_buffer(peer, (self.n,), torch.float64, off)
-            self._views[key] = t
-        return t
+    def _off(self, what, slot=0):
+        return (self.k % 2) * self.set_len + {"lo": 0, "hi": self.n, "iface": 2 * self.n}[what] + slot * self.n
+
+    def view(self, what, slot=0):
+        """This rank's own buffer of the current set."""
+        off = self._off(what, slot)
+        return self.buf[off:off + self.n]
 
     def iface_all(self):
-        off = (self.k % 2) * self.set_len + 2 * self.n
+        off = self._off("iface")
         return self.buf[off:off + self.world * self.n]
 
-    def sync(self, peers, channel):
-        for p in peers:
-            self.h.put_signal(p, channel, self.TIMEOUT_MS)
-        for p in peers:
-            self.h.wait_signal(p, channel, self.TIMEOUT_MS)
+    def exchange(self, copies, peers, stream):
+        """copies: (peer, what, slot, source tensor); then the flag handshake with `peers`."""
+        import ctypes
+        self.epoch += 1
+        n = len(copies)
+        vp = ctypes.c_void_p
+        dst = (vp * max(n, 1))(*[self.base[p] + 8 * self._off(w, s) for p, w, s, _ in copies])
+        src = (vp * max(n, 1))(*[t.data_ptr() for _, _, _, t in copies])
+        nb = (ctypes.c_size_t * max(n, 1))(*[t.numel() * 8 for _, _, _, t in copies])
+        rf = (vp * max(len(peers), 1))(*[self.base[p] + 8 * (self.flag_off + self.rank) for p in peers])
+        lf = (vp * max(len(peers), 1))(*[self.base[self.rank] + 8 * (self.flag_off + p) for p in peers])
+        counter = self.base[self.rank] + 8 * (self.flag_off + self.world)
+        check(self.L, self.L.pb_peer_exchange(n, dst, src, nb, len(peers), rf, lf, self.epoch, counter, stream))
 
 
 class DistributedParcop:
@@ -91,9 +102,10 @@ class DistributedParcop:
         self._xmask = {}
         self._peers = sorted({r for r in (self.lo_rank(), self.hi_rank()) if r is not None and r != self.rank})
         self._pb = None
-        if self.dev.type == "cuda" and self.world > 1 and os.environ.get("PB_NO_PEER_MEMORY", "0") != "1":
+        if (self.dev.type == "cuda" and self.world > 1 and self.plane % 2 == 0  # 16-byte aligned planes
+                and os.environ.get("PB_NO_PEER_MEMORY", "0") != "1"):
             try:
-                self._pb = _PeerBuffers(group, self.rank, self.world, self.plane, self.dev)
+                self._pb = _PeerBuffers(self.plan.L, group, self.rank, self.world, self.plane, self.dev)
             except Exception as exc:  # no IPC / symmetric-memory support: NCCL send/recv instead
                 import warnings
                 warnings.warn("peer-memory exchange unavailable (%s); using NCCL send/recv" % exc)
@@ -135,11 +147,12 @@ class DistributedParcop:
         pl = self._planes(f)
         n = h * self.plane
         if self._pb is not None:
-            if self.hi is not None:
-                self._pb.view(self.hi, "lo")[:n].copy_(pl[pl.shape[0] - h:].reshape(-1))
+            copies = []
+            if self.hi is not None:  # my last planes are the upper neighbour's lower halo
+                copies.append((self.hi, "lo", 0, pl[pl.shape[0] - h:].reshape(-1)))
             if self.lo is not None:
-                self._pb.view(self.lo, "hi")[:n].copy_(pl[:h].reshape(-1))
-            self._pb.sync(self._peers, 0)
+                copies.append((self.lo, "hi", 0, pl[:h].reshape(-1)))
+            self._pb.exchange(copies, self._peers, self._stream())
             return
         ops = []
         if self.hi is not None:
@@ -162,9 +175,9 @@ class DistributedParcop:
         P, L = self.plan, self.plan.L
         if self._pb is not None:  # this operator's set of peer-visible buffers
             self._pb.k += 1
-            recv_lo, recv_hi = self._pb.view(self.rank, "lo"), self._pb.view(self.rank, "hi")
+            recv_lo, recv_hi = self._pb.view("lo"), self._pb.view("hi")
             iface_all = self._pb.iface_all()
-            iface_local = self._pb.view(self.rank, "iface", self.rank)
+            iface_local = self._pb.view("iface", self.rank)
         else:
             recv_lo, recv_hi, iface_all, iface_local = self.recv_lo, self.recv_hi, self.iface_all, self.iface_local
         if self.world > 1:
@@ -194,13 +207,11 @@ class DistributedParcop:
         if self._xmask[code] == "gather":
             dist.all_gather_into_tensor(iface_all, iface_local.clone(), group=self.group)
             if self._pb is not None:
-                self._pb.sync(self._peers, 1)  # keeps the per-operator pairing of the buffer sets
+                self._pb.exchange([], self._peers, self._stream())  # keeps the per-operator pairing of the buffer sets
             return
         n = 4 * self.plane
         if self._pb is not None:
-            for peer in self._peers:
-                self._pb.view(peer, "iface", self.rank).copy_(iface_local)
-            self._pb.sync(self._peers, 1)
+            self._pb.exchange([(peer, "iface", self.rank, iface_local) for peer in self._peers], self._peers, self._stream())
             return
         ops = []
         for peer in self._peers:

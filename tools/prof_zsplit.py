@@ -38,8 +38,8 @@ for name in ("ddz", "sfilterz", "gfilterz", "dd8z"):
         e = [ev() for _ in range(5)]
         if eng._pb is not None:
             eng._pb.k += 1
-            rlo, rhi = eng._pb.view(rank, "lo"), eng._pb.view(rank, "hi")
-            iall, iloc = eng._pb.iface_all(), eng._pb.view(rank, "iface", rank)
+            rlo, rhi = eng._pb.view("lo"), eng._pb.view("hi")
+            iall, iloc = eng._pb.iface_all(), eng._pb.view("iface", rank)
         else:
             rlo, rhi, iall, iloc = eng.recv_lo, eng.recv_hi, eng.iface_all, eng.iface_local
         e[0].record()
