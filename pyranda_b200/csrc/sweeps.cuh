@@ -1279,11 +1279,13 @@ sweep_x_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
 template <int NLT>
 __device__ __forceinline__ bool warp_all_const(const SweepDev &a, int tid, bool cc) {
 #ifdef PB_EMULATE
-  if (NLT != 16) return cc;
-  const int s0 = (tid / NLT) & ~1;
-  return a.has_const && a.ctype[a.perm[s0]] == 0 && a.ctype[a.perm[s0 + 1]] == 0;
+  if (NLT >= 32) return cc;
+  const int per = 32 / NLT, s0 = (tid / NLT) / per * per;
+  bool all = a.has_const != 0;
+  for (int w = 0; w < per; ++w) all = all && a.ctype[a.perm[s0 + w]] == 0;
+  return all;
 #else
-  return NLT == 16 ? __all_sync(0xffffffffu, cc) : cc;
+  return NLT < 32 ? __all_sync(0xffffffffu, cc) : cc;
 #endif
 }
 
@@ -1904,11 +1906,20 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
             // to the TMA unit
             const int q1 = warp_other_chunk<NLX>(a, tid, p);
             if ((tid & 31) == 0) {
-              if constexpr (ACC) tma_reduce_add_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
-              else tma_store_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
-              if (NLX == 16) {
-                if constexpr (ACC) tma_reduce_add_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
-                else tma_store_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
+              if constexpr (NLX >= 16) {
+                if constexpr (ACC) tma_reduce_add_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
+                else tma_store_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
+                if (NLX == 16) {
+                  if constexpr (ACC) tma_reduce_add_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
+                  else tma_store_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
+                }
+              } else {  // 8-line tiles: four chunks per warp
+#pragma unroll
+                for (int w = 0; w < 32 / NLX; ++w) {
+                  const int q = a.perm[tid / NLX + w];
+                  if constexpr (ACC) tma_reduce_add_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+                  else tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+                }
               }
               tma_store_commit();
             }
@@ -2009,7 +2020,7 @@ static cudaError_t launch_yz_t(const SweepDev &a, const double *v, double *out, 
     ++g_launches;
     return cudaGetLastError();
   }
-  if constexpr (NL == 16 || NL == 32) {
+  if constexpr (NL == 8 || NL == 16 || NL == 32) {
     if (g_pipe_kernels && a.C == 32) {
       cudaError_t err;
       if (!PLAIN && epi.mode == EPI_ACC) {  // out += val: the plain-store kernel with TMA reduce-add stores
@@ -2075,7 +2086,7 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
   const long ntiles = ((long)a.nfast + NLX - 1) / NLX;
   int threads = NLX * a.P;
   threads = (threads + 31) / 32 * 32;
-  if constexpr (NLX == 16 || NLX == 32) {
+  if constexpr (NLX == 8 || NLX == 16 || NLX == 32) {
     if (g_pipe_kernels && a.C == 32) {
       cudaError_t err;
       if (!PLAIN && epi.mode == EPI_ACC) {  // out += val: the plain-store kernel with TMA reduce-add stores
@@ -2113,9 +2124,10 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
 template <int FAM, bool ADDV>
 cudaError_t launch_x_f(int lines, const SweepDev &a, const double *v, double *out, const EpiArgs &epi, cudaStream_t st) {
   const bool plain = epi.mode == EPI_STORE;
-  if (!a.implicit && g_pipe_kernels && a.C == 32 && (lines == 16 || lines == 32)) {  // the TMA-pipelined kernel without its solve phases
+  if (!a.implicit && g_pipe_kernels && a.C == 32 && (lines == 8 || lines == 16 || lines == 32)) {  // the TMA-pipelined kernel without its solve phases
     cudaError_t err;
-    if (lines == 16) err = plain ? launch_x_pipe<FAM, 16, true, ADDV>(a, v, out, epi, st) : launch_x_pipe<FAM, 16, false, ADDV>(a, v, out, epi, st);
+    if (lines == 8) err = plain ? launch_x_pipe<FAM, 8, true, ADDV>(a, v, out, epi, st) : launch_x_pipe<FAM, 8, false, ADDV>(a, v, out, epi, st);
+    else if (lines == 16) err = plain ? launch_x_pipe<FAM, 16, true, ADDV>(a, v, out, epi, st) : launch_x_pipe<FAM, 16, false, ADDV>(a, v, out, epi, st);
     else err = plain ? launch_x_pipe<FAM, 32, true, ADDV>(a, v, out, epi, st) : launch_x_pipe<FAM, 32, false, ADDV>(a, v, out, epi, st);
     if (err != cudaErrorNotSupported) return err;
   }

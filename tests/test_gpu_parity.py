@@ -66,9 +66,9 @@ def test_tile_shapes(chunk, lines, oracle_mod):
 
 @pytest.mark.parametrize("periodic", [True, False])
 @pytest.mark.parametrize("n", [(40, 256, 16), (72, 16, 256), (48, 512, 16), (36, 16, 512), (256, 18, 20), (512, 17, 16),
-                               (256, 256, 256)])
+                               (1024, 18, 16), (24, 1024, 16), (24, 16, 1024), (256, 256, 256)])
 def test_pipelined_kernels(n, periodic, oracle_mod):
-    """Line lengths of 256 / 512 take the TMA-pipelined persistent kernels (asserted through the
+    """Line lengths of 256 / 512 / 1024 take the TMA-pipelined persistent kernels (asserted through the
     launch counter): x, y and z sweeps, partial tiles, more tiles than CTAs, every family."""
     from pyranda_b200 import _lib
     L = _lib.load()
