@@ -52,7 +52,9 @@ struct SweepDev {
   int implicit;          // solve after the stencil
   int add_v;             // filters: result += input (null_option == 1)
   double scale;          // 1/d, 1/d^2 or 1
-  int acc;               // pipelined kernels: the stores accumulate (EPI_ACC through the plain-store path, TMA reduce-add)
+  int acc;               // pipelined kernels, plain-store path: 0 store, 1 out += val (TMA reduce-add), 2 out = max(out, val)
+  int ring;              // pipelined kernels, plain-store path: val = |val| * ring_s2 first (ring detector, Cartesian)
+  double ring_s2;
   int wstore;            // pipelined kernels: every warp issues the TMA stores of its own chunks (else one thread per block)
 };
 

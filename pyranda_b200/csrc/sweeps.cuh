@@ -1356,7 +1356,8 @@ __device__ __forceinline__ void stream_chunk_tile(const SweepDev &a, const doubl
   });
 }
 
-template <int FAM, int NL, bool PLAIN, bool ADDV, bool LATE>
+// RING: the plain-store path writes |val| s^2 (ring detector with a constant length scale)
+template <int FAM, int NL, bool PLAIN, bool ADDV, bool LATE, bool RING>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tmain,
                      const __grid_constant__ TileMap tlo, const __grid_constant__ TileMap thi,
@@ -1547,6 +1548,7 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           if (r < CT - 16) vr[r & 15] = __ldg(pv + (long)(r + 16) * rs);
         }
         if (PLAIN) {  // plain stores leave through the stage and the TMA unit, 16 rows of every chunk at a time
+          if constexpr (RING) val = fabs(val) * a.ring_s2;
           stage[(size_t)(p * 16 + (r & 15)) * NL + l] = val;
         } else {
           const double o = epi_value(val, ow[r & 15], oidx, epi);
@@ -1592,8 +1594,13 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
               const int q = a.perm[tid / NL + w];
               const int row = q * CT + r0;
               const int c1 = g.rowdim == 1 ? row : o, c2 = g.rowdim == 1 ? o : row;
-              if (a.acc) tma_reduce_add_3d(&tout, x0, c1, c2, stage + (size_t)q * 16 * NL);
-              else tma_store_3d(&tout, x0, c1, c2, stage + (size_t)q * 16 * NL);
+              if constexpr (RING) {
+                if (a.acc == 2) tma_reduce_max_3d(&tout, x0, c1, c2, stage + (size_t)q * 16 * NL);
+                else tma_store_3d(&tout, x0, c1, c2, stage + (size_t)q * 16 * NL);
+              } else {
+                if (a.acc) tma_reduce_add_3d(&tout, x0, c1, c2, stage + (size_t)q * 16 * NL);
+                else tma_store_3d(&tout, x0, c1, c2, stage + (size_t)q * 16 * NL);
+              }
             }
             tma_store_commit();
           }
@@ -1636,7 +1643,8 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
   TileMap tmain, tlo, thi, tout;
   if (!encode_tile_map(&tmain, v, ax, d1, d2, s1, s2, NL, ysweep ? 256 : 1, ysweep ? 1 : 256)) return cudaErrorNotSupported;
   tlo = tmain; thi = tmain; tout = tmain;
-  if (PLAIN && !encode_tile_map(&tout, out, ax, d1, d2, s1, s2, NL, ysweep ? 16 : 1, ysweep ? 1 : 16)) return cudaErrorNotSupported;
+  if (PLAIN && !encode_tile_map(&tout, out, ax, d1, d2, s1, s2, NL, ysweep ? 16 : 1, ysweep ? 1 : 16, false, a.acc == 2))
+    return cudaErrorNotSupported;
   if (hlo != nullptr) {  // z-slab halo planes received from the neighbours: {ax, ay, H} each
     if (ysweep) return cudaErrorNotSupported;
     if (!encode_tile_map(&tlo, hlo, ax, d1, H, s1, s2, NL, 1, 4) || !encode_tile_map(&thi, hhi, ax, d1, H, s1, s2, NL, 1, 4))
@@ -1649,14 +1657,22 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
   }
   const size_t smem = ((size_t)(m + 8) * NL + 16 * (size_t)a.P * NL + 4 * (size_t)a.P * NL) * sizeof(double) + 16;
   static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
-  auto kfn = (ADDV && late) ? sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, true> : sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, false>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  void (*kfn)(SweepDev, TileMap, TileMap, TileMap, TileMap, PipeGeo, const double *, double *, double *, EpiArgs) = nullptr;
+  int slot;
+  if (a.ring) {
+    if constexpr (PLAIN && !ADDV && FAM == F_R4) kfn = sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, false, true>;
+    slot = 2;
+  } else if (ADDV && late) {
+    kfn = sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, true, false>; slot = 1;
+  } else {
+    kfn = sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, false, false>; slot = 0;
+  }
+  if (kfn == nullptr) return cudaErrorNotSupported;
+  static bool configured[3] = {false, false, false};
+  if (!configured[slot]) {
+    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    configured = true;
+    configured[slot] = true;
   }
   const long ntiles = (long)((a.nfast + NL - 1) / NL) * a.nouter;
   const long want = 2L * sm_count();
@@ -1677,7 +1693,8 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
 // chunk at a time are written, swizzled, into a stage of P boxes and one thread hands them to the
 // TMA unit as stores; composite epilogues read the stage back and store with the old output.
 // MODE 0: implicit operator; 1: implicit with the late add-back (filters); 2: explicit operator (stencil only)
-template <int FAM, int NLX, bool PLAIN, bool ADDV, int MODE, bool ACC>
+// ACC 0: store, 1: out += val, 2: out = max(out, |val| s^2), 3: out = |val| s^2 (ring detector)
+template <int FAM, int NLX, bool PLAIN, bool ADDV, int MODE, int ACC>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tin,
                     const __grid_constant__ TileMap tout, const double *__restrict__ v, double *__restrict__ out,
@@ -1895,8 +1912,9 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
           xa = fma(q0.y * sc, tbk.y, xa);
           double xb = fma(q1.x * sc, tbk.x, rl[r + 1]);
           xb = fma(q1.y * sc, tbk.y, xb);
-          *reinterpret_cast<double2 *>(sb + ((kq << 4) ^ swz)) =
-              ((ADDV && LATE) || !implicit) ? make_double2(xa, xb) : make_double2(xa * scale, xb * scale);
+          double2 ov = ((ADDV && LATE) || !implicit) ? make_double2(xa, xb) : make_double2(xa * scale, xb * scale);
+          if constexpr (PLAIN && ACC >= 2) ov = make_double2(fabs(ov.x) * a.ring_s2, fabs(ov.y) * a.ring_s2);
+          *reinterpret_cast<double2 *>(sb + ((kq << 4) ^ swz)) = ov;
         });
         if (PLAIN) {
           fence_async_smem();
@@ -1907,17 +1925,20 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
             const int q1 = warp_other_chunk<NLX>(a, tid, p);
             if ((tid & 31) == 0) {
               if constexpr (NLX >= 16) {
-                if constexpr (ACC) tma_reduce_add_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
+                if constexpr (ACC == 1) tma_reduce_add_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
+                else if constexpr (ACC == 2) tma_reduce_max_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
                 else tma_store_3d(&tout, p * CT + g * G, (int)L0, 0, stage + (size_t)p * BOXB);
                 if (NLX == 16) {
-                  if constexpr (ACC) tma_reduce_add_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
+                  if constexpr (ACC == 1) tma_reduce_add_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
+                  else if constexpr (ACC == 2) tma_reduce_max_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
                   else tma_store_3d(&tout, q1 * CT + g * G, (int)L0, 0, stage + (size_t)q1 * BOXB);
                 }
               } else {  // 8-line tiles: four chunks per warp
 #pragma unroll
                 for (int w = 0; w < 32 / NLX; ++w) {
                   const int q = a.perm[tid / NLX + w];
-                  if constexpr (ACC) tma_reduce_add_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+                  if constexpr (ACC == 1) tma_reduce_add_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+                  else if constexpr (ACC == 2) tma_reduce_max_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
                   else tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
                 }
               }
@@ -1927,7 +1948,8 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
             __syncthreads();
             if (tid == 0) {
               for (int q = 0; q < P; ++q) {
-                if constexpr (ACC) tma_reduce_add_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+                if constexpr (ACC == 1) tma_reduce_add_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
+                else if constexpr (ACC == 2) tma_reduce_max_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
                 else tma_store_3d(&tout, q * CT + g * G, (int)L0, 0, stage + (size_t)q * BOXB);
               }
               tma_store_commit();
@@ -1976,25 +1998,31 @@ static cudaError_t launch_x_pipe(const SweepDev &a, const double *v, double *out
   TileMap tin, tout;
   const uint64_t rowb = (uint64_t)m * 8;
   if (!encode_tile_map(&tin, v, (uint64_t)m, (uint64_t)a.nfast, 1, rowb, rowb * (uint64_t)a.nfast, 16, NLX, 1, true) ||
-      !encode_tile_map(&tout, out, (uint64_t)m, (uint64_t)a.nfast, 1, rowb, rowb * (uint64_t)a.nfast, 16, NLX, 1, true))
+      !encode_tile_map(&tout, out, (uint64_t)m, (uint64_t)a.nfast, 1, rowb, rowb * (uint64_t)a.nfast, 16, NLX, 1, true, a.acc == 2))
     return cudaErrorNotSupported;
   const size_t smem = (size_t)(m / 16 + 2 + a.P) * NLX * 128 + 4 * (size_t)a.P * NLX * sizeof(double) + 16;
   static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
   void (*kfn)(SweepDev, TileMap, TileMap, const double *, double *, EpiArgs) = nullptr;
   int slot;
   if (!a.implicit) {
-    if constexpr (FAM == F_R4 && ADDV) { kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 2, false>; slot = 2; }
+    if constexpr (FAM == F_R4 && ADDV) { kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 2, 0>; slot = 2; }
     else return cudaErrorNotSupported;
   } else if (ADDV && late) {
-    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 1, false>; slot = 1;
-  } else if (PLAIN && !ADDV && a.acc) {
-    if constexpr (PLAIN && !ADDV) kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0, true>;
+    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 1, 0>; slot = 1;
+  } else if (PLAIN && !ADDV && a.acc == 1) {
+    if constexpr (PLAIN && !ADDV) kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0, 1>;
     slot = 3;
+  } else if (PLAIN && !ADDV && a.acc == 2) {
+    if constexpr (PLAIN && !ADDV && FAM == F_R4) kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0, 2>;
+    slot = 4;
+  } else if (PLAIN && !ADDV && a.ring) {
+    if constexpr (PLAIN && !ADDV && FAM == F_R4) kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0, 3>;
+    slot = 5;
   } else {
-    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0, false>; slot = 0;
+    kfn = sweep_x_pipe_kernel<FAM, NLX, PLAIN, ADDV, 0, 0>; slot = 0;
   }
   if (kfn == nullptr) return cudaErrorNotSupported;
-  static bool configured[4] = {false, false, false, false};
+  static bool configured[6] = {false, false, false, false, false, false};
   if (!configured[slot]) {
     cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -2026,6 +2054,12 @@ static cudaError_t launch_yz_t(const SweepDev &a, const double *v, double *out, 
       if (!PLAIN && epi.mode == EPI_ACC) {  // out += val: the plain-store kernel with TMA reduce-add stores
         SweepDev b = a;
         b.acc = 1;
+        err = launch_yz_pipe<FAM, NL, true, ADDV>(b, v, out, hlo, hhi, iface, epi, st);
+      } else if (!PLAIN && (epi.mode == EPI_RING_SET || epi.mode == EPI_RING_MAX) && epi.field == nullptr && FAM == F_R4) {
+        SweepDev b = a;  // ring detector, constant length scale: |val| s^2 stored or max-reduced by the TMA unit
+        b.ring = 1;
+        b.ring_s2 = epi.s2;
+        b.acc = epi.mode == EPI_RING_MAX ? 2 : 0;
         err = launch_yz_pipe<FAM, NL, true, ADDV>(b, v, out, hlo, hhi, iface, epi, st);
       } else {
         err = launch_yz_pipe<FAM, NL, PLAIN, ADDV>(a, v, out, hlo, hhi, iface, epi, st);
@@ -2092,6 +2126,12 @@ static cudaError_t launch_x_t(const SweepDev &a, const double *v, double *out, c
       if (!PLAIN && epi.mode == EPI_ACC) {  // out += val: the plain-store kernel with TMA reduce-add stores
         SweepDev b = a;
         b.acc = 1;
+        err = launch_x_pipe<FAM, NLX, true, ADDV>(b, v, out, epi, st);
+      } else if (!PLAIN && (epi.mode == EPI_RING_SET || epi.mode == EPI_RING_MAX) && epi.field == nullptr && FAM == F_R4) {
+        SweepDev b = a;  // ring detector, constant length scale
+        b.ring = 1;
+        b.ring_s2 = epi.s2;
+        b.acc = epi.mode == EPI_RING_MAX ? 2 : 0;
         err = launch_x_pipe<FAM, NLX, true, ADDV>(b, v, out, epi, st);
       } else {
         err = launch_x_pipe<FAM, NLX, PLAIN, ADDV>(a, v, out, epi, st);

@@ -68,6 +68,14 @@ __device__ __forceinline__ void tma_reduce_add_3d(const TileMap *map, int c0, in
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(src))
                : "memory");
 }
+// the same box max-reduced into global memory as unsigned 64-bit integers (the tensor map must be
+// encoded as UINT64): for non-negative doubles the IEEE bit pattern orders like the value, so this is
+// max(out, val) for the ring detector without reading the old output into the SM
+__device__ __forceinline__ void tma_reduce_max_3d(const TileMap *map, int c0, int c1, int c2, const void *src) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.max.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(src))
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // waits until the stores of this thread have finished READING shared memory (the buffer may be reused)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -88,7 +96,8 @@ __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async
 // (strides must be multiples of 16 bytes, the base 16-byte aligned): the caller falls back to the
 // register kernels.
 inline bool encode_tile_map(TileMap *map, const double *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
-                            uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle128 = false) {
+                            uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle128 = false,
+                            bool as_u64 = false) {
   typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -108,7 +117,7 @@ inline bool encode_tile_map(TileMap *map, const double *base, uint64_t d0, uint6
   static const int promo = getenv("PB_TMA_PROMO") ? atoi(getenv("PB_TMA_PROMO")) : 2;
   const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, estr,
+  return fn(map, as_u64 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, pr,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -172,11 +181,27 @@ inline void tma_reduce_add_3d(const TileMap *map, int c0, int c1, int c2, const 
         if (in) base[x + y * (long)map->s1 + z * (long)map->s2] += s[emul_box_index(map, i, j, k)];
       }
 }
+inline void tma_reduce_max_3d(const TileMap *map, int c0, int c1, int c2, const void *src) {
+  const double *s = static_cast<const double *>(src);
+  double *base = const_cast<double *>(map->base);
+  for (uint32_t k = 0; k < map->b2; ++k)
+    for (uint32_t j = 0; j < map->b1; ++j)
+      for (uint32_t i = 0; i < map->b0; ++i) {
+        const long x = (long)c0 + i, y = (long)c1 + j, z = (long)c2 + k;
+        const bool in = x >= 0 && y >= 0 && z >= 0 && x < (long)map->d0 && y < (long)map->d1 && z < (long)map->d2;
+        if (in) {
+          double &o = base[x + y * (long)map->s1 + z * (long)map->s2];
+          const double val = s[emul_box_index(map, i, j, k)];
+          o = val > o ? val : o;
+        }
+      }
+}
 inline void tma_store_commit() {}
 inline void tma_store_wait_read() {}
 inline void fence_async_smem() {}
 inline bool encode_tile_map(TileMap *map, const double *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
-                            uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle128 = false) {
+                            uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle128 = false,
+                            bool = false) {
   if ((s1_bytes & 15) || (s2_bytes & 15) || b0 > 256 || b1 > 256 || b2 > 256 || (swizzle128 && b0 != 16)) return false;
   *map = TileMap{base, d0, d1, d2, s1_bytes / 8, s2_bytes / 8, b0, b1, b2, swizzle128};
   return true;
