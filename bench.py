@@ -131,6 +131,7 @@ def tgv_step_time(n, warm=2, steps=3):
         dt = ss.variables["dt"] * 0.5
     torch.cuda.synchronize()
     l0 = ss.B.plan.launch_count()
+    f0 = ss.fuser.launches if ss.fuser is not None else 0
     t0 = time.perf_counter()
     for _ in range(steps):
         time_ = ss.rk4(time_, dt)
@@ -140,6 +141,7 @@ def tgv_step_time(n, warm=2, steps=3):
     return {"config": "Taylor-Green vortex %d^3 periodic fp64, CFL 0.5, deck of examples/TaylorGreen.py" % n,
             "ms_per_rk4_step": sec * 1e3, "steps": steps, "sweeps_per_step": 255,
             "library_launches_per_step": (ss.B.plan.launch_count() - l0) / steps,
+            "fused_pointwise_launches_per_step": ((ss.fuser.launches - f0) / steps) if ss.fuser is not None else 0,
             "gpoints_per_s": n ** 3 / sec / 1e9}
 
 

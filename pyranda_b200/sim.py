@@ -14,6 +14,7 @@ with another operator provider; tests use that to compare the CUDA path with the
 many steps.  The product ships only CudaBackend.
 """
 import math
+import os
 import re
 
 import numpy as np
@@ -162,12 +163,14 @@ def _lines(text):
 
 
 class _Equation:
-    def __init__(self, text):
+    def __init__(self, text, fuser=None):
         self.text = text
         lhs, rhs = text.split("=", 1) if "=" in text else (None, text)
         self.lhs = _VAR.findall(lhs) if lhs is not None else None
         self.kind = "PDE" if "ddt(" in text else "ALG"  # pyrandaEq.py:42-43
         self.src = translate(rhs)
+        if fuser is not None:  # arithmetic between operator calls -> one generated kernel each (fuse.py)
+            self.src = fuser.transform(self.src)
         self.code = compile(self.src, "<eom>", "eval")
 
 
@@ -215,6 +218,11 @@ class pyrandaSim:
         self.GridLen = backend.getvar("GridLen")
         self.zero = backend.zeros()
         self._ns = {"xp": self.xp, "numpy": self.xp, "self": self}
+        self.fuser = None
+        if isinstance(backend, CudaBackend) and os.environ.get("PB_NO_FUSE", "0") != "1":
+            from .fuse import Fuser
+            self.fuser = Fuser(self.xp)
+            self._ns["__fz"] = self.fuser.call
 
     # ---- operator forwards (pyranda.py:607-736) ----
     def ddx(self, v): return 0.0 if self.nx <= 1 else self.B.ddx(v)
@@ -270,7 +278,7 @@ class pyrandaSim:
     # ---- interpreter (pyranda.py:231-416) ----
     def EOM(self, eom):
         for ln in _lines(eom):
-            eq = _Equation(ln)
+            eq = _Equation(ln, self.fuser)
             self.equations.append(eq)
             for nm in _VAR.findall(ln):
                 self.variables.setdefault(nm, self.B.zeros())

@@ -219,6 +219,33 @@ def test_curvilinear(oracle_mod):
     assert rel_linf(p.pring(f), o.pring(f)) < 1e-11
 
 
+def test_fused_expressions_are_bit_identical():
+    """The NVRTC-compiled pointwise kernels of the EOM interpreter (pyranda_b200/fuse.py) reproduce
+    the unfused torch evaluation exactly: three Taylor-Green RK4 steps, every variable compared."""
+    import os
+    import torch
+    from decks import TGV_EOM, TGV_IC, tgv_mesh
+    from pyranda_b200.sim import pyrandaSim
+    sims = []
+    for fuse in (True, False):
+        os.environ["PB_NO_FUSE"] = "0" if fuse else "1"
+        try:
+            ss = pyrandaSim("tgv", tgv_mesh(32))
+        finally:
+            os.environ.pop("PB_NO_FUSE", None)
+        ss.EOM(TGV_EOM)
+        ss.setIC(TGV_IC)
+        t = 0.0
+        for _ in range(3):
+            t = ss.rk4(t, ss.variables["dt"] * 0.5)
+        sims.append(ss)
+    assert sims[0].fuser is not None and sims[0].fuser.enabled and sims[0].fuser.launches > 100
+    assert sims[1].fuser is None
+    for name in ("rho", "rhou", "rhov", "rhow", "Et", "p", "mu", "beta", "tauxy", "enst"):
+        a, b = sims[0].var(name), sims[1].var(name)
+        assert torch.equal(a, b), name
+
+
 def test_taylor_green_100_steps(oracle_mod):
     """north_star: within 1e-10 (relative L-infinity) after 100 RK4 steps of the Taylor-Green case,
     CUDA path vs the oracle running the identical deck driver on numpy arrays (32^3)."""
