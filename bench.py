@@ -145,6 +145,27 @@ def tgv_step_time(n, warm=2, steps=3):
             "gpoints_per_s": n ** 3 / sec / 1e9}
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, NVRTC, torch) may write to stdout; the contract is ONE JSON
+    line there.  Everything written to fd 1 from here on goes to stderr, the line goes to the real one."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -165,7 +186,7 @@ def run_reference(args):
                     "port of its algorithm on all host threads, each step a %d^3 sample of the workload" % n,
             "cpu_baseline": cb, "e2e": {"value": value, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -180,6 +201,7 @@ def main():
     ap.add_argument("--no-tgv", action="store_true")
     ap.add_argument("--tgv-n", type=int, default=256)
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -333,7 +355,7 @@ def main():
             "data": "synthetic",
             "config": bench_config(world, n),
             "per_op": per_op, "tgv": tgv, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
