@@ -99,6 +99,9 @@ int pb_rk4_stage(pb_plan *plan, long n, double dt, double A, double B, const dou
                  double *d_PHI, double *d_U, void *stream);
 /* local (this rank) reduction of n doubles; result written to *host_out after a stream sync */
 int pb_reduce(pb_plan *plan, int kind, long n, const double *d_val, double *host_out, void *stream);
+/* the same reduction with the result left in device memory (*d_out, one double): no stream sync, so
+ * a time-step controller can stay on the device until the host really needs the number */
+int pb_reduce_device(pb_plan *plan, int kind, long n, const double *d_val, double *d_out, void *stream);
 
 /* ---- z-slab multi-GPU pieces (compact_d1.f90:719-746,858-928; compact_r4.f90:640-656,...) ------
  * A distributed z operator is: halo exchange (ncclSend/Recv by the caller, planes sent straight

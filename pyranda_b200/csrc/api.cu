@@ -634,6 +634,12 @@ int pb_reduce(pb_plan *pl, int kind, long n, const double *d_val, double *host_o
   return PB_OK;
 }
 
+int pb_reduce_device(pb_plan *pl, int kind, long n, const double *d_val, double *d_out, void *stream) {
+  if (!pl || !d_val || !d_out || n <= 0 || kind < 0 || kind > 2) return fail(PB_ERR_ARG, "bad argument");
+  PB_CUDA(launch_reduce(kind, n, d_val, pl->red_partial, 2048, d_out, (cudaStream_t)stream));
+  return PB_OK;
+}
+
 // ---- z-slab pieces -------------------------------------------------------------------------------
 static int zop_kind(int zop) {
   switch (zop) {

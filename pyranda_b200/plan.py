@@ -211,5 +211,12 @@ class ParcopPlan:
         check(self.L, self.L.pb_reduce(self._h, REDUCE[kind], t.numel(), t.data_ptr(), ctypes.byref(out), self._stream()))
         return out.value
 
+    def reduce_device(self, kind, t):
+        """The same reduction without the host round trip: returns a 0-dim CUDA tensor."""
+        import torch
+        out = torch.empty((), dtype=torch.float64, device=t.device)
+        check(self.L, self.L.pb_reduce_device(self._h, REDUCE[kind], t.numel(), t.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
     def launch_count(self):
         return int(self.L.pb_launch_count())

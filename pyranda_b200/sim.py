@@ -76,6 +76,9 @@ class CudaBackend:
     def sum3D(self, a): return self.plan.reduce("sum", self._c(a)) if self.isfield(a) else float(a)
     def max3D(self, a): return self.plan.reduce("max", self._c(a)) if self.isfield(a) else float(a)
     def min3D(self, a): return self.plan.reduce("min", self._c(a)) if self.isfield(a) else float(a)
+    # the same, result left on the device (no stream sync): the time-step controller uses these
+    def max3D_dev(self, a): return self.plan.reduce_device("max", self._c(a))
+    def min3D_dev(self, a): return self.plan.reduce_device("min", self._c(a))
 
     def _c(self, a):
         ax, ay, az = self.plan.shape
@@ -223,6 +226,11 @@ class pyrandaSim:
             from .fuse import Fuser
             self.fuser = Fuser(self.xp)
             self._ns["__fz"] = self.fuser.call
+            # the time-step controller as fused expressions (same operations, same order as below)
+            self._courant = compile(self.fuser.transform(
+                "xp.abs(u)/self.d1 + xp.abs(v)/self.d2 + xp.abs(w)/self.d3 + xp.abs(c)/self.GridLen"), "<dt>", "eval")
+            self._diffrate = compile(self.fuser.transform(
+                "density*self.GridLen*self.GridLen/xp.maximum(1.0e-12, bulk)"), "<dt>", "eval")
 
     # ---- operator forwards (pyranda.py:607-736) ----
     def ddx(self, v): return 0.0 if self.nx <= 1 else self.B.ddx(v)
@@ -265,12 +273,16 @@ class pyrandaSim:
 
     # ---- pyrandaTimestep.py:42-77 (Cartesian branch) ----
     def dt_courant(self, u, v, w, c):
+        if self.fuser is not None:  # one kernel + a reduction whose result stays on the device
+            return 1.0 / self.B.max3D_dev(eval(self._courant, self._ns, {"u": u, "v": v, "w": w, "c": c}))
         xp = self.xp
         vrate = xp.abs(u) / self.d1 + xp.abs(v) / self.d2 + xp.abs(w) / self.d3
         crate = xp.abs(c) / self.GridLen
         return 1.0 / self.B.max3D(vrate + crate)
 
     def dt_diff(self, bulk, density):
+        if self.fuser is not None:
+            return self.B.min3D_dev(eval(self._diffrate, self._ns, {"bulk": bulk, "density": density}))
         delta = self.GridLen
         drate = density * delta * delta / self.xp.maximum(1.0e-12, bulk)
         return self.B.min3D(drate)
@@ -323,6 +335,7 @@ class pyrandaSim:
     def rk4(self, time, dt):
         PHI = {U: self.B.zeros() for U in self.conserved}
         time_i = time
+        dt = float(dt)  # a device scalar from the time-step controller: the one host read of the step
         self.deltat = dt
         for ii in range(5):
             FLUX = self.updateFlux()
