@@ -52,6 +52,7 @@ class Fuser:
         self.xp = xp
         self.enabled = enabled
         self.specs = []
+        self.groups = []
         self._rt = None
         self.launches = 0
 
@@ -112,6 +113,133 @@ class Fuser:
         op = _BIN[type(node.op)]
         return "(%s %s %s)" % (lc, op, rc), "(%s %s %s)" % (lp, op, rp)
 
+    # ------------------------------------------------------------------ groups of equations
+    @staticmethod
+    def _var_name(node):
+        """'x' for the node self.variables["x"], else None."""
+        if (isinstance(node, ast.Subscript) and isinstance(node.value, ast.Attribute) and node.value.attr == "variables"
+                and isinstance(node.value.value, ast.Name) and node.value.value.id == "self"):
+            sl = node.slice
+            if isinstance(sl, ast.Constant) and isinstance(sl.value, str):
+                return sl.value
+        return None
+
+    def pure_tree(self, src):
+        """The AST of `src` when it is arithmetic over variables and numbers only, else None."""
+        tree = ast.parse(src, mode="eval").body
+
+        def ok(n):
+            if _is_num(n) or self._var_name(n) is not None:
+                return True
+            if not _is_arith(n):
+                return False
+            kids = n.args if isinstance(n, ast.Call) else ([n.operand] if isinstance(n, ast.UnaryOp) else [n.left, n.right])
+            return all(ok(k) for k in kids)
+        return tree if (_is_arith(tree) and ok(tree)) else None
+
+    def make_group(self, assignments):
+        """assignments: [(lhs name, pure AST)] evaluated in order -> one kernel with several outputs.
+        Inputs are the variables read before the group assigns them; later equations see the values
+        earlier ones produced (kept in registers), exactly like the sequential interpreter."""
+        inputs, produced, stmts = [], {}, []
+
+        def emit(n):
+            if _is_num(n):
+                return "(%s)" % repr(float(n.value)), repr(n.value)
+            nm = self._var_name(n)
+            if nm is not None:
+                if nm in produced:
+                    return "o%d" % produced[nm], "O[%d]" % produced[nm]
+                if nm not in inputs:
+                    inputs.append(nm)
+                return "v%d" % inputs.index(nm), "V[%d]" % inputs.index(nm)
+            if isinstance(n, ast.UnaryOp):
+                c, p = emit(n.operand)
+                s = "-" if isinstance(n.op, ast.USub) else "+"
+                return "(%s%s)" % (s, c), "(%s%s)" % (s, p)
+            if isinstance(n, ast.Call):
+                parts = [emit(a) for a in n.args]
+                return ("%s(%s)" % (_CFUN[n.func.attr], ", ".join(c for c, _ in parts)),
+                        "xp.%s(%s)" % (n.func.attr, ", ".join(p for _, p in parts)))
+            lc, lp = emit(n.left)
+            rc, rp = emit(n.right)
+            if isinstance(n.op, ast.Pow):
+                if _is_num(n.right) and float(n.right.value) == 2.0:
+                    return "(%s * %s)" % (lc, lc), "(%s ** 2)" % lp
+                if _is_num(n.right) and float(n.right.value) == 0.5:
+                    return "sqrt(%s)" % lc, "(%s ** 0.5)" % lp
+                return "pow(%s, %s)" % (lc, rc), "(%s ** %s)" % (lp, rp)
+            op = _BIN[type(n.op)]
+            return "(%s %s %s)" % (lc, op, rc), "(%s %s %s)" % (lp, op, rp)
+
+        outs = []
+        for name, tree in assignments:
+            c, p = emit(tree)
+            stmts.append((c, p))
+            produced[name] = len(outs)  # a variable assigned twice: later readers see the latest value
+            outs.append(name)
+        self.groups.append({"inputs": inputs, "outs": outs, "stmts": stmts, "kernels": {}, "py": None})
+        return len(self.groups) - 1
+
+    def run_group(self, gid, variables):
+        """Evaluates the group into `variables` (fused when every input is a field or a number)."""
+        g = self.groups[gid]
+        vals = [variables[nm] for nm in g["inputs"]]
+        kern = self._group_kernel(g, vals) if self.enabled else None
+        if kern is None:
+            if g["py"] is None:
+                g["py"] = [eval("lambda xp, V, O: " + p) for _, p in g["stmts"]]
+            O = []
+            for name, fn in zip(g["outs"], g["py"]):
+                O.append(fn(self.xp, vals, O))
+                variables[name] = O[-1]
+            return
+        import torch
+        fn, mask, ref = kern
+        n = ref.numel()
+        outs = [torch.empty_strided(ref.shape, ref.stride(), dtype=torch.float64, device=ref.device) for _ in g["outs"]]
+        args = [n] + [v.data_ptr() if m else float(v) for v, m in zip(vals, mask)] + [o.data_ptr() for o in outs]
+        types = ([ctypes.c_long] + [ctypes.c_void_p if m else ctypes.c_double for m in mask] + [ctypes.c_void_p] * len(outs))
+        self._runtime().launch(fn, n, args, types, torch.cuda.current_stream().cuda_stream)
+        self.launches += 1
+        for name, o in zip(g["outs"], outs):
+            variables[name] = o
+
+    def _group_kernel(self, g, vals):
+        import torch
+        mask, ref = [], None
+        for v in vals:
+            if isinstance(v, torch.Tensor):
+                if v.dim() == 0 or v.dtype != torch.float64 or not v.is_cuda:
+                    return None
+                if ref is None:
+                    ref = v
+                elif v.shape != ref.shape or v.stride() != ref.stride():
+                    return None
+                mask.append(True)
+            elif isinstance(v, (int, float)) and not isinstance(v, bool):
+                mask.append(False)
+            else:
+                return None
+        if ref is None or not _dense(ref):
+            return None
+        # every output must depend on at least one field, or the interpreter would have produced a number
+        dep = []
+        for c, _ in g["stmts"]:
+            uses_field = any(("v%d" % i) in _tokens(c) for i, m in enumerate(mask) if m) or any(
+                ("o%d" % j) in _tokens(c) and dep[j] for j in range(len(dep)))
+            dep.append(uses_field)
+        if not all(dep):
+            return None
+        key = tuple(mask)
+        try:
+            if key not in g["kernels"]:
+                g["kernels"][key] = self._runtime().compile(group_kernel_source(g["stmts"], mask))
+        except Exception:
+            self.enabled = False
+            return None
+        return g["kernels"][key], mask, ref
+
     # ------------------------------------------------------------------ run time
     def call(self, idx, *vals):
         spec = self.specs[idx]
@@ -137,13 +265,8 @@ class Fuser:
         if ref is None:
             return spec.fallback(self.xp, *vals)
         n = ref.numel()
-        # dense storage in any axis order: the kernel walks the flat storage
-        st = sorted(zip(ref.stride(), ref.shape))
-        run = 1
-        for s_, e_ in st:
-            if e_ != 1 and s_ != run:
-                return spec.fallback(self.xp, *vals)
-            run *= e_
+        if not _dense(ref):
+            return spec.fallback(self.xp, *vals)
         try:
             rt = self._runtime()
             kern = spec.kernels.get(tuple(mask))
@@ -163,6 +286,39 @@ class Fuser:
         if self._rt is None:
             self._rt = _Nvrtc()
         return self._rt
+
+
+def _dense(ref):
+    """Dense storage in any axis order: the kernels walk the flat storage."""
+    run = 1
+    for s_, e_ in sorted(zip(ref.stride(), ref.shape)):
+        if e_ != 1 and s_ != run:
+            return False
+        run *= e_
+    return True
+
+
+def _tokens(cexpr):
+    import re
+    return set(re.findall(r"[vo]\d+", cexpr))
+
+
+def group_kernel_source(stmts, mask):
+    params = ["long n"]
+    loads = []
+    for i, m in enumerate(mask):
+        if m:
+            params.append("const double *__restrict__ a%d" % i)
+            loads.append("    const double v%d = a%d[t];" % (i, i))
+        else:
+            params.append("double v%d" % i)
+    body = []
+    for j, (c, _) in enumerate(stmts):
+        params.append("double *__restrict__ out%d" % j)
+        body.append("    const double o%d = %s;\n    out%d[t] = o%d;" % (j, c, j, j))
+    return ("extern \"C\" __global__ void __launch_bounds__(256) fz(%s) {\n"
+            "  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {\n"
+            "%s\n%s\n  }\n}\n" % (", ".join(params), "\n".join(loads), "\n".join(body)))
 
 
 def kernel_source(cexpr, mask):

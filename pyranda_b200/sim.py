@@ -172,7 +172,10 @@ class _Equation:
         self.lhs = _VAR.findall(lhs) if lhs is not None else None
         self.kind = "PDE" if "ddt(" in text else "ALG"  # pyrandaEq.py:42-43
         self.src = translate(rhs)
+        self.pure = None  # AST when the right-hand side is arithmetic over variables only (groupable)
         if fuser is not None:  # arithmetic between operator calls -> one generated kernel each (fuse.py)
+            if self.kind == "ALG" and self.lhs is not None and len(self.lhs) == 1:
+                self.pure = fuser.pure_tree(self.src)
             self.src = fuser.transform(self.src)
         self.code = compile(self.src, "<eom>", "eval")
 
@@ -222,6 +225,7 @@ class pyrandaSim:
         self.zero = backend.zeros()
         self._ns = {"xp": self.xp, "numpy": self.xp, "self": self}
         self.fuser = None
+        self._plan = None
         if isinstance(backend, CudaBackend) and os.environ.get("PB_NO_FUSE", "0") != "1":
             from .fuse import Fuser
             self.fuser = Fuser(self.xp)
@@ -308,7 +312,44 @@ class pyrandaSim:
     def updateFlux(self):  # pyranda.py:376-394
         return {eq.lhs[0]: eval(eq.code, self._ns) for eq in self.equations if eq.kind == "PDE"}
 
+    def _alg_plan(self):
+        """Consecutive algebraic equations that are pure arithmetic become one multi-output kernel."""
+        plan, run = [], []
+
+        def flush():
+            if len(run) >= 2:
+                plan.append(("group", self.fuser.make_group([(e.lhs[0], e.pure) for e in run])))
+            else:
+                plan.extend(("eq", e) for e in run)
+            run.clear()
+        for eq in self.equations:
+            if eq.kind != "ALG":
+                continue
+            if self.fuser is not None and eq.pure is not None:
+                run.append(eq)
+            else:
+                flush()
+                plan.append(("eq", eq))
+        flush()
+        return plan
+
     def updateVars(self):  # pyranda.py:397-416
+        if self.fuser is not None:
+            if self._plan is None or self._plan[0] != len(self.equations):
+                self._plan = (len(self.equations), self._alg_plan())
+            for kind, item in self._plan[1]:
+                if kind == "group":
+                    self.fuser.run_group(item, self.variables)
+                    continue
+                rhs = eval(item.code, self._ns)
+                if not item.lhs:
+                    continue
+                if len(item.lhs) == 1:
+                    self.variables[item.lhs[0]] = rhs
+                else:
+                    for nm, r in zip(item.lhs, rhs):
+                        self.variables[nm] = r
+            return
         for eq in self.equations:
             if eq.kind != "ALG":
                 continue

@@ -68,3 +68,39 @@ def test_generated_kernels_compile():
         for mask in ([True] * spec.nleaves, [True] + [False] * (spec.nleaves - 1)):
             cubin = rt.compile_to_cubin(kernel_source(spec.cexpr, mask))
             assert len(cubin) > 100
+
+
+def test_equation_groups_match_sequential_evaluation():
+    """Consecutive pure-arithmetic equations become one multi-output kernel: the group (evaluated
+    through its Python fallback here) must equal the sequential interpreter, and NVRTC must accept
+    the generated multi-output kernels."""
+    import re
+    from pyranda_b200.fuse import group_kernel_source
+    from pyranda_b200.sim import _Equation
+    rng = np.random.default_rng(1)
+    fz = Fuser(_NS, enabled=False)
+    eqs = [_Equation(ln, fz) for ln in _lines(TGV_EOM)]
+    names = set()
+    for ln in _lines(TGV_EOM):
+        names.update(re.findall(r":([A-Za-z_]\w*):", ln))
+    base = {nm: rng.uniform(0.5, 1.5, size=(3, 4, 2)) for nm in names}
+    base["gamma"] = 1.4
+    pure = [e for e in eqs if e.kind == "ALG" and e.pure is not None]
+    assert [e.lhs[0] for e in pure][:4] == ["u", "v", "w", "p"]
+    # sequential reference
+    sim = _Sim(rng)
+    sim.variables = dict(base)
+    ns = {"xp": _NS, "numpy": _NS, "self": sim, "__fz": fz.call}
+    for e in pure:
+        sim.variables[e.lhs[0]] = eval(e.code, ns)
+    # one group over the same equations
+    gid = fz.make_group([(e.lhs[0], e.pure) for e in pure])
+    got = dict(base)
+    fz.run_group(gid, got)
+    for e in pure:
+        assert np.array_equal(np.asarray(got[e.lhs[0]]), np.asarray(sim.variables[e.lhs[0]]), equal_nan=True), e.text
+    pytest.importorskip("cuda.bindings.nvrtc")
+    from pyranda_b200.fuse import _Nvrtc
+    g = fz.groups[gid]
+    mask = [nm != "gamma" for nm in g["inputs"]]
+    assert len(_Nvrtc().compile_to_cubin(group_kernel_source(g["stmts"], mask))) > 100
