@@ -92,6 +92,14 @@ int pb_divergence(pb_plan *plan, const double *d_fx, const double *d_fy, const d
 /* gradS (parcop.f90:371-379, operators.f90:184-212) */
 int pb_grads(pb_plan *plan, const double *d_val, double *d_gx, double *d_gy, double *d_gz,
              void *stream);
+/* divergenceTensor (parcop.f90:213-223, operators.f90:97-123, Cartesian): dfx = ddx fxx + ddy fyx + ddz fzx ... */
+int pb_divergence_tensor(pb_plan *plan, const double *d_fxx, const double *d_fxy, const double *d_fxz,
+                         const double *d_fyx, const double *d_fyy, const double *d_fyz,
+                         const double *d_fzx, const double *d_fzy, const double *d_fzz,
+                         double *d_dfx, double *d_dfy, double *d_dfz, void *stream);
+/* pRingV (parcop.f90:324-333, operators.f90:645-699 with L = 1, Cartesian) */
+int pb_ring_vector(pb_plan *plan, const double *d_vx, const double *d_vy, const double *d_vz,
+                   double *d_out, void *stream);
 
 /* ---- RK4 stage update and reductions (pyranda.py:797-807, pyrandaMPI.py:307-326) --------------
  * PHI = dt*F + A*PHI ; U += B*PHI  for n points, fused (40 B/point). */
@@ -140,6 +148,10 @@ int pb_host_apply(pb_plan *plan, int opcode, const double *h_val, double *h_out)
 int pb_host_divergence(pb_plan *plan, const double *h_fx, const double *h_fy, const double *h_fz,
                        double *h_out);
 int pb_host_grads(pb_plan *plan, const double *h_val, double *h_gx, double *h_gy, double *h_gz);
+/* h_f9 = {fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz}, h_out3 = {dfx, dfy, dfz} */
+int pb_host_divergence_tensor(pb_plan *plan, const double *const *h_f9, double *const *h_out3);
+int pb_host_ring_vector(pb_plan *plan, const double *h_vx, const double *h_vy, const double *h_vz,
+                        double *h_out);
 
 /* ---- introspection for tests / benchmarks ----------------------------------------------------- */
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */

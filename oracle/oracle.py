@@ -48,6 +48,9 @@ def lib():
         L.po_dd8.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp]
         L.po_d2.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp]
         L.po_div.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp]
+        L.po_divT.argtypes = [ctypes.c_void_p] + [_dp] * 12
+        L.po_divT.restype = ctypes.c_int
+        L.po_ringV.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp]
         L.po_grad.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp]
         L.po_filter.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp]
         L.po_gfilter_dir.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp]
@@ -165,6 +168,21 @@ class Oracle:
         fx, fy, fz = _f(fx), _f(fy), _f(fz)
         out = self._new()
         lib().po_div(self._h, _p(fx), _p(fy), _p(fz), _p(out))
+        return out
+
+    def divergencetensor(self, fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz):
+        """parcop.f90:213-223 (Cartesian)."""
+        ins = [_f(a) for a in (fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz)]
+        outs = [self._new(), self._new(), self._new()]
+        if lib().po_divT(self._h, *[_p(a) for a in ins], *[_p(a) for a in outs]) != 0:
+            raise ValueError("divT: only the Cartesian branch is restated")
+        return tuple(outs)
+
+    def pringv(self, vx, vy, vz):
+        """parcop.f90:324-333."""
+        a, b, c = _f(vx), _f(vy), _f(vz)
+        out = self._new()
+        lib().po_ringV(self._h, _p(a), _p(b), _p(c), _p(out))
         return out
 
     def grads(self, val):

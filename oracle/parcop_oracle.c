@@ -1199,6 +1199,53 @@ void po_ring(const po_plan *p, const double *f, double *out) {
   for (int d = 0; d < 3; d++) free(r[d]);
 }
 
+/* operators.f90:97-123 divT, Cartesian branch (parcop.f90:213-223 divergenceTensor): three
+ * divergences of the tensor's columns.  With NONE / PERI boundaries every symmetry selector is +1. */
+int po_divT(const po_plan *p, const double *fxx, const double *fxy, const double *fxz, const double *fyx, const double *fyy,
+            const double *fyz, const double *fzx, const double *fzy, const double *fzz, double *dfx, double *dfy, double *dfz) {
+  if (p->coordsys != 0) return -1;
+  const size_t N = p->npts;
+  double *fA = malloc(sizeof(double) * N), *fB = malloc(sizeof(double) * N), *fC = malloc(sizeof(double) * N);
+  const double *in[3][3] = {{fxx, fyx, fzx}, {fxy, fyy, fzy}, {fxz, fyz, fzz}};
+  double *out[3] = {dfx, dfy, dfz};
+  for (int c = 0; c < 3; c++) {
+    dir_op(p, PO_D1, 0, 0, in[c][0], fA); /* :106,111,116 */
+    dir_op(p, PO_D1, 1, 0, in[c][1], fB);
+    dir_op(p, PO_D1, 2, 0, in[c][2], fC);
+    for (size_t t = 0; t < N; t++) out[c][t] = fA[t] + fB[t] + fC[t]; /* :109,114,119 */
+  }
+  free(fA); free(fB); free(fC);
+  return 0;
+}
+
+/* operators.f90:645-699 ringV with L = 1 (parcop.f90:324-333 pRingV), ringx/y/z :701-753 */
+void po_ringV(const po_plan *p, const double *f, const double *g, const double *h, double *out) {
+  const size_t N = p->npts;
+  const int nn[3] = {p->nx, p->ny, p->nz};
+  const double *comp[3] = {f, g, h};
+  double *r[3][3];
+  for (int c = 0; c < 3; c++)
+    for (int d = 0; d < 3; d++) {
+      r[c][d] = malloc(sizeof(double) * N);
+      if (nn[d] == 1) memset(r[c][d], 0, sizeof(double) * N);
+      else dir_op(p, PO_D8, d, 0, comp[c], r[c][d]);
+    }
+  for (size_t t = 0; t < N; t++) {
+    double L[3];
+    const double dd[3] = {p->d1[t], p->d2[t], p->d3[t]};
+    for (int d = 0; d < 3; d++) { /* :680-682 */
+      double a = fabs(r[0][d][t]), b = fabs(r[1][d][t]), c = fabs(r[2][d][t]);
+      double mx = a > b ? a : b;
+      mx = mx > c ? mx : c;
+      L[d] = mx * dd[d];
+    }
+    double mx = L[0] > L[1] ? L[0] : L[1];
+    out[t] = mx > L[2] ? mx : L[2]; /* :683 */
+  }
+  for (int c = 0; c < 3; c++)
+    for (int d = 0; d < 3; d++) free(r[c][d]);
+}
+
 /* operators.f90:781-896: filtype 'spectral' (which=0, parcop.f90:337-346) or 'smooth' (which=1,
  * parcop.f90:348-357); scalar => x/y/zasym = 1 */
 void po_filter(const po_plan *p, int which, const double *fun, double *bar) {

@@ -21,7 +21,7 @@ REDUCE = dict(sum=0, max=1, min=2)
 EXPORTS = [
     "pb_last_error", "pb_version", "pb_plan_create", "pb_plan_destroy", "pb_plan_extents",
     "pb_plan_spacing", "pb_plan_set_mesh", "pb_getvar", "pb_getvar_device", "pb_apply",
-    "pb_divergence", "pb_grads", "pb_rk4_stage", "pb_reduce", "pb_reduce_device", "pb_z_pack_halo", "pb_z_local",
+    "pb_divergence", "pb_grads", "pb_divergence_tensor", "pb_ring_vector", "pb_host_divergence_tensor", "pb_host_ring_vector", "pb_rk4_stage", "pb_reduce", "pb_reduce_device", "pb_z_pack_halo", "pb_z_local",
     "pb_z_finish", "pb_z_exchange_ranks", "pb_peer_exchange", "pb_host_apply", "pb_host_divergence", "pb_host_grads", "pb_launch_count",
     "pb_pipe_launch_count", "pb_set_tuning",
 ]
@@ -56,6 +56,10 @@ def declare(L):
     L.pb_host_apply.argtypes = [_vp, i, _vp, _vp]
     L.pb_host_divergence.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.pb_host_grads.argtypes = [_vp, _vp, _vp, _vp, _vp]
+    L.pb_divergence_tensor.argtypes = [_vp] * 14
+    L.pb_ring_vector.argtypes = [_vp] * 6
+    L.pb_host_divergence_tensor.argtypes = [_vp, _vp, _vp]
+    L.pb_host_ring_vector.argtypes = [_vp] * 5
     L.pb_reduce_device.argtypes = [_vp, i, ctypes.c_long, _vp, _vp, _vp]
     L.pb_launch_count.restype = ctypes.c_long
     L.pb_pipe_launch_count.restype = ctypes.c_long

@@ -618,6 +618,43 @@ int pb_grads(pb_plan *pl, const double *in, double *gx, double *gy, double *gz, 
   return PB_OK;
 }
 
+// operators.f90:97-123 (Cartesian branch), parcop.f90:213-223: the divergence of each column of the tensor
+int pb_divergence_tensor(pb_plan *pl, const double *fxx, const double *fxy, const double *fxz, const double *fyx,
+                         const double *fyy, const double *fyz, const double *fzx, const double *fzy, const double *fzz,
+                         double *dfx, double *dfy, double *dfz, void *stream) {
+  if (!pl) return fail(PB_ERR_ARG, "plan is NULL");
+  if (pl->coordsys != 0) return fail(PB_ERR_UNSUPPORTED, "divT: only the Cartesian branch is implemented");
+  int rc;
+  if ((rc = pb_divergence(pl, fxx, fyx, fzx, dfx, stream)) != PB_OK) return rc;
+  if ((rc = pb_divergence(pl, fxy, fyy, fzy, dfy, stream)) != PB_OK) return rc;
+  return pb_divergence(pl, fxz, fyz, fzz, dfz, stream);
+}
+
+// operators.f90:645-699 with L = 1 (parcop.f90:324-333): max over the three directions of
+// max(|d8(vx)|, |d8(vy)|, |d8(vz)|) * d -- nine 8th-derivative sweeps that keep a running maximum
+// (multiplying by the positive spacing before or after the maximum rounds identically)
+int pb_ring_vector(pb_plan *pl, const double *vx, const double *vy, const double *vz, double *out, void *stream) {
+  if (!pl || !vx || !vy || !vz || !out) return fail(PB_ERR_ARG, "NULL argument");
+  if (pl->coordsys != 0) return fail(PB_ERR_UNSUPPORTED, "ringV: only the Cartesian branch is implemented");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double *comp[3] = {vx, vy, vz};
+  bool first = true;
+  int rc;
+  for (int d = 0; d < 3; ++d) {
+    if (pl->n[d] == 1 || pl->sw[K_D8][d].null_op) continue;  // ringx/y/z give zero there (operators.f90:709-712)
+    for (int c = 0; c < 3; ++c) {
+      EpiArgs e;
+      e.mode = first ? EPI_RING_SET : EPI_RING_MAX;
+      e.s2 = pl->d[d];
+      e.field = nullptr;
+      if ((rc = apply_dir(pl, pl->sw[K_D8][d], comp[c], out, e, st)) != PB_OK) return rc;
+      first = false;
+    }
+  }
+  if (first) PB_CUDA(launch_fill((long)pl->npts, 0.0, out, st));
+  return PB_OK;
+}
+
 int pb_rk4_stage(pb_plan *pl, long n, double dt, double A, double B, const double *F, double *PHI, double *U, void *stream) {
   if (!pl || !F || !PHI || !U || n < 0) return fail(PB_ERR_ARG, "bad argument");
   PB_CUDA(launch_rk4_stage(n, dt, A, B, F, PHI, U, (cudaStream_t)stream));
@@ -868,6 +905,32 @@ int pb_host_grads(pb_plan *pl, const double *h_val, double *h_gx, double *h_gy, 
   PB_CUDA(cudaMemcpyAsync(h_gx, d[1], bytes, cudaMemcpyDeviceToHost, 0));
   PB_CUDA(cudaMemcpyAsync(h_gy, d[2], bytes, cudaMemcpyDeviceToHost, 0));
   PB_CUDA(cudaMemcpyAsync(h_gz, d[3], bytes, cudaMemcpyDeviceToHost, 0));
+  PB_CUDA(cudaStreamSynchronize(0));
+  return PB_OK;
+}
+
+int pb_host_divergence_tensor(pb_plan *pl, const double *const *h_f9, double *const *h_out3) {
+  // h_f9 = {fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz}; one divergence at a time through four staging fields
+  if (!pl || !h_f9 || !h_out3) return fail(PB_ERR_ARG, "NULL argument");
+  if (pl->coordsys != 0) return fail(PB_ERR_UNSUPPORTED, "divT: only the Cartesian branch is implemented");
+  int rc;
+  for (int c = 0; c < 3; ++c)
+    if ((rc = pb_host_divergence(pl, h_f9[c], h_f9[3 + c], h_f9[6 + c], h_out3[c])) != PB_OK) return rc;
+  return PB_OK;
+}
+
+int pb_host_ring_vector(pb_plan *pl, const double *h_vx, const double *h_vy, const double *h_vz, double *h_out) {
+  if (!pl || !h_vx || !h_vy || !h_vz || !h_out) return fail(PB_ERR_ARG, "NULL argument");
+  double *d[4];
+  int rc;
+  for (int k = 0; k < 4; ++k)
+    if ((rc = get_scratch(pl, 4 + k, &d[k]))) return rc;
+  const size_t bytes = sizeof(double) * pl->npts;
+  PB_CUDA(cudaMemcpyAsync(d[0], h_vx, bytes, cudaMemcpyHostToDevice, 0));
+  PB_CUDA(cudaMemcpyAsync(d[1], h_vy, bytes, cudaMemcpyHostToDevice, 0));
+  PB_CUDA(cudaMemcpyAsync(d[2], h_vz, bytes, cudaMemcpyHostToDevice, 0));
+  if ((rc = pb_ring_vector(pl, d[0], d[1], d[2], d[3], nullptr)) != PB_OK) return rc;
+  PB_CUDA(cudaMemcpyAsync(h_out, d[3], bytes, cudaMemcpyDeviceToHost, 0));
   PB_CUDA(cudaStreamSynchronize(0));
   return PB_OK;
 }

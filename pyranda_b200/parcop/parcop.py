@@ -92,6 +92,9 @@ def sfilter(val): return _cur().sfilter(val)
 def gfilter(val): return _cur().gfilter(val)
 def gfilterdir(val, direction): return _cur().gfilterdir(val, direction)
 def divergence(fx, fy, fz): return _cur().divergence(fx, fy, fz)
+def divergencetensor(fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz):  # parcop.f90:213-223
+    return _cur().divergencetensor(fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz)
+def pringv(vx, vy, vz): return _cur().pringv(vx, vy, vz)  # parcop.f90:324-333
 def grads(val): return _cur().grads(val)
 
 

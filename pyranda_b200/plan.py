@@ -174,6 +174,32 @@ class ParcopPlan:
     def gfilterdir(self, val, direction):
         return self.apply(("gfilterx", "gfiltery", "gfilterz")[int(direction) - 1], val)
 
+    def divergencetensor(self, fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz):
+        """parcop.f90:213-223: (dfx, dfy, dfz), host arrays or device tensors."""
+        ins = (fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz)
+        if _is_torch(fxx):
+            t = [self._dev_in(a) for a in ins]
+            outs = [self.empty_device(t[0]) for _ in range(3)]
+            check(self.L, self.L.pb_divergence_tensor(self._h, *[a.data_ptr() for a in t], *[o.data_ptr() for o in outs], self._stream()))
+            return tuple(outs)
+        h = [self._host_in(a) for a in ins]
+        outs = [self._host_out() for _ in range(3)]
+        vp = ctypes.c_void_p
+        check(self.L, self.L.pb_host_divergence_tensor(self._h, (vp * 9)(*[a.ctypes.data for a in h]), (vp * 3)(*[o.ctypes.data for o in outs])))
+        return tuple(outs)
+
+    def pringv(self, vx, vy, vz):
+        """parcop.f90:324-333."""
+        if _is_torch(vx):
+            a, b, c = self._dev_in(vx), self._dev_in(vy), self._dev_in(vz)
+            out = self.empty_device(a)
+            check(self.L, self.L.pb_ring_vector(self._h, a.data_ptr(), b.data_ptr(), c.data_ptr(), out.data_ptr(), self._stream()))
+            return out
+        a, b, c = self._host_in(vx), self._host_in(vy), self._host_in(vz)
+        out = self._host_out()
+        check(self.L, self.L.pb_host_ring_vector(self._h, a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data))
+        return out
+
     def sfilterdir(self, val, direction):
         return self.apply(("sfilterx", "sfiltery", "sfilterz")[int(direction) - 1], val)
 

@@ -45,6 +45,18 @@ def test_emulated_operators_match_oracle(periodic, oracle_mod, emul_lib):
         assert rel_linf(a, b) < 1e-13
 
 
+@pytest.mark.parametrize("periodic", [True, False])
+def test_emulated_tensor_divergence_and_vector_ring(periodic, oracle_mod, emul_lib):
+    """divergenceTensor and pRingV (parcop.f90:213-223,324-333), Cartesian."""
+    o, p, f = _pair((32, 24, 20), periodic, oracle_mod, emul_lib)
+    g = np.asarray(np.cos(2 * f) + 0.3 * f, order="F")
+    h = np.asarray(f * f - 0.5, order="F")
+    ins = (f, g, h, 2 * g, f + h, -f, h * g, 0.5 * f, g - h)
+    for a, b in zip(p.divergencetensor(*ins), o.divergencetensor(*ins)):
+        assert rel_linf(a, b) < 1e-13
+    assert rel_linf(p.pringv(f, g, h), o.pringv(f, g, h)) < 1e-13
+
+
 def test_emulated_partial_tiles_and_single_chunk(oracle_mod, emul_lib):
     """nx not a multiple of the tile width, line count not a multiple of the x tile, P == 1."""
     emul_lib.pb_set_tuning(16, 16, 64)

@@ -48,6 +48,20 @@ def test_div_grad(periodic, oracle_mod):
         assert rel_linf(a, b) < TOL
 
 
+@pytest.mark.parametrize("n", [(48, 64, 32), (256, 256, 32)])
+@pytest.mark.parametrize("periodic", [True, False])
+def test_tensor_divergence_and_vector_ring(n, periodic, oracle_mod):
+    """divergenceTensor and pRingV (parcop.f90:213-223,324-333), Cartesian; the second size goes
+    through the TMA kernels with reduce-add / reduce-max stores."""
+    o, p, f = _pair(n, periodic, oracle_mod)
+    g = np.asfortranarray(np.cos(2 * f) + 0.3 * f)
+    h = np.asfortranarray(f * f - 0.5)
+    ins = (f, g, h, 2 * g, f + h, -f, h * g, 0.5 * f, g - h)
+    for a, b in zip(p.divergencetensor(*ins), o.divergencetensor(*ins)):
+        assert rel_linf(a, b) < TOL
+    assert rel_linf(p.pringv(f, g, h), o.pringv(f, g, h)) < TOL
+
+
 @pytest.mark.parametrize("chunk", [16, 32, 64])
 @pytest.mark.parametrize("lines", [8, 16, 32])
 def test_tile_shapes(chunk, lines, oracle_mod):
