@@ -137,13 +137,15 @@ _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-8
     "dd8y": "self.dd8y", "dd8z": "self.dd8z", "sum": "self.B.sum3D", "max": "self.B.max3D", "min": "self.B.min3D",
     "mean": "self.mean", "sign": "xp.sign", "abs": "xp.abs", "sqrt": "xp.sqrt", "sin": "xp.sin", "cos": "xp.cos",
     "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar",
-    "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff", "numpy.minimum": "xp.minimum",
+    "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff",
+    "bc.extrap": "self.bc.extrap", "bc.const": "self.bc.const", "bc.field": "self.bc.field",  # pyrandaBC.py:28-38
+    "numpy.minimum": "xp.minimum",
     "numpy.maximum": "xp.maximum", "numpy.sqrt": "xp.sqrt", "numpy.abs": "xp.abs", "numpy.where": "xp.where",
 }
 _NAMES = {"simtime": "self.time", "deltat": "self.deltat", "pi": "xp.pi", "meshx": 'self.variables["meshx"]',
           "meshy": 'self.variables["meshy"]', "meshz": 'self.variables["meshz"]', "gridLen": "self.GridLen"}
 _VAR = re.compile(r":([A-Za-z_]\w*):")
-_CALL = re.compile(r"(?<![\w.\"])((?:dt\.|numpy\.)?[A-Za-z_3]\w*)\(")
+_CALL = re.compile(r"(?<![\w.\"])((?:dt\.|numpy\.|bc\.)?[A-Za-z_3]\w*)\(")
 _WORD = re.compile(r"(?<![\w.\"])([A-Za-z_]\w*)(?![\w(\"])")
 
 
@@ -168,7 +170,11 @@ def _lines(text):
 class _Equation:
     def __init__(self, text, fuser=None):
         self.text = text
-        lhs, rhs = text.split("=", 1) if "=" in text else (None, text)
+        # an assignment has only variables (or ddt(variable)) left of its "="; a package call such as
+        # `bc.extrap([...], [...], order=1)` is evaluated for its side effect
+        head = text.split("=", 1)[0]
+        assign = "=" in text and re.fullmatch(r"\s*(ddt\(\s*)?\[?\s*:\w+:\s*(,\s*:\w+:\s*)*\]?\s*\)?\s*", head) is not None
+        lhs, rhs = text.split("=", 1) if assign else (None, text)
         self.lhs = _VAR.findall(lhs) if lhs is not None else None
         self.kind = "PDE" if "ddt(" in text else "ALG"  # pyrandaEq.py:42-43
         self.src = translate(rhs)
@@ -224,6 +230,8 @@ class pyrandaSim:
         self.GridLen = backend.getvar("GridLen")
         self.zero = backend.zeros()
         self._ns = {"xp": self.xp, "numpy": self.xp, "self": self}
+        from .bc import BoundaryConditions
+        self.bc = BoundaryConditions(self.variables)  # the `BC` package (pyrandaBC.py), on the fields in place
         self.fuser = None
         self._plan = None
         if isinstance(backend, CudaBackend) and os.environ.get("PB_NO_FUSE", "0") != "1":

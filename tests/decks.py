@@ -89,3 +89,25 @@ def run_tgv(ss, tstop=None, nsteps=None, cfl=0.5):
         enst = ss.B.sum3D(ss.variables["enst"]) / enst0
         n += 1
     return enst, time, n
+
+
+# A bounded (non-periodic) 2-D advection deck with the BC package, in the style of the reference's
+# boundary-driven examples (examples/advection.py + pyrandaBC usage in examples/cylinder.py:70-90).
+def bc_mesh(n):
+    return "\n".join(["xdom = (0.0, 1.0, %d)" % n, "ydom = (0.0, 1.0, %d)" % n, "zdom = (0.0, 1.0, 1)"])
+
+
+BC_EOM = """
+ddt(:phi:)  =  - :c: * ddx(:phi:) - 0.5 * :c: * ddy(:phi:)
+:phi:       =  fbar(:phi:)
+bc.extrap(['phi'],['xn','yn'])
+bc.const(['phi'],['x1'],0.0)
+bc.extrap(['phi'],['y1'],order=1)
+:grad2:     =  ddx(:phi:)*ddx(:phi:) + ddy(:phi:)*ddy(:phi:)
+bc.field('grad2',['x1'],:phi:)
+"""
+
+BC_IC = """
+:c:   = 1.0
+:phi: = exp(-((meshx-0.4)**2 + (meshy-0.5)**2)/0.02)
+"""

@@ -1,0 +1,60 @@
+"""The BC package of the interpreter (pyranda_b200/bc.py; pyrandaBC.py:40-186): plane semantics on
+numpy and on Fortran-strided torch tensors, and a bounded deck through the oracle-backed driver."""
+import numpy as np
+import pytest
+
+from decks import BC_EOM, BC_IC, bc_mesh
+from pyranda_b200.bc import BoundaryConditions
+
+
+def _fields(kind):
+    rng = np.random.default_rng(3)
+    a = np.asfortranarray(rng.uniform(-1, 1, size=(6, 5, 4)))
+    if kind == "numpy":
+        return a.copy(order="F"), a
+    import torch
+    t = torch.from_numpy(a.transpose(2, 1, 0).copy(order="C")).permute(2, 1, 0)  # own memory, strides (1, nx, nx*ny)
+    return t, a
+
+
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+def test_planes(kind):
+    f, a = _fields(kind)
+    g, _ = _fields(kind)
+    bc = BoundaryConditions({"f": f, "g": g})
+    bc.extrap("f", ["x1", "yn"])
+    bc.extrap(["f"], "zn", order=1)
+    bc.const(["f", "g"], ["y1"], 2.5)
+    bc.field("g", ["xn", "z1"], f)
+    e = a.copy()
+    e[0, :, :] = 2 * e[1, :, :] - e[2, :, :]
+    e[:, -1, :] = 2 * e[:, -2, :] - e[:, -3, :]
+    e[:, :, -1] = e[:, :, -2]
+    e[:, 0, :] = 2.5
+    eg = a.copy()
+    eg[:, 0, :] = 2.5
+    eg[-1, :, :] = e[-1, :, :]
+    eg[:, :, 0] = e[:, :, 0]
+    assert np.array_equal(np.asarray(f), e) and np.array_equal(np.asarray(g), eg)
+    bc2 = BoundaryConditions({"f": f}, owns={"x1": False})
+    before = np.asarray(f).copy()
+    bc2.const("f", ["x1", "xn"], 9.0)  # not this rank's boundaries: untouched
+    assert np.array_equal(np.asarray(f), before)
+    with pytest.raises(ValueError):
+        bc.const("f", "w1", 0.0)
+
+
+def test_bounded_deck_with_bc_lines(oracle_mod):
+    from oracle_backend import make_sim
+    ss = make_sim(oracle_mod, "bc", bc_mesh(32))
+    ss.EOM(BC_EOM)
+    ss.setIC(BC_IC)
+    t, dt = 0.0, 2.0e-3
+    for _ in range(5):
+        t = ss.rk4(t, dt)
+    phi, g2 = ss.variables["phi"], ss.variables["grad2"]
+    assert np.all(phi[0, :, :] == 0.0)
+    assert np.array_equal(phi[-1, 1:, :], (2 * phi[-2, :, :] - phi[-3, :, :])[1:, :])
+    assert np.array_equal(phi[:, 0, :], phi[:, 1, :])
+    assert np.array_equal(g2[0, :, :], phi[0, :, :])
+    assert np.isfinite(phi).all() and 0.5 < phi.max() < 1.1

@@ -233,6 +233,27 @@ def test_curvilinear(oracle_mod):
     assert rel_linf(p.pring(f), o.pring(f)) < 1e-11
 
 
+def test_bounded_deck_with_boundary_package(oracle_mod):
+    """A non-periodic 2-D deck with bc.extrap / bc.const / bc.field lines (pyrandaBC.py:40-186): the
+    device-resident driver against the oracle-backed one, ten RK4 steps."""
+    from decks import BC_EOM, BC_IC, bc_mesh
+    from oracle_backend import make_sim
+    from pyranda_b200.sim import pyrandaSim
+    ref = make_sim(oracle_mod, "bc", bc_mesh(64))
+    gpu = pyrandaSim("bc", bc_mesh(64))
+    for ss in (ref, gpu):
+        ss.EOM(BC_EOM)
+        ss.setIC(BC_IC)
+    t_ref = t_gpu = 0.0
+    for _ in range(10):
+        t_ref = ref.rk4(t_ref, 1.0e-3)
+        t_gpu = gpu.rk4(t_gpu, 1.0e-3)
+    for name in ("phi", "grad2"):
+        a, b = gpu.variables[name].cpu().numpy(), ref.variables[name]
+        assert np.abs(a - b).max() <= 1e-11 * np.abs(b).max(), name
+    assert float(gpu.variables["phi"][0, :, :].abs().max()) == 0.0
+
+
 def test_fused_expressions_are_bit_identical():
     """The NVRTC-compiled pointwise kernels of the EOM interpreter (pyranda_b200/fuse.py) reproduce
     the unfused torch evaluation exactly: three Taylor-Green RK4 steps, every variable compared."""
