@@ -139,6 +139,7 @@ _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-8
     "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar",
     "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff",
     "bc.extrap": "self.bc.extrap", "bc.const": "self.bc.const", "bc.field": "self.bc.field",  # pyrandaBC.py:28-38
+    "ibmV": "self.ibm.velocity_slip", "ibmWall": "self.ibm.velocity_wall", "ibmS": "self.ibm.scalar",  # pyrandaIBM.py:27-31
     "numpy.minimum": "xp.minimum",
     "numpy.maximum": "xp.maximum", "numpy.sqrt": "xp.sqrt", "numpy.abs": "xp.abs", "numpy.where": "xp.where",
 }
@@ -232,6 +233,8 @@ class pyrandaSim:
         self._ns = {"xp": self.xp, "numpy": self.xp, "self": self}
         from .bc import BoundaryConditions
         self.bc = BoundaryConditions(self.variables)  # the `BC` package (pyrandaBC.py), on the fields in place
+        from .ibm import ImmersedBoundary
+        self.ibm = ImmersedBoundary(self)             # the `IBM` package (pyrandaIBM.py)
         self.fuser = None
         self._plan = None
         if isinstance(backend, CudaBackend) and os.environ.get("PB_NO_FUSE", "0") != "1":
