@@ -376,6 +376,36 @@ class pyrandaSim:
     def var(self, name):
         return self.variables[name]
 
+    # ---- restart (pyranda.py:475-588: the whole state, for a later run) ----
+    def writeRestart(self, path):
+        """One .npz with every variable (fields staged device -> host, numbers as they are), the
+        equation strings, time, cycle and the last time step.  Off the step loop: the only D2H of a run."""
+        fields, scalars = {}, {}
+        for nm, val in self.variables.items():
+            if self.B.isfield(val) and getattr(val, "ndim", 3) == 3:
+                fields["f_" + nm] = np.asarray(self.B.tohost(val))
+            else:
+                scalars[nm] = float(val)
+        meta = {"time": self.time, "cycle": self.cycle, "deltat": float(self.deltat), "scalars": scalars,
+                "equations": [eq.text for eq in self.equations], "nn": [self.nx, self.ny, self.nz]}
+        np.savez(path, __meta__=np.array(repr(meta)), **fields)
+
+    def readRestart(self, path):
+        """Restores a state written by writeRestart on a simulation built with the same mesh."""
+        import ast as _ast
+        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz") as z:
+            meta = _ast.literal_eval(str(z["__meta__"]))
+            if list(meta["nn"]) != [self.nx, self.ny, self.nz]:
+                raise ValueError("restart was written on a %s grid" % (meta["nn"],))
+            if not self.equations:
+                self.EOM("\n".join(meta["equations"]))
+            for key in z.files:
+                if key.startswith("f_"):
+                    self.variables[key[2:]] = self.B.asfield(np.asfortranarray(z[key]))
+        self.variables.update(meta["scalars"])
+        self.time, self.cycle, self.deltat = meta["time"], meta["cycle"], meta["deltat"]
+        return self.time
+
     # ---- pyranda.py:758-810 ----
     ARK = (0.0, -6234157559845. / 12983515589748., -6194124222391. / 4410992767914.,
            -31623096876824. / 15682348800105., -12251185447671. / 11596622555746.)

@@ -45,3 +45,26 @@ def test_advection_1d_golden(oracle_mod):
             dt = min(dt_max, (tt - time))
         err = float(np.sum((ss.variables["phi"] - ss.variables["phi2"]) ** 2))
         assert abs(err - golden) / golden < 1e-3, (npts, err, golden)
+
+
+def test_restart_roundtrip(oracle_mod, tmp_path):
+    """writeRestart / readRestart (pyranda.py:475-588): a restarted run continues bit for bit."""
+    from decks import TGV_EOM, TGV_IC, tgv_mesh
+    from oracle_backend import make_sim
+    a = make_sim(oracle_mod, "tgv", tgv_mesh(16))
+    a.EOM(TGV_EOM)
+    a.setIC(TGV_IC)
+    t = 0.0
+    for _ in range(2):
+        t = a.rk4(t, float(a.variables["dt"]) * 0.5)
+    a.writeRestart(tmp_path / "state")
+    for _ in range(2):
+        t = a.rk4(t, float(a.variables["dt"]) * 0.5)
+    b = make_sim(oracle_mod, "tgv", tgv_mesh(16))
+    tb = b.readRestart(tmp_path / "state")
+    assert b.cycle == 2 and len(b.equations) == len(a.equations)
+    for _ in range(2):
+        tb = b.rk4(tb, float(b.variables["dt"]) * 0.5)
+    assert tb == t
+    for nm in ("rho", "rhou", "Et", "p", "mu"):
+        assert np.array_equal(a.variables[nm], b.variables[nm]), nm
