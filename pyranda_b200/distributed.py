@@ -87,7 +87,8 @@ class DistributedParcop:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.plan = ParcopPlan(nx, ny, nz, x1, xn, y1, yn, z1, zn, periodic=periodic, px=1, py=1, pz=self.world,
-                               coords=(0, 0, self.rank), coordsys=coordsys, device=device, lib=lib)
+                               coords=(0, 0, self.rank), coordsys=coordsys, device=device, lib=lib,
+                               tensor_device="cpu" if (tensor_device is not None and torch.device(tensor_device).type == "cpu") else "cuda")
         self.periodic_z = bool(periodic[2])
         ax, ay, az = self.plan.shape
         self.plane = ax * ay
@@ -304,3 +305,61 @@ class DistributedParcop:
         from ._lib import REDUCE
         check(self.plan.L, self.plan.L.pb_reduce(self.plan._h, REDUCE[kind], f.numel(), f.data_ptr(), ctypes.byref(out), self._stream()))
         return out.value
+
+
+# --------------------------------------------------------------------------------------------------
+def _make_backend():
+    from .sim import CudaBackend
+
+    class DistributedBackend(CudaBackend):
+        """Backend of the EOM interpreter (pyranda_b200.sim.pyrandaSim) on a z-slab partition: every
+        operator goes through the engine above (x / y sweeps local, z sweeps with the peer exchange),
+        reductions are completed with an all-reduce (pyrandaMPI.py:307-326).  Fields are this rank's
+        slab; the interpreter itself is unchanged."""
+
+        def __init__(self, eng):
+            CudaBackend.__init__(self, eng.plan)
+            self.eng = eng
+            self.device = eng.dev
+            # which physical boundaries this rank holds (pyrandaMPI x1proc ... znproc)
+            self.owns = {"x1": True, "xn": True, "y1": True, "yn": True,
+                         "z1": eng.rank == 0, "zn": eng.rank == eng.world - 1}
+
+        def _op(self, name, v): return self.eng.apply(name, self._f(v))
+        def ddx(self, v): return self._op("ddx", v)
+        def ddy(self, v): return self._op("ddy", v)
+        def ddz(self, v): return self._op("ddz", v)
+        def dd8x(self, v): return self._op("dd8x", v)
+        def dd8y(self, v): return self._op("dd8y", v)
+        def dd8z(self, v): return self._op("dd8z", v)
+        def filter(self, v): return self._op("sfilter", v)
+        def gfilter(self, v): return self._op("gfilter", v)
+        def gfilterdir(self, v, d): return self._op(("gfilterx", "gfiltery", "gfilterz")[int(d) - 1], v)
+        def ring(self, v): return self._op("ring", v)
+        def laplacian(self, v): return self._op("laplacian", v)
+        def div(self, a, b, c): return self.eng.divergence(self._f(a), self._f(b), self._f(c))
+        def grad(self, v): return self.eng.grads(self._f(v))
+
+        def sum3D(self, a): return self.eng.sum3D(self._c(a)) if self.isfield(a) else float(a)
+        def max3D(self, a): return self.eng.max3D(self._c(a)) if self.isfield(a) else float(a)
+        def min3D(self, a): return self.eng.min3D(self._c(a)) if self.isfield(a) else float(a)
+
+        def _all(self, t, op):
+            dist.all_reduce(t, op=op, group=self.eng.group)  # stays on the device: no host read
+            return t
+
+        def max3D_dev(self, a): return self._all(self.plan.reduce_device("max", self._c(a)).reshape(1), dist.ReduceOp.MAX)[0]
+        def min3D_dev(self, a): return self._all(self.plan.reduce_device("min", self._c(a)).reshape(1), dist.ReduceOp.MIN)[0]
+
+    return DistributedBackend
+
+
+def distributed_sim(name, mesh, device=-1, group=None, lib=None, tensor_device=None):
+    """`pyrandaSim` on a z-slab partition of the mesh (one process per GPU): the same deck strings,
+    each rank holding nz / world planes.  `mesh` is the deck's mesh string (or parsed options)."""
+    from .sim import parse_mesh, pyrandaSim
+    opt = parse_mesh(mesh) if isinstance(mesh, str) else mesh
+    eng = DistributedParcop(*opt["nn"], opt["x1"][0], opt["xn"][0], opt["x1"][1], opt["xn"][1], opt["x1"][2], opt["xn"][2],
+                            periodic=tuple(opt["periodic"]), device=device, group=group, lib=lib, tensor_device=tensor_device)
+    eng.plan.set_mesh()
+    return pyrandaSim(name, opt, backend=_make_backend()(eng))

@@ -232,7 +232,8 @@ class pyrandaSim:
         self.zero = backend.zeros()
         self._ns = {"xp": self.xp, "numpy": self.xp, "self": self}
         from .bc import BoundaryConditions
-        self.bc = BoundaryConditions(self.variables)  # the `BC` package (pyrandaBC.py), on the fields in place
+        # the `BC` package (pyrandaBC.py), on the fields in place; a z-slab backend says which faces are its own
+        self.bc = BoundaryConditions(self.variables, getattr(backend, "owns", None))
         from .ibm import ImmersedBoundary
         self.ibm = ImmersedBoundary(self)             # the `IBM` package (pyrandaIBM.py)
         self.fuser = None

@@ -67,6 +67,73 @@ dist.destroy_process_group()
 """
 
 
+SIM_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+from decks import TGV_EOM, TGV_IC, BC_EOM, BC_IC
+from oracle import oracle
+from oracle_backend import make_sim
+from pyranda_b200 import _lib
+from pyranda_b200.distributed import distributed_sim
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+L = _lib.load(os.path.join({emul!r}, "libparcop_emul.so"))
+L.pb_set_tuning(16, 16, 16)
+nz = 16 * world
+Lx = str(2 * np.pi * 15 / 16); Lz = str(2 * np.pi * (nz - 1) / nz)
+mesh = "xdom = (0.0, %s, 16, periodic=True)\nydom = (0.0, %s, 16, periodic=True)\nzdom = (0.0, %s, %d, periodic=True)" % (Lx, Lx, Lz, nz)
+ref = make_sim(oracle, "tgv", mesh)
+par = distributed_sim("tgv", mesh, lib=L, tensor_device="cpu")
+for ss in (ref, par):
+    ss.EOM(TGV_EOM)
+    ss.setIC(TGV_IC)
+sl = slice(rank * 16, (rank + 1) * 16)
+assert abs(float(par.variables["dt"]) - float(ref.variables["dt"])) < 1e-13 * float(ref.variables["dt"])
+t1 = t2 = 0.0
+for _ in range(3):
+    dt = float(ref.variables["dt"]) * 0.5
+    t1 = ref.rk4(t1, dt)
+    t2 = par.rk4(t2, dt)
+worst = 0.0
+for nm in ("rho", "rhou", "rhov", "Et", "p"):
+    a, b = par.variables[nm].numpy(), ref.variables[nm][:, :, sl]
+    err = np.abs(a - b).max() / np.abs(ref.variables[nm]).max()
+    worst = max(worst, err)
+    assert err < 1e-11, (nm, rank, err)
+# a bounded deck with the BC package: z faces belong to the first / last rank only
+mesh = "xdom = (0.0, 1.0, 16)\nydom = (0.0, 1.0, 16)\nzdom = (0.0, 1.0, %d)" % nz
+eom = BC_EOM.replace("['xn','yn']", "['xn','zn']").replace("['y1'],order=1", "['z1'],order=1")
+ref = make_sim(oracle, "bc", mesh)
+par = distributed_sim("bc", mesh, lib=L, tensor_device="cpu")
+for ss in (ref, par):
+    ss.EOM(eom)
+    ss.setIC(BC_IC)
+t1 = t2 = 0.0
+for _ in range(3):
+    t1 = ref.rk4(t1, 1.0e-3)
+    t2 = par.rk4(t2, 1.0e-3)
+a, b = par.variables["phi"].numpy(), ref.variables["phi"][:, :, sl]
+assert np.abs(a - b).max() < 1e-11 * np.abs(ref.variables["phi"]).max(), rank
+print("rank", rank, "worst", worst)
+dist.destroy_process_group()
+"""
+
+
+def test_distributed_interpreter_gloo(tmp_path):
+    """The EOM interpreter on a 2-rank z-slab (pyranda_b200.distributed.distributed_sim): Taylor-Green
+    and a bounded deck with BC lines against the one-rank oracle-backed driver."""
+    subprocess.check_call(["make", "-C", EMUL, "-s"])
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    script = tmp_path / "sim_worker.py"
+    script.write_text(SIM_WORKER.format(root=ROOT, emul=EMUL))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    r = subprocess.run(cmd, env=dict(os.environ, OMP_NUM_THREADS="2"), capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("worst") == 2
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
