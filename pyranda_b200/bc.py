@@ -1,7 +1,8 @@
-"""Boundary-plane packages of the EOM interpreter: bc.extrap / bc.const / bc.field.
+"""Boundary-plane packages of the EOM interpreter: bc.extrap / bc.const / bc.field / bc.symm.
 
-Reference: pyranda/pyrandaBC.py:40-186 (the `BC` package: `bc.extrap(vars, dirs, order)`,
-`bc.const(vars, dirs, val)`, `bc.field(var, dirs, field)` lines inside an EOM string).  They sit in
+Reference: pyranda/pyrandaBC.py:40-186,748-786 (the `BC` package: `bc.extrap(vars, dirs, order)`,
+`bc.const(vars, dirs, val)`, `bc.field(var, dirs, field)`, `bc.symm(vars, dirs, anti, npts)` lines
+inside an EOM string).  They sit in
 `updateVars`, i.e. they run after every RK4 stage, so with device-resident fields they must not
 leave the GPU: everything here is in-place slicing on the field object (a CUDA tensor with Fortran
 strides, or a numpy array in the oracle-backed test driver) -- one tiny strided kernel per plane.
@@ -53,6 +54,20 @@ class BoundaryConditions:
     def const(self, var, direction, val):
         for f, d in self._each(var, direction):
             f[self._plane(d, 0)] = val
+
+    # pyrandaBC.py:748-786: the first `npts` planes mirror the next `npts` (sign flipped for `anti`)
+    def symm(self, var, direction, anti=False, npts=4):
+        sign = -1.0 if anti else 1.0
+        for f, d in self._each(var, direction):
+            axis = _AXIS[d[0]]
+            ghost, image = [slice(None)] * 3, [slice(None)] * 3
+            if d[1] == "1":
+                ghost[axis], image[axis] = slice(0, npts), slice(npts, 2 * npts)
+            else:
+                ghost[axis], image[axis] = slice(-npts, None), slice(-2 * npts, -npts)
+            src = f[tuple(image)]
+            src = src.flip(axis) if hasattr(src, "flip") else src[tuple(slice(None, None, -1) if k == axis else slice(None) for k in range(3))]
+            f[tuple(ghost)] = src * sign
 
     # pyrandaBC.py:162-186
     def field(self, var, direction, field):

@@ -44,6 +44,22 @@ def test_planes(kind):
         bc.const("f", "w1", 0.0)
 
 
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+def test_symmetric_planes(kind):
+    """bc.symm (pyrandaBC.py:748-786): ghost planes mirror their images, optionally with the sign flipped."""
+    f, a = _fields(kind)
+    g, _ = _fields(kind)
+    bc = BoundaryConditions({"f": f, "g": g})
+    bc.symm("f", ["x1", "yn"], npts=2)
+    bc.symm(["g"], "z1", anti=True, npts=2)
+    e = a.copy()
+    e[0:2, :, :] = e[2:4, :, :][::-1, :, :]
+    e[:, -2:, :] = e[:, -4:-2, :][:, ::-1, :]
+    eg = a.copy()
+    eg[:, :, 0:2] = -eg[:, :, 2:4][:, :, ::-1]
+    assert np.array_equal(np.asarray(f), e) and np.array_equal(np.asarray(g), eg)
+
+
 def test_bounded_deck_with_bc_lines(oracle_mod):
     from oracle_backend import make_sim
     ss = make_sim(oracle_mod, "bc", bc_mesh(32))
