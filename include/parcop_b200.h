@@ -46,7 +46,11 @@ enum {
   PB_OP_GFILTER = 12,                                   /* parcop.f90:348-357  gFilter            */
   PB_OP_GFILTERX = 13, PB_OP_GFILTERY = 14, PB_OP_GFILTERZ = 15, /* parcop.f90:359-368 gFilterDir */
   PB_OP_SFILTERX = 16, PB_OP_SFILTERY = 17, PB_OP_SFILTERZ = 18, /* compact_operators.f90:385-497 */
-  PB_OP_COUNT = 19
+  /* d1x/d1y/d1z(v, dv, bc = -1) (compact_operators.f90:13-50,52-89,91-128): the first derivative
+   * of a field that is ODD across the axis' symmetry planes ("SYMM"); without a symmetry plane they
+   * are ddx/ddy/ddz.  The reference reaches them through divV / divT (operators.f90:48-50,106-120). */
+  PB_OP_DDX_ODD = 19, PB_OP_DDY_ODD = 20, PB_OP_DDZ_ODD = 21,
+  PB_OP_COUNT = 22
 };
 
 enum { PB_REDUCE_SUM = 0, PB_REDUCE_MAX = 1, PB_REDUCE_MIN = 2 };
@@ -59,8 +63,11 @@ const char *pb_version(void);
  * nx,ny,nz: GLOBAL sizes; px,py,pz: processor grid; cx,cy,cz: this rank's coordinates in it
  * (the reference derives them from MPI_CART_COORDS, comm.f90:150); x1..zn: node extents exactly as
  * Python passes them; b??: 4-character boundary strings "NONE" / "PERI" / "SYMM".
- * Round-1 scope: px = py = 1 (z-slab), coordsys 0 (Cartesian) or 3 (curvilinear), "SYMM" is
- * refused with PB_ERR_UNSUPPORTED.  `device` is the CUDA ordinal (-1: current device). */
+ * "SYMM" ends build the reference's symmetric / antisymmetric operator pair (compact.f90:77-91):
+ * every one-field operator uses the even member, pb_divergence / pb_divergence_tensor pick the odd
+ * first derivative for flux components normal to a symmetry plane (patch.f90:86-91 isymX/Y/Z).
+ * Round-1 scope: px = py = 1 (z-slab), coordsys 0 (Cartesian) or 3 (curvilinear).
+ * `device` is the CUDA ordinal (-1: current device). */
 int pb_plan_create(pb_plan **plan, int nx, int ny, int nz, int px, int py, int pz, int cx, int cy,
                    int cz, int coordsys, double x1, double xn, double y1, double yn, double z1,
                    double zn, const char *bx1, const char *bxn, const char *by1, const char *byn,

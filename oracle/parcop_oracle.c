@@ -1200,7 +1200,7 @@ void po_ring(const po_plan *p, const double *f, double *out) {
 }
 
 /* operators.f90:97-123 divT, Cartesian branch (parcop.f90:213-223 divergenceTensor): three
- * divergences of the tensor's columns.  With NONE / PERI boundaries every symmetry selector is +1. */
+ * divergences of the tensor's columns, each direction with its symmetry selector. */
 int po_divT(const po_plan *p, const double *fxx, const double *fxy, const double *fxz, const double *fyx, const double *fyy,
             const double *fyz, const double *fzx, const double *fzy, const double *fzz, double *dfx, double *dfy, double *dfz) {
   if (p->coordsys != 0) return -1;
@@ -1209,9 +1209,10 @@ int po_divT(const po_plan *p, const double *fxx, const double *fxy, const double
   const double *in[3][3] = {{fxx, fyx, fzx}, {fxy, fyy, fzy}, {fxz, fyz, fzz}};
   double *out[3] = {dfx, dfy, dfz};
   for (int c = 0; c < 3; c++) {
-    dir_op(p, PO_D1, 0, 0, in[c][0], fA); /* :106,111,116 */
-    dir_op(p, PO_D1, 1, 0, in[c][1], fB);
-    dir_op(p, PO_D1, 2, 0, in[c][2], fC);
+    /* :106-108,112-114,118-120: selector isym(d), squared (= +1) on the diagonal */
+    dir_op(p, PO_D1, 0, c == 0 ? 1 : isym(p, 0), in[c][0], fA);
+    dir_op(p, PO_D1, 1, c == 1 ? 1 : isym(p, 1), in[c][1], fB);
+    dir_op(p, PO_D1, 2, c == 2 ? 1 : isym(p, 2), in[c][2], fC);
     for (size_t t = 0; t < N; t++) out[c][t] = fA[t] + fB[t] + fC[t]; /* :109,114,119 */
   }
   free(fA); free(fB); free(fC);

@@ -55,7 +55,10 @@ struct pb_plan {
   double d[3], x1f[3], xnf[3];
   bool periodic[3], null_dir[3];
   size_t npts = 0;
-  SweepPlan sw[K_COUNT][3];
+  int bcode[3][2];                 // 0 NONE, 1 PERI, 2 SYMM
+  int isym[3];                     // patch.f90:86-91: -1 when either end of the axis is a symmetry plane
+  SweepPlan sw[K_COUNT][3];        // iop 1: even fields at symmetry planes (compact.f90:77-91)
+  SweepPlan d1_odd[3];             // iop 2 of the first derivative: odd fields (the normal flux in divV)
   SweepPlan custom_d1[3];
   std::vector<double *> scratch;   // device work fields, npts each
   double *red_partial = nullptr, *red_result = nullptr, *red_host = nullptr;
@@ -85,9 +88,11 @@ void free_sweep(SweepPlan &sp) {
 }
 
 // One operator along one axis: compact_basetype.f90:65-209 re-expressed for the chunked kernels.
-int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic) {
+// bc_lo / bc_hi: 0 one-sided closure, +1 / -1 symmetry plane below an even / odd field
+int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic, int bc_lo = 0, int bc_hi = 0) {
   sp.kind = kind; sp.dir = dir; sp.n = pl->n[dir]; sp.np = pl->p[dir]; sp.rank = pl->c[dir];
-  sp.st = make_stencil((Kind)kind);
+  try { sp.st = make_stencil((Kind)kind, periodic ? 0 : bc_lo, periodic ? 0 : bc_hi); }
+  catch (const std::exception &ex) { return fail(PB_ERR_ARG, ex.what()); }
   sp.null_op = pl->n[dir] < 4;  // compact.f90:95-97, compact_basetype.f90:101-103
   sp.split = sp.np > 1;
   sp.built = true;
@@ -297,6 +302,22 @@ int filter3(pb_plan *pl, int kind, const double *in, double *out, cudaStream_t s
   return apply_dir(pl, pl->sw[kind][2], tmp, out, kStore, st);
 }
 
+// d1x(v, dv, bc) of compact_operators.f90:13-50: bc = -1 selects the operator built for odd fields
+// when the axis has a symmetry plane, and the ordinary one otherwise (:35-38)
+SweepPlan &d1_plan(pb_plan *pl, int dir, int bc) {
+  return (bc == -1 && pl->d1_odd[dir].built) ? pl->d1_odd[dir] : pl->sw[K_D1][dir];
+}
+
+// the Cartesian divergence with a symmetry selector per direction (operators.f90:48-52, :106-120)
+int div_cart(pb_plan *pl, const double *fx, const double *fy, const double *fz, double *out, int bx, int by, int bz,
+             cudaStream_t st) {
+  const EpiArgs acc = {EPI_ACC, 0.0, nullptr};
+  int rc;
+  if ((rc = apply_dir(pl, d1_plan(pl, 0, bx), fx, out, kStore, st)) != PB_OK) return rc;
+  if ((rc = apply_dir(pl, d1_plan(pl, 1, by), fy, out, acc, st)) != PB_OK) return rc;
+  return apply_dir(pl, d1_plan(pl, 2, bz), fz, out, acc, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -330,7 +351,6 @@ int pb_plan_create(pb_plan **plan, int nx, int ny, int nz, int px, int py, int p
   for (int d = 0; d < 3; ++d)
     for (int s = 0; s < 2; ++s) {
       if (bc_code(bs[d][s], &bcode[d][s]) != PB_OK) return fail(PB_ERR_ARG, "boundary strings must be NONE, PERI or SYMM");
-      if (bcode[d][s] == 2) return fail(PB_ERR_UNSUPPORTED, "SYMM boundaries are not implemented on the CUDA path");
     }
   if (device >= 0) PB_CUDA(cudaSetDevice(device));
   int dev = 0;
@@ -347,12 +367,20 @@ int pb_plan_create(pb_plan **plan, int nx, int ny, int nz, int px, int py, int p
     pl->x1f[d] = lo[d] - dn / 2.0; pl->xnf[d] = hi[d] + dn / 2.0;
     pl->d[d] = (pl->xnf[d] - pl->x1f[d]) / (double)nn[d];
     pl->periodic[d] = bcode[d][0] == 1;  // patch.f90:89-109: periodicity follows the lower string
+    pl->bcode[d][0] = bcode[d][0]; pl->bcode[d][1] = bcode[d][1];
+    pl->isym[d] = (bcode[d][0] == 2 || bcode[d][1] == 2) ? -1 : 1;
     pl->null_dir[d] = nn[d] < 4;
   }
   pl->npts = (size_t)pl->a[0] * pl->a[1] * pl->a[2];
   for (int k = 0; k < K_COUNT; ++k)
     for (int d = 0; d < 3; ++d) {
-      int rc = build_sweep(pl, pl->sw[k][d], k, d, pl->periodic[d]);
+      // compact.f90:77-91: SYMM ends carry the pair (+1, -1); iop 1 takes the even member
+      int rc = build_sweep(pl, pl->sw[k][d], k, d, pl->periodic[d], bcode[d][0] == 2 ? 1 : 0, bcode[d][1] == 2 ? 1 : 0);
+      if (rc != PB_OK) { pb_plan_destroy(pl); return rc; }
+    }
+  for (int d = 0; d < 3; ++d)
+    if (pl->isym[d] == -1) {
+      int rc = build_sweep(pl, pl->d1_odd[d], K_D1, d, pl->periodic[d], bcode[d][0] == 2 ? -1 : 0, bcode[d][1] == 2 ? -1 : 0);
       if (rc != PB_OK) { pb_plan_destroy(pl); return rc; }
     }
   if (cudaMalloc(&pl->red_partial, sizeof(double) * 2048) != cudaSuccess ||
@@ -369,7 +397,7 @@ int pb_plan_destroy(pb_plan *pl) {
   if (!pl) return PB_OK;
   for (int k = 0; k < K_COUNT; ++k)
     for (int d = 0; d < 3; ++d) free_sweep(pl->sw[k][d]);
-  for (int d = 0; d < 3; ++d) free_sweep(pl->custom_d1[d]);
+  for (int d = 0; d < 3; ++d) { free_sweep(pl->custom_d1[d]); free_sweep(pl->d1_odd[d]); }
   for (double *q : pl->scratch) cudaFree(q);
   for (auto &kv : pl->mesh) cudaFree(kv.second);
   if (pl->red_partial) cudaFree(pl->red_partial);
@@ -521,6 +549,8 @@ int pb_apply(pb_plan *pl, int opcode, const double *in, double *out, void *strea
   switch (opcode) {
     case PB_OP_DDX: case PB_OP_DDY: case PB_OP_DDZ:
       return apply_dir(pl, pl->sw[K_D1][opcode - PB_OP_DDX], in, out, kStore, st);
+    case PB_OP_DDX_ODD: case PB_OP_DDY_ODD: case PB_OP_DDZ_ODD:
+      return apply_dir(pl, d1_plan(pl, opcode - PB_OP_DDX_ODD, -1), in, out, kStore, st);
     case PB_OP_DD8X: case PB_OP_DD8Y: case PB_OP_DD8Z:
       return apply_dir(pl, pl->sw[K_D8][opcode - PB_OP_DD8X], in, out, kStore, st);
     case PB_OP_D2X: case PB_OP_D2Y: case PB_OP_D2Z:
@@ -581,11 +611,8 @@ int pb_divergence(pb_plan *pl, const double *fx, const double *fy, const double 
   cudaStream_t st = (cudaStream_t)stream;
   const EpiArgs acc = {EPI_ACC, 0.0, nullptr};
   int rc;
-  if (pl->coordsys == 0) {  // operators.f90:48-52
-    if ((rc = apply_dir(pl, pl->sw[K_D1][0], fx, out, kStore, st)) != PB_OK) return rc;
-    if ((rc = apply_dir(pl, pl->sw[K_D1][1], fy, out, acc, st)) != PB_OK) return rc;
-    return apply_dir(pl, pl->sw[K_D1][2], fz, out, acc, st);
-  }
+  if (pl->coordsys == 0)  // operators.f90:48-52: each flux component is odd across its own symmetry plane
+    return div_cart(pl, fx, fy, fz, out, pl->isym[0], pl->isym[1], pl->isym[2], st);
   if (!pl->mesh_set) return fail(PB_ERR_STATE, "curvilinear divergence needs pb_plan_set_mesh");
   double *fA, *fB, *fC;
   if ((rc = get_scratch(pl, 1, &fA)) || (rc = get_scratch(pl, 2, &fB)) || (rc = get_scratch(pl, 3, &fC))) return rc;
@@ -624,10 +651,14 @@ int pb_divergence_tensor(pb_plan *pl, const double *fxx, const double *fxy, cons
                          double *dfx, double *dfy, double *dfz, void *stream) {
   if (!pl) return fail(PB_ERR_ARG, "plan is NULL");
   if (pl->coordsys != 0) return fail(PB_ERR_UNSUPPORTED, "divT: only the Cartesian branch is implemented");
+  if (!fxx || !fxy || !fxz || !fyx || !fyy || !fyz || !fzx || !fzy || !fzz || !dfx || !dfy || !dfz)
+    return fail(PB_ERR_ARG, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int *is = pl->isym;  // operators.f90:106-120: the diagonal components are even (isym**2)
   int rc;
-  if ((rc = pb_divergence(pl, fxx, fyx, fzx, dfx, stream)) != PB_OK) return rc;
-  if ((rc = pb_divergence(pl, fxy, fyy, fzy, dfy, stream)) != PB_OK) return rc;
-  return pb_divergence(pl, fxz, fyz, fzz, dfz, stream);
+  if ((rc = div_cart(pl, fxx, fyx, fzx, dfx, 1, is[1], is[2], st)) != PB_OK) return rc;
+  if ((rc = div_cart(pl, fxy, fyy, fzy, dfy, is[0], 1, is[2], st)) != PB_OK) return rc;
+  return div_cart(pl, fxz, fyz, fzz, dfz, is[0], is[1], 1, st);
 }
 
 // operators.f90:645-699 with L = 1 (parcop.f90:324-333): max over the three directions of
@@ -680,7 +711,7 @@ int pb_reduce_device(pb_plan *pl, int kind, long n, const double *d_val, double 
 // ---- z-slab pieces -------------------------------------------------------------------------------
 static int zop_kind(int zop) {
   switch (zop) {
-    case PB_OP_DDZ: return K_D1;
+    case PB_OP_DDZ: case PB_OP_DDZ_ODD: return K_D1;
     case PB_OP_DD8Z: return K_D8;
     case PB_OP_D2Z: return K_D2;
     case PB_OP_SFILTERZ: return K_SF;
@@ -692,7 +723,7 @@ static int zop_kind(int zop) {
 int pb_z_pack_halo(pb_plan *pl, int zop, const double *d_val, double *send_lo, double *send_hi, void *stream) {
   const int k = zop_kind(zop);
   if (!pl || k < 0 || !d_val || !send_lo || !send_hi) return fail(PB_ERR_ARG, "bad argument");
-  const SweepPlan &sp = pl->sw[k][2];
+  const SweepPlan &sp = zop == PB_OP_DDZ_ODD ? d1_plan(pl, 2, -1) : pl->sw[k][2];
   if (sp.null_op) return PB_OK;
   const long plane = (long)pl->a[0] * pl->a[1];
   PB_CUDA(launch_pack_planes(d_val, plane, pl->a[2], sp.st.nor, send_lo, send_hi, (cudaStream_t)stream));
@@ -703,7 +734,7 @@ int pb_z_local(pb_plan *pl, int zop, const double *d_val, const double *recv_lo,
                double *iface_local, void *stream) {
   const int k = zop_kind(zop);
   if (!pl || k < 0 || !d_val || !d_out) return fail(PB_ERR_ARG, "bad argument");
-  SweepPlan &sp = pl->sw[k][2];
+  SweepPlan &sp = zop == PB_OP_DDZ_ODD ? d1_plan(pl, 2, -1) : pl->sw[k][2];
   cudaStream_t st = (cudaStream_t)stream;
   if (sp.null_op || !sp.split) {
     // not distributed: the whole operator in one call
@@ -719,7 +750,7 @@ int pb_z_local(pb_plan *pl, int zop, const double *d_val, const double *recv_lo,
 int pb_z_finish(pb_plan *pl, int zop, const double *d_val, const double *iface_all, double *d_out, void *stream) {
   const int k = zop_kind(zop);
   if (!pl || k < 0 || !d_out) return fail(PB_ERR_ARG, "bad argument");
-  SweepPlan &sp = pl->sw[k][2];
+  SweepPlan &sp = zop == PB_OP_DDZ_ODD ? d1_plan(pl, 2, -1) : pl->sw[k][2];
   if (sp.null_op || !sp.split || !sp.st.implicit) return PB_OK;  // explicit operators are complete after pb_z_local
   if (!iface_all) return fail(PB_ERR_ARG, "missing interface buffer");
   (void)d_val;
@@ -755,7 +786,7 @@ int pb_peer_exchange(int ncopies, void *const *dst, const void *const *src, cons
 int pb_z_exchange_ranks(pb_plan *pl, int zop, unsigned long long *mask) {
   const int k = zop_kind(zop);
   if (!pl || k < 0 || !mask) return fail(PB_ERR_ARG, "bad argument");
-  const SweepPlan &sp = pl->sw[k][2];
+  const SweepPlan &sp = zop == PB_OP_DDZ_ODD ? d1_plan(pl, 2, -1) : pl->sw[k][2];
   *mask = (sp.null_op || !sp.split || !sp.st.implicit) ? 0ull : sp.rank_mask;
   return PB_OK;
 }
@@ -877,8 +908,9 @@ int pb_host_apply(pb_plan *pl, int opcode, const double *h_val, double *h_out) {
   return PB_OK;
 }
 
-int pb_host_divergence(pb_plan *pl, const double *h_fx, const double *h_fy, const double *h_fz, double *h_out) {
-  if (!pl || !h_fx || !h_fy || !h_fz || !h_out) return fail(PB_ERR_ARG, "NULL argument");
+// three host fields in, one out; sel = nullptr: the plan's own divergence (pb_divergence), otherwise
+// the Cartesian sum with the given symmetry selectors
+static int host_div(pb_plan *pl, const double *h_fx, const double *h_fy, const double *h_fz, double *h_out, const int *sel) {
   double *d[4];
   int rc;
   for (int k = 0; k < 4; ++k)
@@ -887,10 +919,17 @@ int pb_host_divergence(pb_plan *pl, const double *h_fx, const double *h_fy, cons
   PB_CUDA(cudaMemcpyAsync(d[0], h_fx, bytes, cudaMemcpyHostToDevice, 0));
   PB_CUDA(cudaMemcpyAsync(d[1], h_fy, bytes, cudaMemcpyHostToDevice, 0));
   PB_CUDA(cudaMemcpyAsync(d[2], h_fz, bytes, cudaMemcpyHostToDevice, 0));
-  if ((rc = pb_divergence(pl, d[0], d[1], d[2], d[3], nullptr)) != PB_OK) return rc;
+  if (sel) rc = div_cart(pl, d[0], d[1], d[2], d[3], sel[0], sel[1], sel[2], nullptr);
+  else rc = pb_divergence(pl, d[0], d[1], d[2], d[3], nullptr);
+  if (rc != PB_OK) return rc;
   PB_CUDA(cudaMemcpyAsync(h_out, d[3], bytes, cudaMemcpyDeviceToHost, 0));
   PB_CUDA(cudaStreamSynchronize(0));
   return PB_OK;
+}
+
+int pb_host_divergence(pb_plan *pl, const double *h_fx, const double *h_fy, const double *h_fz, double *h_out) {
+  if (!pl || !h_fx || !h_fy || !h_fz || !h_out) return fail(PB_ERR_ARG, "NULL argument");
+  return host_div(pl, h_fx, h_fy, h_fz, h_out, nullptr);
 }
 
 int pb_host_grads(pb_plan *pl, const double *h_val, double *h_gx, double *h_gy, double *h_gz) {
@@ -914,8 +953,11 @@ int pb_host_divergence_tensor(pb_plan *pl, const double *const *h_f9, double *co
   if (!pl || !h_f9 || !h_out3) return fail(PB_ERR_ARG, "NULL argument");
   if (pl->coordsys != 0) return fail(PB_ERR_UNSUPPORTED, "divT: only the Cartesian branch is implemented");
   int rc;
-  for (int c = 0; c < 3; ++c)
-    if ((rc = pb_host_divergence(pl, h_f9[c], h_f9[3 + c], h_f9[6 + c], h_out3[c])) != PB_OK) return rc;
+  for (int c = 0; c < 3; ++c) {
+    int sel[3] = {pl->isym[0], pl->isym[1], pl->isym[2]};
+    sel[c] = 1;  // operators.f90:106,113,120: isym**2 on the diagonal
+    if ((rc = host_div(pl, h_f9[c], h_f9[3 + c], h_f9[6 + c], h_out3[c], sel)) != PB_OK) return rc;
+  }
   return PB_OK;
 }
 

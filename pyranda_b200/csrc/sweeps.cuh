@@ -69,10 +69,11 @@ __device__ __forceinline__ double rhs_center(const double *w, const double *ar) 
 template <int FAM>
 __device__ __forceinline__ void rhs_lo4(const double *vv, const double (*b)[9], double *r) {
   if (FAM == F_D1) {
+    // column 8 is sigma, the row sum: non-zero only below an antisymmetric plane (compact_d1.f90:124-126)
     const double v0 = vv[0];
-    r[0] = b[0][4] * (vv[1] - v0) + b[0][5] * (vv[2] - v0) + b[0][6] * (vv[3] - v0);
-    r[1] = b[1][3] * (vv[1] - v0) + b[1][4] * (vv[2] - v0) + b[1][5] * (vv[3] - v0) + b[1][6] * (vv[4] - v0);
-    r[2] = b[2][4] * (vv[3] - vv[1]) + b[2][5] * (vv[4] - v0) + b[2][6] * (vv[5] - v0);
+    r[0] = b[0][8] * v0 + b[0][4] * (vv[1] - v0) + b[0][5] * (vv[2] - v0) + b[0][6] * (vv[3] - v0);
+    r[1] = b[1][8] * v0 + b[1][3] * (vv[1] - v0) + b[1][4] * (vv[2] - v0) + b[1][5] * (vv[3] - v0) + b[1][6] * (vv[4] - v0);
+    r[2] = b[2][8] * v0 + b[2][4] * (vv[3] - vv[1]) + b[2][5] * (vv[4] - v0) + b[2][6] * (vv[5] - v0);
     r[3] = b[3][4] * (vv[4] - vv[2]) + b[3][5] * (vv[5] - vv[1]) + b[3][6] * (vv[6] - v0);
   } else if (FAM == F_R3) {
 #pragma unroll
@@ -104,9 +105,9 @@ __device__ __forceinline__ void rhs_hi4(const double *u, const double (*h)[9], d
   if (FAM == F_D1) {
     const double vm = u[7];
     r[0] = h[0][4] * (u[5] - u[3]) + h[0][5] * (u[6] - u[2]) + h[0][6] * (u[7] - u[1]);
-    r[1] = h[1][0] * (u[2] - vm) + h[1][1] * (u[3] - vm) + h[1][2] * (u[4] - u[6]);
-    r[2] = h[2][0] * (u[3] - vm) + h[2][1] * (u[4] - vm) + h[2][2] * (u[5] - vm) + h[2][3] * (u[6] - vm);
-    r[3] = h[3][0] * (u[4] - vm) + h[3][1] * (u[5] - vm) + h[3][2] * (u[6] - vm);
+    r[1] = h[1][8] * vm + h[1][0] * (u[2] - vm) + h[1][1] * (u[3] - vm) + h[1][2] * (u[4] - u[6]);
+    r[2] = h[2][8] * vm + h[2][0] * (u[3] - vm) + h[2][1] * (u[4] - vm) + h[2][2] * (u[5] - vm) + h[2][3] * (u[6] - vm);
+    r[3] = h[3][8] * vm + h[3][0] * (u[4] - vm) + h[3][1] * (u[5] - vm) + h[3][2] * (u[6] - vm);
   } else if (FAM == F_R3) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

@@ -43,18 +43,75 @@ void difference_form(Stencil &s) {
 // (direct = true gives  A out = B v  without an add-back; it is NOT used for the compact filter:
 // its matrix is nearly singular at the Nyquist wavenumber, cond ~ 2e3, and the direct form loses
 // three digits against the reference -- measured 3e-13 instead of 2e-15 per application.)
-void set_reference_slots(Stencil &s, bool direct) {
+// At an antisymmetric end (bc = -1) the reference evaluates the closure rows as plain dot products
+// (compact_r4.f90:112-115,163-166): the folded weights do not sum to zero, and sigma carries their sum.
+void set_reference_slots(Stencil &s, bool direct, bool direct_lo = false, bool direct_hi = false) {
   auto rowsum = [](const double *w) { double t = 0.0; for (int l = 0; l < 9; ++l) t += w[l]; return t; };
   s.ari[4] = direct ? rowsum(s.ari) : 0.0;
   for (int i = 0; i < 4; ++i) {
-    s.arb_lo[i][4 - i] = direct ? rowsum(s.arb_lo[i]) : 0.0;
-    s.arb_hi[i][7 - i] = direct ? rowsum(s.arb_hi[i]) : 0.0;
+    s.arb_lo[i][4 - i] = (direct || direct_lo) ? rowsum(s.arb_lo[i]) : 0.0;
+    s.arb_hi[i][7 - i] = (direct || direct_hi) ? rowsum(s.arb_hi[i]) : 0.0;
+  }
+}
+
+// Symmetry planes (stencils.f90:2390-2453, lower/upper_symm_weights_int): the plane lies half a
+// cell outside the first / last point, so the interior stencil's out-of-range weight at distance
+// i beyond the plane folds onto the in-range point at distance i inside it, with the sign of the
+// field's parity (syml for the lhs, symr for the rhs).  Every closure row of that end is the
+// folded interior row.
+void fold_lower(Stencil &s, int syml, int symr) {
+  for (int r = 0; r < 4; ++r) {
+    for (int l = 0; l < 5; ++l) s.alb_lo[r][l] = l < s.ncl ? s.ali[l] : 0.0;
+    for (int l = 0; l < 9; ++l) s.arb_lo[r][l] = l < s.ncr ? s.ari[l] : 0.0;
+    for (int k = s.nol - r, i = 1; i <= k; ++i) {  // columns k-i (outside) -> k+i-1 (inside), 0-based
+      s.alb_lo[r][k + i - 1] += syml * s.alb_lo[r][k - i];
+      s.alb_lo[r][k - i] = 0.0;
+    }
+    for (int k = s.nor - r, i = 1; i <= k; ++i) {
+      s.arb_lo[r][k + i - 1] += symr * s.arb_lo[r][k - i];
+      s.arb_lo[r][k - i] = 0.0;
+    }
+  }
+}
+void fold_upper(Stencil &s, int syml, int symr) {
+  for (int r = 0; r < 4; ++r) {  // row r is point n-4+r: 3-r points remain above it
+    for (int l = 0; l < 5; ++l) s.alb_hi[r][l] = l < s.ncl ? s.ali[l] : 0.0;
+    for (int l = 0; l < 9; ++l) s.arb_hi[r][l] = l < s.ncr ? s.ari[l] : 0.0;
+    for (int k = s.nol - (3 - r), i = 1; i <= k; ++i) {
+      const int noff = s.ncl - k;  // first out-of-range column
+      s.alb_hi[r][noff - i] += syml * s.alb_hi[r][noff + i - 1];
+      s.alb_hi[r][noff + i - 1] = 0.0;
+    }
+    for (int k = s.nor - (3 - r), i = 1; i <= k; ++i) {
+      const int noff = s.ncr - k;
+      s.arb_hi[r][noff - i] += symr * s.arb_hi[r][noff + i - 1];
+      s.arb_hi[r][noff + i - 1] = 0.0;
+    }
+  }
+}
+
+// bc = +1 (even field) / -1 (odd field) at either end; d1 flips the parity between lhs and rhs
+// (stencils.f90:256-259), every other set keeps it (e.g. :407-410)
+void apply_symmetry(Stencil &s, int bc_lo, int bc_hi) {
+  const bool d1 = s.fam == F_D1;
+  if (bc_lo) fold_lower(s, d1 ? -bc_lo : bc_lo, bc_lo);
+  if (bc_hi) fold_upper(s, d1 ? -bc_hi : bc_hi, bc_hi);
+}
+
+// The first-derivative kernels difference the closure rows against the boundary point and have no
+// sigma column of their own: it rides in the unused column 8 (compact_d1.f90:124-126,166-168 are
+// plain dot products at bc = -1).
+void set_sigma_column(Stencil &s, int bc_lo, int bc_hi) {
+  auto rowsum = [&](const double *w) { double t = 0.0; for (int l = 0; l < s.ncr; ++l) t += w[l]; return t; };
+  for (int r = 0; r < 4; ++r) {
+    s.arb_lo[r][8] = bc_lo == -1 ? rowsum(s.arb_lo[r]) : 0.0;
+    s.arb_hi[r][8] = bc_hi == -1 ? rowsum(s.arb_hi[r]) : 0.0;
   }
 }
 
 }  // namespace
 
-Stencil make_stencil(Kind k) {
+Stencil make_stencil(Kind k, int bc_lo, int bc_hi) {
   Stencil s;
   switch (k) {
     case K_D1: {  // 10th-order compact first derivative, stencils.f90:207-254
@@ -71,6 +128,8 @@ Stencil make_stencil(Kind k) {
       set_row(s.arb_lo[2], {0.0, -1.23515625, -7.905, 0.0, 7.905, 1.23515625, 0.0});
       set_row(s.arb_lo[3], {-0.015, -1.53, -6.66984375, 0.0, 6.66984375, 1.53, 0.015});
       mirror_closures(s, -1.0);
+      apply_symmetry(s, bc_lo, bc_hi);
+      set_sigma_column(s, bc_lo, bc_hi);
       break;
     }
     case K_D2: {  // 10th-order compact second derivative, stencils.f90:358-405
@@ -87,6 +146,9 @@ Stencil make_stencil(Kind k) {
       set_row(s.arb_lo[2], {0.0, 465.0, 1920.0, -4770.0, 1920.0, 465.0, 0.0});
       set_row(s.arb_lo[3], {79.0, 4671.0, 9585.0, -28670.0, 9585.0, 4671.0, 79.0});
       mirror_closures(s, 1.0);
+      apply_symmetry(s, bc_lo, bc_hi);
+      if (bc_lo == -1 || bc_hi == -1)  // no entry point of parcop.f90 reaches d2 with bc = -1 (operators.f90:513-526)
+        throw std::invalid_argument("make_stencil: the second derivative has no antisymmetric variant on this path");
       break;
     }
     case K_D8: {  // compact 8th derivative (ringing detector), stencils.f90:515-591
@@ -105,7 +167,8 @@ Stencil make_stencil(Kind k) {
       set_row(s.arb_lo[2], {0.0, 0.0, dd + cc, ee + bb, aa, bb, cc, dd, ee});
       set_row(s.arb_lo[3], {0.0, ee + dd, cc, bb, aa, bb, cc, dd, ee});
       mirror_closures(s, 1.0);
-      set_reference_slots(s, false);
+      apply_symmetry(s, bc_lo, bc_hi);
+      set_reference_slots(s, false, bc_lo == -1, bc_hi == -1);
       break;
     }
     case K_SF: {  // 8th-order compact "9/10" filter, telescoped closures, stencils.f90:713-835
@@ -124,8 +187,9 @@ Stencil make_stencil(Kind k) {
       set_row(s.arb_lo[2], {0.0, 0.0, 1.668e-1, 6.6656e-1, 9.9952e-1, 6.6656e-1, 1.668e-1, 0.0, 0.0});
       set_row(s.arb_lo[3], {0.0, 4.0e-5, 1.6672e-1, 6.6652e-1, 9.9968e-1, 6.6652e-1, 1.6672e-1, 4.0e-5, 0.0});
       mirror_closures(s, 1.0);
+      apply_symmetry(s, bc_lo, bc_hi);
       difference_form(s);
-      set_reference_slots(s, false);
+      set_reference_slots(s, false, bc_lo == -1, bc_hi == -1);
       s.add_back = true;
       break;
     }
@@ -142,8 +206,9 @@ Stencil make_stencil(Kind k) {
       set_row(s.arb_lo[2], {0.0, 0.0, c + d, b + e, a, b, c, d, e});
       set_row(s.arb_lo[3], {0.0, d + e, c, b, a, b, c, d, e});
       mirror_closures(s, 1.0);
+      apply_symmetry(s, bc_lo, bc_hi);
       difference_form(s);
-      set_reference_slots(s, false);
+      set_reference_slots(s, false, bc_lo == -1, bc_hi == -1);
       s.add_back = true;
       break;
     }

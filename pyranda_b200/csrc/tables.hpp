@@ -16,7 +16,9 @@ namespace pb {
 enum Kind { K_D1 = 0, K_D2 = 1, K_D8 = 2, K_SF = 3, K_GF = 4, K_COUNT = 5 };
 enum Fam { F_D1 = 0, F_R3 = 1, F_R4 = 2 };
 
-// One operator's coefficients with the one-sided ("NONE", bc = 0) boundary closures.
+// One operator's coefficients with its boundary closures: one-sided ("NONE", bc = 0) or the
+// interior stencil folded across a symmetry plane ("SYMM": bc = +1 for an even field, -1 for an
+// odd one; compact.f90:77-91, stencils.f90:2390-2453).
 struct Stencil {
   int nol = 0, nor = 0, ncl = 1, ncr = 1;
   bool implicit = false;
@@ -29,7 +31,7 @@ struct Stencil {
   double alb_lo[4][5] = {}, alb_hi[4][5] = {};
   double arb_lo[4][9] = {}, arb_hi[4][9] = {};
 };
-Stencil make_stencil(Kind k);
+Stencil make_stencil(Kind k, int bc_lo = 0, int bc_hi = 0);
 
 // A line system A x = b of m unknowns, pentadiagonal (or identity for explicit operators), split
 // into P equal chunks of C rows.  Per chunk: LU of the chunk's diagonal block (couplings to other

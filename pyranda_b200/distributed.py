@@ -21,8 +21,8 @@ from ._lib import OP, check
 from .plan import ParcopPlan
 
 # z operator behind each distributed call and its halo width (nor of the stencil)
-_ZOPS = {"ddz": ("ddz", 3), "dd8z": ("dd8z", 4), "d2z": ("d2z", 3), "sfilterz": ("sfilterz", 4), "gfilterz": ("gfilterz", 4)}
-_IMPLICIT = {"ddz": True, "dd8z": True, "d2z": True, "sfilterz": True, "gfilterz": False}
+_ZOPS = {"ddz": ("ddz", 3), "ddz_odd": ("ddz_odd", 3), "dd8z": ("dd8z", 4), "d2z": ("d2z", 3), "sfilterz": ("sfilterz", 4), "gfilterz": ("gfilterz", 4)}
+_IMPLICIT = {"ddz": True, "ddz_odd": True, "dd8z": True, "d2z": True, "sfilterz": True, "gfilterz": False}
 
 
 class _PeerBuffers:
@@ -82,12 +82,13 @@ class _PeerBuffers:
 
 class DistributedParcop:
     def __init__(self, nx, ny, nz, x1=0.0, xn=1.0, y1=0.0, yn=1.0, z1=0.0, zn=1.0, periodic=(False, False, False),
-                 coordsys=0, device=-1, group=None, lib=None, tensor_device=None):
+                 coordsys=0, device=-1, group=None, lib=None, tensor_device=None,
+                 symmetric=((False, False), (False, False), (False, False))):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.plan = ParcopPlan(nx, ny, nz, x1, xn, y1, yn, z1, zn, periodic=periodic, px=1, py=1, pz=self.world,
-                               coords=(0, 0, self.rank), coordsys=coordsys, device=device, lib=lib,
+                               coords=(0, 0, self.rank), coordsys=coordsys, device=device, lib=lib, symmetric=symmetric,
                                tensor_device="cpu" if (tensor_device is not None and torch.device(tensor_device).type == "cpu") else "cuda")
         self.periodic_z = bool(periodic[2])
         ax, ay, az = self.plan.shape
@@ -229,7 +230,7 @@ class DistributedParcop:
 
     def apply_into(self, name, f, out):
         """ddx ddy ddz dd8x dd8y dd8z d2x d2y d2z sfilter gfilter gfilterx/y/z laplacian ring."""
-        if name in ("ddx", "ddy", "dd8x", "dd8y", "d2x", "d2y", "gfilterx", "gfiltery", "sfilterx", "sfiltery"):
+        if name in ("ddx", "ddy", "ddx_odd", "ddy_odd", "dd8x", "dd8y", "d2x", "d2y", "gfilterx", "gfiltery", "sfilterx", "sfiltery"):
             return self._local_into(name, f, out)
         if name in _ZOPS:
             return self.zop_into(name, f, out)
@@ -260,14 +261,14 @@ class DistributedParcop:
     def apply(self, name, f):
         return self.apply_into(name, f, self.empty())
 
-    def divergence(self, fx, fy, fz):  # operators.f90:48-52
+    def divergence(self, fx, fy, fz):  # operators.f90:48-52 (each flux is odd across its own symmetry plane)
         out = self.empty()
         if self._tmp is None:
             self._tmp = self.empty()
-        self._local_into("ddx", fx, out)
-        self._local_into("ddy", fy, self._tmp)
+        self._local_into("ddx_odd", fx, out)
+        self._local_into("ddy_odd", fy, self._tmp)
         out.add_(self._tmp)
-        self.zop_into("ddz", fz, self._tmp)
+        self.zop_into("ddz_odd", fz, self._tmp)
         return out.add_(self._tmp)
 
     def grads(self, f):  # operators.f90:191-193

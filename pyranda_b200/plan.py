@@ -160,6 +160,10 @@ class ParcopPlan:
     def ddx(self, val): return self.apply("ddx", val)
     def ddy(self, val): return self.apply("ddy", val)
     def ddz(self, val): return self.apply("ddz", val)
+    # d1x/d1y/d1z(v, dv, bc=-1) (compact_operators.f90:13-128): fields odd across the symmetry planes
+    def ddx_odd(self, val): return self.apply("ddx_odd", val)
+    def ddy_odd(self, val): return self.apply("ddy_odd", val)
+    def ddz_odd(self, val): return self.apply("ddz_odd", val)
     def dd8x(self, val): return self.apply("dd8x", val)
     def dd8y(self, val): return self.apply("dd8y", val)
     def dd8z(self, val): return self.apply("dd8z", val)

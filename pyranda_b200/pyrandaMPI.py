@@ -52,6 +52,8 @@ class pyrandaMPI:
         self.dz = (xn[2] - x1[2]) / max(self.nz - 1, 1)
         self.periodic = tuple(bool(p) for p in opt.get("periodic", (False,) * 3))
         self.coordsys = int(opt.get("coordsys", 0))
+        # meshOptions['symmetric'] -> "SYMM" boundary strings (pyrandaMPI.py:51,120-131)
+        self.symmetric = tuple((bool(a), bool(b)) for a, b in opt.get("symmetric", ((False, False),) * 3))
         self.order = (10, 10, 10)
         self.filter_type = ("compact", "compact", "compact")
         world, rank = 1, 0
@@ -67,11 +69,12 @@ class pyrandaMPI:
         args = (self.nx, self.ny, self.nz, x1[0], xn[0], x1[1], xn[1], x1[2], xn[2])
         if world > 1:
             from .distributed import DistributedParcop
-            self._dist = DistributedParcop(*args, periodic=self.periodic, coordsys=self.coordsys, device=dev, group=comm)
+            self._dist = DistributedParcop(*args, periodic=self.periodic, coordsys=self.coordsys, device=dev, group=comm,
+                                           symmetric=self.symmetric)
             self.plan = self._dist.plan
         else:
             self._dist = None
-            self.plan = ParcopPlan(*args, periodic=self.periodic, coordsys=self.coordsys, device=dev)
+            self.plan = ParcopPlan(*args, periodic=self.periodic, coordsys=self.coordsys, device=dev, symmetric=self.symmetric)
         self.ax, self.ay, self.az = self.plan.shape
         self.chunk_3d_size = np.array(self.plan.shape, dtype=np.int32)
         self.chunk_3d_lo = np.array([0, 0, rank * self.az], dtype=np.int32)

@@ -189,7 +189,8 @@ class _Equation:
 
 def parse_mesh(text):
     """`xdom = (x1, xn, n, periodic=True)` lines (pyrandaMesh.py:33-56)."""
-    opt = {"x1": [0.0, 0.0, 0.0], "xn": [1.0, 1.0, 1.0], "nn": [1, 1, 1], "periodic": [False, False, False]}
+    opt = {"x1": [0.0, 0.0, 0.0], "xn": [1.0, 1.0, 1.0], "nn": [1, 1, 1], "periodic": [False, False, False],
+           "symmetric": [[False, False], [False, False], [False, False]]}  # pyrandaMesh.py:222
 
     def setter(ind):
         def f(x1, xn, nn, periodic=False):
@@ -216,7 +217,8 @@ class pyrandaSim:
         if backend is None:
             from .plan import ParcopPlan
             plan = ParcopPlan(self.nx, self.ny, self.nz, opt["x1"][0], opt["xn"][0], opt["x1"][1], opt["xn"][1],
-                              opt["x1"][2], opt["xn"][2], periodic=tuple(opt["periodic"]), device=device)
+                              opt["x1"][2], opt["xn"][2], periodic=tuple(opt["periodic"]), device=device,
+                              symmetric=tuple(tuple(s) for s in opt.get("symmetric", ((False, False),) * 3)))
             plan.set_mesh()
             backend = CudaBackend(plan)
         self.B = backend

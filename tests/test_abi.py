@@ -40,8 +40,8 @@ def test_bad_arguments_are_refused_without_a_gpu():
     rc = L.pb_plan_create(ctypes.byref(h), 64, 64, 63, 1, 1, 2, 0, 0, 0, 0, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0,
                           b"NONE", b"NONE", b"NONE", b"NONE", b"NONE", b"NONE", -1)
     assert rc == -1 and b"divisible" in L.pb_last_error()
-    rc = L.pb_plan_create(ctypes.byref(h), *args, b"SYMM", b"NONE", b"NONE", b"NONE", b"NONE", b"NONE", -1)
-    assert rc == -2 and b"SYMM" in L.pb_last_error()
+    rc = L.pb_plan_create(ctypes.byref(h), *args, b"WALL", b"NONE", b"NONE", b"NONE", b"NONE", b"NONE", -1)
+    assert rc == -1 and b"SYMM" in L.pb_last_error()
     rc = L.pb_plan_create(ctypes.byref(h), 64, 64, 64, 2, 1, 1, 0, 0, 0, 0, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0,
                           b"NONE", b"NONE", b"NONE", b"NONE", b"NONE", b"NONE", -1)
     assert rc == -2

@@ -45,6 +45,21 @@ for periodic in (True, False):
     assert rel_linf(got, o.divergence(f, 2 * f, f * f)[:, :, sl]) < 1e-12
     assert abs(eng.sum3D(loc) - f.sum()) < 1e-9 * np.abs(f).sum()
     assert eng.max3D(loc) == f.max() and eng.min3D(loc) == f.min()
+# symmetry planes on the z faces (first / last rank) and one x face: even closures for every operator,
+# the odd first derivative for the normal fluxes of the divergence
+symm = ((True, False), (False, False), (True, True))
+(x1, xn), (y1, yn), (z1, zn) = domain(n, False)
+o = oracle.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(False,) * 3, symmetric=symm)
+f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+eng = DistributedParcop(*n, x1, xn, y1, yn, z1, zn, periodic=(False,) * 3, lib=L, tensor_device="cpu", symmetric=symm)
+sl = slice(rank * az, (rank + 1) * az)
+loc = eng.empty(); loc.copy_(torch.from_numpy(f[:, :, sl].copy()))
+for name, ref in (("ddx", o.ddx), ("ddz", o.ddz), ("dd8z", o.dd8z), ("d2z", o.d2z), ("sfilter", o.sfilter), ("gfilter", o.gfilter),
+                  ("ddz_odd", lambda v: o.dir_op("d1", 2, v, bc=-1))):
+    err = rel_linf(eng.apply(name, loc).numpy(), ref(f)[:, :, sl])
+    worst = max(worst, err)
+    assert err < 1e-12, (name, "symm", rank, err)
+assert rel_linf(eng.divergence(loc, loc * 2, loc * loc).numpy(), o.divergence(f, 2 * f, f * f)[:, :, sl]) < 1e-12
 # long slabs: the reduced system couples only neighbouring ranks and the all-gather is replaced by
 # a pair of sends; the correction touches only the rows near the slab faces
 from pyranda_b200._lib import OP

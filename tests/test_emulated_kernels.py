@@ -57,6 +57,53 @@ def test_emulated_tensor_divergence_and_vector_ring(periodic, oracle_mod, emul_l
     assert rel_linf(p.pringv(f, g, h), o.pringv(f, g, h)) < 1e-13
 
 
+SYMM_CASES = [((True, True), (True, False), (False, True)), ((True, False), (False, False), (True, True))]
+
+
+@pytest.mark.parametrize("symm", SYMM_CASES)
+def test_emulated_symmetry_planes(symm, oracle_mod, emul_lib):
+    """SYMM ends (compact.f90:77-91, stencils.f90:2390-2453): every one-field operator with the even
+    closure rows, the divergences with the odd first derivative on the normal flux."""
+    from pyranda_b200 import ParcopPlan
+    n = (32, 48, 32)
+    (x1, xn), (y1, yn), (z1, zn) = domain(n, False)
+    o = oracle_mod.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(False,) * 3, symmetric=symm)
+    p = ParcopPlan(*n, x1, xn, y1, yn, z1, zn, periodic=(False,) * 3, symmetric=symm, lib=emul_lib)
+    p.set_mesh()
+    f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+    for name in ("ddx", "ddy", "ddz", "dd8x", "dd8y", "dd8z", "d2x", "d2y", "d2z", "sfilter", "gfilter", "plaplacian", "pring"):
+        assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < 1e-13, name
+    for d, name in enumerate(("ddx_odd", "ddy_odd", "ddz_odd")):
+        assert rel_linf(getattr(p, name)(f), o.dir_op("d1", d, f, bc=-1)) < 1e-13, name
+    g = np.asarray(np.cos(2 * f) + 0.3 * f, order="F")
+    h = np.asarray(f * f - 0.5, order="F")
+    assert rel_linf(p.divergence(f, g, h), o.divergence(f, g, h)) < 1e-13
+    ins = (f, g, h, 2 * g, f + h, -f, h * g, 0.5 * f, g - h)
+    for a, b in zip(p.divergencetensor(*ins), o.divergencetensor(*ins)):
+        assert rel_linf(a, b) < 1e-13
+
+
+def test_emulated_symmetry_equals_mirrored_periodic_line(oracle_mod, emul_lib):
+    """A symmetry plane is the interior stencil on the mirrored field: cos(kx) / sin(kx) on N cells
+    of [0, pi] with SYMM ends give what the periodic operators give on 2N cells of [0, 2 pi]."""
+    from pyranda_b200 import ParcopPlan
+    N, ny, nz = 32, 16, 16
+    dx = np.pi / N
+    per = ParcopPlan(2 * N, ny, nz, dx / 2, 2 * np.pi - dx / 2, 0, 1, 0, 1, periodic=(True, False, False), lib=emul_lib)
+    sym = ParcopPlan(N, ny, nz, dx / 2, np.pi - dx / 2, 0, 1, 0, 1, periodic=(False,) * 3,
+                     symmetric=((True, True), (False, False), (False, False)), lib=emul_lib)
+    per.set_mesh(); sym.set_mesh()
+    X = per.getvar("x")
+    rng = np.random.default_rng(7)
+    amp = rng.uniform(-1, 1, size=6)
+    even = np.asfortranarray(sum(a * np.cos(k * X) for k, a in enumerate(amp)))
+    odd = np.asfortranarray(sum(a * np.sin((k + 1) * X) for k, a in enumerate(amp)))
+    # (the 8th derivative of these smooth modes cancels seven digits: weights ~4e3 on values ~1 give ~2e-3)
+    for name, tol in (("ddx", 1e-12), ("d2x", 1e-11), ("dd8x", 1e-8), ("sfilter", 1e-12), ("gfilter", 1e-12)):
+        assert rel_linf(getattr(sym, name)(np.asfortranarray(even[:N])), getattr(per, name)(even)[:N]) < tol, name
+    assert rel_linf(sym.ddx_odd(np.asfortranarray(odd[:N])), per.ddx(odd)[:N]) < 1e-12
+
+
 def test_emulated_partial_tiles_and_single_chunk(oracle_mod, emul_lib):
     """nx not a multiple of the tile width, line count not a multiple of the x tile, P == 1."""
     emul_lib.pb_set_tuning(16, 16, 64)

@@ -1,0 +1,58 @@
+"""SYMM boundaries on the CUDA path (compact.f90:77-91, stencils.f90:2390-2453):
+parity against the oracle, and the size-independent property that a symmetry plane is the interior
+stencil applied to the mirrored field.  (The file name sorts last on purpose: newest GPU tests run
+after the established ones.)
+"""
+import numpy as np
+import pytest
+
+from conftest import domain, rel_linf, synthetic_field
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+UNARY = ["ddx", "ddy", "ddz", "dd8x", "dd8y", "dd8z", "d2x", "d2y", "d2z", "plaplacian", "pring", "sfilter", "gfilter"]
+CASES = [((True, True), (True, False), (False, True)), ((True, False), (False, False), (True, True))]
+
+
+@pytest.mark.parametrize("symm", CASES)
+@pytest.mark.parametrize("n", [(64, 48, 32), (256, 256, 32)])  # the second size runs the TMA kernels
+def test_symmetry_planes_match_oracle(n, symm, oracle_mod):
+    from pyranda_b200 import ParcopPlan
+    (x1, xn), (y1, yn), (z1, zn) = domain(n, False)
+    o = oracle_mod.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(False,) * 3, symmetric=symm)
+    p = ParcopPlan(*n, x1, xn, y1, yn, z1, zn, periodic=(False,) * 3, symmetric=symm)
+    p.set_mesh()
+    f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+    for name in UNARY:
+        assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < TOL, (name, n)
+    for d, name in enumerate(("ddx_odd", "ddy_odd", "ddz_odd")):
+        assert rel_linf(getattr(p, name)(f), o.dir_op("d1", d, f, bc=-1)) < TOL, (name, n)
+    g = np.asfortranarray(np.cos(2 * f) + 0.3 * f)
+    h = np.asfortranarray(f * f - 0.5)
+    assert rel_linf(p.divergence(f, g, h), o.divergence(f, g, h)) < TOL
+    ins = (f, g, h, 2 * g, f + h, -f, h * g, 0.5 * f, g - h)
+    for a, b in zip(p.divergencetensor(*ins), o.divergencetensor(*ins)):
+        assert rel_linf(a, b) < TOL
+
+
+@pytest.mark.parametrize("N", [64, 512])
+def test_symmetry_equals_mirrored_periodic_line(N):
+    """cos(kx) / sin(kx) on N cells of [0, pi] with SYMM ends against the periodic operators on 2N
+    cells of [0, 2 pi] -- no oracle involved, any size."""
+    import torch
+    from pyranda_b200 import ParcopPlan
+    ny = nz = 32
+    dx = np.pi / N
+    per = ParcopPlan(2 * N, ny, nz, dx / 2, 2 * np.pi - dx / 2, 0, 1, 0, 1, periodic=(True, False, False))
+    sym = ParcopPlan(N, ny, nz, dx / 2, np.pi - dx / 2, 0, 1, 0, 1, periodic=(False,) * 3,
+                     symmetric=((True, True), (False, False), (False, False)))
+    per.set_mesh(); sym.set_mesh()
+    X = per.getvar("x")
+    amp = np.random.default_rng(7).uniform(-1, 1, size=6)
+    even = np.asfortranarray(sum(a * np.cos(k * X) for k, a in enumerate(amp)))
+    odd = np.asfortranarray(sum(a * np.sin((k + 1) * X) for k, a in enumerate(amp)))
+    # the 8th derivative of smooth modes cancels ~ (N / 6)^8 / 4e3 digits: it is compared on the filters' scale instead
+    for name, tol in (("ddx", 1e-11), ("d2x", 1e-10), ("sfilter", 1e-12), ("gfilter", 1e-12)):
+        assert rel_linf(getattr(sym, name)(np.asfortranarray(even[:N])), getattr(per, name)(even)[:N]) < tol, (name, N)
+    assert rel_linf(sym.ddx_odd(np.asfortranarray(odd[:N])), per.ddx(odd)[:N]) < 1e-11
