@@ -50,7 +50,10 @@ enum {
    * of a field that is ODD across the axis' symmetry planes ("SYMM"); without a symmetry plane they
    * are ddx/ddy/ddz.  The reference reaches them through divV / divT (operators.f90:48-50,106-120). */
   PB_OP_DDX_ODD = 19, PB_OP_DDY_ODD = 20, PB_OP_DDZ_ODD = 21,
-  PB_OP_COUNT = 22
+  /* parcop.f90:255-277 dd4x/dd4y/dd4z: explicit 4th derivative, no metric scale
+   * (stencils.f90:430-513 e4d4, compact_operators.f90:208-278) */
+  PB_OP_DD4X = 22, PB_OP_DD4Y = 23, PB_OP_DD4Z = 24,
+  PB_OP_COUNT = 25
 };
 
 enum { PB_REDUCE_SUM = 0, PB_REDUCE_MAX = 1, PB_REDUCE_MIN = 2 };

@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-KINDS = {"d1": 0, "d2": 1, "d8": 2, "sf": 3, "gf": 4}
+KINDS = {"d1": 0, "d2": 1, "d8": 2, "sf": 3, "gf": 4, "d4": 5}
 BC = {"NONE": 0, "PERI": 1, "SYMM": 2}
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -47,6 +47,7 @@ def lib():
             getattr(L, name).argtypes = [ctypes.c_void_p, _dp, _dp]
         L.po_dd8.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp]
         L.po_d2.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp]
+        L.po_dd4.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp]
         L.po_div.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp]
         L.po_divT.argtypes = [ctypes.c_void_p] + [_dp] * 12
         L.po_divT.restype = ctypes.c_int
@@ -146,6 +147,9 @@ class Oracle:
     def dd8x(self, val): return self._unary(lib().po_dd8, val, 0)
     def dd8y(self, val): return self._unary(lib().po_dd8, val, 1)
     def dd8z(self, val): return self._unary(lib().po_dd8, val, 2)
+    def dd4x(self, val): return self._unary(lib().po_dd4, val, 0)
+    def dd4y(self, val): return self._unary(lib().po_dd4, val, 1)
+    def dd4z(self, val): return self._unary(lib().po_dd4, val, 2)
     def d2x(self, val): return self._unary(lib().po_d2, val, 0)
     def d2y(self, val): return self._unary(lib().po_d2, val, 1)
     def d2z(self, val): return self._unary(lib().po_d2, val, 2)

@@ -32,7 +32,7 @@
 
 #define PO_NB 8 /* lines per bundle */
 
-enum { PO_D1 = 0, PO_D2 = 1, PO_D8 = 2, PO_SF = 3, PO_GF = 4, PO_NKIND = 5 };
+enum { PO_D1 = 0, PO_D2 = 1, PO_D8 = 2, PO_SF = 3, PO_GF = 4, PO_D4 = 5, PO_NKIND = 6 };
 enum { FAM_D1 = 0, FAM_R3 = 1, FAM_R4 = 2 };
 enum { BC_NONE = 0, BC_PERI = 1, BC_SYMM = 2 };
 
@@ -241,6 +241,30 @@ static void cgfs4(po_weight *w) {
     }
 }
 
+/* stencils.f90:430-513 e4d4 (explicit 4th derivative, d4spec = 1).  The reference declares four
+ * closure rows per end (nbc1 = nbc2 = 4, :436) but assigns three (:480-493): lower row 4 and the
+ * last upper row are never written (unallocated-initialised memory), and the three upper rows it does
+ * assign land one row early (alb2/arb2(:,1:3) are rows n-3..n-1, compact_basetype.f90:128-133).
+ * NONE ends are therefore not reproducible from the source; this restatement completes them the
+ * way every other set of the file is built (c10d1 :243-254): row 4 is the interior stencil and the
+ * upper rows mirror the lower ones.  Periodic and SYMM axes never read those rows. */
+static void e4d4(po_weight *w) {
+  const double agau = 28.0 / 3.0, bgau = -6.5, cgau = 2.0, dgau = -1.0 / 6.0;
+  weight_common(w, 0, 3, 0, 0);
+  w->ali[0] = 1.0;
+  SET7(w->ari, dgau, cgau, bgau, agau, bgau, cgau, dgau);
+  for (int r = 0; r < 4; r++) w->alb1[1][r][0] = 1.0;
+  SET7(w->arb1[1][0], 0.0, 0.0, 0.0, agau + bgau, bgau + cgau, cgau + dgau, dgau);
+  SET7(w->arb1[1][1], 0.0, 0.0, bgau + cgau, agau + dgau, bgau, 0.0, 0.0);
+  SET7(w->arb1[1][2], 0.0, cgau + dgau, bgau, agau, bgau, cgau, 0.0);
+  cpy(w->arb1[1][3], w->ari, 7);
+  mirror_bc0(w, 1.0);
+  lower_symm(w->alb1[2], w->arb1[2], w->ali, w->ari, w->ncl, w->ncr, 0, 3, +1, +1); /* :496-499 */
+  lower_symm(w->alb1[0], w->arb1[0], w->ali, w->ari, w->ncl, w->ncr, 0, 3, -1, -1);
+  upper_symm(w->alb2[2], w->arb2[2], w->ali, w->ari, w->ncl, w->ncr, 0, 3, +1, +1);
+  upper_symm(w->alb2[0], w->arb2[0], w->ali, w->ari, w->ncl, w->ncr, 0, 3, -1, -1);
+}
+
 static void make_weight(int kind, po_weight *w) {
   switch (kind) {
     case PO_D1: c10d1(w); break;
@@ -248,11 +272,12 @@ static void make_weight(int kind, po_weight *w) {
     case PO_D8: c10d8(w); break;
     case PO_SF: c8ff8(w); break;   /* sfspec = 2, compact.f90:28 */
     case PO_GF: cgfs4(w); break;   /* gfspec = 6 */
+    case PO_D4: e4d4(w); break;    /* d4spec = 1 */
     default: memset(w, 0, sizeof(*w));
   }
 }
 static int kind_family(int kind) {
-  return kind == PO_D1 ? FAM_D1 : (kind == PO_D2 ? FAM_R3 : FAM_R4);
+  return kind == PO_D1 ? FAM_D1 : ((kind == PO_D2 || kind == PO_D4) ? FAM_R3 : FAM_R4); /* compact.f90:39-44 */
 }
 
 /* export for tests: ali(5) ari(9) alb1 alb2 (4*4*5) arb1 arb2 (4*4*9), plus ints */
@@ -1095,7 +1120,7 @@ po_plan *po_setup(int nx, int ny, int nz, int px, int py, int pz, int coordsys, 
   return p;
 }
 
-static const int post_of_kind[PO_NKIND] = {1, 2, 0, 0, 0};
+static const int post_of_kind[PO_NKIND] = {1, 2, 0, 0, 0, 0}; /* d4: "No metric... unity assumed" (compact_operators.f90:229) */
 
 /* d1x/d2x/d8x/filterx dispatch (compact_operators.f90:13-50,130-154,280-313,385-421).
  * bc: 0 => iop 1; -1 => iop 2 if it exists; >0 => iop = bc. */
@@ -1125,6 +1150,8 @@ void po_ddz(const po_plan *p, const double *v, double *dv) { dir_op(p, PO_D1, 2,
 /* parcop.f90:279-301 */
 void po_dd8(const po_plan *p, int dir, const double *v, double *dv) { dir_op(p, PO_D8, dir, 0, v, dv); }
 void po_d2(const po_plan *p, int dir, const double *v, double *dv) { dir_op(p, PO_D2, dir, 0, v, dv); }
+/* parcop.f90:255-277 dd4x/dd4y/dd4z -> d4x/d4y/d4z (compact_operators.f90:208-278) */
+void po_dd4(const po_plan *p, int dir, const double *v, double *dv) { dir_op(p, PO_D4, dir, 0, v, dv); }
 
 static int isym(const po_plan *p, int d) { return (p->bcs[d][0] == BC_SYMM || p->bcs[d][1] == BC_SYMM) ? -1 : 1; } /* patch.f90:86-88 */
 

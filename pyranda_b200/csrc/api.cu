@@ -555,6 +555,8 @@ int pb_apply(pb_plan *pl, int opcode, const double *in, double *out, void *strea
       return apply_dir(pl, pl->sw[K_D8][opcode - PB_OP_DD8X], in, out, kStore, st);
     case PB_OP_D2X: case PB_OP_D2Y: case PB_OP_D2Z:
       return apply_dir(pl, pl->sw[K_D2][opcode - PB_OP_D2X], in, out, kStore, st);
+    case PB_OP_DD4X: case PB_OP_DD4Y: case PB_OP_DD4Z:
+      return apply_dir(pl, pl->sw[K_D4][opcode - PB_OP_DD4X], in, out, kStore, st);
     case PB_OP_GFILTERX: case PB_OP_GFILTERY: case PB_OP_GFILTERZ:
       return apply_dir(pl, pl->sw[K_GF][opcode - PB_OP_GFILTERX], in, out, kStore, st);
     case PB_OP_SFILTERX: case PB_OP_SFILTERY: case PB_OP_SFILTERZ:
@@ -714,6 +716,7 @@ static int zop_kind(int zop) {
     case PB_OP_DDZ: case PB_OP_DDZ_ODD: return K_D1;
     case PB_OP_DD8Z: return K_D8;
     case PB_OP_D2Z: return K_D2;
+    case PB_OP_DD4Z: return K_D4;
     case PB_OP_SFILTERZ: return K_SF;
     case PB_OP_GFILTERZ: return K_GF;
     default: return -1;
@@ -885,6 +888,7 @@ int pb_host_apply(pb_plan *pl, int opcode, const double *h_val, double *h_out) {
     if (opcode >= PB_OP_DDX && opcode <= PB_OP_DDZ) { kind = K_D1; dir = opcode - PB_OP_DDX; }
     else if (opcode >= PB_OP_DD8X && opcode <= PB_OP_DD8Z) { kind = K_D8; dir = opcode - PB_OP_DD8X; }
     else if (opcode >= PB_OP_D2X && opcode <= PB_OP_D2Z) { kind = K_D2; dir = opcode - PB_OP_D2X; }
+    else if (opcode >= PB_OP_DD4X && opcode <= PB_OP_DD4Z) { kind = K_D4; dir = opcode - PB_OP_DD4X; }
     else if (opcode >= PB_OP_GFILTERX && opcode <= PB_OP_GFILTERZ) { kind = K_GF; dir = opcode - PB_OP_GFILTERX; }
     else if (opcode >= PB_OP_SFILTERX && opcode <= PB_OP_SFILTERZ) { kind = K_SF; dir = opcode - PB_OP_SFILTERX; }
     else if (opcode == PB_OP_GFILTER) kind = K_GF;

@@ -212,6 +212,27 @@ Stencil make_stencil(Kind k, int bc_lo, int bc_hi) {
       s.add_back = true;
       break;
     }
+    case K_D4: {  // explicit 4th-order 4th derivative, stencils.f90:430-513; evaluated by the 7-point
+      // difference-form sweep (compact.f90:41) without a metric scale (compact_operators.f90:229).
+      // The reference assigns three of its four closure rows per end (:480-493) and places the upper
+      // three one row early; as in every other set, row 4 is completed with the interior stencil and
+      // the upper rows mirror the lower ones (periodic and SYMM axes never read them).
+      const double a = 28.0 / 3.0, b = -6.5, c = 2.0, d = -1.0 / 6.0;
+      s.nol = 0; s.nor = 3; s.implicit = false; s.null_option = 0; s.post = 0; s.fam = F_R3;
+      s.ncl = 1; s.ncr = 7;
+      s.ali[0] = 1.0;
+      set_row(s.ari, {d, c, b, a, b, c, d});
+      for (int r = 0; r < 4; ++r) s.alb_lo[r][0] = 1.0;
+      set_row(s.arb_lo[0], {0.0, 0.0, 0.0, a + b, b + c, c + d, d});
+      set_row(s.arb_lo[1], {0.0, 0.0, b + c, a + d, b, 0.0, 0.0});
+      set_row(s.arb_lo[2], {0.0, c + d, b, a, b, c, 0.0});
+      set_row(s.arb_lo[3], {d, c, b, a, b, c, d});
+      mirror_closures(s, 1.0);
+      apply_symmetry(s, bc_lo, bc_hi);
+      if (bc_lo == -1 || bc_hi == -1)  // parcop.f90:255-277 calls d4x/y/z without a symmetry selector
+        throw std::invalid_argument("make_stencil: the fourth derivative has no antisymmetric variant on this path");
+      break;
+    }
     default:
       throw std::invalid_argument("make_stencil: unknown operator kind");
   }

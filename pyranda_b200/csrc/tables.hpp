@@ -13,7 +13,7 @@
 
 namespace pb {
 
-enum Kind { K_D1 = 0, K_D2 = 1, K_D8 = 2, K_SF = 3, K_GF = 4, K_COUNT = 5 };
+enum Kind { K_D1 = 0, K_D2 = 1, K_D8 = 2, K_SF = 3, K_GF = 4, K_D4 = 5, K_COUNT = 6 };
 enum Fam { F_D1 = 0, F_R3 = 1, F_R4 = 2 };
 
 // One operator's coefficients with its boundary closures: one-sided ("NONE", bc = 0) or the

@@ -21,8 +21,8 @@ from ._lib import OP, check
 from .plan import ParcopPlan
 
 # z operator behind each distributed call and its halo width (nor of the stencil)
-_ZOPS = {"ddz": ("ddz", 3), "ddz_odd": ("ddz_odd", 3), "dd8z": ("dd8z", 4), "d2z": ("d2z", 3), "sfilterz": ("sfilterz", 4), "gfilterz": ("gfilterz", 4)}
-_IMPLICIT = {"ddz": True, "ddz_odd": True, "dd8z": True, "d2z": True, "sfilterz": True, "gfilterz": False}
+_ZOPS = {"ddz": ("ddz", 3), "ddz_odd": ("ddz_odd", 3), "dd4z": ("dd4z", 3), "dd8z": ("dd8z", 4), "d2z": ("d2z", 3), "sfilterz": ("sfilterz", 4), "gfilterz": ("gfilterz", 4)}
+_IMPLICIT = {"ddz": True, "ddz_odd": True, "dd4z": False, "dd8z": True, "d2z": True, "sfilterz": True, "gfilterz": False}
 
 
 class _PeerBuffers:
@@ -230,7 +230,7 @@ class DistributedParcop:
 
     def apply_into(self, name, f, out):
         """ddx ddy ddz dd8x dd8y dd8z d2x d2y d2z sfilter gfilter gfilterx/y/z laplacian ring."""
-        if name in ("ddx", "ddy", "ddx_odd", "ddy_odd", "dd8x", "dd8y", "d2x", "d2y", "gfilterx", "gfiltery", "sfilterx", "sfiltery"):
+        if name in ("ddx", "ddy", "ddx_odd", "ddy_odd", "dd4x", "dd4y", "dd8x", "dd8y", "d2x", "d2y", "gfilterx", "gfiltery", "sfilterx", "sfiltery"):
             return self._local_into(name, f, out)
         if name in _ZOPS:
             return self.zop_into(name, f, out)
@@ -330,6 +330,9 @@ def _make_backend():
         def ddx(self, v): return self._op("ddx", v)
         def ddy(self, v): return self._op("ddy", v)
         def ddz(self, v): return self._op("ddz", v)
+        def dd4x(self, v): return self._op("dd4x", v)
+        def dd4y(self, v): return self._op("dd4y", v)
+        def dd4z(self, v): return self._op("dd4z", v)
         def dd8x(self, v): return self._op("dd8x", v)
         def dd8y(self, v): return self._op("dd8y", v)
         def dd8z(self, v): return self._op("dd8z", v)

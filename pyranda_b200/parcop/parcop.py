@@ -83,6 +83,9 @@ def mesh_getgridlen(nx=None, ny=None, nz=None): return _cur().getvar("GridLen")
 def ddx(val): return _cur().ddx(val)
 def ddy(val): return _cur().ddy(val)
 def ddz(val): return _cur().ddz(val)
+def dd4x(val): return _cur().dd4x(val)  # parcop.f90:255-277
+def dd4y(val): return _cur().dd4y(val)
+def dd4z(val): return _cur().dd4z(val)
 def dd8x(val): return _cur().dd8x(val)
 def dd8y(val): return _cur().dd8y(val)
 def dd8z(val): return _cur().dd8z(val)

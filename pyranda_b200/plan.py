@@ -164,6 +164,9 @@ class ParcopPlan:
     def ddx_odd(self, val): return self.apply("ddx_odd", val)
     def ddy_odd(self, val): return self.apply("ddy_odd", val)
     def ddz_odd(self, val): return self.apply("ddz_odd", val)
+    def dd4x(self, val): return self.apply("dd4x", val)
+    def dd4y(self, val): return self.apply("dd4y", val)
+    def dd4z(self, val): return self.apply("dd4z", val)
     def dd8x(self, val): return self.apply("dd8x", val)
     def dd8y(self, val): return self.apply("dd8y", val)
     def dd8z(self, val): return self.apply("dd8z", val)

@@ -18,6 +18,9 @@ class parcop_der:
     def ddx(self, val): return self._e.op("ddx", val)
     def ddy(self, val): return self._e.op("ddy", val)
     def ddz(self, val): return self._e.op("ddz", val)
+    def dd4x(self, val): return self._e.op("dd4x", val)  # pyrandaMPI.py:678-686
+    def dd4y(self, val): return self._e.op("dd4y", val)
+    def dd4z(self, val): return self._e.op("dd4z", val)
     def dd8x(self, val): return self._e.op("dd8x", val)
     def dd8y(self, val): return self._e.op("dd8y", val)
     def dd8z(self, val): return self._e.op("dd8z", val)

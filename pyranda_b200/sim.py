@@ -60,6 +60,9 @@ class CudaBackend:
     def ddx(self, v): return self.plan.ddx(self._f(v))
     def ddy(self, v): return self.plan.ddy(self._f(v))
     def ddz(self, v): return self.plan.ddz(self._f(v))
+    def dd4x(self, v): return self.plan.dd4x(self._f(v))
+    def dd4y(self, v): return self.plan.dd4y(self._f(v))
+    def dd4z(self, v): return self.plan.dd4z(self._f(v))
     def dd8x(self, v): return self.plan.dd8x(self._f(v))
     def dd8y(self, v): return self.plan.dd8y(self._f(v))
     def dd8z(self, v): return self.plan.dd8z(self._f(v))
@@ -134,6 +137,7 @@ _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-8
     "ddx": "self.ddx", "ddy": "self.ddy", "ddz": "self.ddz", "div": "self.div", "grad": "self.grad",
     "fbar": "self.filter", "gbar": "self.gfilter", "gbarx": "self.gfilterx", "gbary": "self.gfiltery",
     "gbarz": "self.gfilterz", "lap": "self.laplacian", "ring": "self.ring", "dd8x": "self.dd8x",
+    "dd4x": "self.dd4x", "dd4y": "self.dd4y", "dd4z": "self.dd4z",  # pyranda.py:833-835
     "dd8y": "self.dd8y", "dd8z": "self.dd8z", "sum": "self.B.sum3D", "max": "self.B.max3D", "min": "self.B.min3D",
     "mean": "self.mean", "sign": "xp.sign", "abs": "xp.abs", "sqrt": "xp.sqrt", "sin": "xp.sin", "cos": "xp.cos",
     "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar",
@@ -254,6 +258,9 @@ class pyrandaSim:
     def ddx(self, v): return 0.0 if self.nx <= 1 else self.B.ddx(v)
     def ddy(self, v): return 0.0 if self.ny <= 1 else self.B.ddy(v)
     def ddz(self, v): return 0.0 if self.nz <= 1 else self.B.ddz(v)
+    def dd4x(self, v): return self.B.dd4x(v)  # pyranda.py:622-629
+    def dd4y(self, v): return self.B.dd4y(v)
+    def dd4z(self, v): return self.B.dd4z(v)
     def dd8x(self, v): return self.B.dd8x(v)
     def dd8y(self, v): return self.B.dd8y(v)
     def dd8z(self, v): return self.B.dd8z(v)

@@ -20,6 +20,9 @@ class NumpyOracleBackend:
     def ddx(self, v): return self.o.ddx(self._f(v))
     def ddy(self, v): return self.o.ddy(self._f(v))
     def ddz(self, v): return self.o.ddz(self._f(v))
+    def dd4x(self, v): return self.o.dd4x(self._f(v))
+    def dd4y(self, v): return self.o.dd4y(self._f(v))
+    def dd4z(self, v): return self.o.dd4z(self._f(v))
     def dd8x(self, v): return self.o.dd8x(self._f(v))
     def dd8y(self, v): return self.o.dd8y(self._f(v))
     def dd8z(self, v): return self.o.dd8z(self._f(v))

@@ -35,7 +35,7 @@ for periodic in (True, False):
     az = n[2] // world
     sl = slice(rank * az, (rank + 1) * az)
     loc = eng.empty(); loc.copy_(torch.from_numpy(f[:, :, sl].copy()))
-    for name, ref in (("ddx", o.ddx), ("ddy", o.ddy), ("ddz", o.ddz), ("dd8z", o.dd8z), ("d2z", o.d2z),
+    for name, ref in (("ddx", o.ddx), ("ddy", o.ddy), ("ddz", o.ddz), ("dd8z", o.dd8z), ("d2z", o.d2z), ("dd4x", o.dd4x), ("dd4z", o.dd4z),
                       ("sfilter", o.sfilter), ("gfilter", o.gfilter), ("laplacian", o.plaplacian), ("ring", o.pring)):
         got = eng.apply(name, loc).numpy()
         err = rel_linf(got, ref(f)[:, :, sl])

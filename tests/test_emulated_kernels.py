@@ -38,7 +38,7 @@ def _pair(n, periodic, oracle_mod, lib):
 @pytest.mark.parametrize("periodic", [True, False])
 def test_emulated_operators_match_oracle(periodic, oracle_mod, emul_lib):
     o, p, f = _pair((32, 48, 32), periodic, oracle_mod, emul_lib)
-    for name in ("ddx", "ddy", "ddz", "dd8x", "dd8z", "d2y", "sfilter", "gfilter", "plaplacian", "pring"):
+    for name in ("ddx", "ddy", "ddz", "dd8x", "dd8z", "d2y", "sfilter", "gfilter", "plaplacian", "pring", "dd4x", "dd4y", "dd4z"):
         assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < 1e-13, (name, periodic)
     assert rel_linf(p.divergence(f, 2 * f, f * f), o.divergence(f, 2 * f, f * f)) < 1e-13
     for a, b in zip(p.grads(f), o.grads(f)):
@@ -71,7 +71,8 @@ def test_emulated_symmetry_planes(symm, oracle_mod, emul_lib):
     p = ParcopPlan(*n, x1, xn, y1, yn, z1, zn, periodic=(False,) * 3, symmetric=symm, lib=emul_lib)
     p.set_mesh()
     f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
-    for name in ("ddx", "ddy", "ddz", "dd8x", "dd8y", "dd8z", "d2x", "d2y", "d2z", "sfilter", "gfilter", "plaplacian", "pring"):
+    for name in ("ddx", "ddy", "ddz", "dd8x", "dd8y", "dd8z", "d2x", "d2y", "d2z", "sfilter", "gfilter", "plaplacian", "pring",
+                 "dd4x", "dd4y", "dd4z"):
         assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < 1e-13, name
     for d, name in enumerate(("ddx_odd", "ddy_odd", "ddz_odd")):
         assert rel_linf(getattr(p, name)(f), o.dir_op("d1", d, f, bc=-1)) < 1e-13, name

@@ -162,3 +162,20 @@ def test_golden_vectors(oracle_mod):
         f = np.asfortranarray(data["f_" + tag])
         for name in GOLDEN_OPS:
             assert rel_linf(getattr(o, name)(f), data["%s_%s" % (name, tag)]) < 1e-14, (name, tag)
+
+
+def test_fourth_derivative_transfer_function(oracle_mod):
+    """e4d4 (stencils.f90:430-513) on a periodic axis: the oracle's dd4 of sin(kx) is the 7-point
+    stencil's transfer function times sin(kx), which tends to (k dx)^4 (no metric scale,
+    compact_operators.f90:229)."""
+    N = 48
+    o = oracle_mod.Oracle(N, 8, 8, 0.0, 2 * np.pi * (N - 1) / N, 0, 1, 0, 1, periodic=(True, False, False))
+    X = o.getvar("x")
+    dx = 2 * np.pi / N
+    a, b, c, d = 28.0 / 3.0, -6.5, 2.0, -1.0 / 6.0
+    for k in (1, 2, 5, 11):
+        T = a + 2 * b * np.cos(k * dx) + 2 * c * np.cos(2 * k * dx) + 2 * d * np.cos(3 * k * dx)
+        f = np.asfortranarray(np.sin(k * X))
+        assert np.abs(o.dd4x(f) - T * f).max() < 1e-13
+        if k <= 2:
+            assert abs(T - (k * dx) ** 4) < 0.3 * (k * dx) ** 8  # 4th-order accurate: error O(th^8)

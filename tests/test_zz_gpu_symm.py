@@ -11,7 +11,8 @@ from conftest import domain, rel_linf, synthetic_field
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-12
-UNARY = ["ddx", "ddy", "ddz", "dd8x", "dd8y", "dd8z", "d2x", "d2y", "d2z", "plaplacian", "pring", "sfilter", "gfilter"]
+UNARY = ["ddx", "ddy", "ddz", "dd8x", "dd8y", "dd8z", "d2x", "d2y", "d2z", "plaplacian", "pring", "sfilter", "gfilter",
+         "dd4x", "dd4y", "dd4z"]
 CASES = [((True, True), (True, False), (False, True)), ((True, False), (False, False), (True, True))]
 
 
@@ -56,3 +57,30 @@ def test_symmetry_equals_mirrored_periodic_line(N):
     for name, tol in (("ddx", 1e-11), ("d2x", 1e-10), ("sfilter", 1e-12), ("gfilter", 1e-12)):
         assert rel_linf(getattr(sym, name)(np.asfortranarray(even[:N])), getattr(per, name)(even)[:N]) < tol, (name, N)
     assert rel_linf(sym.ddx_odd(np.asfortranarray(odd[:N])), per.ddx(odd)[:N]) < 1e-11
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("n", [(64, 48, 32), (256, 256, 32), (1040, 32, 32)])
+def test_fourth_derivative(n, periodic, oracle_mod):
+    """dd4x/dd4y/dd4z (parcop.f90:255-277, stencils.f90:430-513): explicit, 7-point, no metric scale;
+    host arrays and device tensors; on a periodic axis also against the stencil's transfer function."""
+    import torch
+    from pyranda_b200 import ParcopPlan
+    (x1, xn), (y1, yn), (z1, zn) = domain(n, periodic)
+    o = oracle_mod.Oracle(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3)
+    p = ParcopPlan(*n, x1, xn, y1, yn, z1, zn, periodic=(periodic,) * 3)
+    p.set_mesh()
+    f = synthetic_field(o.getvar("x"), o.getvar("y"), o.getvar("z"))
+    t = p.empty_device()
+    t.copy_(torch.from_numpy(f))
+    for name in ("dd4x", "dd4y", "dd4z"):
+        ref = getattr(o, name)(f)
+        assert rel_linf(getattr(p, name)(f), ref) < TOL, (name, n, periodic)
+        assert rel_linf(getattr(p, name)(t).cpu().numpy(), ref) < TOL, (name, n, periodic, "device")
+    if periodic:
+        a, b, c, d = 28.0 / 3.0, -6.5, 2.0, -1.0 / 6.0
+        X, k = o.getvar("x"), 5
+        th = k * p.dx
+        T = a + 2 * b * np.cos(th) + 2 * c * np.cos(2 * th) + 2 * d * np.cos(3 * th)
+        g = np.asfortranarray(np.sin(k * X))
+        assert np.abs(p.dd4x(g) - T * g).max() < 1e-12
