@@ -1230,6 +1230,12 @@ void po_ring(const po_plan *p, const double *f, double *out) {
  * divergences of the tensor's columns, each direction with its symmetry selector. */
 int po_divT(const po_plan *p, const double *fxx, const double *fxy, const double *fxz, const double *fyx, const double *fyy,
             const double *fyz, const double *fzx, const double *fzy, const double *fzz, double *dfx, double *dfy, double *dfz) {
+  if (p->coordsys == 3) { /* :176-179: divV of each row */
+    po_div(p, fxx, fxy, fxz, dfx);
+    po_div(p, fyx, fyy, fyz, dfy);
+    po_div(p, fzx, fzy, fzz, dfz);
+    return 0;
+  }
   if (p->coordsys != 0) return -1;
   const size_t N = p->npts;
   double *fA = malloc(sizeof(double) * N), *fB = malloc(sizeof(double) * N), *fC = malloc(sizeof(double) * N);
@@ -1256,7 +1262,7 @@ void po_ringV(const po_plan *p, const double *f, const double *g, const double *
     for (int d = 0; d < 3; d++) {
       r[c][d] = malloc(sizeof(double) * N);
       if (nn[d] == 1) memset(r[c][d], 0, sizeof(double) * N);
-      else dir_op(p, PO_D8, d, 0, comp[c], r[c][d]);
+      else dir_op(p, PO_D8, d, c == d ? isym(p, d) : 0, comp[c], r[c][d]); /* :661-671 */
     }
   for (size_t t = 0; t < N; t++) {
     double L[3];

@@ -1,8 +1,11 @@
-"""Boundary-plane packages of the EOM interpreter: bc.extrap / bc.const / bc.field / bc.symm.
+"""Boundary-plane packages of the EOM interpreter: bc.extrap / bc.const / bc.field / bc.symm /
+bc.exit / bc.slip.
 
 Reference: pyranda/pyrandaBC.py:40-186,748-786 (the `BC` package: `bc.extrap(vars, dirs, order)`,
 `bc.const(vars, dirs, val)`, `bc.field(var, dirs, field)`, `bc.symm(vars, dirs, anti, npts)` lines
-inside an EOM string).  They sit in
+inside an EOM string), :468-522 (`bc.exit(vars, dirs, norm)`, the bounded essentially-non-oscillatory
+outflow extrapolation) and :186-466 (`bc.slip([[u, v(, w)]], dirs)`, free slip on a curvilinear
+wall: extrapolate, then remove the wall-normal velocity).  They sit in
 `updateVars`, i.e. they run after every RK4 stage, so with device-resident fields they must not
 leave the GPU: everything here is in-place slicing on the field object (a CUDA tensor with Fortran
 strides, or a numpy array in the oracle-backed test driver) -- one tiny strided kernel per plane.
@@ -19,10 +22,21 @@ def _as_list(a):
     return list(a) if isinstance(a, (list, tuple)) else [a]
 
 
+def _xp(f):
+    """The array module of a field: torch for device tensors, numpy for the oracle-backed driver."""
+    if type(f).__module__.startswith("torch"):
+        import torch
+        return torch
+    import numpy
+    return numpy
+
+
 class BoundaryConditions:
-    def __init__(self, variables, owns=None):
+    def __init__(self, variables, owns=None, getvar=None):
         self.variables = variables
         self.owns = owns if owns is not None else {n: True for n in ("x1", "xn", "y1", "yn", "z1", "zn")}
+        self.getvar = getvar   # mesh metrics by name (pyranda.getVar), needed by bc.slip
+        self.BCdata = {}       # wall normals, cached per boundary (pyrandaBC.py:24,281-291)
 
     @staticmethod
     def _plane(direction, depth):
@@ -73,3 +87,78 @@ class BoundaryConditions:
     def field(self, var, direction, field):
         for f, d in self._each(var, direction):
             f[self._plane(d, 0)] = field[self._plane(d, 0)]
+
+    # pyrandaBC.py:468-522: x and y boundaries only (the reference has no z branch)
+    def exit(self, var, direction, norm=False):
+        for f, d in self._each(var, direction):
+            if d[0] == "z":
+                continue
+            u1, u2, u3 = f[self._plane(d, 0)], f[self._plane(d, 1)], f[self._plane(d, 2)]
+            f[self._plane(d, 0)] = self._beno(u1, u2, u3, norm)
+
+    @staticmethod
+    def _beno(u1, u2, u3, norm):
+        """pyrandaBC.py:510-521: the smaller of the first- and second-order extrapolation increments,
+        none at an extremum; `norm` keeps a normal velocity between 0 and its inner neighbour."""
+        xp = _xp(u1)
+        d1 = u2 - u1
+        d2 = (2.0 * u2 - u3) - u1
+        beno = xp.where(xp.abs(d1) <= xp.abs(d2), u1 + d1, u1 + d2)
+        beno = xp.where(d1 * d2 <= 0.0, u1, beno)
+        if norm:
+            zero = u2 * 0.0
+            beno = xp.maximum(xp.minimum(beno, xp.maximum(zero, u2)), xp.minimum(zero, u2))
+        return beno
+
+    # pyrandaBC.py:202-265: unit normal of the constant-A / B / C surfaces from the inverse metrics
+    def _normals(self, d):
+        key = "slipbc-" + d
+        if key not in self.BCdata:
+            if self.getvar is None:
+                raise ValueError("bc.slip needs the mesh metrics (curvilinear mesh)")
+            g = {k: self.getvar(k) for k in ("dAx", "dAy", "dAz", "dBx", "dBy", "dBz", "dCx", "dCy", "dCz", "dtJ")}
+            J = g["dtJ"]
+            m = {"xA": (-g["dBz"] * g["dCy"] + g["dBy"] * g["dCz"]) * J, "xB": (g["dAz"] * g["dCy"] - g["dAy"] * g["dCz"]) * J,
+                 "xC": (-g["dAz"] * g["dBy"] + g["dAy"] * g["dBz"]) * J,
+                 "yA": (g["dBz"] * g["dCx"] - g["dBx"] * g["dCz"]) * J, "yB": (-g["dAz"] * g["dCx"] + g["dAx"] * g["dCz"]) * J,
+                 "yC": (g["dAz"] * g["dBx"] - g["dAx"] * g["dBz"]) * J,
+                 "zA": (-g["dBy"] * g["dCx"] + g["dBx"] * g["dCy"]) * J, "zB": (g["dAy"] * g["dCx"] - g["dAx"] * g["dCy"]) * J,
+                 "zC": (-g["dAy"] * g["dBx"] + g["dAx"] * g["dBy"]) * J}
+            t1, t2 = {"x": ("B", "C"), "y": ("A", "C"), "z": ("A", "B")}[d[0]]
+            a1, a2, a3 = m["x" + t1], m["y" + t1], m["z" + t1]
+            b1, b2, b3 = m["x" + t2], m["y" + t2], m["z" + t2]
+            n1, n2, n3 = (a2 * b3 - a3 * b2), -(a1 * b3 - a3 * b1), (a1 * b2 - a2 * b1)
+            mag = _xp(n1).sqrt(n1 * n1 + n2 * n2 + n3 * n3)
+            pl = self._plane(d, 0)
+            self.BCdata[key] = [(n1 / mag)[pl], (n2 / mag)[pl], (n3 / mag)[pl]]
+        return self.BCdata[key]
+
+    # pyrandaBC.py:186-200,267-466: `bc.slip([['u','v']], ['y1'])`; x and y walls, as in the reference
+    def slip(self, var, direction):
+        for d in _as_list(direction):
+            if d[0] not in ("x", "y") or d[1:] not in ("1", "n"):
+                continue
+            for velocity in _as_list(var):
+                velocity = _as_list(velocity)
+                norms = self._normals(d)
+                self.extrap(velocity, d, order=2)  # "for free slip, always extrapolate first"
+                if not self.owns.get(d, False):
+                    continue
+                pl = self._plane(d, 0)
+                U = [self.variables[v] for v in velocity]
+                xp = _xp(U[0])
+                udotn = 0.0
+                for u, n in zip(U, norms):
+                    udotn = udotn + u[pl] * n
+                mag0 = 0.0
+                for u in U:
+                    mag0 = mag0 + u[pl] ** 2
+                mag0 = xp.sqrt(mag0)
+                for u, n in zip(U, norms):
+                    u[pl] = u[pl] - udotn * n
+                magF = 0.0
+                for u in U:
+                    magF = magF + u[pl] ** 2
+                magF = xp.sqrt(magF)
+                for u in U:  # the projection must not lengthen the vector
+                    u[pl] = xp.where(magF > mag0, u[pl] * mag0 / magF, u[pl])

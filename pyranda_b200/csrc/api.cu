@@ -59,6 +59,7 @@ struct pb_plan {
   int isym[3];                     // patch.f90:86-91: -1 when either end of the axis is a symmetry plane
   SweepPlan sw[K_COUNT][3];        // iop 1: even fields at symmetry planes (compact.f90:77-91)
   SweepPlan d1_odd[3];             // iop 2 of the first derivative: odd fields (the normal flux in divV)
+  SweepPlan d8_odd[3];             // iop 2 of the 8th derivative (the normal component in ringV, operators.f90:661-671)
   SweepPlan custom_d1[3];
   std::vector<double *> scratch;   // device work fields, npts each
   double *red_partial = nullptr, *red_result = nullptr, *red_host = nullptr;
@@ -381,6 +382,8 @@ int pb_plan_create(pb_plan **plan, int nx, int ny, int nz, int px, int py, int p
   for (int d = 0; d < 3; ++d)
     if (pl->isym[d] == -1) {
       int rc = build_sweep(pl, pl->d1_odd[d], K_D1, d, pl->periodic[d], bcode[d][0] == 2 ? -1 : 0, bcode[d][1] == 2 ? -1 : 0);
+      if (rc == PB_OK)
+        rc = build_sweep(pl, pl->d8_odd[d], K_D8, d, pl->periodic[d], bcode[d][0] == 2 ? -1 : 0, bcode[d][1] == 2 ? -1 : 0);
       if (rc != PB_OK) { pb_plan_destroy(pl); return rc; }
     }
   if (cudaMalloc(&pl->red_partial, sizeof(double) * 2048) != cudaSuccess ||
@@ -397,7 +400,7 @@ int pb_plan_destroy(pb_plan *pl) {
   if (!pl) return PB_OK;
   for (int k = 0; k < K_COUNT; ++k)
     for (int d = 0; d < 3; ++d) free_sweep(pl->sw[k][d]);
-  for (int d = 0; d < 3; ++d) { free_sweep(pl->custom_d1[d]); free_sweep(pl->d1_odd[d]); }
+  for (int d = 0; d < 3; ++d) { free_sweep(pl->custom_d1[d]); free_sweep(pl->d1_odd[d]); free_sweep(pl->d8_odd[d]); }
   for (double *q : pl->scratch) cudaFree(q);
   for (auto &kv : pl->mesh) cudaFree(kv.second);
   if (pl->red_partial) cudaFree(pl->red_partial);
@@ -652,35 +655,53 @@ int pb_divergence_tensor(pb_plan *pl, const double *fxx, const double *fxy, cons
                          const double *fyy, const double *fyz, const double *fzx, const double *fzy, const double *fzz,
                          double *dfx, double *dfy, double *dfz, void *stream) {
   if (!pl) return fail(PB_ERR_ARG, "plan is NULL");
-  if (pl->coordsys != 0) return fail(PB_ERR_UNSUPPORTED, "divT: only the Cartesian branch is implemented");
   if (!fxx || !fxy || !fxz || !fyx || !fyy || !fyz || !fzx || !fzy || !fzz || !dfx || !dfy || !dfz)
     return fail(PB_ERR_ARG, "NULL argument");
+  int rc;
+  if (pl->coordsys == 3) {  // operators.f90:176-179: the divergence of each ROW of the tensor
+    if ((rc = pb_divergence(pl, fxx, fxy, fxz, dfx, stream)) != PB_OK) return rc;
+    if ((rc = pb_divergence(pl, fyx, fyy, fyz, dfy, stream)) != PB_OK) return rc;
+    return pb_divergence(pl, fzx, fzy, fzz, dfz, stream);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int *is = pl->isym;  // operators.f90:106-120: the diagonal components are even (isym**2)
-  int rc;
   if ((rc = div_cart(pl, fxx, fyx, fzx, dfx, 1, is[1], is[2], st)) != PB_OK) return rc;
   if ((rc = div_cart(pl, fxy, fyy, fzy, dfy, is[0], 1, is[2], st)) != PB_OK) return rc;
   return div_cart(pl, fxz, fyz, fzz, dfz, is[0], is[1], 1, st);
 }
 
 // operators.f90:645-699 with L = 1 (parcop.f90:324-333): max over the three directions of
-// max(|d8(vx)|, |d8(vy)|, |d8(vz)|) * d -- nine 8th-derivative sweeps that keep a running maximum
-// (multiplying by the positive spacing before or after the maximum rounds identically)
+// max(|d8(vx)|, |d8(vy)|, |d8(vz)|) * d -- nine 8th-derivative sweeps that keep a running maximum.
+// The component normal to a symmetry plane is odd across it (ringx(f, ., isymX), :661-671).
+// Cartesian: d is a constant, multiplied in the sweeps' epilogue (multiplying by the positive spacing
+// before or after the maximum rounds identically).  Curvilinear: per direction the running maximum
+// goes to a work field and one pointwise pass multiplies by mesh d1 / d2 / d3 and folds it in.
 int pb_ring_vector(pb_plan *pl, const double *vx, const double *vy, const double *vz, double *out, void *stream) {
   if (!pl || !vx || !vy || !vz || !out) return fail(PB_ERR_ARG, "NULL argument");
-  if (pl->coordsys != 0) return fail(PB_ERR_UNSUPPORTED, "ringV: only the Cartesian branch is implemented");
   cudaStream_t st = (cudaStream_t)stream;
   const double *comp[3] = {vx, vy, vz};
+  const char *dn[3] = {"d1", "d2", "d3"};
+  const bool curv = pl->coordsys != 0;
+  double *tmp = nullptr;
   bool first = true;
   int rc;
+  if (curv) {
+    if (!pl->mesh_set) return fail(PB_ERR_STATE, "curvilinear ringV needs pb_plan_set_mesh");
+    if ((rc = get_scratch(pl, 0, &tmp)) != PB_OK) return rc;
+  }
   for (int d = 0; d < 3; ++d) {
     if (pl->n[d] == 1 || pl->sw[K_D8][d].null_op) continue;  // ringx/y/z give zero there (operators.f90:709-712)
     for (int c = 0; c < 3; ++c) {
+      SweepPlan &sp = (c == d && pl->d8_odd[d].built) ? pl->d8_odd[d] : pl->sw[K_D8][d];
       EpiArgs e;
-      e.mode = first ? EPI_RING_SET : EPI_RING_MAX;
-      e.s2 = pl->d[d];
       e.field = nullptr;
-      if ((rc = apply_dir(pl, pl->sw[K_D8][d], comp[c], out, e, st)) != PB_OK) return rc;
+      if (curv) { e.mode = c == 0 ? EPI_RING_SET : EPI_RING_MAX; e.s2 = 1.0; }
+      else { e.mode = first ? EPI_RING_SET : EPI_RING_MAX; e.s2 = pl->d[d]; }
+      if ((rc = apply_dir(pl, sp, comp[c], curv ? tmp : out, e, st)) != PB_OK) return rc;
+      if (!curv) first = false;
+    }
+    if (curv) {
+      PB_CUDA(launch_mul_max((long)pl->npts, tmp, mesh_arr(pl, dn[d]), out, first ? 1 : 0, st));
       first = false;
     }
   }
@@ -955,8 +976,12 @@ int pb_host_grads(pb_plan *pl, const double *h_val, double *h_gx, double *h_gy, 
 int pb_host_divergence_tensor(pb_plan *pl, const double *const *h_f9, double *const *h_out3) {
   // h_f9 = {fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz}; one divergence at a time through four staging fields
   if (!pl || !h_f9 || !h_out3) return fail(PB_ERR_ARG, "NULL argument");
-  if (pl->coordsys != 0) return fail(PB_ERR_UNSUPPORTED, "divT: only the Cartesian branch is implemented");
   int rc;
+  if (pl->coordsys == 3) {  // rows of the tensor through the curvilinear divergence (operators.f90:176-179)
+    for (int c = 0; c < 3; ++c)
+      if ((rc = host_div(pl, h_f9[3 * c], h_f9[3 * c + 1], h_f9[3 * c + 2], h_out3[c], nullptr)) != PB_OK) return rc;
+    return PB_OK;
+  }
   for (int c = 0; c < 3; ++c) {
     int sel[3] = {pl->isym[0], pl->isym[1], pl->isym[2]};
     sel[c] = 1;  // operators.f90:106,113,120: isym**2 on the diagonal

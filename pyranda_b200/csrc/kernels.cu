@@ -256,6 +256,11 @@ __global__ void copy_kernel(long n, const double *__restrict__ a, double *__rest
 __global__ void fill_kernel(long n, double val, double *__restrict__ o) { PB_GRID_STRIDE(t, n) o[t] = val; }
 __global__ void mul_kernel(long n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ o) { PB_GRID_STRIDE(t, n) o[t] = a[t] * b[t]; }
 __global__ void div_kernel(long n, const double *a, const double *b, double *o) { PB_GRID_STRIDE(t, n) o[t] = a[t] / b[t]; }
+// ringV with per-point length scales (operators.f90:680-683): out = a*b, or max(out, a*b)
+__global__ void mul_max_kernel(long n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ o, int first) {
+  PB_GRID_STRIDE(t, n) { const double r = a[t] * b[t]; o[t] = first ? r : fmax(o[t], r); }
+}
+cudaError_t launch_mul_max(long n, const double *a, const double *b, double *out, int first, cudaStream_t st) { PB_LAUNCH(mul_max_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, a, b, out, first); ++g_launches; return cudaGetLastError(); }
 cudaError_t launch_copy(long n, const double *a, double *out, cudaStream_t st) { PB_LAUNCH(copy_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, a, out); ++g_launches; return cudaGetLastError(); }
 cudaError_t launch_fill(long n, double val, double *out, cudaStream_t st) { PB_LAUNCH(fill_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, val, out); ++g_launches; return cudaGetLastError(); }
 cudaError_t launch_mul(long n, const double *a, const double *b, double *out, cudaStream_t st) { PB_LAUNCH(mul_kernel, PB_EW_GRID(n), PB_EW_BLOCK, 0, st, n, a, b, out); ++g_launches; return cudaGetLastError(); }

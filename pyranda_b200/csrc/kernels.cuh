@@ -100,6 +100,7 @@ cudaError_t launch_copy(long n, const double *a, double *out, cudaStream_t st);
 cudaError_t launch_fill(long n, double val, double *out, cudaStream_t st);
 cudaError_t launch_mul(long n, const double *a, const double *b, double *out, cudaStream_t st);
 cudaError_t launch_div(long n, const double *a, const double *b, double *out, cudaStream_t st);
+cudaError_t launch_mul_max(long n, const double *a, const double *b, double *out, int first, cudaStream_t st);
 // curvilinear divergence pre-contraction: fA/fB/fC = (fx*dAdx + fy*dAdy + fz*dAdz)*det ...
 cudaError_t launch_contra(long n, const double *fx, const double *fy, const double *fz,
                           const double *const *metric9, const double *det, double *fA, double *fB,

@@ -142,7 +142,8 @@ _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-8
     "mean": "self.mean", "sign": "xp.sign", "abs": "xp.abs", "sqrt": "xp.sqrt", "sin": "xp.sin", "cos": "xp.cos",
     "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar",
     "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff",
-    "bc.extrap": "self.bc.extrap", "bc.const": "self.bc.const", "bc.field": "self.bc.field", "bc.symm": "self.bc.symm",  # pyrandaBC.py:28-38
+    "bc.extrap": "self.bc.extrap", "bc.const": "self.bc.const", "bc.field": "self.bc.field", "bc.symm": "self.bc.symm",
+    "bc.exit": "self.bc.exit", "bc.slip": "self.bc.slip",  # pyrandaBC.py:28-38
     "ibmV": "self.ibm.velocity_slip", "ibmWall": "self.ibm.velocity_wall", "ibmS": "self.ibm.scalar",  # pyrandaIBM.py:27-31
     "numpy.minimum": "xp.minimum",
     "numpy.maximum": "xp.maximum", "numpy.sqrt": "xp.sqrt", "numpy.abs": "xp.abs", "numpy.where": "xp.where",
@@ -239,7 +240,7 @@ class pyrandaSim:
         self._ns = {"xp": self.xp, "numpy": self.xp, "self": self}
         from .bc import BoundaryConditions
         # the `BC` package (pyrandaBC.py), on the fields in place; a z-slab backend says which faces are its own
-        self.bc = BoundaryConditions(self.variables, getattr(backend, "owns", None))
+        self.bc = BoundaryConditions(self.variables, getattr(backend, "owns", None), getvar=backend.getvar)
         from .ibm import ImmersedBoundary
         self.ibm = ImmersedBoundary(self)             # the `IBM` package (pyrandaIBM.py)
         self.fuser = None

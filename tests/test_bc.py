@@ -74,3 +74,43 @@ def test_bounded_deck_with_bc_lines(oracle_mod):
     assert np.array_equal(phi[:, 0, :], phi[:, 1, :])
     assert np.array_equal(g2[0, :, :], phi[0, :, :])
     assert np.isfinite(phi).all() and 0.5 < phi.max() < 1.1
+
+
+def _golden_case(kind, oracle_mod):
+    """Fields and metrics of tests/golden/make_bc_golden.py (the reference's own BC package ran there)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_bc_golden", os.path.join(os.path.dirname(__file__), "golden", "make_bc_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    X, Y, Z, Xd, Yd, Zd = gen.mesh()
+    o = oracle_mod.Oracle(*gen.N, 0, 1, 0, 1, 0, 1, coordsys=3, mesh_xyz=(Xd, Yd, Zd))
+    f = gen.fields(X, Y, Z)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "bc_20x18.npz"))
+    if kind == "numpy":
+        return {k: a.copy(order="F") for k, a in f.items()}, o.getvar, gold
+    import torch
+    conv = lambda a: torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0))).permute(2, 1, 0)
+    return {k: conv(a) for k, a in f.items()}, (lambda name: conv(o.getvar(name))), gold
+
+
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+def test_exit_and_slip_match_the_reference_package(kind, oracle_mod):
+    """bc.exit (pyrandaBC.py:468-522) and bc.slip (:186-466) against golden planes produced by the
+    reference's own package on a curvilinear 2-D grid (tests/golden/make_bc_golden.py)."""
+    v, getvar, gold = _golden_case(kind, oracle_mod)
+    bc = BoundaryConditions(v, getvar=getvar)
+    bc.exit(["rho", "w"], ["x1", "xn", "y1", "yn"])
+    bc.exit("u", ["x1", "yn"], norm=True)
+    for k in ("rho", "w", "u"):
+        assert np.abs(np.asarray(v[k]) - gold["exit_" + k]).max() < 1e-14, k
+    v, getvar, gold = _golden_case(kind, oracle_mod)
+    bc = BoundaryConditions(v, getvar=getvar)
+    bc.slip([["u", "v"]], ["x1", "yn"])
+    bc.slip([["u", "v", "w"]], ["xn", "y1"])
+    for k in ("u", "v", "w"):
+        assert np.abs(np.asarray(v[k]) - gold["slip_" + k]).max() < 1e-13, k
+    # the wall-normal velocity is gone and the speed did not grow
+    n1, n2, _ = bc._normals("y1")
+    un = np.asarray(v["u"])[:, 0, :] * np.asarray(n1) + np.asarray(v["v"])[:, 0, :] * np.asarray(n2)
+    assert np.abs(un).max() < 1e-13

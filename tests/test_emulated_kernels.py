@@ -82,6 +82,7 @@ def test_emulated_symmetry_planes(symm, oracle_mod, emul_lib):
     ins = (f, g, h, 2 * g, f + h, -f, h * g, 0.5 * f, g - h)
     for a, b in zip(p.divergencetensor(*ins), o.divergencetensor(*ins)):
         assert rel_linf(a, b) < 1e-13
+    assert rel_linf(p.pringv(f, g, h), o.pringv(f, g, h)) < 1e-13  # the normal component through the odd d8
 
 
 def test_emulated_symmetry_equals_mirrored_periodic_line(oracle_mod, emul_lib):
@@ -137,3 +138,10 @@ def test_emulated_curvilinear(oracle_mod, emul_lib):
         assert rel_linf(a, b) < 1e-12
     assert rel_linf(p.sfilter(f), o.sfilter(f)) < 1e-12
     assert rel_linf(p.pring(f), o.pring(f)) < 1e-12
+    # divT: divergence of each row (operators.f90:176-179); ringV with the per-point d1, d2, d3 (:680-683)
+    g = np.asarray(np.cos(2 * f) + 0.3 * f, order="F")
+    h = np.asarray(f * f - 0.5, order="F")
+    ins = (f, g, h, 2 * g, f + h, -f, h * g, 0.5 * f, g - h)
+    for a, b in zip(p.divergencetensor(*ins), o.divergencetensor(*ins)):
+        assert rel_linf(a, b) < 1e-12
+    assert rel_linf(p.pringv(f, g, h), o.pringv(f, g, h)) < 1e-12

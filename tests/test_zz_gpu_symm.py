@@ -35,6 +35,7 @@ def test_symmetry_planes_match_oracle(n, symm, oracle_mod):
     ins = (f, g, h, 2 * g, f + h, -f, h * g, 0.5 * f, g - h)
     for a, b in zip(p.divergencetensor(*ins), o.divergencetensor(*ins)):
         assert rel_linf(a, b) < TOL
+    assert rel_linf(p.pringv(f, g, h), o.pringv(f, g, h)) < TOL
 
 
 @pytest.mark.parametrize("N", [64, 512])
@@ -84,3 +85,55 @@ def test_fourth_derivative(n, periodic, oracle_mod):
         T = a + 2 * b * np.cos(th) + 2 * c * np.cos(2 * th) + 2 * d * np.cos(3 * th)
         g = np.asfortranarray(np.sin(k * X))
         assert np.abs(p.dd4x(g) - T * g).max() < 1e-12
+
+
+def test_curvilinear_tensor_divergence_and_vector_ring(oracle_mod):
+    """coordsys = 3: divT is the curvilinear divergence of each row (operators.f90:176-179), ringV
+    scales by the per-point d1 / d2 / d3 (:680-683)."""
+    import torch
+    from pyranda_b200 import ParcopPlan
+    n = (64, 48, 32)
+    xs = [np.linspace(0, 1, k) for k in n]
+    X, Y, Z = np.meshgrid(*xs, indexing="ij")
+    Xd = X + 0.05 * np.sin(2 * np.pi * Y) * np.sin(np.pi * X)
+    Yd = Y + 0.04 * np.sin(2 * np.pi * X) * Z
+    Zd = Z * (1 + 0.1 * X)
+    o = oracle_mod.Oracle(*n, 0, 1, 0, 1, 0, 1, coordsys=3, mesh_xyz=(Xd, Yd, Zd))
+    p = ParcopPlan(*n, 0, 1, 0, 1, 0, 1, coordsys=3)
+    p.set_mesh(Xd, Yd, Zd)
+    f = synthetic_field(X, Y, Z)
+    g = np.asfortranarray(np.cos(2 * f) + 0.3 * f)
+    h = np.asfortranarray(f * f - 0.5)
+    ins = (f, g, h, 2 * g, f + h, -f, h * g, 0.5 * f, g - h)
+    ref = o.divergencetensor(*ins)
+    for a, b in zip(p.divergencetensor(*ins), ref):
+        assert rel_linf(a, b) < 1e-11
+    dev = []
+    for a in ins:
+        t = p.empty_device(); t.copy_(torch.from_numpy(a)); dev.append(t)
+    for a, b in zip(p.divergencetensor(*dev), ref):
+        assert rel_linf(a.cpu().numpy(), b) < 1e-11
+    assert rel_linf(p.pringv(f, g, h), o.pringv(f, g, h)) < 1e-11
+    assert rel_linf(p.pringv(*dev[:3]).cpu().numpy(), o.pringv(f, g, h)) < 1e-11
+
+
+def test_exit_and_slip_on_device_fields(oracle_mod):
+    """bc.exit / bc.slip (pyrandaBC.py:186-522) on CUDA tensors with Fortran strides against the
+    golden planes of the reference's own package (tests/golden/make_bc_golden.py)."""
+    import torch
+    from pyranda_b200.bc import BoundaryConditions
+    from test_bc import _golden_case
+    for case in ("exit", "slip"):
+        v, getvar, gold = _golden_case("torch", oracle_mod)
+        dev = {k: a.permute(2, 1, 0).contiguous().cuda().permute(2, 1, 0) for k, a in v.items()}
+        bc = BoundaryConditions(dev, getvar=lambda name: getvar(name).permute(2, 1, 0).contiguous().cuda().permute(2, 1, 0))
+        if case == "exit":
+            bc.exit(["rho", "w"], ["x1", "xn", "y1", "yn"])
+            bc.exit("u", ["x1", "yn"], norm=True)
+            names = ("rho", "w", "u")
+        else:
+            bc.slip([["u", "v"]], ["x1", "yn"])
+            bc.slip([["u", "v", "w"]], ["xn", "y1"])
+            names = ("u", "v", "w")
+        for k in names:
+            assert dev[k].is_cuda and np.abs(dev[k].cpu().numpy() - gold[case + "_" + k]).max() < 1e-13, (case, k)
