@@ -1,11 +1,13 @@
 """Boundary-plane packages of the EOM interpreter: bc.extrap / bc.const / bc.field / bc.symm /
-bc.exit / bc.slip.
+bc.exit / bc.slip / bc.farfield.
 
 Reference: pyranda/pyrandaBC.py:40-186,748-786 (the `BC` package: `bc.extrap(vars, dirs, order)`,
 `bc.const(vars, dirs, val)`, `bc.field(var, dirs, field)`, `bc.symm(vars, dirs, anti, npts)` lines
 inside an EOM string), :468-522 (`bc.exit(vars, dirs, norm)`, the bounded essentially-non-oscillatory
 outflow extrapolation) and :186-466 (`bc.slip([[u, v(, w)]], dirs)`, free slip on a curvilinear
-wall: extrapolate, then remove the wall-normal velocity).  They sit in
+wall: extrapolate, then remove the wall-normal velocity) and :524-746 (`bc.farfield(dirs)`,
+characteristic far-field values from the Riemann invariants; its reference state is stored by the
+deck in `BCdata['farfield-properties-<dir>']`, as in examples/cylinder_O_grid.py:84).  They sit in
 `updateVars`, i.e. they run after every RK4 stage, so with device-resident fields they must not
 leave the GPU: everything here is in-place slicing on the field object (a CUDA tensor with Fortran
 strides, or a numpy array in the oracle-backed test driver) -- one tiny strided kernel per plane.
@@ -162,3 +164,38 @@ class BoundaryConditions:
                 magF = xp.sqrt(magF)
                 for u in U:  # the projection must not lengthen the vector
                     u[pl] = xp.where(magF > mag0, u[pl] * mag0 / magF, u[pl])
+
+    # pyrandaBC.py:612-746 with Reimann (:566-608): boundary plane from the plane next to it and the
+    # free-stream state, through the incoming / outgoing Riemann invariants along the face normal
+    def farfield(self, direction):
+        for d in _as_list(direction):
+            if d[0] not in _AXIS or d[1:] not in ("1", "n"):
+                raise ValueError("unknown boundary '%s'" % d)
+            if not self.owns.get(d, False):
+                continue
+            ref = self.BCdata["farfield-properties-%s" % d]
+            gamma = ref["gamma"]
+            nx, ny, nz = self._normals(d)
+            inner, edge = self._plane(d, 1), self._plane(d, 0)
+            V = {k: self.variables[ref[k]] for k in ("rho", "u", "v", "w", "p")}
+            rhoi, Ui, Vi, Wi, Pi = (V[k][inner] for k in ("rho", "u", "v", "w", "p"))
+            xp = _xp(Ui)
+            one = Ui * 0.0 + 1.0
+            rhoo, Uo, Vo, Wo, Po = (one * ref[k] for k in ("rho0", "u0", "v0", "w0", "p0"))
+            Vni = Ui * nx + Vi * ny + Wi * nz
+            Vno = Uo * nx + Vo * ny + Wo * nz
+            SSo = xp.sqrt(gamma * Po / rhoo)
+            SSi = xp.sqrt(gamma * Pi / rhoi)
+            mach = xp.sqrt(Ui ** 2 + Vi ** 2 + Wi ** 2) / SSi
+            Rplus = xp.where(mach >= 1.0, Vno + 2.0 * SSo / (gamma - 1.0), Vni + 2.0 * SSi / (gamma - 1.0))
+            Rminus = xp.where(mach >= 1.0, Vni - 2.0 * SSi / (gamma - 1.0), Vno - 2.0 * SSo / (gamma - 1.0))
+            Vnormal = (Rminus + Rplus) * 0.5
+            SSb = (Rplus - Rminus) * (gamma - 1.0) * 0.25
+            out = Vnormal >= 0.0
+            Ub = xp.where(out, Ui + (Vnormal - Vni) * nx, Uo + (Vnormal - Vno) * nx)
+            Vb = xp.where(out, Vi + (Vnormal - Vni) * ny, Vo + (Vnormal - Vno) * ny)
+            Wb = xp.where(out, Wi + (Vnormal - Vni) * nz, Wo + (Vnormal - Vno) * nz)
+            aux = 1.0 / (gamma - 1.0)
+            rhob = xp.where(out, ((rhoi ** gamma * SSb ** 2) / (gamma * Pi)) ** aux, ((rhoo ** gamma * SSb ** 2) / (gamma * Po)) ** aux)
+            Pb = rhob * SSb ** 2 / gamma
+            V["rho"][edge], V["u"][edge], V["v"][edge], V["w"][edge], V["p"][edge] = rhob, Ub, Vb, Wb, Pb

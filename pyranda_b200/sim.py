@@ -143,7 +143,7 @@ _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-8
     "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar",
     "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff",
     "bc.extrap": "self.bc.extrap", "bc.const": "self.bc.const", "bc.field": "self.bc.field", "bc.symm": "self.bc.symm",
-    "bc.exit": "self.bc.exit", "bc.slip": "self.bc.slip",  # pyrandaBC.py:28-38
+    "bc.exit": "self.bc.exit", "bc.slip": "self.bc.slip", "bc.farfield": "self.bc.farfield",  # pyrandaBC.py:28-38
     "ibmV": "self.ibm.velocity_slip", "ibmWall": "self.ibm.velocity_wall", "ibmS": "self.ibm.scalar",  # pyrandaIBM.py:27-31
     "numpy.minimum": "xp.minimum",
     "numpy.maximum": "xp.maximum", "numpy.sqrt": "xp.sqrt", "numpy.abs": "xp.abs", "numpy.where": "xp.where",

@@ -2,7 +2,8 @@
 (/root/reference/pyranda/pyrandaBC.py, loaded with a stub for its package base class, because
 `import pyranda` needs mpi4py and the compiled parcop module) on a small curvilinear grid, the mesh
 metrics served by the CPU oracle.  Covers `bc.exit` (exitbc / BENO, with and without `norm`) and
-`bc.slip` (slipbc) on the x1 / xn / y1 / yn boundaries.  Run in the development container only:
+`bc.slip` (slipbc) on the x1 / xn / y1 / yn boundaries and `bc.farfield` (farfieldbc / Reimann) with a
+subsonic and a supersonic free stream.  Run in the development container only:
 
     python tests/golden/make_bc_golden.py
 """
@@ -49,7 +50,11 @@ def fields(X, Y, Z):
     rng = np.random.default_rng(11)
     mk = lambda a: np.asfortranarray(a + 0.2 * rng.uniform(-1, 1, size=X.shape))
     return {"u": mk(np.sin(3 * X) * np.cos(2 * Y)), "v": mk(np.cos(4 * X + Y)), "w": mk(0.3 * np.sin(5 * Z + X)),
-            "rho": mk(1.0 + 0.3 * np.cos(5 * X) * np.sin(3 * Y))}
+            "rho": mk(1.0 + 0.3 * np.cos(5 * X) * np.sin(3 * Y)), "p": mk(1.0 + 0.3 * np.sin(4 * X - Y))}
+
+
+FARFIELD = {"yn": {"rho0": 1.0, "p0": 1.0, "u0": 0.4, "v0": 0.1, "w0": 0.0, "gamma": 1.4},
+            "x1": {"rho0": 0.9, "p0": 0.2, "u0": 1.5, "v0": -0.2, "w0": 0.1, "gamma": 1.4}}
 
 
 def main():
@@ -82,6 +87,14 @@ def main():
     bc.slipbc([["u", "v", "w"]], ["xn", "y1"])
     for k in ("u", "v", "w"):
         out["slip_" + k] = sim.variables[k].data
+    sim = Sim(f0)
+    sim.variables["u"].data[1, :, :] *= 3.0  # part of the x1 face supersonic
+    bc = load_reference_bc()(sim)
+    for d, ref in FARFIELD.items():
+        bc.BCdata["farfield-properties-%s" % d] = dict(ref, rho="rho", u="u", v="v", w="w", p="p")
+    bc.farfieldbc(["yn", "x1"])
+    for k in ("rho", "u", "v", "w", "p"):
+        out["far_" + k] = sim.variables[k].data
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "bc_20x18.npz"), **out)
     print({k: float(np.abs(a - f0[k.split("_")[1]]).max()) for k, a in out.items()})
 

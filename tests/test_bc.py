@@ -76,6 +76,15 @@ def test_bounded_deck_with_bc_lines(oracle_mod):
     assert np.isfinite(phi).all() and 0.5 < phi.max() < 1.1
 
 
+def gen_farfield():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_bc_golden", os.path.join(os.path.dirname(__file__), "golden", "make_bc_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    return gen.FARFIELD
+
+
 def _golden_case(kind, oracle_mod):
     """Fields and metrics of tests/golden/make_bc_golden.py (the reference's own BC package ran there)."""
     import importlib.util
@@ -96,7 +105,7 @@ def _golden_case(kind, oracle_mod):
 
 @pytest.mark.parametrize("kind", ["numpy", "torch"])
 def test_exit_and_slip_match_the_reference_package(kind, oracle_mod):
-    """bc.exit (pyrandaBC.py:468-522) and bc.slip (:186-466) against golden planes produced by the
+    """bc.exit (pyrandaBC.py:468-522) bc.slip (:186-466) and bc.farfield (:524-746) against golden planes produced by the
     reference's own package on a curvilinear 2-D grid (tests/golden/make_bc_golden.py)."""
     v, getvar, gold = _golden_case(kind, oracle_mod)
     bc = BoundaryConditions(v, getvar=getvar)
@@ -114,3 +123,11 @@ def test_exit_and_slip_match_the_reference_package(kind, oracle_mod):
     n1, n2, _ = bc._normals("y1")
     un = np.asarray(v["u"])[:, 0, :] * np.asarray(n1) + np.asarray(v["v"])[:, 0, :] * np.asarray(n2)
     assert np.abs(un).max() < 1e-13
+    v, getvar, gold = _golden_case(kind, oracle_mod)
+    v["u"][1, :, :] *= 3.0
+    bc = BoundaryConditions(v, getvar=getvar)
+    for d, ref in gen_farfield().items():
+        bc.BCdata["farfield-properties-%s" % d] = dict(ref, rho="rho", u="u", v="v", w="w", p="p")
+    bc.farfield(["yn", "x1"])
+    for k in ("rho", "u", "v", "w", "p"):
+        assert np.abs(np.asarray(v[k]) - gold["far_" + k]).max() < 1e-13, k

@@ -117,20 +117,28 @@ def test_curvilinear_tensor_divergence_and_vector_ring(oracle_mod):
     assert rel_linf(p.pringv(*dev[:3]).cpu().numpy(), o.pringv(f, g, h)) < 1e-11
 
 
-def test_exit_and_slip_on_device_fields(oracle_mod):
-    """bc.exit / bc.slip (pyrandaBC.py:186-522) on CUDA tensors with Fortran strides against the
+def test_exit_slip_farfield_on_device_fields(oracle_mod):
+    """bc.exit / bc.slip / bc.farfield (pyrandaBC.py:186-746) on CUDA tensors with Fortran strides against the
     golden planes of the reference's own package (tests/golden/make_bc_golden.py)."""
     import torch
     from pyranda_b200.bc import BoundaryConditions
     from test_bc import _golden_case
-    for case in ("exit", "slip"):
+    from test_bc import gen_farfield
+    for case in ("exit", "slip", "far"):
         v, getvar, gold = _golden_case("torch", oracle_mod)
+        if case == "far":
+            v["u"][1, :, :] *= 3.0
         dev = {k: a.permute(2, 1, 0).contiguous().cuda().permute(2, 1, 0) for k, a in v.items()}
         bc = BoundaryConditions(dev, getvar=lambda name: getvar(name).permute(2, 1, 0).contiguous().cuda().permute(2, 1, 0))
         if case == "exit":
             bc.exit(["rho", "w"], ["x1", "xn", "y1", "yn"])
             bc.exit("u", ["x1", "yn"], norm=True)
             names = ("rho", "w", "u")
+        elif case == "far":
+            for d, ref in gen_farfield().items():
+                bc.BCdata["farfield-properties-%s" % d] = dict(ref, rho="rho", u="u", v="v", w="w", p="p")
+            bc.farfield(["yn", "x1"])
+            names = ("rho", "u", "v", "w", "p")
         else:
             bc.slip([["u", "v"]], ["x1", "yn"])
             bc.slip([["u", "v", "w"]], ["xn", "y1"])
