@@ -140,7 +140,7 @@ _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-8
     "dd4x": "self.dd4x", "dd4y": "self.dd4y", "dd4z": "self.dd4z",  # pyranda.py:833-835
     "dd8y": "self.dd8y", "dd8z": "self.dd8z", "sum": "self.B.sum3D", "max": "self.B.max3D", "min": "self.B.min3D",
     "mean": "self.mean", "sign": "xp.sign", "abs": "xp.abs", "sqrt": "xp.sqrt", "sin": "xp.sin", "cos": "xp.cos",
-    "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar",
+    "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar", "random3D": "self.random3D",
     "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff",
     "bc.extrap": "self.bc.extrap", "bc.const": "self.bc.const", "bc.field": "self.bc.field", "bc.symm": "self.bc.symm",
     "bc.exit": "self.bc.exit", "bc.slip": "self.bc.slip", "bc.farfield": "self.bc.farfield",  # pyrandaBC.py:28-38
@@ -155,11 +155,17 @@ _CALL = re.compile(r"(?<![\w.\"])((?:dt\.|numpy\.|bc\.)?[A-Za-z_3]\w*)\(")
 _WORD = re.compile(r"(?<![\w.\"])([A-Za-z_]\w*)(?![\w(\"])")
 
 
-def translate(expr):
-    """Deck expression -> Python source evaluated with `self` (the sim) and `xp` in scope."""
+def translate(expr, user=()):
+    """Deck expression -> Python source evaluated with `self` (the sim) and `xp` in scope.
+    `user`: names added with addUserDefinedFunction, called as f(self, ...) (pyranda.py:156-161)."""
     expr = expr.replace(" ", "").strip()
     expr = _VAR.sub(lambda m: 'self.variables["%s"]' % m.group(1), expr)
-    expr = _CALL.sub(lambda m: (_FUNCS[m.group(1)] + "(") if m.group(1) in _FUNCS else m.group(0), expr)
+
+    def call(m):
+        if m.group(1) in user:
+            return "self.userDefined['%s'](self," % m.group(1)
+        return (_FUNCS[m.group(1)] + "(") if m.group(1) in _FUNCS else m.group(0)
+    expr = _CALL.sub(call, expr)
     expr = _WORD.sub(lambda m: _NAMES.get(m.group(1), m.group(1)), expr)
     return expr
 
@@ -174,7 +180,7 @@ def _lines(text):
 
 
 class _Equation:
-    def __init__(self, text, fuser=None):
+    def __init__(self, text, fuser=None, user=()):
         self.text = text
         # an assignment has only variables (or ddt(variable)) left of its "="; a package call such as
         # `bc.extrap([...], [...], order=1)` is evaluated for its side effect
@@ -183,7 +189,7 @@ class _Equation:
         lhs, rhs = text.split("=", 1) if assign else (None, text)
         self.lhs = _VAR.findall(lhs) if lhs is not None else None
         self.kind = "PDE" if "ddt(" in text else "ALG"  # pyrandaEq.py:42-43
-        self.src = translate(rhs)
+        self.src = translate(rhs, user)
         self.pure = None  # AST when the right-hand side is arithmetic over variables only (groupable)
         if fuser is not None:  # arithmetic between operator calls -> one generated kernel each (fuse.py)
             if self.kind == "ALG" and self.lhs is not None and len(self.lhs) == 1:
@@ -229,6 +235,7 @@ class pyrandaSim:
         self.B = backend
         self.xp = backend.xp
         self.variables = {}
+        self.userDefined = {}
         self.equations = []
         self.conserved = []
         self.time, self.deltat, self.cycle = 0.0, 0.0, 0
@@ -314,21 +321,40 @@ class pyrandaSim:
         return self.B.min3D(drate)
 
     # ---- interpreter (pyranda.py:231-416) ----
-    def EOM(self, eom):
+    @staticmethod
+    def _apply_dict(text, d):
+        """pyranda.py:219-228: every key of the dictionary is replaced by str(value), textually."""
+        for key in (d or {}):
+            text = text.replace(key, str(d[key]))
+        return text
+
+    def addUserDefinedFunction(self, name, function):
+        """pyranda.py:156-161: `name(args)` in a deck line calls function(sim, args)."""
+        if name in _FUNCS:
+            raise ValueError("cannot add user-defined function '%s': the name is taken" % name)
+        self.userDefined[name] = function
+
+    def random3D(self):
+        """`random3D()` of a deck (pyranda.py:857): numpy's global stream, so numpy.random.seed applies."""
+        return self.B.asfield(np.asfortranarray(np.random.random(tuple(self.zero.shape))))
+
+    def EOM(self, eom, eomDict=None):
+        eom = self._apply_dict(eom, eomDict)
         for ln in _lines(eom):
-            eq = _Equation(ln, self.fuser)
+            eq = _Equation(ln, self.fuser, tuple(self.userDefined))
             self.equations.append(eq)
             for nm in _VAR.findall(ln):
                 self.variables.setdefault(nm, self.B.zeros())
             if eq.kind == "PDE":
                 self.conserved.append(eq.lhs[0])
 
-    def setIC(self, ics):
+    def setIC(self, ics, icDict=None):
+        ics = self._apply_dict(ics, icDict)
         local = {}
         for ln in _lines(ics):
             for nm in _VAR.findall(ln):
                 self.variables.setdefault(nm, self.B.zeros())
-            exec(translate(ln), self._ns, local)
+            exec(translate(ln, tuple(self.userDefined)), self._ns, local)
         self.updateVars()
 
     def updateFlux(self):  # pyranda.py:376-394

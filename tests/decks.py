@@ -111,3 +111,136 @@ BC_IC = """
 :c:   = 1.0
 :phi: = exp(-((meshx-0.4)**2 + (meshy-0.5)**2)/0.02)
 """
+
+
+# ---- examples/RT3D.py (the deck of tests/cases/testRT.py and of BASELINE config 4) ---------------
+def rt_mesh(npts, two_d=True):
+    """examples/RT3D.py:28-43."""
+    ff = 2 * float(np.pi) * float(npts - 1) / npts
+    if two_d:
+        dom = ((2.8 * float(np.pi), int(npts * 1.4), False), (ff, npts, True), (ff, 1, True))
+    else:
+        dom = ((3.0 * float(np.pi), int(npts * 1.5), False), (ff, npts, True), (ff, npts, True))
+    return "\n".join("%sdom = (0.0, %r, %d, periodic=%s)" % (c, L, n, p) for c, (L, n, p) in zip("xyz", dom))
+
+
+def RT_PARMS(npts):
+    """examples/RT3D.py:46-65 (the dictionary is applied to the deck text, pyranda.py:219-228)."""
+    return {"gx": -0.01, "CPh": 1.4, "CPl": 1.4, "CVh": 1.0, "CVl": 1.0, "mwH": 3.0, "mwL": 1.0, "Runiv": 1.0,
+            "waveLength": 4, "rho_l": 1.0, "rho_h": 3.0, "delta": 2.0 * np.pi / npts * 4}
+
+
+# examples/RT3D.py:86-185
+RT_EOM = """
+ddt(:rhoYh:)  =  -ddx(:rhoYh:*:u: - :Jx:)    - ddy(:rhoYh:*:v: - :Jy:)   - ddz(:rhoYh:*:w: - :Jz:)
+ddt(:rhoYl:)  =  -ddx(:rhoYl:*:u: + :Jx:)    - ddy(:rhoYl:*:v: + :Jy:)   - ddz(:rhoYl:*:w: + :Jz:)
+ddt(:rhou:)   =  -ddx(:rhou:*:u: - :tauxx:)  - ddy(:rhou:*:v: - :tauxy:) - ddz(:rhou:*:w: - :tauxz:) + :rho:*gx
+ddt(:rhov:)   =  -ddx(:rhov:*:u: - :tauxy:)  - ddy(:rhov:*:v: - :tauyy:) - ddz(:rhov:*:w: - :tauyz:)
+ddt(:rhow:)   =  -ddx(:rhow:*:u: - :tauxz:)  - ddy(:rhow:*:v: - :tauyz:) - ddz(:rhow:*:w: - :tauzz:)
+ddt(:Et:)     =  -ddx( (:Et: - :tauxx:)*:u: - :tauxy:*:v: - :tauxz:*:w: - :tx:*:kappa:) - ddy( (:Et: - :tauyy:)*:v: -:tauxy:*:u: - :tauyz:*:w: - :ty:*:kappa:) - ddz( (:Et: - :tauzz:)*:w: - :tauxz:*:u: - :tauyz:*:v: - :tz:*:kappa:) + :rho:*gx*:u:
+:rhoYh:     =  fbar( :rhoYh:  )
+:rhoYl:     =  fbar( :rhoYl:  )
+:rhou:      =  fbar( :rhou: )
+:rhov:      =  fbar( :rhov: )
+:rhow:      =  fbar( :rhow: )
+:Et:        =  fbar( :Et:   )
+:mybar: = xbar(:rho:*:u:*:u:)
+:rho:       = :rhoYh: + :rhoYl:
+:Yh:        =  :rhoYh: / :rho:
+:Yl:        =  :rhoYl: / :rho:
+:u:         =  :rhou: / :rho:
+:v:         =  :rhov: / :rho:
+:w:         =  :rhow: / :rho:
+:cv:        = :Yh:*CVh + :Yl:*CVl
+:cp:        = :Yh:*CPh + :Yl:*CPl
+:gamma:     = :cp:/:cv:
+:p:         =  ( :Et: - .5*:rho:*(:u:*:u: + :v:*:v:) ) * ( :gamma: - 1.0 )
+:mw:        = 1.0 / ( :Yh: / mwH + :Yl: / mwL )
+:R:         = Runiv / :mw:
+:T:         = :p: / (:rho: * :R: )
+:ux:        =  ddx(:u:)
+:vy:        =  ddy(:v:)
+:wz:        =  ddz(:w:)
+:div:       =  :ux: + :vy: + :wz:
+:uy:        =  ddy(:u:)
+:uz:        =  ddz(:u:)
+:vx:        =  ddx(:v:)
+:vz:        =  ddz(:v:)
+:wy:        =  ddy(:w:)
+:wx:        =  ddx(:w:)
+:Yx:        =  ddx(:Yh:)
+:Yy:        =  ddy(:Yh:)
+:Yz:        =  ddz(:Yh:)
+:enst:      = sqrt( (:uy:-:vx:)**2 + (:uz: - :wx:)**2 + (:vz:-:wy:)**2 )
+:S:         = sqrt( :ux:*:ux: + :vy:*:vy: + :wz:*:wz: + .5*((:uy:+:vx:)**2 + (:uz: + :wx:)**2 + (:vz:+:wy:)**2) )
+:mu:        = 1.0e-4 * gbar( abs(ring(:S:  )) ) * :rho:
+:beta:      = 7.0e-2 * gbar( abs(ring(:div:)) * :rho: )
+:Dsgs:      =  1.0e-4 * ring(:Yh:)
+:Ysgs:      =  1.0e2  * (abs(:Yh:) - 1.0 + abs(1.0-:Yh: ) )*gridLen**2
+:adiff:     =  gbar( :rho:*numpy.maximum(:Dsgs:,:Ysgs:) / :dt: )
+:Jx:        =  :adiff:*:Yx:
+:Jy:        =  :adiff:*:Yy:
+:Jz:        =  :adiff:*:Yz:
+:taudia:    =  (:beta:-2./3.*:mu:) *:div: - :p:
+:tauxx:     =  2.0*:mu:*:ux:   + :taudia:
+:tauyy:     =  2.0*:mu:*:vy:   + :taudia:
+:tauzz:     =  2.0*:mu:*:wz:   + :taudia:
+:tauxy:     = :mu:*(:uy:+:vx:)
+:tauxz:     = :mu:*(:uz:+:wx:)
+:tauyz:     = :mu:*(:vz:+:wz:)
+[:tx:,:ty:,:tz:] = grad(:T:)
+:kappa:     = 1.0e-3 * gbar( ring(:T:)* :rho:*:cv:/(:T: * :dt: ) )
+:cs:        = sqrt( :p: / :rho: * :gamma: )
+:dt:        = dt.courant(:u:,:v:,:w:,:cs:)*1.0
+:dt:        = numpy.minimum(:dt:,0.2 * dt.diff(:beta:,:rho:))
+:dt:        = numpy.minimum(:dt:,0.2 * dt.diff(:mu:,:rho:))
+:dt:        = numpy.minimum(:dt:,0.2 * dt.diff(:adiff:,:rho:))
+bc.const(['Yh'],['xn'],1.0)
+bc.const(['Yh'],['x1'],0.0)
+bc.const(['Yl'],['x1'],1.0)
+bc.const(['Yl'],['xn'],0.0)
+bc.extrap(['rho','Et'],['x1','xn'])
+bc.const(['u','v','w'],['x1','xn'],0.0)
+:leftBC:  = 1.0 - 0.5 * (1.0 + tanh( (meshx-1.0) / .1 ) )
+:rightBC: = 0.5 * (1.0 + tanh( (meshx-8.0) / .1 ) )
+:BC: = numpy.maximum(:leftBC:,:rightBC:)
+:u: = gbar(:u:)*:BC: + :u:*(1.0 - :BC:)
+:rho: = gbar(:rho:)*:BC: + :rho:*(1.0 - :BC:)
+:Et: = gbar(:Et:)*:BC: + :Et:*(1.0 - :BC:)
+:rhoYh: = :rho:*:Yh:
+:rhoYl: = :rho:*:Yl:
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:rhow: = :rho:*:w:
+:mix:  = 4.0*:Yh:*:Yl:
+"""
+
+# examples/RT3D.py:192-222
+RT_IC = """
+:gamma:= 5./3.
+p0     = 1.0
+At     = ( (rho_h - rho_l)/(rho_h + rho_l) )
+u0     = sqrt( abs(gx*At/waveLength) ) * .1
+:Yl: = .5 * (1.0-tanh( sqrt(pi)*( meshx - 1.4*pi ) / delta ))
+:Yh: = 1.0 - :Yl:
+:p:  += p0
+wgt = 4*:Yh:*:Yl:
+:v: *= 0.0
+:w: *= 0.0
+:u: = wgt * gbar( (random3D()-0.5)*u0 )
+:rho:       = rho_h * :Yh: + rho_l * :Yl:
+:cv:        = :Yh:*CVh + :Yl:*CVl
+:cp:        = :Yh:*CPh + :Yl:*CPl
+:gamma:     = :cp:/:cv:
+:mw:        = 1.0 / ( :Yh: / mwH + :Yl: / mwL )
+:R:         = Runiv / :mw:
+:T:         = :p: / (:rho: * :R: )
+:rhoYh: = :rho:*:Yh:
+:rhoYl: = :rho:*:Yl:
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:rhow: = :rho:*:w:
+:Et:  = :p: / (:gamma:-1.0) + 0.5*:rho:*(:u:*:u: + :v:*:v: + :w:*:w:)
+:cs:  = sqrt( :p: / :rho: * :gamma: )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)
+"""

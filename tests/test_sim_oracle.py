@@ -47,6 +47,40 @@ def test_advection_1d_golden(oracle_mod):
         assert abs(err - golden) / golden < 1e-3, (npts, err, golden)
 
 
+def test_rayleigh_taylor_2d_golden_curve(oracle_mod):
+    """tests/cases/testRT.py (examples/RT3D.py 32 1 1, BASELINE config 4 in 2-D): the reference's own
+    baseline file tests/baselines/RT_2D.dat -- mixing width every 20 cycles up to t = 100, 828 RK4
+    steps on 44 x 32 -- through the interpreter on the oracle.  Non-periodic x with one-sided closures,
+    ddx/ddy, grad, fbar, gbar, ring, the BC package, the dt package, a user-defined function and the
+    seeded random3D().  The reference's tolerance is 1e-4; the curve is reproduced to ~1e-12."""
+    import os
+    from decks import RT_EOM, RT_IC, RT_PARMS, rt_mesh
+    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "RT_2D.dat"))
+    npts = 32
+    ss = make_sim(oracle_mod, "RT_2D", rt_mesh(npts))
+    ss.addUserDefinedFunction("xbar", lambda sim, data: np.asfortranarray(
+        np.broadcast_to(data.mean(axis=(1, 2), keepdims=True), data.shape)))  # examples/RT3D.py:73-79
+    parm = RT_PARMS(npts)
+    ss.EOM(RT_EOM, parm)
+    np.random.seed(1234)  # examples/RT3D.py:225
+    ss.setIC(RT_IC, parm)
+    trapz = getattr(np, "trapezoid", None) or np.trapz
+    time, cfl = 0.0, 1.0
+    dt = float(ss.variables["dt"]) * cfl
+    dtmax = dt * .1
+    mix_w, time_w = [], []
+    while time < 100.0:  # examples/RT3D.py:248-262
+        time = ss.rk4(time, dt)
+        dt = min(float(ss.variables["dt"]) * cfl, dtmax * 1.1)
+        dtmax = dt * 1.0
+        if ss.cycle % 20 == 0:
+            mix_w.append(trapz(ss.variables["mix"].mean(axis=(1, 2)), ss.variables["meshx"][:, 0, 0]))
+            time_w.append(time)
+    assert len(time_w) == gold.shape[1] == 41
+    assert np.abs(np.array(time_w) / gold[0] - 1).max() < 1e-9
+    assert np.abs(np.array(mix_w) / gold[1] - 1).max() < 1e-9
+
+
 def test_restart_roundtrip(oracle_mod, tmp_path):
     """writeRestart / readRestart (pyranda.py:475-588): a restarted run continues bit for bit."""
     from decks import TGV_EOM, TGV_IC, tgv_mesh
