@@ -244,3 +244,108 @@ wgt = 4*:Yh:*:Yl:
 :cs:  = sqrt( :p: / :rho: * :gamma: )
 :dt: = dt.courant(:u:,:v:,:w:,:cs:)
 """
+
+
+# ---- examples/KH.py (tests/cases/test2deuler.py: KH-2d-64) ----------------------------------------
+def kh_mesh(npts):
+    """examples/KH.py:48-52."""
+    L = 1.0 * (npts - 1.0) / npts
+    return "xdom = (0.0, %r, %d, periodic=True)\nydom = (0.0, %r, %d, periodic=True)" % (L, npts, L, npts)
+
+
+KH_GAMMA = 5. / 3.
+KH_EOM_PARMS = {"gamma": KH_GAMMA, "R0": 1.0, "cv": 1.0 / (1.0 - 1.0 / KH_GAMMA) - 1.0}  # examples/KH.py:8-21,104
+KH_IC_PARMS = {"gamma": KH_GAMMA, "u1": 0.5, "u2": -0.5, "p0": 2.5, "rho1": 1.0, "rho2": 2.0, "L": 0.025, "Vmean": 0.0}
+
+# examples/KH.py:60-101
+KH_EOM = """
+ddt(:rho:)  =  -ddx(:rho:*:u:)            - ddy(:rho:*:v:)
+ddt(:rhou:) =  -ddx(:rhou:*:u: - :tauxx:) - ddy(:rhou:*:v: - :tauxy:)
+ddt(:rhov:) =  -ddx(:rhov:*:u: - :tauxy:) - ddy(:rhov:*:v: - :tauyy:)
+ddt(:Et:)   =  -ddx( (:Et: - :tauxx:)*:u: - :tauxy:*:v:  - :tx:*:kappa: )  - ddy( (:Et: - :tauyy:)*:v: -:tauxy:*:u:- :ty:*:kappa: )
+:rho:       =  fbar( :rho:  )
+:rhou:      =  fbar( :rhou: )
+:rhov:      =  fbar( :rhov: )
+:Et:        =  fbar( :Et:   )
+:u:         =  :rhou: / :rho:
+:v:         =  :rhov: / :rho:
+:p:         =  ( :Et: - .5*:rho:*(:u:*:u: + :v:*:v:) ) * ( gamma - 1.0 )
+:ux:        =  ddx(:u:)
+:vy:        =  ddy(:v:)
+:div:       =  :ux: + :vy:
+:uy:        =  ddy(:u:)
+:vx:        =  ddx(:v:)
+:enst:      = sqrt( (:uy:-:vx:)**2 )
+:tke:       = :rho:*(:u:*:u: + :v:*:v: )
+:S:         = sqrt( :ux:*:ux: + :vy:*:vy:  + .5*((:uy:+:vx:)**2  ) )
+:mu:        =  gbar( abs(ring(:S:  )) ) * :rho: * 1.0e-4
+:beta:      =  gbar( abs(ring(:div:)) * :rho: )  * 7.0e-3
+:taudia:    =  (:beta:-2./3.*:mu:) *:div: - :p:
+:tauxx:     =  2.0*:mu:*:ux:   + :taudia:
+:tauyy:     =  2.0*:mu:*:vy:   + :taudia:
+:tauxy:     = :mu:*(:uy:+:vx:)
+:T:         = :p: / (:rho: * R0 )
+[:tx:,:ty:,:tz:] = grad(:T:)
+:kappa:     = gbar( ring(:T:)* :rho:*cv/(:T: * :dt: ) ) * 1.0e-3
+:cs:  = sqrt( :p: / :rho: * gamma )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)*1.0
+:dt: = numpy.minimum(:dt:,0.2 * dt.diff(:beta:,:rho:))
+:dt: = numpy.minimum(:dt:,0.2 * dt.diff(:mu:,:rho:))
+"""
+
+# examples/KH.py:108-127
+KH_IC = """
+Um = (u1-u2)/2.0
+rhoM = (rho1-rho2)/2.0
+:u: =                     u1-Um*exp( -(meshy-.75)/L)
+:u: = where( meshy < .75, u2+Um*exp( -(.75-meshy)/L) , :u: )
+:u: = where( meshy < .50, u2+Um*exp( (-meshy+.25)/L) , :u: )
+:u: = where( meshy < .25, u1-Um*exp(  (meshy-.25)/L) , :u: )
+:v: = 0.01*sin( 4.*pi*meshx ) + Vmean
+:rho: =                     rho1-rhoM*exp( -(meshy-.75)/L)
+:rho: = where( meshy < .75, rho2+rhoM*exp( -(.75-meshy)/L) , :rho: )
+:rho: = where( meshy < .50, rho2+rhoM*exp( (-meshy+.25)/L) , :rho: )
+:rho: = where( meshy < .25, rho1-rhoM*exp(  (meshy-.25)/L) , :rho: )
+:p: += p0
+:Et: = :p:/( gamma - 1.0 ) + .5*:rho:*(:u:*:u: + :v:*:v:)
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:cs:  = sqrt( :p: / :rho: * gamma )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)*.1
+"""
+
+
+# ---- examples/euler.py, dim = 2, problem = 'sod' (tests/cases/test2deuler.py: euler-2d-64) --------
+def euler2d_mesh(npts):
+    """examples/euler.py:36-47."""
+    Lp = float(np.pi) * 2.0 * (npts - 1.0) / npts
+    return {"x1": [0.0, 0.0, 0.0], "xn": [Lp, Lp, Lp], "nn": [npts, npts, 1], "periodic": [False, False, True]}
+
+
+# examples/euler.py:53-74
+EULER2D_EOM = """
+ddt(:rho:)  =  -ddx(:rho:*:u:)                  - ddy(:rho:*:v:)
+ddt(:rhou:) =  -ddx(:rhou:*:u: + :p: - :tau:)   - ddy(:rhou:*:v:)
+ddt(:rhov:) =  -ddx(:rhov:*:u:)                 - ddy(:rhov:*:v: + :p: - :tau:)
+ddt(:Et:)   =  -ddx( (:Et: + :p: - :tau:)*:u: ) - ddy( (:Et: + :p: - :tau:)*:v: )
+:rho:       =  fbar( :rho:  )
+:rhou:      =  fbar( :rhou: )
+:rhov:      =  fbar( :rhov: )
+:Et:        =  fbar( :Et:   )
+:u:         =  :rhou: / :rho:
+:v:         =  :rhov: / :rho:
+:p:         =  ( :Et: - .5*:rho:*(:u:*:u: + :v:*:v:) ) * ( :gamma: - 1.0 )
+:div:       =  ddx(:u:) + ddy(:v:)
+:beta:      =  gbar(abs(ring(:div:))) * :rho: * 7.0e-2
+:tau:       =  :beta:*:div:
+bc.extrap(['rho','Et'],['x1','xn','y1','yn'])
+bc.const(['u','v'],['x1','xn','y1','yn'],0.0)
+"""
+
+# examples/euler.py:88-113
+EULER2D_IC = """
+rad = sqrt( (meshx-pi)**2  +  (meshy-pi)**2 )
+:gamma: = 1.4
+:Et:  = gbar( where( rad < pi/2.0, 1.0/(:gamma:-1.0) , .1 /(:gamma:-1.0) ) )
+:rho: = gbar( where( rad < pi/2.0, 1.0    , .125 ) )
+"""

@@ -47,7 +47,7 @@ class NumpyOracleBackend:
 
 def make_sim(oracle_mod, name, mesh):
     from pyranda_b200.sim import parse_mesh, pyrandaSim
-    opt = parse_mesh(mesh)
+    opt = parse_mesh(mesh) if isinstance(mesh, str) else mesh
     o = oracle_mod.Oracle(*opt["nn"], opt["x1"][0], opt["xn"][0], opt["x1"][1], opt["xn"][1], opt["x1"][2], opt["xn"][2],
                           periodic=tuple(opt["periodic"]))
     return pyrandaSim(name, opt, backend=NumpyOracleBackend(o))

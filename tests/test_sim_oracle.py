@@ -1,6 +1,7 @@
 """The deck interpreter + RK4 driver (pyranda_b200.sim) on the numpy / oracle backend, pinned to the
 reference's golden scalars for whole simulations (tolerance 1e-4, tests/run_tests.py:84)."""
 import numpy as np
+import pytest
 
 from decks import run_tgv, tgv_mesh
 from oracle_backend import make_sim
@@ -79,6 +80,52 @@ def test_rayleigh_taylor_2d_golden_curve(oracle_mod):
     assert len(time_w) == gold.shape[1] == 41
     assert np.abs(np.array(time_w) / gold[0] - 1).max() < 1e-9
     assert np.abs(np.array(mix_w) / gold[1] - 1).max() < 1e-9
+
+
+def test_kelvin_helmholtz_2d_golden_curve(oracle_mod):
+    """tests/cases/test2deuler.py KH-2d-64 (examples/KH.py 64 0 . 1): density along j = 3 ny / 4 at
+    t = 1.5 against the reference's baseline file (tolerance there 1e-4; reproduced to ~1e-12).
+    Periodic 2-D: ddx/ddy, grad, fbar, gbar, ring, the dt package, deck dictionaries, where()."""
+    import os
+    from decks import KH_EOM, KH_EOM_PARMS, KH_IC, KH_IC_PARMS, kh_mesh
+    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "KH-2d-64.dat"))
+    npts = 64
+    ss = make_sim(oracle_mod, "KH", kh_mesh(npts))
+    ss.EOM(KH_EOM, KH_EOM_PARMS)
+    ss.setIC(KH_IC, KH_IC_PARMS)
+    t_final, dt_max, time = 1.5, 1.0, 0.0
+    dt = float(ss.variables["dt"])
+    while t_final > time:  # examples/KH.py:141-146
+        time = ss.rk4(time, dt)
+        dt = min(float(ss.variables["dt"]), 1.1 * dt)
+        dt = min(dt_max, dt)
+        dt = min(dt, (t_final - time))
+    j = int(3 * npts / 4)
+    assert np.abs(ss.variables["meshx"][:, j, 0] - gold[0]).max() < 1e-14
+    assert np.abs(ss.variables["rho"][:, j, 0] - gold[1]).max() < 1e-9
+
+
+@pytest.mark.parametrize("npts", [64, 128])
+def test_euler_2d_sod_golden_curve(npts, oracle_mod):
+    """tests/cases/test2deuler.py euler-2d-64 / euler-2d-128 (examples/euler.py, cylindrical Sod
+    problem in a box): density along j = ny / 2 at t = pi / 4 against the reference's baseline files.
+    Bounded x and y: one-sided closures of d1, both filters and the ring detector, bc.extrap,
+    bc.const.  The curves are reproduced to the last printed digit."""
+    import os
+    from decks import EULER2D_EOM, EULER2D_IC, euler2d_mesh
+    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "euler-2d-%d.dat" % npts))
+    ss = make_sim(oracle_mod, "sod", euler2d_mesh(npts))
+    ss.EOM(EULER2D_EOM)
+    ss.setIC(EULER2D_IC)
+    dt_max = 1.0 / npts * 0.75  # examples/euler.py:137-155
+    tt = np.pi * 2.0 * .125
+    time, dt = 0.0, dt_max
+    while tt > time:
+        time = ss.rk4(time, dt)
+        dt = min(dt_max, (tt - time))
+    j = int(npts / 2)
+    assert np.abs(ss.variables["meshx"][:, j, 0] - gold[0]).max() < 1e-14
+    assert np.abs(ss.variables["rho"][:, j, 0] - gold[1]).max() < 1e-12
 
 
 def test_restart_roundtrip(oracle_mod, tmp_path):
