@@ -216,6 +216,24 @@ def parse_mesh(text):
     return opt
 
 
+def curvilinear_coordinates(opt, lo=(0, 0, 0), shape=None):
+    """Coordinates of a `coordsys = 3` mesh as pyrandaMesh.makeMesh builds them
+    (pyrandaMesh.py:93-129): the uniform grid between x1 and xn, overwritten point by point with
+    `function(i, j, k)` of the GLOBAL indices when the options carry one.  `lo` / `shape`: the local
+    block of a decomposed mesh."""
+    nn = opt["nn"]
+    shape = tuple(nn) if shape is None else tuple(shape)
+    ax = [np.linspace(opt["x1"][d], opt["xn"][d], num=nn[d])[lo[d]:lo[d] + shape[d]] for d in range(3)]
+    x, y, z = (np.asfortranarray(a) for a in np.meshgrid(*ax, indexing="ij"))
+    fn = opt.get("function")
+    if fn:
+        for i in range(shape[0]):
+            for j in range(shape[1]):
+                for k in range(shape[2]):
+                    x[i, j, k], y[i, j, k], z[i, j, k] = fn(i + lo[0], j + lo[1], k + lo[2])
+    return x, y, z
+
+
 class pyrandaSim:
     """`ss = pyrandaSim(name, mesh); ss.EOM(eom); ss.setIC(ic); ss.rk4(time, dt)` on the device."""
 
@@ -225,17 +243,23 @@ class pyrandaSim:
         self.meshOptions = opt
         self.nx, self.ny, self.nz = opt["nn"]
         self.npts = self.nx * self.ny * self.nz
+        self.coordsys = int(opt.get("coordsys", 0))
         if backend is None:
             from .plan import ParcopPlan
             plan = ParcopPlan(self.nx, self.ny, self.nz, opt["x1"][0], opt["xn"][0], opt["x1"][1], opt["xn"][1],
                               opt["x1"][2], opt["xn"][2], periodic=tuple(opt["periodic"]), device=device,
+                              coordsys=self.coordsys,
                               symmetric=tuple(tuple(s) for s in opt.get("symmetric", ((False, False),) * 3)))
-            plan.set_mesh()
+            if self.coordsys == 3:  # pyrandaMesh.py:93-135: the grid comes from Python
+                plan.set_mesh(*curvilinear_coordinates(opt), periodic_grid=bool(opt.get("periodicGrid", True)))
+            else:
+                plan.set_mesh()
             backend = CudaBackend(plan)
         self.B = backend
         self.xp = backend.xp
         self.variables = {}
         self.userDefined = {}
+        self._cmetric = None
         self.equations = []
         self.conserved = []
         self.time, self.deltat, self.cycle = 0.0, 0.0, 0
@@ -304,8 +328,19 @@ class pyrandaSim:
     def mean(self, a):
         return 1.0 / float(self.npts) * self.B.sum3D(a)
 
-    # ---- pyrandaTimestep.py:42-77 (Cartesian branch) ----
+    # ---- pyrandaTimestep.py:42-77 ----
     def dt_courant(self, u, v, w, c):
+        if self.coordsys == 3:  # :45-55: velocities along the (2-D) grid lines over the local spacings
+            xp = self.xp
+            if self._cmetric is None:
+                g = {k: self.B.getvar(k) for k in ("dAx", "dAy", "dBx", "dBy")}
+                self._cmetric = (g, xp.sqrt(g["dAx"] * g["dAx"] + g["dAy"] * g["dAy"]),
+                                 xp.sqrt(g["dBx"] * g["dBx"] + g["dBy"] * g["dBy"]))
+            g, magA, magB = self._cmetric
+            uA = (u * g["dAx"] + v * g["dAy"]) / magA
+            uB = (u * g["dBx"] + v * g["dBy"]) / magB
+            vrate = xp.abs(uA) / self.d1 + xp.abs(uB) / self.d2
+            return 1.0 / self.B.max3D(vrate + xp.abs(c) / self.GridLen)
         if self.fuser is not None:  # one kernel + a reduction whose result stays on the device
             return 1.0 / self.B.max3D_dev(eval(self._courant, self._ns, {"u": u, "v": v, "w": w, "c": c}))
         xp = self.xp

@@ -349,3 +349,172 @@ rad = sqrt( (meshx-pi)**2  +  (meshy-pi)**2 )
 :Et:  = gbar( where( rad < pi/2.0, 1.0/(:gamma:-1.0) , .1 /(:gamma:-1.0) ) )
 :rho: = gbar( where( rad < pi/2.0, 1.0    , .125 ) )
 """
+
+
+# ---- examples/cylinder.py (tests/cases/testCylinder.py: cylinder-2d-32 / -64) ---------------------
+def cylinder_mesh(npts):
+    """examples/cylinder.py:33-41."""
+    Lp = float(np.pi) * 2.0 * (npts - 1.0) / npts
+    return {"x1": [0.0, 0.0, 0.0], "xn": [Lp, Lp, Lp], "nn": [npts, npts, 1], "periodic": [False, False, False]}
+
+
+# examples/cylinder.py:51-57,104,130: Mach-2 inflow; the deck text is patched with str() of these
+CYL_MACH = 2.0
+CYL_U0 = float(np.sqrt(1.0 / 1.0 * 1.4)) * CYL_MACH
+
+# examples/cylinder.py:61-103
+CYLINDER_EOM = """
+ddt(:rho:)  =  -ddx(:rho:*:u:)                  - ddy(:rho:*:v:)
+ddt(:rhou:) =  -ddx(:rhou:*:u: + :p: - :tau:)   - ddy(:rhou:*:v:)
+ddt(:rhov:) =  -ddx(:rhov:*:u:)                 - ddy(:rhov:*:v: + :p: - :tau:)
+ddt(:Et:)   =  -ddx( (:Et: + :p: - :tau:)*:u: - :tx:*:kappa:) - ddy( (:Et: + :p: - :tau:)*:v: - :ty:*:kappa: )
+:rho:       =  fbar( :rho:  )
+:rhou:      =  fbar( :rhou: )
+:rhov:      =  fbar( :rhov: )
+:Et:        =  fbar( :Et:   )
+:u:         =  :rhou: / :rho:
+:v:         =  :rhov: / :rho:
+:p:         =  ( :Et: - .5*:rho:*(:u:*:u: + :v:*:v:) ) * ( :gamma: - 1.0 )
+:T:         = :p: / (:rho: * :R: )
+:div:       =  ddx(:u:) + ddy(:v:)
+:beta:      =  gbar( ring(:div:) * :rho: ) * 7.0e-2
+:tau:       = :beta:*:div:
+[:tx:,:ty:,:tz:] = grad(:T:)
+:kappa:     = gbar( ring(:T:)* :rho:*:cv:/(:T: * :dt: ) ) * 1.0e-3
+[:u:,:v:,:w:] = ibmV( [:u:,:v:,:w:], :phi:, [:gx:,:gy:,:gz:], [:u1:,:u2:,0.0] )
+:rho: = ibmS( :rho: , :phi:, [:gx:,:gy:,:gz:] )
+:p:   = ibmS( :p:   , :phi:, [:gx:,:gy:,:gz:] )
+bc.extrap(['rho','p','u'],['xn'])
+bc.const(['u'],['x1','y1','yn'],u0)
+bc.const(['v'],['x1','xn','y1','yn'],0.0)
+bc.const(['rho'],['x1','y1','yn'],rho0)
+bc.const(['p'],['x1','y1','yn'],p0)
+:Et:  = :p: / ( :gamma: - 1.0 )  + .5*:rho:*(:u:*:u: + :v:*:v:)
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:cs:  = sqrt( :p: / :rho: * :gamma: )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)
+:dtB: = 0.2* dt.diff(:beta:,:rho:)
+:dt: = numpy.minimum(:dt:,:dtB:)
+:umag: = sqrt( :u:*:u: + :v:*:v: )
+""".replace('u0', str(CYL_U0)).replace('p0', str(1.0)).replace('rho0', str(1.0))
+
+# examples/cylinder.py:110-129
+CYLINDER_IC = """
+:gamma: = 1.4
+:R: = 1.0
+:cp: = :R: / (1.0 - 1.0/:gamma: )
+:cv: = :cp: - :R:
+rad = sqrt( (meshx-pi)**2  +  (meshy-pi)**2 )
+:phi: = rad - pi/4.0
+:rho: = 1.0 + 3d()
+:p:  =  1.0 + 3d() #exp( -(meshx-1.5)**2/.25**2)*.1
+:u: = where( :phi:>0.5, mach * sqrt( :p: / :rho: * :gamma:) , 0.0 )
+:u: = gbar( gbar( :u: ) )
+:v: = 0.0 + 3d()
+:Et: = :p:/( :gamma: - 1.0 ) + .5*:rho:*(:u:*:u: + :v:*:v:)
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:cs:  = sqrt( :p: / :rho: * :gamma: )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)*.1
+[:gx:,:gy:,:gz:] = grad( :phi: )
+:gx: = gbar( :gx: )
+:gy: = gbar( :gy: )
+""".replace('mach', str(CYL_MACH))
+
+
+# ---- examples/cylinder_curv.py (tests/cases/testCylinder.py: cylinder_curved-2d-64; BASELINE config 5) ----
+def zoom_mesh_1d(npts, x1, xn, xa, xb, tt, dxf):
+    """examples/meshTest.py:7-55 zoomMesh_solve: spacing dxf inside [xa, xb], blended by tanh into a
+    coarse spacing found by a secant iteration so that the last node lands on xn."""
+    def zoom(dxc):
+        x = np.zeros((npts))
+        x[0] = x1
+        dx = dxc
+        for i in range(1, npts):
+            x[i] = x[i - 1] + dx
+            xmin = (xa + xb) / 2.0
+            xh = (xb - xa) / 2.0
+            xpr = np.abs(x[i] - xmin)
+            w = 0.5 * (np.tanh((xpr - xh) / tt) + 1.0)
+            dx = w * dxc + (1.0 - w) * dxf
+        return x
+    nmin = (xb - xa) / dxf
+    dxc = ((xn - x1) - (xb - xa)) / (npts - nmin)
+    delta, f1, cnt = 1.0001, xn, 1
+    while (abs(f1) > .01 * xn) and cnt < 100:
+        f1 = zoom(dxc)[-1] - xn
+        f2 = zoom(dxc * delta)[-1] - xn
+        dxc = dxc * (1.0 - f1 / (f2 - f1) * (delta - 1.0))
+        cnt += 1
+    return zoom(dxc)
+
+
+def cylinder_curv_mesh(npts):
+    """examples/cylinder_curv.py:33-62."""
+    Lp = float(np.pi) * 2.0 * (npts - 1.0) / npts
+    dxf = 4 * Lp / float(npts) * .3
+    xS = zoom_mesh_1d(npts, -2. * Lp, 2. * Lp, -2., 2., 1.0, dxf)
+    return {"coordsys": 3, "function": lambda i, j, k: (xS[i], xS[j], 0.0), "periodic": [False, False, True],
+            "periodicGrid": False, "x1": [-2 * Lp, -2 * Lp, 0.0], "xn": [2 * Lp, 2 * Lp, Lp], "nn": [npts, npts, 1]}
+
+
+# examples/cylinder_curv.py:83-119
+CYLINDER_CURV_EOM = """
+ddt(:rho:)  =  -div(:rho:*:u:,  :rho:*:v:)
+ddt(:rhou:) =  -div(:rhou:*:u: + :p: - :tau:, :rhou:*:v:)
+ddt(:rhov:) =  -div(:rhov:*:u:, :rhov:*:v: + :p: - :tau:)
+ddt(:Et:)   =  -div( (:Et: + :p: - :tau:)*:u: - :tx:*:kappa:, (:Et: + :p: - :tau:)*:v: - :ty:*:kappa: )
+:rho:       =  fbar( :rho:  )
+:rhou:      =  fbar( :rhou: )
+:rhov:      =  fbar( :rhov: )
+:Et:        =  fbar( :Et:   )
+:u:         =  :rhou: / :rho:
+:v:         =  :rhov: / :rho:
+:p:         =  ( :Et: - .5*:rho:*(:u:*:u: + :v:*:v:) ) * ( :gamma: - 1.0 )
+:T:         = :p: / (:rho: * :R: )
+:div:       =  div(:u:,:v:)
+:beta:      =  gbar( ring(:div:) * :rho: ) * 7.0e-3
+:tau:       =  :beta: * :div:
+[:tx:,:ty:,:tz:] = grad(:T:)
+:kappa:     = gbar( ring(:T:)* :rho:*:cv:/(:T: * :dt: ) ) * 1.0e-3
+[:u:,:v:,:w:] = ibmV( [:u:,:v:,:w:], :phi:, [:gx:,:gy:,:gz:], [:u1:,:u2:,0.0] )
+:rho: = ibmS( :rho: , :phi:, [:gx:,:gy:,:gz:] )
+:p:   = ibmS( :p:   , :phi:, [:gx:,:gy:,:gz:] )
+bc.extrap(['rho','p','u'],['xn'])
+bc.const(['u'],['x1','y1','yn'],u0)
+bc.const(['v'],['x1','xn','y1','yn'],0.0)
+bc.const(['rho'],['x1','y1','yn'],rho0)
+bc.const(['p'],['x1','y1','yn'],p0)
+:Et:  = :p: / ( :gamma: - 1.0 )  + .5*:rho:*(:u:*:u: + :v:*:v:)
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:cs:  = sqrt( :p: / :rho: * :gamma: )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)
+:dtB: = 0.2* dt.diff(:beta:,:rho:)
+:dt: = numpy.minimum(:dt:,:dtB:)
+:umag: = sqrt( :u:*:u: + :v:*:v: )
+""".replace('u0', str(CYL_U0)).replace('p0', str(1.0)).replace('rho0', str(1.0))
+
+# examples/cylinder_curv.py:126-146
+CYLINDER_CURV_IC = """
+:gamma: = 1.4
+:R: = 1.0
+:cp: = :R: / (1.0 - 1.0/:gamma: )
+:cv: = :cp: - :R:
+rad = sqrt( meshx**2  +  meshy**2 )
+:phi: = rad - pi/4.0
+:rho: = 1.0 + 3d()
+:p:  =  1.0 + 3d() #exp( -(meshx-1.5)**2/.25**2)*.1
+:u: = where( :phi:>0.5, mach * sqrt( :p: / :rho: * :gamma:) , 0.0 )
+:u: = gbar( gbar( :u: ) )
+:v: = 0.0 + 3d()
+:Et: = :p:/( :gamma: - 1.0 ) + .5*:rho:*(:u:*:u: + :v:*:v:)
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:cs:  = sqrt( :p: / :rho: * :gamma: )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)
+[:gx:,:gy:,:gz:] = grad( :phi: )
+:gx: = gbar( :gx: )
+:gy: = gbar( :gy: )
+""".replace('mach', str(CYL_MACH))

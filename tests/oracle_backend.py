@@ -46,8 +46,11 @@ class NumpyOracleBackend:
 
 
 def make_sim(oracle_mod, name, mesh):
-    from pyranda_b200.sim import parse_mesh, pyrandaSim
+    from pyranda_b200.sim import curvilinear_coordinates, parse_mesh, pyrandaSim
     opt = parse_mesh(mesh) if isinstance(mesh, str) else mesh
+    kw = {}
+    if int(opt.get("coordsys", 0)) == 3:
+        kw = {"coordsys": 3, "mesh_xyz": curvilinear_coordinates(opt), "periodic_grid": bool(opt.get("periodicGrid", True))}
     o = oracle_mod.Oracle(*opt["nn"], opt["x1"][0], opt["xn"][0], opt["x1"][1], opt["xn"][1], opt["x1"][2], opt["xn"][2],
-                          periodic=tuple(opt["periodic"]))
+                          periodic=tuple(opt["periodic"]), **kw)
     return pyrandaSim(name, opt, backend=NumpyOracleBackend(o))

@@ -128,6 +128,56 @@ def test_euler_2d_sod_golden_curve(npts, oracle_mod):
     assert np.abs(ss.variables["rho"][:, j, 0] - gold[1]).max() < 1e-12
 
 
+@pytest.mark.parametrize("npts", [32, 64])
+def test_cylinder_ibm_golden_curve(npts, oracle_mod):
+    """tests/cases/testCylinder.py cylinder-2d-32 / -64 (examples/cylinder.py): Mach-2 flow over an
+    immersed cylinder, pressure along j = ny / 2 at t = 1.5 against the reference's baseline files.
+    Bounded box: one-sided closures, grad, fbar, gbar, ring, the IBM package (ibmV with a frame
+    velocity, ibmS), the BC package and the dt package.  Reproduced to the last printed digit."""
+    import os
+    from decks import CYLINDER_EOM, CYLINDER_IC, cylinder_mesh
+    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "cylinder-2d-%d.dat" % npts))
+    ss = make_sim(oracle_mod, "cylinder_test", cylinder_mesh(npts))
+    ss.EOM(CYLINDER_EOM)
+    ss.setIC(CYLINDER_IC)
+    tt, cfl, time = 1.5, 1.0, 0.0
+    dt = float(ss.variables["dt"]) * cfl * .1  # examples/cylinder.py:147-153
+    with np.errstate(all="ignore"):  # the IBM package divides by the level set on the surface, as the reference does
+        while tt > time:
+            time = ss.rk4(time, dt)
+            dt = min(float(ss.variables["dt"]) * cfl, 1.1 * dt)
+            dt = min(dt, (tt - time))
+    j = int(npts / 2)
+    assert np.abs(ss.variables["meshx"][:, j, 0] - gold[0]).max() < 1e-14
+    assert np.abs(ss.variables["p"][:, j, 0] - gold[1]).max() < 1e-11
+
+
+def test_curvilinear_cylinder_golden_curve(oracle_mod):
+    """tests/cases/testCylinder.py cylinder_curved-2d-64 (examples/cylinder_curv.py, the deck of
+    BASELINE config 5 at 64 x 64): velocity magnitude along j = ny / 2 at t = 3 against the
+    reference's baseline file.  coordsys = 3 on the tanh-stretched zoomMesh: metrics from the compact
+    derivatives of the coordinates, div through contravariant fluxes, grad, the cell-volume weighted
+    filter, gbar, ring with per-point lengths, the IBM, BC and dt packages (curvilinear Courant
+    branch).  Reference tolerance 1e-4; reproduced to ~1e-13."""
+    import os
+    from decks import CYLINDER_CURV_EOM, CYLINDER_CURV_IC, cylinder_curv_mesh
+    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "cylinder_curved-2d-64.dat"))
+    npts = 64
+    ss = make_sim(oracle_mod, "cylinder_curvilinear", cylinder_curv_mesh(npts))
+    ss.EOM(CYLINDER_CURV_EOM)
+    ss.setIC(CYLINDER_CURV_IC)
+    tt, cfl, time = 3.0, 1.0, 0.0
+    dt = float(ss.variables["dt"]) * cfl * .01  # examples/cylinder_curv.py:165,187-191
+    with np.errstate(all="ignore"):
+        while tt > time:
+            time = ss.rk4(time, dt)
+            dt = min(float(ss.variables["dt"]) * cfl, dt * 1.1)
+            dt = min(dt, (tt - time))
+    j = int(npts / 2)
+    assert np.abs(ss.variables["meshx"][:, j, 0] - gold[0]).max() < 1e-13
+    assert np.abs(ss.variables["umag"][:, j, 0] - gold[1]).max() < 1e-10
+
+
 def test_restart_roundtrip(oracle_mod, tmp_path):
     """writeRestart / readRestart (pyranda.py:475-588): a restarted run continues bit for bit."""
     from decks import TGV_EOM, TGV_IC, tgv_mesh
