@@ -518,3 +518,69 @@ rad = sqrt( meshx**2  +  meshy**2 )
 :gx: = gbar( :gx: )
 :gy: = gbar( :gy: )
 """.replace('mach', str(CYL_MACH))
+
+
+# ---- examples/cylinder_curv2.py (tests/cases/testCylinder.py: cylinder_omesh-2d-64) ----------------
+def cylinder_omesh(npts):
+    """examples/cylinder_curv2.py:33-60: an O-grid around the cylinder, periodic in the angle."""
+    Lp = float(np.pi) * 2.0 * (npts - 1.0) / npts
+    Ri, Rf, NX, NY = 1.0, 10.0, npts, npts
+
+    def cyl(i, j, k):
+        theta = float(i) / float(NX) * 2.0 * np.pi
+        r = float(j) / float(NY - 1) * (Rf - Ri) + Ri
+        return r * np.cos(theta), r * np.sin(theta), 0.0
+    return {"coordsys": 3, "function": cyl, "periodic": [True, False, False], "periodicGrid": False,
+            "x1": [-2 * Lp, -2 * Lp, 0.0], "xn": [2 * Lp, 2 * Lp, Lp], "nn": [NX, NY, 1]}
+
+
+OMESH_MACH = 1.5
+OMESH_U0 = float(np.sqrt(1.0 / 1.0 * 1.4)) * OMESH_MACH  # examples/cylinder_curv2.py:69-75
+
+# examples/cylinder_curv2.py:78-107
+OMESH_EOM = """
+ddt(:rho:)  =  -div(:rho:*:u:,  :rho:*:v:)
+ddt(:rhou:) =  -div(:rhou:*:u: + :p: - :tau:, :rhou:*:v:)
+ddt(:rhov:) =  -div(:rhov:*:u:, :rhov:*:v: + :p: - :tau:)
+ddt(:Et:)   =  -div( (:Et: + :p: - :tau:)*:u: , (:Et: + :p: - :tau:)*:v:  )
+:rho:       =  fbar( :rho:  )
+:rhou:      =  fbar( :rhou: )
+:rhov:      =  fbar( :rhov: )
+:Et:        =  fbar( :Et:   )
+:u:         =  :rhou: / :rho:
+:v:         =  :rhov: / :rho:
+:p:         =  ( :Et: - .5*:rho:*(:u:*:u: + :v:*:v:) ) * ( :gamma: - 1.0 )
+:div:       =  div(:u:,:v:)
+:beta:      =  gbar( ring(:div:) * :rho: ) * 7.0e-2
+:tau:       = :beta:*:div:
+bc.extrap(['u','v','rho','p'],['yn'])
+bc.const(['u'],['yn'],u0)
+bc.const(['v'],['yn'],0.0)
+bc.extrap(['rho','p'],['y1'])
+bc.slip([ ['u','v']  ],['y1'])
+:Et:  = :p: / ( :gamma: - 1.0 )  + .5*:rho:*(:u:*:u: + :v:*:v:)
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:cs:  = sqrt( :p: / :rho: * :gamma: )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)
+:dtB: = dt.diff(:beta:,:rho:)
+:umag: = sqrt( :u:*:u: + :v:*:v: )
+""".replace('u0', str(OMESH_U0)).replace('p0', str(1.0)).replace('rho0', str(1.0))
+
+# examples/cylinder_curv2.py:113-128
+OMESH_IC = """
+:gamma: = 1.4
+:R: = 1.0
+:cp: = :R: / (1.0 - 1.0/:gamma: )
+:cv: = :cp: - :R:
+rad = sqrt( meshx**2  +  meshy**2 )
+:rho: = 1.0 + 3d()
+:p:  =  1.0 + 3d() #exp( -(meshx-1.5)**2/.25**2)*.1
+:u: = mach * sqrt( :p: / :rho: * :gamma:)
+:v: = 0.0 + 3d()
+:Et: = :p:/( :gamma: - 1.0 ) + .5*:rho:*(:u:*:u: + :v:*:v:)
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:cs:  = sqrt( :p: / :rho: * :gamma: )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)
+""".replace('mach', str(OMESH_MACH))

@@ -145,3 +145,13 @@ def test_emulated_curvilinear(oracle_mod, emul_lib):
     for a, b in zip(p.divergencetensor(*ins), o.divergencetensor(*ins)):
         assert rel_linf(a, b) < 1e-12
     assert rel_linf(p.pringv(f, g, h), o.pringv(f, g, h)) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["RT_2D", "cylinder_curv", "cylinder_omesh"])
+def test_emulated_example_decks_on_the_device_backend(case, oracle_mod, emul_lib):
+    """BASELINE configs 4 and 5 as 2-D decks (and the O-grid deck with bc.slip) through the device
+    backend of the interpreter, compute in the emulated build of the CUDA sources, against the
+    oracle-backed driver whose full runs reproduce the reference's golden curves
+    (tests/test_sim_oracle.py)."""
+    from deck_parity import worst_difference
+    assert worst_difference(case, 32, oracle_mod, lib=emul_lib, tensor_device="cpu") < 1e-11

@@ -27,10 +27,11 @@ def test_taylor_green_golden(oracle_mod):
 
 def test_advection_1d_golden(oracle_mod):
     """tests/cases/test1DAdvection.py:3-4 (examples/advection.py): sum((phi - phi0)^2) after one
-    period of periodic 1-D advection, N = 50 and 100."""
+    period of periodic 1-D advection, N = 50, 100 and 200 (the N = 300 / 400 baselines, 3e-14 and
+    5e-15, are sums of squared rounding errors and pin nothing)."""
     from pyranda_b200.sim import pyrandaSim
     from oracle_backend import NumpyOracleBackend
-    for npts, golden in ((50, 9.65612670412e-09), (100, 7.6111541815e-11)):
+    for npts, golden in ((50, 9.65612670412e-09), (100, 7.6111541815e-11), (200, 5.93285138337e-13)):
         L = np.pi * 2.0
         mesh = {"x1": [0.0, 0.0, 0.0], "xn": [L * (npts - 1) / npts, 1.0, 1.0], "nn": [npts, 1, 1], "periodic": [True, False, False]}
         o = oracle_mod.Oracle(npts, 1, 1, 0.0, mesh["xn"][0], 0, 1, 0, 1, periodic=(True, False, False))
@@ -176,6 +177,54 @@ def test_curvilinear_cylinder_golden_curve(oracle_mod):
     j = int(npts / 2)
     assert np.abs(ss.variables["meshx"][:, j, 0] - gold[0]).max() < 1e-13
     assert np.abs(ss.variables["umag"][:, j, 0] - gold[1]).max() < 1e-10
+
+
+def test_omesh_cylinder_golden_curve(oracle_mod):
+    """tests/cases/testCylinder.py cylinder_omesh-2d-64 (examples/cylinder_curv2.py): Mach-1.5 flow
+    around a cylinder on an O-grid, |u| along j = ny / 2 at t = 3 against the reference's baseline
+    file.  coordsys = 3 with a periodic direction whose coordinates are not periodic (periodicGrid =
+    False: metrics through the one-sided first derivative, mesh.f90:251-304) and the free-slip wall
+    `bc.slip` of this repository's BC package inside the step.  Reproduced to ~2e-13."""
+    import os
+    from decks import OMESH_EOM, OMESH_IC, cylinder_omesh
+    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "cylinder_omesh-2d-64.dat"))
+    npts = 64
+    ss = make_sim(oracle_mod, "cylinder_omesh", cylinder_omesh(npts))
+    ss.EOM(OMESH_EOM)
+    ss.setIC(OMESH_IC)
+    tt, cfl, time = 3.0, 0.8, 0.0
+    dt = float(ss.variables["dt"]) * cfl * .1
+    with np.errstate(all="ignore"):
+        while tt > time:  # examples/cylinder_curv2.py:150-167
+            time = ss.rk4(time, dt)
+            dt = float(ss.variables["dt"]) * cfl
+            dt = min(0.2 * float(ss.variables["dtB"]), dt)
+            dt = min(dt, (tt - time))
+    j = int(npts / 2)
+    assert np.abs(ss.variables["meshx"][:, j, 0] - gold[0]).max() < 1e-13
+    assert np.abs(ss.variables["umag"][:, j, 0] - gold[1]).max() < 1e-10
+
+
+@pytest.mark.parametrize("npts", [16, 64])
+def test_heat_1d_steady_profile(npts, oracle_mod):
+    """tests/cases/testHeat1D.py heat1D-analytic-N -- 0.0 (examples/heat1D.py): the linear steady
+    profile of ddt(phi) = c lap(phi) between two bc.const ends stays put for 500 steps; the summed
+    error against the analytic line is the baseline's 0.0.  Pins the bounded second derivative."""
+    L = np.pi * 2.0
+    Lp = L * (npts - 1.0) / npts
+    mesh = {"x1": [0.0, 0.0, 0.0], "xn": [Lp, Lp, Lp], "nn": [npts, 1, 1], "periodic": [False, True, True]}
+    ss = make_sim(oracle_mod, "heat_equation", mesh)
+    ss.EOM("ddt(:phi:)  =  :c: * lap(:phi:)\nbc.const(['phi'],['x1'],2.0)\nbc.const(['phi'],['xn'],1.0)")
+    ss.setIC("xnn = meshx[-1,0,0]\n:phi: = 1.0 + 1.0*(xnn - meshx)/xnn\n:c:   = 1.0")
+    dt_max = L / npts * .005
+    tt = dt_max * 500
+    time, dt = 0.0, dt_max
+    while tt > time:
+        time = ss.rk4(time, dt)
+        dt = min(dt_max, (tt - time))
+    x = ss.variables["meshx"]
+    anl = 1.0 + 1.0 * (x[-1, 0, 0] - x) / x[-1, 0, 0]
+    assert ss.cycle >= 500 and np.sum(np.abs(anl - ss.variables["phi"])[:, 0]) < 1e-11
 
 
 def test_restart_roundtrip(oracle_mod, tmp_path):
