@@ -11,11 +11,15 @@
  * emulated in-process: a "rank" is a contiguous segment of each grid line, MPI_Sendrecv becomes a
  * copy of neighbour rows and mpi_allgather a copy of every rank's 4 interface values.
  *
- * Parity pinning (see oracle/README.md, tests/test_oracle_pins.py): the reference's own golden
- * scalars (tests/cases/testUnit.py:3, testTaylorGreen.py:3, test1DAdvection.py:3-7) at the
- * reference's 1e-4 tolerance, the analytic transfer functions of the stencils on periodic grids
- * (1e-13), and np-rank emulation == 1-rank (1e-13).  The 1e-12 comparison against a Fortran/MPI
- * binary is NOT possible in this container.
+ * Parity pinning (tests/test_oracle_pins.py, tests/test_sim_oracle.py; table in DESIGN.md section 5):
+ * the reference's own golden scalars (tests/cases/testUnit.py:3, testTaylorGreen.py:3,
+ * test1DAdvection.py:3-5, testHeat1D.py) and golden curve files (tests/baselines/RT_2D.dat,
+ * cylinder-2d-32/64.dat, cylinder_curved-2d-64.dat, cylinder_omesh-2d-64.dat, euler-2d-64/128.dat,
+ * KelvinHelmholtzKH-2d-64.dat; copies under tests/golden/), reproduced to 1e-12 or to the last
+ * printed digit against the reference's own 1e-4 tolerance; the analytic transfer functions of the
+ * stencils on periodic grids (1e-13); symmetry planes == periodic operators on the mirrored field;
+ * np-rank emulation == 1-rank (1e-13).  A direct comparison against a Fortran/MPI binary is NOT
+ * possible in this container.
  *
  * Lines are processed in bundles of PO_NB adjacent lines so the sequential recurrences vectorise
  * across lines (the same idea as the reference's transposed `bpp_lus_opt` CPU branch,
