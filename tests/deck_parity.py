@@ -13,6 +13,7 @@ from oracle_backend import make_sim
 
 CASES = {
     "RT_2D": lambda n: (rt_mesh(n), RT_EOM, RT_IC, RT_PARMS(n), ("rho", "Yh", "Et", "p")),
+    "RT_3D": lambda n: (rt_mesh(n, two_d=False), RT_EOM, RT_IC, RT_PARMS(n), ("rho", "Yh", "Et", "p")),
     "cylinder_curv": lambda n: (cylinder_curv_mesh(n), CYLINDER_CURV_EOM, CYLINDER_CURV_IC, None, ("rho", "u", "v", "p")),
     "cylinder_omesh": lambda n: (cylinder_omesh(n), OMESH_EOM, OMESH_IC, None, ("rho", "u", "v", "p")),
 }

@@ -147,11 +147,12 @@ def test_emulated_curvilinear(oracle_mod, emul_lib):
     assert rel_linf(p.pringv(f, g, h), o.pringv(f, g, h)) < 1e-12
 
 
-@pytest.mark.parametrize("case", ["RT_2D", "cylinder_curv", "cylinder_omesh"])
+@pytest.mark.parametrize("case", ["RT_2D", "RT_3D", "cylinder_curv", "cylinder_omesh"])
 def test_emulated_example_decks_on_the_device_backend(case, oracle_mod, emul_lib):
     """BASELINE configs 4 and 5 as 2-D decks (and the O-grid deck with bc.slip) through the device
     backend of the interpreter, compute in the emulated build of the CUDA sources, against the
     oracle-backed driver whose full runs reproduce the reference's golden curves
     (tests/test_sim_oracle.py)."""
     from deck_parity import worst_difference
-    assert worst_difference(case, 32, oracle_mod, lib=emul_lib, tensor_device="cpu") < 1e-11
+    n, steps = (16, 2) if case == "RT_3D" else (32, 5)  # the 3-D deck is slow under one-thread-per-CUDA-thread emulation
+    assert worst_difference(case, n, oracle_mod, nsteps=steps, lib=emul_lib, tensor_device="cpu") < 1e-11

@@ -147,11 +147,11 @@ def test_exit_slip_farfield_on_device_fields(oracle_mod):
             assert dev[k].is_cuda and np.abs(dev[k].cpu().numpy() - gold[case + "_" + k]).max() < 1e-13, (case, k)
 
 
-@pytest.mark.parametrize("case", ["RT_2D", "cylinder_curv", "cylinder_omesh"])
+@pytest.mark.parametrize("case", ["RT_2D", "RT_3D", "cylinder_curv", "cylinder_omesh"])
 def test_example_decks_on_the_gpu(case, oracle_mod):
     """BASELINE configs 4 and 5 as 2-D decks (examples/RT3D.py, examples/cylinder_curv.py) and the
     O-grid deck with bc.slip: five RK4 steps on device-resident fields (fused pointwise kernels, BC /
     IBM / dt packages on the device) against the oracle-backed driver, whose full runs reproduce the
     reference's golden curves (tests/test_sim_oracle.py).  north_star tolerance for 100 steps: 1e-10."""
     from deck_parity import worst_difference
-    assert worst_difference(case, 64, oracle_mod) < 1e-10
+    assert worst_difference(case, 32 if case == "RT_3D" else 64, oracle_mod) < 1e-10
