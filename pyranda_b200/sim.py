@@ -141,7 +141,7 @@ _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-8
     "dd8y": "self.dd8y", "dd8z": "self.dd8z", "sum": "self.B.sum3D", "max": "self.B.max3D", "min": "self.B.min3D",
     "mean": "self.mean", "sign": "xp.sign", "abs": "xp.abs", "sqrt": "xp.sqrt", "sin": "xp.sin", "cos": "xp.cos",
     "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar", "random3D": "self.random3D",
-    "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff",
+    "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff", "dt.diffDir": "self.dt_diff_dir",
     "bc.extrap": "self.bc.extrap", "bc.const": "self.bc.const", "bc.field": "self.bc.field", "bc.symm": "self.bc.symm",
     "bc.exit": "self.bc.exit", "bc.slip": "self.bc.slip", "bc.farfield": "self.bc.farfield",  # pyrandaBC.py:28-38
     "ibmV": "self.ibm.velocity_slip", "ibmWall": "self.ibm.velocity_wall", "ibmS": "self.ibm.scalar",  # pyrandaIBM.py:27-31
@@ -354,6 +354,9 @@ class pyrandaSim:
         delta = self.GridLen
         drate = density * delta * delta / self.xp.maximum(1.0e-12, bulk)
         return self.B.min3D(drate)
+
+    def dt_diff_dir(self, bulk, density, delta):  # pyrandaTimestep.py:79-85: the same limit with a caller-given length
+        return self.B.min3D(density * delta * delta / self.xp.maximum(1.0e-12, bulk))
 
     # ---- interpreter (pyranda.py:231-416) ----
     @staticmethod
