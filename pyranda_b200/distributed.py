@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ._lib import OP, check
+from ._lib import OP, ParcopError, check
 from .plan import ParcopPlan
 
 # z operator behind each distributed call and its halo width (nor of the stencil)
@@ -91,6 +91,7 @@ class DistributedParcop:
                                coords=(0, 0, self.rank), coordsys=coordsys, device=device, lib=lib, symmetric=symmetric,
                                tensor_device="cpu" if (tensor_device is not None and torch.device(tensor_device).type == "cpu") else "cuda")
         self.periodic_z = bool(periodic[2])
+        self.symmetric = tuple((bool(a), bool(b)) for a, b in symmetric)
         ax, ay, az = self.plan.shape
         self.plane = ax * ay
         if tensor_device is None:
@@ -271,6 +272,41 @@ class DistributedParcop:
         self.zop_into("ddz_odd", fz, self._tmp)
         return out.add_(self._tmp)
 
+    def divergencetensor(self, fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz):
+        """operators.f90:97-123 (Cartesian): the divergence of each column; the diagonal components are
+        even across their own symmetry plane (isym**2), the others odd."""
+        if self.plan.coordsys != 0:
+            raise ParcopError("divT on a z-slab: only the Cartesian branch is implemented")
+        cols = ((fxx, fyx, fzx), (fxy, fyy, fzy), (fxz, fyz, fzz))
+        outs = []
+        if self._tmp is None:
+            self._tmp = self.empty()
+        for c, (a, b, g) in enumerate(cols):
+            out = self.empty()
+            self._local_into("ddx" if c == 0 else "ddx_odd", a, out)
+            self._local_into("ddy" if c == 1 else "ddy_odd", b, self._tmp)
+            out.add_(self._tmp)
+            self.zop_into("ddz" if c == 2 else "ddz_odd", g, self._tmp)
+            outs.append(out.add_(self._tmp))
+        return tuple(outs)
+
+    def pringv(self, vx, vy, vz):
+        """operators.f90:645-699 with L = 1 (Cartesian): max over directions of max over components of
+        |d8| times the spacing; nine sweeps, three of them distributed."""
+        if self.plan.coordsys != 0:
+            raise ParcopError("ringV on a z-slab: only the Cartesian branch is implemented")
+        if any(s for pair in self.symmetric for s in pair):
+            raise ParcopError("ringV on a z-slab with symmetry planes is not implemented")
+        if self._tmp is None:
+            self._tmp = self.empty()
+        out, tmp = self.empty(), self._tmp
+        out.zero_()
+        for nm, d in (("dd8x", self.plan.dx), ("dd8y", self.plan.dy), ("dd8z", self.plan.dz)):
+            for comp in (vx, vy, vz):
+                self.apply_into(nm, comp, tmp)
+                torch.maximum(out, tmp.abs_().mul_(d), out=out)
+        return out
+
     def grads(self, f):  # operators.f90:191-193
         return self.apply("ddx", f), self.apply("ddy", f), self.apply("ddz", f)
 
@@ -342,6 +378,8 @@ def _make_backend():
         def ring(self, v): return self._op("ring", v)
         def laplacian(self, v): return self._op("laplacian", v)
         def div(self, a, b, c): return self.eng.divergence(self._f(a), self._f(b), self._f(c))
+        def divT(self, *f9): return self.eng.divergencetensor(*[self._f(a) for a in f9])
+        def ringV(self, a, b, c): return self.eng.pringv(self._f(a), self._f(b), self._f(c))
         def grad(self, v): return self.eng.grads(self._f(v))
 
         def sum3D(self, a): return self.eng.sum3D(self._c(a)) if self.isfield(a) else float(a)

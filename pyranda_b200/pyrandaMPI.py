@@ -27,6 +27,8 @@ class parcop_der:
     def laplacian(self, val): return self._e.op("laplacian", val)
     def ring(self, val): return self._e.op("ring", val)
     def div(self, fx, fy, fz): return self._e.div(fx, fy, fz)
+    def divT(self, *f9): return self._e.divT(*f9)                  # pyrandaMPI.py:699-700
+    def ringV(self, vx, vy, vz): return self._e.ringV(vx, vy, vz)  # pyrandaMPI.py:711-712
     def grad(self, val): return self._e.grad(val)
 
 
@@ -98,6 +100,12 @@ class pyrandaMPI:
 
     def grad(self, val):
         return self._dist.grads(val) if self._dist is not None else self.plan.grads(val)
+
+    def divT(self, *f9):
+        return self._dist.divergencetensor(*f9) if self._dist is not None else self.plan.divergencetensor(*f9)
+
+    def ringV(self, vx, vy, vz):
+        return self._dist.pringv(vx, vy, vz) if self._dist is not None else self.plan.pringv(vx, vy, vz)
 
     def setPatch(self):  # pyrandaMPI.py:246-247: one plan per instance, nothing to select
         pass

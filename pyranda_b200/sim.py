@@ -60,6 +60,8 @@ class CudaBackend:
     def ddx(self, v): return self.plan.ddx(self._f(v))
     def ddy(self, v): return self.plan.ddy(self._f(v))
     def ddz(self, v): return self.plan.ddz(self._f(v))
+    def divT(self, *f9): return self.plan.divergencetensor(*[self._f(a) for a in f9])
+    def ringV(self, a, b, c): return self.plan.pringv(self._f(a), self._f(b), self._f(c))
     def dd4x(self, v): return self.plan.dd4x(self._f(v))
     def dd4y(self, v): return self.plan.dd4y(self._f(v))
     def dd4z(self, v): return self.plan.dd4z(self._f(v))
@@ -134,7 +136,7 @@ class _TorchNS:
 
 # --------------------------------------------------------------------------------------------------
 _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-858)
-    "ddx": "self.ddx", "ddy": "self.ddy", "ddz": "self.ddz", "div": "self.div", "grad": "self.grad",
+    "ddx": "self.ddx", "ddy": "self.ddy", "ddz": "self.ddz", "div": "self.div", "divT": "self.divT", "ringV": "self.ringV", "grad": "self.grad",
     "fbar": "self.filter", "gbar": "self.gfilter", "gbarx": "self.gfilterx", "gbary": "self.gfiltery",
     "gbarz": "self.gfilterz", "lap": "self.laplacian", "ring": "self.ring", "dd8x": "self.dd8x",
     "dd4x": "self.dd4x", "dd4y": "self.dd4y", "dd4z": "self.dd4z",  # pyranda.py:833-835
@@ -290,6 +292,8 @@ class pyrandaSim:
     def ddx(self, v): return 0.0 if self.nx <= 1 else self.B.ddx(v)
     def ddy(self, v): return 0.0 if self.ny <= 1 else self.B.ddy(v)
     def ddz(self, v): return 0.0 if self.nz <= 1 else self.B.ddz(v)
+    def divT(self, *f9): return self.B.divT(*f9)          # pyranda.py:673-674
+    def ringV(self, vx, vy, vz): return self.B.ringV(vx, vy, vz)  # pyranda.py:686-687
     def dd4x(self, v): return self.B.dd4x(v)  # pyranda.py:622-629
     def dd4y(self, v): return self.B.dd4y(v)
     def dd4z(self, v): return self.B.dd4z(v)

@@ -33,6 +33,8 @@ class NumpyOracleBackend:
     def laplacian(self, v): return self.o.plaplacian(self._f(v))
     def div(self, a, b, c): return self.o.divergence(self._f(a), self._f(b), self._f(c))
     def grad(self, v): return self.o.grads(self._f(v))
+    def divT(self, *f9): return self.o.divergencetensor(*[self._f(a) for a in f9])
+    def ringV(self, a, b, c): return self.o.pringv(self._f(a), self._f(b), self._f(c))
     def getvar(self, name): return self.o.getvar(name)
     def sum3D(self, a): return float(np.sum(a))
     def max3D(self, a): return float(np.max(a))

@@ -43,6 +43,11 @@ for periodic in (True, False):
         assert err < 1e-12, (name, periodic, rank, err)
     got = eng.divergence(loc, loc * 2, loc * loc).numpy()
     assert rel_linf(got, o.divergence(f, 2 * f, f * f)[:, :, sl]) < 1e-12
+    g9 = [loc, loc * 2, loc * loc, loc + 1, loc * 0.5, -loc, loc * loc * 0.1, loc - 2, loc * 3]
+    h9 = [f, f * 2, f * f, f + 1, f * 0.5, -f, f * f * 0.1, f - 2, f * 3]
+    for a, b in zip(eng.divergencetensor(*g9), o.divergencetensor(*h9)):
+        assert rel_linf(a.numpy(), b[:, :, sl]) < 1e-12
+    assert rel_linf(eng.pringv(loc, loc * loc, loc * 2 + 1).numpy(), o.pringv(f, f * f, f * 2 + 1)[:, :, sl]) < 1e-12
     assert abs(eng.sum3D(loc) - f.sum()) < 1e-9 * np.abs(f).sum()
     assert eng.max3D(loc) == f.max() and eng.min3D(loc) == f.min()
 # symmetry planes on the z faces (first / last rank) and one x face: even closures for every operator,
@@ -60,6 +65,10 @@ for name, ref in (("ddx", o.ddx), ("ddz", o.ddz), ("dd8z", o.dd8z), ("d2z", o.d2
     worst = max(worst, err)
     assert err < 1e-12, (name, "symm", rank, err)
 assert rel_linf(eng.divergence(loc, loc * 2, loc * loc).numpy(), o.divergence(f, 2 * f, f * f)[:, :, sl]) < 1e-12
+g9 = [loc, loc * 2, loc * loc, loc + 1, loc * 0.5, -loc, loc * loc * 0.1, loc - 2, loc * 3]
+h9 = [f, f * 2, f * f, f + 1, f * 0.5, -f, f * f * 0.1, f - 2, f * 3]
+for a, b in zip(eng.divergencetensor(*g9), o.divergencetensor(*h9)):
+    assert rel_linf(a.numpy(), b[:, :, sl]) < 1e-12
 # long slabs: the reduced system couples only neighbouring ranks and the all-gather is replaced by
 # a pair of sends; the correction touches only the rows near the slab faces
 from pyranda_b200._lib import OP

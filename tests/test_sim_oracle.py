@@ -227,6 +227,22 @@ def test_heat_1d_steady_profile(npts, oracle_mod):
     assert ss.cycle >= 500 and np.sum(np.abs(anl - ss.variables["phi"])[:, 0]) < 1e-11
 
 
+def test_deck_functions_reach_every_operator(oracle_mod):
+    """divT, ringV, dd4x..z, lap, gbarx..z in deck lines (pyranda.py:817-858) evaluate to the operators'
+    own results."""
+    mesh = "xdom = (0.0, 1.0, 16)\nydom = (0.0, 1.0, 18)\nzdom = (0.0, 1.0, 20)"
+    ss = make_sim(oracle_mod, "ops", mesh)
+    ss.EOM("ddt(:a:) = -ddx(:a:)\n[:tx:,:ty:,:tz:] = divT(:a:,:b:,:a:,:b:,:a:,:b:,:a:,:b:,:a:)\n:r: = ringV(:a:,:b:,:a:)\n"
+           ":d4: = dd4x(:a:) + dd4y(:a:) + dd4z(:a:)\n:g: = gbarx(:a:) + gbary(:a:) + gbarz(:a:) + lap(:b:)")
+    ss.setIC(":a: = sin(3.0*meshx)*cos(2.0*meshy)*cos(meshz)\n:b: = meshx*meshy + cos(4.0*meshz)")
+    o, a, b = ss.B.o, ss.variables["a"], ss.variables["b"]
+    for got, ref in zip((ss.variables[k] for k in ("tx", "ty", "tz")), o.divergencetensor(a, b, a, b, a, b, a, b, a)):
+        assert np.array_equal(got, ref)
+    assert np.array_equal(ss.variables["r"], o.pringv(a, b, a))
+    assert np.array_equal(ss.variables["d4"], o.dd4x(a) + o.dd4y(a) + o.dd4z(a))
+    assert np.array_equal(ss.variables["g"], o.gfilterdir(a, 1) + o.gfilterdir(a, 2) + o.gfilterdir(a, 3) + o.plaplacian(b))
+
+
 def test_restart_roundtrip(oracle_mod, tmp_path):
     """writeRestart / readRestart (pyranda.py:475-588): a restarted run continues bit for bit."""
     from decks import TGV_EOM, TGV_IC, tgv_mesh
