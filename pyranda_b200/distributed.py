@@ -361,6 +361,20 @@ def _make_backend():
             # which physical boundaries this rank holds (pyrandaMPI x1proc ... znproc)
             self.owns = {"x1": True, "xn": True, "y1": True, "yn": True,
                          "z1": eng.rank == 0, "zn": eng.rank == eng.world - 1}
+            self.chunk_lo = (0, 0, eng.rank * eng.plan.shape[2])
+
+        # directional sums of user code (pyrandaMPI.py:330-357): complete a local partial sum over z
+        def allsum(self, part):
+            part = part.contiguous()
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.eng.group)
+            return part
+
+        def allgather_z(self, part):
+            """`part` has the local z extent as its last axis: concatenate the ranks' pieces."""
+            part = part.contiguous()
+            pieces = [torch.empty_like(part) for _ in range(self.eng.world)]
+            dist.all_gather(pieces, part, group=self.eng.group)
+            return torch.cat(pieces, dim=-1)
 
         def _op(self, name, v): return self.eng.apply(name, self._f(v))
         def ddx(self, v): return self._op("ddx", v)
@@ -402,6 +416,7 @@ def distributed_sim(name, mesh, device=-1, group=None, lib=None, tensor_device=N
     from .sim import parse_mesh, pyrandaSim
     opt = parse_mesh(mesh) if isinstance(mesh, str) else mesh
     eng = DistributedParcop(*opt["nn"], opt["x1"][0], opt["xn"][0], opt["x1"][1], opt["xn"][1], opt["x1"][2], opt["xn"][2],
-                            periodic=tuple(opt["periodic"]), device=device, group=group, lib=lib, tensor_device=tensor_device)
+                            periodic=tuple(opt["periodic"]), device=device, group=group, lib=lib, tensor_device=tensor_device,
+                            symmetric=tuple(tuple(s) for s in opt.get("symmetric", ((False, False),) * 3)))
     eng.plan.set_mesh()
     return pyrandaSim(name, opt, backend=_make_backend()(eng))

@@ -218,6 +218,74 @@ def parse_mesh(text):
     return opt
 
 
+class _Data:
+    """`.data` holder, the one attribute of pyrandaVar that user-defined functions of the example
+    decks read (`pysim.mesh.indices[0].data`, `pysim.mesh.coords[0].data`)."""
+
+    def __init__(self, data):
+        self.data = data
+
+
+class _MeshView:
+    """`pysim.mesh` as user code sees it (pyrandaMesh.py:58-208): coords, global indices, nn, GridLen."""
+
+    def __init__(self, sim, lo):
+        B = sim.B
+        self.nn = [sim.nx, sim.ny, sim.nz]
+        self.coordsys = sim.coordsys
+        self.coords = [_Data(sim.variables[k]) for k in ("meshx", "meshy", "meshz")]
+        self.GridLen = sim.GridLen
+        self.d1, self.d2, self.d3 = sim.d1, sim.d2, sim.d3
+        shape = tuple(sim.zero.shape)
+        idx = np.meshgrid(*[np.arange(shape[d]) + lo[d] for d in range(3)], indexing="ij")
+        self.indices = [_Data(B.asfield(np.asfortranarray(a, dtype=np.float64))) for a in idx]  # pyrandaMesh.py:63-81
+        self.shape = list(shape)
+
+
+class _PyMPIView:
+    """`pysim.PyMPI` as user code sees it: sizes, ownership flags and the directional sums of
+    pyrandaMPI.py:307-357 on fields of the backend (device tensors or numpy arrays).  On a z-slab
+    the sums over z are completed across the ranks by the backend's `allsum` / `allgather`."""
+
+    def __init__(self, sim, lo):
+        self._sim = sim
+        B = sim.B
+        self.nx, self.ny, self.nz = sim.nx, sim.ny, sim.nz
+        self.ax, self.ay, self.az = tuple(sim.zero.shape)
+        self.chunk_3d_lo = np.array(lo, dtype=np.int32)
+        self.chunk_3d_hi = self.chunk_3d_lo + np.array([self.ax, self.ay, self.az], dtype=np.int32) - 1
+        owns = getattr(B, "owns", None) or {}
+        for nm in ("x1", "xn", "y1", "yn", "z1", "zn"):
+            setattr(self, nm + "proc", bool(owns.get(nm, True)))
+        self.master = lo[2] == 0
+        self.sum3D, self.max3D, self.min3D = B.sum3D, B.max3D, B.min3D
+
+    def _sum(self, data, axes):
+        return data.sum(axis=axes) if isinstance(data, np.ndarray) else data.sum(dim=axes)
+
+    def _z_complete(self, part, z_summed):
+        """Local partial sums -> global result: summed over the ranks when z was reduced, gathered
+        along z otherwise (one rank: nothing to do)."""
+        B = self._sim.B
+        if z_summed:
+            return B.allsum(part) if hasattr(B, "allsum") else part
+        return B.allgather_z(part) if hasattr(B, "allgather_z") else part
+
+    # reduction along two directions -> global 1-D profile (pyrandaMPI.py:349-357)
+    def yzsum(self, data): return self._z_complete(self._sum(data, (1, 2)), True)
+    def xzsum(self, data): return self._z_complete(self._sum(data, (0, 2)), True)
+    def xysum(self, data): return self._z_complete(self._sum(data, (0, 1)), False)
+    # reduction along one direction -> global 2-D array (pyrandaMPI.py:330-347)
+    def xsum(self, data): return self._z_complete(self._sum(data, (0,)), False)
+    def ysum(self, data): return self._z_complete(self._sum(data, (1,)), False)
+    def zsum(self, data): return self._z_complete(self._sum(data, (2,)), True)
+    xbar, ybar, zbar = xsum, ysum, zsum
+
+    def iprint(self, sprnt):
+        if self.master:
+            print(sprnt, flush=True)
+
+
 def curvilinear_coordinates(opt, lo=(0, 0, 0), shape=None):
     """Coordinates of a `coordsys = 3` mesh as pyrandaMesh.makeMesh builds them
     (pyrandaMesh.py:93-129): the uniform grid between x1 and xn, overwritten point by point with
@@ -271,6 +339,9 @@ class pyrandaSim:
         self.GridLen = backend.getvar("GridLen")
         self.zero = backend.zeros()
         self._ns = {"xp": self.xp, "numpy": self.xp, "self": self}
+        lo = tuple(getattr(backend, "chunk_lo", (0, 0, 0)))  # first global index of this rank's block
+        self.mesh = _MeshView(self, lo)
+        self.PyMPI = _PyMPIView(self, lo)
         from .bc import BoundaryConditions
         # the `BC` package (pyrandaBC.py), on the fields in place; a z-slab backend says which faces are its own
         self.bc = BoundaryConditions(self.variables, getattr(backend, "owns", None), getvar=backend.getvar)

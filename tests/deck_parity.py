@@ -8,11 +8,11 @@ cylinder_curv2.py (O-grid, periodic direction with a non-periodic grid, bc.slip)
 import numpy as np
 
 from decks import (CYLINDER_CURV_EOM, CYLINDER_CURV_IC, OMESH_EOM, OMESH_IC, RT_EOM, RT_IC, RT_PARMS, cylinder_curv_mesh,
-                   cylinder_omesh, rt_mesh)
+                   cylinder_omesh, rt_mesh, rt_xbar)
 from oracle_backend import make_sim
 
 CASES = {
-    "RT_2D": lambda n: (rt_mesh(n), RT_EOM, RT_IC, RT_PARMS(n), ("rho", "Yh", "Et", "p")),
+    "RT_2D": lambda n: (rt_mesh(n), RT_EOM, RT_IC, RT_PARMS(n), ("rho", "Yh", "Et", "p", "mybar")),
     "RT_3D": lambda n: (rt_mesh(n, two_d=False), RT_EOM, RT_IC, RT_PARMS(n), ("rho", "Yh", "Et", "p")),
     "cylinder_curv": lambda n: (cylinder_curv_mesh(n), CYLINDER_CURV_EOM, CYLINDER_CURV_IC, None, ("rho", "u", "v", "p")),
     "cylinder_omesh": lambda n: (cylinder_omesh(n), OMESH_EOM, OMESH_IC, None, ("rho", "u", "v", "p")),
@@ -38,7 +38,7 @@ def worst_difference(case, npts, oracle_mod, nsteps=5, **plan_kw):
     mesh, eom, ic, parm, names = CASES[case](npts)
     sims = [make_sim(oracle_mod, case, mesh), device_sim(case, mesh, **plan_kw)]
     for ss in sims:
-        ss.addUserDefinedFunction("xbar", lambda sim, data: data * 0 + data.mean())
+        ss.addUserDefinedFunction("xbar", rt_xbar)
         ss.EOM(eom, parm)
         np.random.seed(1234)
         ss.setIC(ic, parm)

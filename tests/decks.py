@@ -124,6 +124,17 @@ def rt_mesh(npts, two_d=True):
     return "\n".join("%sdom = (0.0, %r, %d, periodic=%s)" % (c, L, n, p) for c, (L, n, p) in zip("xyz", dom))
 
 
+def rt_xbar(pysim, data):
+    """examples/RT3D.py:73-79 `meanXto3d`, as written there: the y-z mean as a 3-D field, through
+    `pysim.PyMPI.yzsum`, `pysim.emptyScalar()` and `pysim.mesh.indices`."""
+    meanX = pysim.PyMPI.yzsum(data) / (pysim.PyMPI.ny * pysim.PyMPI.nz)
+    tmp = pysim.emptyScalar()
+    for i in range(tmp.shape[0]):
+        ii = int(pysim.mesh.indices[0].data[i, 0, 0])
+        tmp[i, :, :] = meanX[ii]
+    return tmp
+
+
 def RT_PARMS(npts):
     """examples/RT3D.py:46-65 (the dictionary is applied to the deck text, pyranda.py:219-228)."""
     return {"gx": -0.01, "CPh": 1.4, "CPl": 1.4, "CVh": 1.0, "CVl": 1.0, "mwH": 3.0, "mwL": 1.0, "Runiv": 1.0,

@@ -141,8 +141,9 @@ a, b = par.variables["phi"].numpy(), ref.variables["phi"][:, :, sl]
 assert np.abs(a - b).max() < 1e-11 * np.abs(ref.variables["phi"]).max(), rank
 # BASELINE config 4 (examples/RT3D.py, 3-D): bounded x, periodic y and z, the z axis split over the
 # ranks; the random perturbation is replaced by a deterministic one (the reference draws per-rank
-# random numbers, which no one-rank run reproduces) and xbar by a local stand-in
-from decks import RT_EOM, RT_IC, RT_PARMS
+# random numbers, which no one-rank run reproduces); xbar is the deck's own function, whose y-z sums
+# are completed across the ranks by PyMPI.yzsum
+from decks import RT_EOM, RT_IC, RT_PARMS, rt_xbar
 npts = 16
 ff = 2 * np.pi * (nz - 1) / nz
 mesh = "xdom = (0.0, %r, 24, periodic=False)\nydom = (0.0, %r, 16, periodic=True)\nzdom = (0.0, %r, %d, periodic=True)" % (3.0 * np.pi, 2 * np.pi * 15 / 16, ff, nz)
@@ -150,7 +151,7 @@ ic = RT_IC.replace("random3D()", "(0.5+0.4*sin(3.0*meshy)*cos(2.0*meshz))")
 ref = make_sim(oracle, "rt", mesh)
 par = distributed_sim("rt", mesh, lib=L, tensor_device="cpu")
 for ss in (ref, par):
-    ss.addUserDefinedFunction("xbar", lambda sim, data: data * 0)
+    ss.addUserDefinedFunction("xbar", rt_xbar)
     ss.EOM(RT_EOM, RT_PARMS(npts))
     ss.setIC(ic, RT_PARMS(npts))
 t1 = t2 = 0.0
@@ -159,11 +160,16 @@ for _ in range(2):
     t1 = ref.rk4(t1, dt)
     t2 = par.rk4(t2, dt)
 assert abs(float(par.variables["dt"]) - float(ref.variables["dt"])) < 1e-12 * float(ref.variables["dt"])
-for nm in ("rho", "Yh", "Et", "p", "u"):
+for nm in ("rho", "Yh", "Et", "p", "u", "mybar"):
     a, b = par.variables[nm].numpy(), ref.variables[nm][:, :, sl]
     err = np.abs(a - b).max() / np.abs(ref.variables[nm]).max()
     worst = max(worst, err)
     assert err < 1e-11, (nm, rank, err)
+# the other directional sums of PyMPI (pyrandaMPI.py:330-357) against numpy on the global field
+g, l = ref.variables["rho"], par.variables["rho"]
+for name, axes in (("yzsum", (1, 2)), ("xzsum", (0, 2)), ("xysum", (0, 1)), ("xsum", (0,)), ("ysum", (1,)), ("zsum", (2,))):
+    got = getattr(par.PyMPI, name)(l).numpy()
+    assert got.shape == g.sum(axis=axes).shape and np.abs(got - g.sum(axis=axes)).max() < 1e-11 * np.abs(g.sum(axis=axes)).max(), name
 print("rank", rank, "worst", worst)
 dist.destroy_process_group()
 """

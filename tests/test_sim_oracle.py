@@ -56,12 +56,11 @@ def test_rayleigh_taylor_2d_golden_curve(oracle_mod):
     ddx/ddy, grad, fbar, gbar, ring, the BC package, the dt package, a user-defined function and the
     seeded random3D().  The reference's tolerance is 1e-4; the curve is reproduced to ~1e-12."""
     import os
-    from decks import RT_EOM, RT_IC, RT_PARMS, rt_mesh
+    from decks import RT_EOM, RT_IC, RT_PARMS, rt_mesh, rt_xbar
     gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "RT_2D.dat"))
     npts = 32
     ss = make_sim(oracle_mod, "RT_2D", rt_mesh(npts))
-    ss.addUserDefinedFunction("xbar", lambda sim, data: np.asfortranarray(
-        np.broadcast_to(data.mean(axis=(1, 2), keepdims=True), data.shape)))  # examples/RT3D.py:73-79
+    ss.addUserDefinedFunction("xbar", rt_xbar)  # examples/RT3D.py:73-81, verbatim
     parm = RT_PARMS(npts)
     ss.EOM(RT_EOM, parm)
     np.random.seed(1234)  # examples/RT3D.py:225
