@@ -102,12 +102,16 @@ int pb_divergence(pb_plan *plan, const double *d_fx, const double *d_fy, const d
 /* gradS (parcop.f90:371-379, operators.f90:184-212) */
 int pb_grads(pb_plan *plan, const double *d_val, double *d_gx, double *d_gy, double *d_gz,
              void *stream);
-/* divergenceTensor (parcop.f90:213-223, operators.f90:97-123, Cartesian): dfx = ddx fxx + ddy fyx + ddz fzx ... */
+/* divergenceTensor (parcop.f90:213-223, operators.f90:97-123,176-179).  Cartesian: the divergence of
+ * each COLUMN, dfx = ddx fxx + ddy fyx + ddz fzx ...; curvilinear (coordsys 3): pb_divergence of
+ * each ROW, dfx = div(fxx, fxy, fxz) ... -- the reference's own (different) groupings. */
 int pb_divergence_tensor(pb_plan *plan, const double *d_fxx, const double *d_fxy, const double *d_fxz,
                          const double *d_fyx, const double *d_fyy, const double *d_fyz,
                          const double *d_fzx, const double *d_fzy, const double *d_fzz,
                          double *d_dfx, double *d_dfy, double *d_dfz, void *stream);
-/* pRingV (parcop.f90:324-333, operators.f90:645-699 with L = 1, Cartesian) */
+/* pRingV (parcop.f90:324-333, operators.f90:645-699 with L = 1): max over directions of
+ * max(|d8 vx|, |d8 vy|, |d8 vz|) * d, d = the spacing (Cartesian) or the mesh's d1 / d2 / d3 fields
+ * (curvilinear, needs pb_plan_set_mesh) */
 int pb_ring_vector(pb_plan *plan, const double *d_vx, const double *d_vy, const double *d_vz,
                    double *d_out, void *stream);
 
