@@ -329,6 +329,7 @@ class pyrandaSim:
         self.xp = backend.xp
         self.variables = {}
         self.userDefined = {}
+        self.vizDumpHistory = []
         self._cmetric = None
         self.equations = []
         self.conserved = []
@@ -525,6 +526,48 @@ class pyrandaSim:
 
     def var(self, name):
         return self.variables[name]
+
+    # ---- viz dumps (pyranda.py:431-470, pyrandaIO.py:53-231) ----
+    def write(self, wVars=(), root=None):
+        """`ss.write(['rho', 'u'])`: one legacy-VTK STRUCTURED_GRID file per rank and dump under
+        `<root>/vis<cycle>/proc-<rank>.<cycle>.vtk` plus the `pyranda.visit` index, with the
+        reference's names (pyranda.py:440-470).  Binary, big-endian float32 as VTK requires; CYCLE and
+        TIME field data as pyrandaIO.py:79-84.  Off the step loop: each variable is staged device ->
+        host once.  Blocks are written without the reference's one-plane ghost overlap
+        (pyrandaMPI.ghost), so the pieces of a z-slab run abut instead of sharing a plane."""
+        names = list(wVars) if wVars else list(self.conserved)
+        root = self.name if root is None else root
+        rank = int(self.PyMPI.chunk_3d_lo[2] // max(self.PyMPI.az, 1))
+        nblocks = max(self.nz // max(self.PyMPI.az, 1), 1)
+        dump = "vis" + str(self.cycle).zfill(7)
+        os.makedirs(os.path.join(root, dump), exist_ok=True)
+        path = os.path.join(root, dump, "proc-%s.%s.vtk" % (str(rank).zfill(6), str(self.cycle).zfill(7)))
+        host = lambda a: np.asarray(self.B.tohost(a), dtype=np.float64)
+        xyz = [host(self.variables[k]) for k in ("meshx", "meshy", "meshz")]
+        ax, ay, az = xyz[0].shape
+        with open(path, "wb") as fid:
+            fid.write(b"# vtk DataFile Version 3.0\nvtk output\nBINARY\nDATASET STRUCTURED_GRID\n")
+            fid.write(b"FIELD FieldData 2\nCYCLE 1 1 int\n")
+            fid.write(np.array([self.cycle], dtype=">i4").tobytes())
+            fid.write(b"\nTIME 1 1 double\n")
+            fid.write(np.array([self.time], dtype=">f8").tobytes())
+            fid.write(("\nDIMENSIONS %d %d %d\nPOINTS %d float\n" % (ax, ay, az, ax * ay * az)).encode())
+            pts = np.stack([a.ravel(order="F") for a in xyz], axis=1)  # x fastest, as the reference's loops
+            fid.write(pts.astype(">f4").tobytes())
+            fid.write(("\nPOINT_DATA %d\n" % (ax * ay * az)).encode())
+            for nm in names:
+                fid.write(("SCALARS %s float\nLOOKUP_TABLE default\n" % nm).encode())
+                fid.write(host(self.variables[nm]).ravel(order="F").astype(">f4").tobytes())
+                fid.write(b"\n")
+        self.vizDumpHistory.append([self.cycle, self.time])
+        if rank == 0:
+            with open(os.path.join(root, "pyranda.visit"), "w") as vid:
+                vid.write("!NBLOCKS %s \n" % nblocks)
+                for cyc, tm in self.vizDumpHistory:
+                    vid.write("!TIME %s \n" % tm)
+                    for p_ in range(nblocks):
+                        vid.write("%s\n" % os.path.join("vis" + str(cyc).zfill(7), "proc-%s.%s.vtk" % (str(p_).zfill(6), str(cyc).zfill(7))))
+        return path
 
     # ---- restart (pyranda.py:475-588: the whole state, for a later run) ----
     def writeRestart(self, path):

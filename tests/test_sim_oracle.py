@@ -1,5 +1,7 @@
 """The deck interpreter + RK4 driver (pyranda_b200.sim) on the numpy / oracle backend, pinned to the
 reference's golden scalars for whole simulations (tolerance 1e-4, tests/run_tests.py:84)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -240,6 +242,28 @@ def test_deck_functions_reach_every_operator(oracle_mod):
     assert np.array_equal(ss.variables["r"], o.pringv(a, b, a))
     assert np.array_equal(ss.variables["d4"], o.dd4x(a) + o.dd4y(a) + o.dd4z(a))
     assert np.array_equal(ss.variables["g"], o.gfilterdir(a, 1) + o.gfilterdir(a, 2) + o.gfilterdir(a, 3) + o.plaplacian(b))
+
+
+def test_viz_dump_vtk(oracle_mod, tmp_path):
+    """ss.write (pyranda.py:431-470): a binary legacy-VTK structured grid per dump with the
+    reference's directory / file names and the .visit index; read back here."""
+    ss = make_sim(oracle_mod, "viz", "xdom = (0.0, 1.0, 16)\nydom = (0.0, 2.0, 18)\nzdom = (0.0, 3.0, 20)")
+    ss.EOM("ddt(:a:) = -ddx(:a:)\n:b: = 2.0*:a:")
+    ss.setIC(":a: = sin(3.0*meshx)*cos(2.0*meshy)*cos(meshz)")
+    ss.rk4(0.0, 1.0e-3)
+    path = ss.write(["a", "b"], root=str(tmp_path))
+    assert path.endswith(os.path.join("vis0000001", "proc-000000.0000001.vtk"))
+    raw = open(path, "rb").read()
+    assert raw.startswith(b"# vtk DataFile Version 3.0") and b"DIMENSIONS 16 18 20" in raw
+    n = 16 * 18 * 20
+    at = raw.index(b"POINTS %d float\n" % n) + len(b"POINTS %d float\n" % n)
+    pts = np.frombuffer(raw[at:at + 12 * n], dtype=">f4").reshape(n, 3)
+    assert np.allclose(pts[:, 1], ss.variables["meshy"].ravel(order="F"), rtol=1e-6)
+    at = raw.index(b"SCALARS b float\nLOOKUP_TABLE default\n") + len(b"SCALARS b float\nLOOKUP_TABLE default\n")
+    b = np.frombuffer(raw[at:at + 4 * n], dtype=">f4")
+    assert np.allclose(b, ss.variables["b"].ravel(order="F"), rtol=1e-6, atol=1e-7)
+    visit = open(os.path.join(str(tmp_path), "pyranda.visit")).read()
+    assert "!NBLOCKS 1" in visit and "proc-000000.0000001.vtk" in visit
 
 
 def test_restart_roundtrip(oracle_mod, tmp_path):
