@@ -15,7 +15,7 @@
  * the reference's own golden scalars (tests/cases/testUnit.py:3, testTaylorGreen.py:3,
  * test1DAdvection.py:3-5, testHeat1D.py) and golden curve files (tests/baselines/RT_2D.dat,
  * cylinder-2d-32/64.dat, cylinder_curved-2d-64.dat, cylinder_omesh-2d-64.dat, euler-2d-64/128.dat,
- * KelvinHelmholtzKH-2d-64.dat; copies under tests/golden/), reproduced to 1e-12 or to the last
+ * KelvinHelmholtzKH-2d-64.dat; packed into tests/golden/reference_baselines.npz), reproduced to 1e-12 or to the last
  * printed digit against the reference's own 1e-4 tolerance; the analytic transfer functions of the
  * stencils on periodic grids (1e-13); symmetry planes == periodic operators on the mirrored field;
  * np-rank emulation == 1-rank (1e-13).  A direct comparison against a Fortran/MPI binary is NOT

@@ -9,6 +9,12 @@ from decks import run_tgv, tgv_mesh
 from oracle_backend import make_sim
 
 
+def baseline(key):
+    """A golden curve of the reference's regression suite (tests/golden/make_baseline_fixtures.py)."""
+    with np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_baselines.npz")) as z:
+        return z[key]
+
+
 def test_translate():
     from pyranda_b200.sim import translate
     s = translate(":mu: = gbar( abs(ring(:S:)) ) * :rho: * 1.0e-4")
@@ -59,7 +65,7 @@ def test_rayleigh_taylor_2d_golden_curve(oracle_mod):
     seeded random3D().  The reference's tolerance is 1e-4; the curve is reproduced to ~1e-12."""
     import os
     from decks import RT_EOM, RT_IC, RT_PARMS, rt_mesh, rt_xbar
-    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "RT_2D.dat"))
+    gold = baseline("RT_2D")
     npts = 32
     ss = make_sim(oracle_mod, "RT_2D", rt_mesh(npts))
     ss.addUserDefinedFunction("xbar", rt_xbar)  # examples/RT3D.py:73-81, verbatim
@@ -90,7 +96,7 @@ def test_kelvin_helmholtz_2d_golden_curve(oracle_mod):
     Periodic 2-D: ddx/ddy, grad, fbar, gbar, ring, the dt package, deck dictionaries, where()."""
     import os
     from decks import KH_EOM, KH_EOM_PARMS, KH_IC, KH_IC_PARMS, kh_mesh
-    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "KH-2d-64.dat"))
+    gold = baseline("KH-2d-64")
     npts = 64
     ss = make_sim(oracle_mod, "KH", kh_mesh(npts))
     ss.EOM(KH_EOM, KH_EOM_PARMS)
@@ -115,7 +121,7 @@ def test_euler_2d_sod_golden_curve(npts, oracle_mod):
     bc.const.  The curves are reproduced to the last printed digit."""
     import os
     from decks import EULER2D_EOM, EULER2D_IC, euler2d_mesh
-    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "euler-2d-%d.dat" % npts))
+    gold = baseline("euler-2d-%d" % npts)
     ss = make_sim(oracle_mod, "sod", euler2d_mesh(npts))
     ss.EOM(EULER2D_EOM)
     ss.setIC(EULER2D_IC)
@@ -138,7 +144,7 @@ def test_cylinder_ibm_golden_curve(npts, oracle_mod):
     velocity, ibmS), the BC package and the dt package.  Reproduced to the last printed digit."""
     import os
     from decks import CYLINDER_EOM, CYLINDER_IC, cylinder_mesh
-    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "cylinder-2d-%d.dat" % npts))
+    gold = baseline("cylinder-2d-%d" % npts)
     ss = make_sim(oracle_mod, "cylinder_test", cylinder_mesh(npts))
     ss.EOM(CYLINDER_EOM)
     ss.setIC(CYLINDER_IC)
@@ -163,7 +169,7 @@ def test_curvilinear_cylinder_golden_curve(oracle_mod):
     branch).  Reference tolerance 1e-4; reproduced to ~1e-13."""
     import os
     from decks import CYLINDER_CURV_EOM, CYLINDER_CURV_IC, cylinder_curv_mesh
-    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "cylinder_curved-2d-64.dat"))
+    gold = baseline("cylinder_curved-2d-64")
     npts = 64
     ss = make_sim(oracle_mod, "cylinder_curvilinear", cylinder_curv_mesh(npts))
     ss.EOM(CYLINDER_CURV_EOM)
@@ -188,7 +194,7 @@ def test_omesh_cylinder_golden_curve(oracle_mod):
     `bc.slip` of this repository's BC package inside the step.  Reproduced to ~2e-13."""
     import os
     from decks import OMESH_EOM, OMESH_IC, cylinder_omesh
-    gold = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "cylinder_omesh-2d-64.dat"))
+    gold = baseline("cylinder_omesh-2d-64")
     npts = 64
     ss = make_sim(oracle_mod, "cylinder_omesh", cylinder_omesh(npts))
     ss.EOM(OMESH_EOM)
