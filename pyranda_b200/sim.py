@@ -142,7 +142,7 @@ _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-8
     "dd4x": "self.dd4x", "dd4y": "self.dd4y", "dd4z": "self.dd4z",  # pyranda.py:833-835
     "dd8y": "self.dd8y", "dd8z": "self.dd8z", "sum": "self.B.sum3D", "max": "self.B.max3D", "min": "self.B.min3D",
     "mean": "self.mean", "sign": "xp.sign", "abs": "xp.abs", "sqrt": "xp.sqrt", "sin": "xp.sin", "cos": "xp.cos",
-    "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar", "random3D": "self.random3D",
+    "tanh": "xp.tanh", "exp": "xp.exp", "where": "xp.where", "3d": "self.emptyScalar", "random3D": "self.random3D", "meshVar": "self.B.getvar",
     "dt.courant": "self.dt_courant", "dt.diff": "self.dt_diff", "dt.diffDir": "self.dt_diff_dir",
     "bc.extrap": "self.bc.extrap", "bc.const": "self.bc.const", "bc.field": "self.bc.field", "bc.symm": "self.bc.symm",
     "bc.exit": "self.bc.exit", "bc.slip": "self.bc.slip", "bc.farfield": "self.bc.farfield",  # pyrandaBC.py:28-38
@@ -151,7 +151,8 @@ _FUNCS = {  # deck function -> method of the simulation object (pyranda.py:817-8
     "numpy.maximum": "xp.maximum", "numpy.sqrt": "xp.sqrt", "numpy.abs": "xp.abs", "numpy.where": "xp.where",
 }
 _NAMES = {"simtime": "self.time", "deltat": "self.deltat", "pi": "xp.pi", "meshx": 'self.variables["meshx"]',
-          "meshy": 'self.variables["meshy"]', "meshz": 'self.variables["meshz"]', "gridLen": "self.GridLen"}
+          "meshy": 'self.variables["meshy"]', "meshz": 'self.variables["meshz"]', "gridLen": "self.GridLen",
+          "meshi": "self.mesh.indices[0].data", "meshj": "self.mesh.indices[1].data", "meshk": "self.mesh.indices[2].data"}  # pyranda.py:864-866
 _VAR = re.compile(r":([A-Za-z_]\w*):")
 _CALL = re.compile(r"(?<![\w.\"])((?:dt\.|numpy\.|bc\.)?[A-Za-z_3]\w*)\(")
 _WORD = re.compile(r"(?<![\w.\"])([A-Za-z_]\w*)(?![\w(\"])")
@@ -236,10 +237,17 @@ class _MeshView:
         self.coords = [_Data(sim.variables[k]) for k in ("meshx", "meshy", "meshz")]
         self.GridLen = sim.GridLen
         self.d1, self.d2, self.d3 = sim.d1, sim.d2, sim.d3
-        shape = tuple(sim.zero.shape)
-        idx = np.meshgrid(*[np.arange(shape[d]) + lo[d] for d in range(3)], indexing="ij")
-        self.indices = [_Data(B.asfield(np.asfortranarray(a, dtype=np.float64))) for a in idx]  # pyrandaMesh.py:63-81
-        self.shape = list(shape)
+        self.shape = list(tuple(sim.zero.shape))
+        self._B, self._lo, self._indices = B, lo, None
+
+    @property
+    def indices(self):
+        """Global index fields iloc / jloc / kloc (pyrandaMesh.py:63-81), built on first use: three
+        more fields that most decks never read."""
+        if self._indices is None:
+            idx = np.meshgrid(*[np.arange(self.shape[d]) + self._lo[d] for d in range(3)], indexing="ij")
+            self._indices = [_Data(self._B.asfield(np.asfortranarray(a, dtype=np.float64))) for a in idx]
+        return self._indices
 
 
 class _PyMPIView:

@@ -248,6 +248,12 @@ def test_deck_functions_reach_every_operator(oracle_mod):
     assert np.array_equal(ss.variables["r"], o.pringv(a, b, a))
     assert np.array_equal(ss.variables["d4"], o.dd4x(a) + o.dd4y(a) + o.dd4z(a))
     assert np.array_equal(ss.variables["g"], o.gfilterdir(a, 1) + o.gfilterdir(a, 2) + o.gfilterdir(a, 3) + o.plaplacian(b))
+    ss2 = make_sim(oracle_mod, "names", mesh)
+    ss2.EOM("ddt(:a:) = -ddx(:a:)\n:k: = meshi + 100.0*meshj + 10000.0*meshk\n:v: = meshVar('CellVol')")
+    ss2.setIC(":a: = meshx")
+    i, j, k = np.meshgrid(np.arange(16), np.arange(18), np.arange(20), indexing="ij")
+    assert np.array_equal(ss2.variables["k"], i + 100.0 * j + 10000.0 * k)
+    assert np.array_equal(ss2.variables["v"], o.getvar("CellVol"))
 
 
 def test_viz_dump_vtk(oracle_mod, tmp_path):
