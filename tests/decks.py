@@ -595,3 +595,29 @@ rad = sqrt( meshx**2  +  meshy**2 )
 :cs:  = sqrt( :p: / :rho: * :gamma: )
 :dt: = dt.courant(:u:,:v:,:w:,:cs:)
 """.replace('mach', str(OMESH_MACH))
+
+
+# ---- a box with symmetry planes (no reference example uses meshOptions['symmetric']; this deck exists to
+# run the SYMM operators -- even closures everywhere, the odd first derivative inside div -- through
+# the interpreter on both backends) ------------------------------------------------------------------
+def symm_box_mesh():
+    return {"x1": [0.0, 0.0, 0.0], "xn": [1.0, 1.0, 1.0], "nn": [32, 24, 20], "periodic": [False, False, False],
+            "symmetric": [[True, True], [True, False], [False, True]]}
+
+
+SYMM_EOM = """
+ddt(:phi:) = -div(:phi:*:u:, :phi:*:v:, :phi:*:w:) + 0.01*lap(:phi:)
+:phi: = fbar(:phi:)
+[:gx:,:gy:,:gz:] = grad(:phi:)
+:r: = ring(:phi:) + gbar(:phi:) + 1.0e-4*(dd4x(:phi:) + dd4y(:phi:) + dd4z(:phi:))
+:dt: = dt.courant(:u:,:v:,:w:,:c:)
+"""
+
+SYMM_IC = """
+:phi: = 1.0 + 0.2*cos(pi*meshx)*cos(2.0*pi*meshy)*cos(pi*meshz)
+:u: = 0.3*sin(pi*meshx)*cos(pi*meshy)
+:v: = -0.3*cos(pi*meshx)*sin(pi*meshy)
+:w: = 0.1*sin(2.0*pi*meshz)
+:c: = 1.0 + 3d()
+:dt: = dt.courant(:u:,:v:,:w:,:c:)
+"""

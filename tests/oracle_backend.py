@@ -53,6 +53,8 @@ def make_sim(oracle_mod, name, mesh):
     kw = {}
     if int(opt.get("coordsys", 0)) == 3:
         kw = {"coordsys": 3, "mesh_xyz": curvilinear_coordinates(opt), "periodic_grid": bool(opt.get("periodicGrid", True))}
+    if "symmetric" in opt:
+        kw["symmetric"] = tuple(tuple(bool(b) for b in pair) for pair in opt["symmetric"])
     o = oracle_mod.Oracle(*opt["nn"], opt["x1"][0], opt["xn"][0], opt["x1"][1], opt["xn"][1], opt["x1"][2], opt["xn"][2],
                           periodic=tuple(opt["periodic"]), **kw)
     return pyrandaSim(name, opt, backend=NumpyOracleBackend(o))

@@ -147,7 +147,7 @@ def test_exit_slip_farfield_on_device_fields(oracle_mod):
             assert dev[k].is_cuda and np.abs(dev[k].cpu().numpy() - gold[case + "_" + k]).max() < 1e-13, (case, k)
 
 
-@pytest.mark.parametrize("case", ["RT_2D", "RT_3D", "cylinder_curv", "cylinder_omesh"])
+@pytest.mark.parametrize("case", ["RT_2D", "RT_3D", "cylinder_curv", "cylinder_omesh", "symm_box"])
 def test_example_decks_on_the_gpu(case, oracle_mod):
     """BASELINE configs 4 and 5 as 2-D decks (examples/RT3D.py, examples/cylinder_curv.py) and the
     O-grid deck with bc.slip: five RK4 steps on device-resident fields (fused pointwise kernels, BC /
