@@ -11,6 +11,7 @@ over NCCL.
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference        # the CPU path (oracle port, all host threads)
+    ... bench.py --gpus N --global-n 1024   # BASELINE configs[2]: fixed 1024^3 grid, strong scaling
 """
 import argparse
 import json
@@ -33,11 +34,15 @@ NPER = 512  # points per side per GPU
 NCU_TRAFFIC_DDZ_512 = 2109160000
 
 
-def bench_config(world, n):
-    """The workload both arms are quoted on (BASELINE.json configs[1]: 512^3 fp64 per GPU)."""
+def bench_config(world, n, global_n=0):
+    """The workload both arms are quoted on (BASELINE.json configs[1]: 512^3 fp64 per GPU); with
+    --global-n N the fixed N^3 grid of configs[2] split into z-slabs (strong scaling)."""
+    grid = [global_n] * 3 if global_n else [n, n, n * world]
+    per = [grid[0], grid[1], grid[2] // world]
     return {"workload": "operator microbench: ddx, ddy, ddz, filter, gfilter once each per step on a periodic fp64 field",
-            "global_grid": [n, n, n * world], "per_gpu_grid": [n, n, n], "partition": "z-slab x%d" % world,
-            "l2": "input 1.07 GB per field, larger than the 126 MB L2; no explicit flush", "chunk_len": 32}
+            "global_grid": grid, "per_gpu_grid": per, "partition": "z-slab x%d" % world,
+            "l2": "input %.2f GB per field per GPU, larger than the 126 MB L2; no explicit flush" % (per[0] * per[1] * per[2] * 8 / 1e9),
+            "chunk_len": 32}
 
 
 def peaks():
@@ -196,6 +201,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=NPER, help="points per side per GPU (default 512)")
+    ap.add_argument("--global-n", type=int, default=0,
+                    help="fixed global N^3 grid split into z-slabs (strong scaling; BASELINE configs[2] is N = 1024)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tgv", action="store_true")
@@ -224,6 +231,10 @@ def main():
     warm = max(args.warmup, 3)
     n = args.n
     nx, ny, nz = n, n, n * world
+    if args.global_n:
+        if args.global_n % world or args.global_n // world < 16:
+            raise SystemExit("--global-n %d cannot be split into %d z-slabs of at least 16 planes" % (args.global_n, world))
+        nx = ny = nz = args.global_n
     Lx, Ly, Lz = (2 * np.pi * (k - 1) / k for k in (nx, ny, nz))
 
     if world > 1:
@@ -340,7 +351,7 @@ def main():
     dom = "ddz" if world == 1 else "ddy"
     ach = 16.0 * npts / (per_op_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "sweep_yz_pipe_kernel<D1,16> (%s, one launch per application)" % dom, "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_DDZ_512 if (n == 512 and world == 1) else None,
+                "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_DDZ_512 if (n == 512 and world == 1 and not args.global_n) else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the ddz launch in profiles/r1_v7_tma_kernels_ncu_full.txt",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": 16 * npts}
@@ -351,9 +362,9 @@ def main():
     if cpu:
         cpu.pop("seconds_per_step", None)
     line = {"metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": K, "warmup": warm,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.global_n else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": bench_config(world, n),
+            "config": bench_config(world, n, args.global_n),
             "per_op": per_op, "tgv": tgv, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     emit(line)
     if world > 1:
