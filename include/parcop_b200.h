@@ -53,7 +53,10 @@ enum {
   /* parcop.f90:255-277 dd4x/dd4y/dd4z: explicit 4th derivative, no metric scale
    * (stencils.f90:430-513 e4d4, compact_operators.f90:208-278) */
   PB_OP_DD4X = 22, PB_OP_DD4Y = 23, PB_OP_DD4Z = 24,
-  PB_OP_COUNT = 25
+  /* d8x/d8y/d8z(v, dv, bc = -1) (compact_operators.f90:280-383): the 8th derivative of a field that is
+   * odd across the axis' symmetry planes; the reference reaches it inside ringV (operators.f90:661-671) */
+  PB_OP_DD8X_ODD = 25, PB_OP_DD8Y_ODD = 26, PB_OP_DD8Z_ODD = 27,
+  PB_OP_COUNT = 28
 };
 
 enum { PB_REDUCE_SUM = 0, PB_REDUCE_MAX = 1, PB_REDUCE_MIN = 2 };

@@ -15,7 +15,7 @@ _vp = ctypes.c_void_p
 # opcodes (include/parcop_b200.h)
 OP = dict(ddx=0, ddy=1, ddz=2, dd8x=3, dd8y=4, dd8z=5, d2x=6, d2y=7, d2z=8, laplacian=9, ring=10,
           sfilter=11, gfilter=12, gfilterx=13, gfiltery=14, gfilterz=15, sfilterx=16, sfiltery=17,
-          sfilterz=18, ddx_odd=19, ddy_odd=20, ddz_odd=21, dd4x=22, dd4y=23, dd4z=24)
+          sfilterz=18, ddx_odd=19, ddy_odd=20, ddz_odd=21, dd4x=22, dd4y=23, dd4z=24, dd8x_odd=25, dd8y_odd=26, dd8z_odd=27)
 REDUCE = dict(sum=0, max=1, min=2)
 
 EXPORTS = [

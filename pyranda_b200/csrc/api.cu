@@ -560,6 +560,10 @@ int pb_apply(pb_plan *pl, int opcode, const double *in, double *out, void *strea
       return apply_dir(pl, pl->sw[K_D2][opcode - PB_OP_D2X], in, out, kStore, st);
     case PB_OP_DD4X: case PB_OP_DD4Y: case PB_OP_DD4Z:
       return apply_dir(pl, pl->sw[K_D4][opcode - PB_OP_DD4X], in, out, kStore, st);
+    case PB_OP_DD8X_ODD: case PB_OP_DD8Y_ODD: case PB_OP_DD8Z_ODD: {
+      const int d = opcode - PB_OP_DD8X_ODD;
+      return apply_dir(pl, pl->d8_odd[d].built ? pl->d8_odd[d] : pl->sw[K_D8][d], in, out, kStore, st);
+    }
     case PB_OP_GFILTERX: case PB_OP_GFILTERY: case PB_OP_GFILTERZ:
       return apply_dir(pl, pl->sw[K_GF][opcode - PB_OP_GFILTERX], in, out, kStore, st);
     case PB_OP_SFILTERX: case PB_OP_SFILTERY: case PB_OP_SFILTERZ:
@@ -732,10 +736,17 @@ int pb_reduce_device(pb_plan *pl, int kind, long n, const double *d_val, double 
 }
 
 // ---- z-slab pieces -------------------------------------------------------------------------------
+// the z sweep plan of a z-slab opcode: the odd variants exist only on axes with a symmetry plane
+static SweepPlan &zplan(pb_plan *pl, int zop, int k) {
+  if (zop == PB_OP_DDZ_ODD) return d1_plan(pl, 2, -1);
+  if (zop == PB_OP_DD8Z_ODD && pl->d8_odd[2].built) return pl->d8_odd[2];
+  return pl->sw[k][2];
+}
+
 static int zop_kind(int zop) {
   switch (zop) {
     case PB_OP_DDZ: case PB_OP_DDZ_ODD: return K_D1;
-    case PB_OP_DD8Z: return K_D8;
+    case PB_OP_DD8Z: case PB_OP_DD8Z_ODD: return K_D8;
     case PB_OP_D2Z: return K_D2;
     case PB_OP_DD4Z: return K_D4;
     case PB_OP_SFILTERZ: return K_SF;
@@ -747,7 +758,7 @@ static int zop_kind(int zop) {
 int pb_z_pack_halo(pb_plan *pl, int zop, const double *d_val, double *send_lo, double *send_hi, void *stream) {
   const int k = zop_kind(zop);
   if (!pl || k < 0 || !d_val || !send_lo || !send_hi) return fail(PB_ERR_ARG, "bad argument");
-  const SweepPlan &sp = zop == PB_OP_DDZ_ODD ? d1_plan(pl, 2, -1) : pl->sw[k][2];
+  const SweepPlan &sp = zplan(pl, zop, k);
   if (sp.null_op) return PB_OK;
   const long plane = (long)pl->a[0] * pl->a[1];
   PB_CUDA(launch_pack_planes(d_val, plane, pl->a[2], sp.st.nor, send_lo, send_hi, (cudaStream_t)stream));
@@ -758,7 +769,7 @@ int pb_z_local(pb_plan *pl, int zop, const double *d_val, const double *recv_lo,
                double *iface_local, void *stream) {
   const int k = zop_kind(zop);
   if (!pl || k < 0 || !d_val || !d_out) return fail(PB_ERR_ARG, "bad argument");
-  SweepPlan &sp = zop == PB_OP_DDZ_ODD ? d1_plan(pl, 2, -1) : pl->sw[k][2];
+  SweepPlan &sp = zplan(pl, zop, k);
   cudaStream_t st = (cudaStream_t)stream;
   if (sp.null_op || !sp.split) {
     // not distributed: the whole operator in one call
@@ -774,7 +785,7 @@ int pb_z_local(pb_plan *pl, int zop, const double *d_val, const double *recv_lo,
 int pb_z_finish(pb_plan *pl, int zop, const double *d_val, const double *iface_all, double *d_out, void *stream) {
   const int k = zop_kind(zop);
   if (!pl || k < 0 || !d_out) return fail(PB_ERR_ARG, "bad argument");
-  SweepPlan &sp = zop == PB_OP_DDZ_ODD ? d1_plan(pl, 2, -1) : pl->sw[k][2];
+  SweepPlan &sp = zplan(pl, zop, k);
   if (sp.null_op || !sp.split || !sp.st.implicit) return PB_OK;  // explicit operators are complete after pb_z_local
   if (!iface_all) return fail(PB_ERR_ARG, "missing interface buffer");
   (void)d_val;
@@ -810,7 +821,7 @@ int pb_peer_exchange(int ncopies, void *const *dst, const void *const *src, cons
 int pb_z_exchange_ranks(pb_plan *pl, int zop, unsigned long long *mask) {
   const int k = zop_kind(zop);
   if (!pl || k < 0 || !mask) return fail(PB_ERR_ARG, "bad argument");
-  const SweepPlan &sp = zop == PB_OP_DDZ_ODD ? d1_plan(pl, 2, -1) : pl->sw[k][2];
+  const SweepPlan &sp = zplan(pl, zop, k);
   *mask = (sp.null_op || !sp.split || !sp.st.implicit) ? 0ull : sp.rank_mask;
   return PB_OK;
 }

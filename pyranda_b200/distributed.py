@@ -21,8 +21,8 @@ from ._lib import OP, ParcopError, check
 from .plan import ParcopPlan
 
 # z operator behind each distributed call and its halo width (nor of the stencil)
-_ZOPS = {"ddz": ("ddz", 3), "ddz_odd": ("ddz_odd", 3), "dd4z": ("dd4z", 3), "dd8z": ("dd8z", 4), "d2z": ("d2z", 3), "sfilterz": ("sfilterz", 4), "gfilterz": ("gfilterz", 4)}
-_IMPLICIT = {"ddz": True, "ddz_odd": True, "dd4z": False, "dd8z": True, "d2z": True, "sfilterz": True, "gfilterz": False}
+_ZOPS = {"ddz": ("ddz", 3), "ddz_odd": ("ddz_odd", 3), "dd4z": ("dd4z", 3), "dd8z": ("dd8z", 4), "dd8z_odd": ("dd8z_odd", 4), "d2z": ("d2z", 3), "sfilterz": ("sfilterz", 4), "gfilterz": ("gfilterz", 4)}
+_IMPLICIT = {"ddz": True, "ddz_odd": True, "dd4z": False, "dd8z": True, "dd8z_odd": True, "d2z": True, "sfilterz": True, "gfilterz": False}
 
 
 class _PeerBuffers:
@@ -231,7 +231,7 @@ class DistributedParcop:
 
     def apply_into(self, name, f, out):
         """ddx ddy ddz dd8x dd8y dd8z d2x d2y d2z sfilter gfilter gfilterx/y/z laplacian ring."""
-        if name in ("ddx", "ddy", "ddx_odd", "ddy_odd", "dd4x", "dd4y", "dd8x", "dd8y", "d2x", "d2y", "gfilterx", "gfiltery", "sfilterx", "sfiltery"):
+        if name in ("ddx", "ddy", "ddx_odd", "ddy_odd", "dd4x", "dd4y", "dd8x_odd", "dd8y_odd", "dd8x", "dd8y", "d2x", "d2y", "gfilterx", "gfiltery", "sfilterx", "sfiltery"):
             return self._local_into(name, f, out)
         if name in _ZOPS:
             return self.zop_into(name, f, out)
@@ -295,15 +295,13 @@ class DistributedParcop:
         |d8| times the spacing; nine sweeps, three of them distributed."""
         if self.plan.coordsys != 0:
             raise ParcopError("ringV on a z-slab: only the Cartesian branch is implemented")
-        if any(s for pair in self.symmetric for s in pair):
-            raise ParcopError("ringV on a z-slab with symmetry planes is not implemented")
         if self._tmp is None:
             self._tmp = self.empty()
         out, tmp = self.empty(), self._tmp
         out.zero_()
-        for nm, d in (("dd8x", self.plan.dx), ("dd8y", self.plan.dy), ("dd8z", self.plan.dz)):
-            for comp in (vx, vy, vz):
-                self.apply_into(nm, comp, tmp)
+        for k, (nm, d) in enumerate((("dd8x", self.plan.dx), ("dd8y", self.plan.dy), ("dd8z", self.plan.dz))):
+            for c, comp in enumerate((vx, vy, vz)):  # the component normal to a symmetry plane is odd across it (:661-671)
+                self.apply_into(nm + "_odd" if c == k else nm, comp, tmp)
                 torch.maximum(out, tmp.abs_().mul_(d), out=out)
         return out
 

@@ -164,6 +164,9 @@ class ParcopPlan:
     def ddx_odd(self, val): return self.apply("ddx_odd", val)
     def ddy_odd(self, val): return self.apply("ddy_odd", val)
     def ddz_odd(self, val): return self.apply("ddz_odd", val)
+    def dd8x_odd(self, val): return self.apply("dd8x_odd", val)  # d8x(v, dv, bc=-1), compact_operators.f90:280-313
+    def dd8y_odd(self, val): return self.apply("dd8y_odd", val)
+    def dd8z_odd(self, val): return self.apply("dd8z_odd", val)
     def dd4x(self, val): return self.apply("dd4x", val)
     def dd4y(self, val): return self.apply("dd4y", val)
     def dd4z(self, val): return self.apply("dd4z", val)

@@ -69,6 +69,8 @@ g9 = [loc, loc * 2, loc * loc, loc + 1, loc * 0.5, -loc, loc * loc * 0.1, loc - 
 h9 = [f, f * 2, f * f, f + 1, f * 0.5, -f, f * f * 0.1, f - 2, f * 3]
 for a, b in zip(eng.divergencetensor(*g9), o.divergencetensor(*h9)):
     assert rel_linf(a.numpy(), b[:, :, sl]) < 1e-12
+assert rel_linf(eng.pringv(loc, loc * loc, loc * 2 + 1).numpy(), o.pringv(f, f * f, f * 2 + 1)[:, :, sl]) < 1e-12
+assert rel_linf(eng.apply("dd8z_odd", loc).numpy(), o.dir_op("d8", 2, f, bc=-1)[:, :, sl]) < 1e-12
 # long slabs: the reduced system couples only neighbouring ranks and the all-gather is replaced by
 # a pair of sends; the correction touches only the rows near the slab faces
 from pyranda_b200._lib import OP

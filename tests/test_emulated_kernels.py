@@ -76,6 +76,8 @@ def test_emulated_symmetry_planes(symm, oracle_mod, emul_lib):
         assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < 1e-13, name
     for d, name in enumerate(("ddx_odd", "ddy_odd", "ddz_odd")):
         assert rel_linf(getattr(p, name)(f), o.dir_op("d1", d, f, bc=-1)) < 1e-13, name
+    for d, name in enumerate(("dd8x_odd", "dd8y_odd", "dd8z_odd")):
+        assert rel_linf(getattr(p, name)(f), o.dir_op("d8", d, f, bc=-1)) < 1e-13, name
     g = np.asarray(np.cos(2 * f) + 0.3 * f, order="F")
     h = np.asarray(f * f - 0.5, order="F")
     assert rel_linf(p.divergence(f, g, h), o.divergence(f, g, h)) < 1e-13

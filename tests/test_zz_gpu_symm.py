@@ -29,6 +29,8 @@ def test_symmetry_planes_match_oracle(n, symm, oracle_mod):
         assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < TOL, (name, n)
     for d, name in enumerate(("ddx_odd", "ddy_odd", "ddz_odd")):
         assert rel_linf(getattr(p, name)(f), o.dir_op("d1", d, f, bc=-1)) < TOL, (name, n)
+    for d, name in enumerate(("dd8x_odd", "dd8y_odd", "dd8z_odd")):
+        assert rel_linf(getattr(p, name)(f), o.dir_op("d8", d, f, bc=-1)) < TOL, (name, n)
     g = np.asfortranarray(np.cos(2 * f) + 0.3 * f)
     h = np.asfortranarray(f * f - 0.5)
     assert rel_linf(p.divergence(f, g, h), o.divergence(f, g, h)) < TOL
