@@ -30,7 +30,8 @@ def test_taylor_green_golden(oracle_mod):
     """tests/cases/testTaylorGreen.py:3: enstrophy ratio 1.00106718415 at t = 0.1 on 32^3."""
     ss = make_sim(oracle_mod, "TGvortex", tgv_mesh(32))
     enst, time, n = run_tgv(ss, tstop=0.1)
-    assert abs(enst - 1.00106718415) / 1.00106718415 < 1e-4, (enst, time, n)
+    # the reference accepts 1e-4 (tests/run_tests.py:84); the baseline is printed with 12 digits and is met to 5e-12
+    assert abs(enst - 1.00106718415) / 1.00106718415 < 1e-10, (enst, time, n)
 
 
 def test_advection_1d_golden(oracle_mod):
@@ -54,7 +55,8 @@ def test_advection_1d_golden(oracle_mod):
             time = ss.rk4(time, dt)
             dt = min(dt_max, (tt - time))
         err = float(np.sum((ss.variables["phi"] - ss.variables["phi2"]) ** 2))
-        assert abs(err - golden) / golden < 1e-3, (npts, err, golden)
+        # 4e-11 / 8e-10 / 9e-9 relative: the baselines themselves are sums of squares of 1e-5 ... 1e-7 errors
+        assert abs(err - golden) / golden < 1e-6, (npts, err, golden)
 
 
 def test_rayleigh_taylor_2d_golden_curve(oracle_mod):
