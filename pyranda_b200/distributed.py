@@ -87,6 +87,10 @@ class DistributedParcop:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        if coordsys != 0 and self.world > 1:
+            # divergence / grads / sfilter (CellVol weighting) / ring take their metric branches from the
+            # mesh arrays of an unsplit plan; on a z-slab only the Cartesian branches are built
+            raise ParcopError("a z-slab partition supports coordsys 0 only (curvilinear metrics on a split axis are not built)")
         self.plan = ParcopPlan(nx, ny, nz, x1, xn, y1, yn, z1, zn, periodic=periodic, px=1, py=1, pz=self.world,
                                coords=(0, 0, self.rank), coordsys=coordsys, device=device, lib=lib, symmetric=symmetric,
                                tensor_device="cpu" if (tensor_device is not None and torch.device(tensor_device).type == "cpu") else "cuda")
@@ -413,6 +417,8 @@ def distributed_sim(name, mesh, device=-1, group=None, lib=None, tensor_device=N
     each rank holding nz / world planes.  `mesh` is the deck's mesh string (or parsed options)."""
     from .sim import parse_mesh, pyrandaSim
     opt = parse_mesh(mesh) if isinstance(mesh, str) else mesh
+    if int(opt.get("coordsys", 0)) != 0:
+        raise ParcopError("distributed_sim: coordsys %s decks need one rank (z-slab operators are Cartesian)" % opt.get("coordsys"))
     eng = DistributedParcop(*opt["nn"], opt["x1"][0], opt["xn"][0], opt["x1"][1], opt["xn"][1], opt["x1"][2], opt["xn"][2],
                             periodic=tuple(opt["periodic"]), device=device, group=group, lib=lib, tensor_device=tensor_device,
                             symmetric=tuple(tuple(s) for s in opt.get("symmetric", ((False, False),) * 3)))

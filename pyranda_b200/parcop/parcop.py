@@ -25,9 +25,10 @@ def _cur():
 
 
 def setup(patch, level, comm, nx, ny, nz, px, py, pz, coordsys, x1, xn, y1, yn, z1, zn,
-          bx1, bxn, by1, byn, bz1, bzn, coords=(0, 0, 0), device=-1):
+          bx1, bxn, by1, byn, bz1, bzn, coords=(0, 0, 0), device=-1, lib=None, tensor_device="cuda"):
     """parcop.f90:23-61.  `comm` is accepted for call compatibility (the reference passes an MPI
-    Fortran handle); rank coordinates come from `coords` (z-slab: (0, 0, rank))."""
+    Fortran handle); rank coordinates come from `coords` (z-slab: (0, 0, rank)).  `lib` / `tensor_device`
+    select another build of the library (the host-emulated one of tests/emul in CPU tests)."""
     global _current
     periodic = tuple(str(b).strip().upper() == "PERI" for b in (bx1, by1, bz1))
     symmetric = tuple((str(a).strip().upper() == "SYMM", str(b).strip().upper() == "SYMM")
@@ -36,7 +37,8 @@ def setup(patch, level, comm, nx, ny, nz, px, py, pz, coordsys, x1, xn, y1, yn, 
     if key in _plans:
         _plans[key].close()
     _plans[key] = ParcopPlan(nx, ny, nz, x1, xn, y1, yn, z1, zn, periodic=periodic, px=px, py=py, pz=pz,
-                             coords=coords, coordsys=coordsys, symmetric=symmetric, device=device)
+                             coords=coords, coordsys=coordsys, symmetric=symmetric, device=device, lib=lib,
+                             tensor_device=tensor_device)
     _current = key
 
 
@@ -99,17 +101,6 @@ def divergencetensor(fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz):  # parcop.f90
     return _cur().divergencetensor(fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz)
 def pringv(vx, vy, vz): return _cur().pringv(vx, vy, vz)  # parcop.f90:324-333
 def grads(val): return _cur().grads(val)
-
-
-def _unsupported(name):
-    def f(*a, **k):
-        raise ParcopError("%s is outside the hot path rebuilt here (SURVEY.md section 8f)" % name)
-    f.__name__ = name
-    return f
-
-
-dd4x, dd4y, dd4z = _unsupported("dd4x"), _unsupported("dd4y"), _unsupported("dd4z")
-divergencetensor, pringv = _unsupported("divergencetensor"), _unsupported("pringv")
 
 
 # communicator getters (parcop.f90:406-440): there is no MPI here; ranks are torch.distributed ranks

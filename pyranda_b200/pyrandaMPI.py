@@ -48,8 +48,11 @@ class parcop_gfil:
 
 
 class pyrandaMPI:
-    def __init__(self, mesh, comm=None, device=None):
+    def __init__(self, mesh, comm=None, device=None, lib=None, tensor_device=None):
         opt = mesh.options if hasattr(mesh, "options") else mesh
+        if isinstance(opt, str):
+            from .sim import parse_mesh
+            opt = parse_mesh(opt)
         self.nx, self.ny, self.nz = (int(v) for v in opt["nn"])
         x1, xn = opt["x1"], opt["xn"]
         self.dx = (xn[0] - x1[0]) / max(self.nx - 1, 1)  # pyrandaMPI.py:43-45
@@ -75,12 +78,22 @@ class pyrandaMPI:
         if world > 1:
             from .distributed import DistributedParcop
             self._dist = DistributedParcop(*args, periodic=self.periodic, coordsys=self.coordsys, device=dev, group=comm,
-                                           symmetric=self.symmetric)
+                                           symmetric=self.symmetric, lib=lib, tensor_device=tensor_device)
             self.plan = self._dist.plan
         else:
             self._dist = None
-            self.plan = ParcopPlan(*args, periodic=self.periodic, coordsys=self.coordsys, device=dev, symmetric=self.symmetric)
+            kw = {} if tensor_device is None else {"tensor_device": tensor_device}
+            self.plan = ParcopPlan(*args, periodic=self.periodic, coordsys=self.coordsys, device=dev, symmetric=self.symmetric,
+                                   lib=lib, **kw)
         self.ax, self.ay, self.az = self.plan.shape
+        # makeMesh always ends in setup_mesh / setup_mesh_x3 (pyrandaMPI.py:151-174, pyrandaMesh.py:93-135):
+        # ring, getVar and the curvilinear operators need the mesh arrays
+        if self.coordsys == 3:
+            from .sim import curvilinear_coordinates
+            lo = (0, 0, rank * self.az)
+            self.plan.set_mesh(*curvilinear_coordinates(opt, lo, self.plan.shape), periodic_grid=bool(opt.get("periodicGrid", True)))
+        else:
+            self.plan.set_mesh()
         self.chunk_3d_size = np.array(self.plan.shape, dtype=np.int32)
         self.chunk_3d_lo = np.array([0, 0, rank * self.az], dtype=np.int32)
         self.chunk_3d_hi = self.chunk_3d_lo + self.chunk_3d_size - 1

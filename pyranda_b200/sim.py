@@ -86,13 +86,23 @@ class CudaBackend:
     def min3D_dev(self, a): return self.plan.reduce_device("min", self._c(a))
 
     def _c(self, a):
+        """`a` as a field with Fortran strides (1, ax, ax*ay): the kernels walk flat memory."""
         ax, ay, az = self.plan.shape
-        return a if a.stride() == (1, ax, ax * ay) else self._f(a.contiguous()).copy_(a)
+        return a if a.stride() == (1, ax, ax * ay) else self.plan.empty_device(a).copy_(a)
+
+    def storage_key(self, a):
+        return a.data_ptr()
+
+    def clone(self, a):
+        return self.plan.empty_device(a).copy_(a)
 
     def rk4_stage(self, dt, A, B, F, PHI, U):
         """pyranda.py:800-804 fused; returns the new U (updated in place)."""
         F = self._c(self._f(F))
         U = self._c(U)
+        ax, ay, az = self.plan.shape
+        for t in (F, PHI, U):
+            assert t.stride() == (1, ax, ax * ay), "rk4_stage operands must share the Fortran layout"
         self.plan.rk4_stage(dt, A, B, F, PHI, U)
         return U
 
@@ -615,6 +625,25 @@ class pyrandaSim:
     ETA = (494393426753. / 4806282396855., 4702696611523. / 9636871101405., 3614488396635. / 5249666457482.,
            9766892798963. / 10823461281321., 1.0)
 
+    def _unshare_conserved(self):
+        """The stage update is in place on the device.  The reference rebinds `variables[U].data` to a
+        new array every stage (pyranda.py:800-804), so a deck line such as `:phi0: = :phi:` or
+        `:phi: = meshx` leaves the copy untouched; here a conserved field that shares its storage
+        with another variable or a mesh array gets its own before every stage update."""
+        B = self.B
+        if not hasattr(B, "storage_key"):
+            return
+        count = {}
+        for v in list(self.variables.values()) + [self.GridLen, self.d1, self.d2, self.d3, self.zero]:
+            if B.isfield(v):
+                k = B.storage_key(v)
+                count[k] = count.get(k, 0) + 1
+        for U in self.conserved:
+            u = self.variables[U]
+            if B.isfield(u) and count.get(B.storage_key(u), 0) > 1:
+                count[B.storage_key(u)] -= 1
+                self.variables[U] = B.clone(u)
+
     def rk4(self, time, dt):
         PHI = {U: self.B.zeros() for U in self.conserved}
         time_i = time
@@ -622,6 +651,7 @@ class pyrandaSim:
         self.deltat = dt
         for ii in range(5):
             FLUX = self.updateFlux()
+            self._unshare_conserved()
             for U in self.conserved:
                 self.variables[U] = self.B.rk4_stage(dt, self.ARK[ii], self.BRK[ii], FLUX[U], PHI[U], self.variables[U])
             time = time_i + self.ETA[ii] * dt
