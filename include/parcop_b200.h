@@ -154,6 +154,33 @@ int pb_z_finish(pb_plan *plan, int zop, const double *d_val, const double *d_ifa
 int pb_peer_exchange(int ncopies, void *const *d_dst, const void *const *d_src, const size_t *bytes,
                      int npeers, void *const *d_remote_flags, void *const *d_local_flags,
                      unsigned long long epoch, void *d_counter, void *stream);
+/* ---- the fused z-slab sweep (ring kernel) -------------------------------------------------------
+ * The same distributed operator as ONE kernel per sweep and without a correction pass: the slabs
+ * are consecutive chunks of the global line, factored once as a whole (compact_basetype.f90:150-198
+ * builds a per-rank factorisation + reduced system instead), and the two-value states of the chunks
+ * next to a slab face are written straight into the neighbouring ranks' memory (NVLink peer
+ * mapping) as self-validating records which the consuming CTA polls, tile by tile.  The caller
+ * provides, per rank, two record buffers of  slots * ax * ay * 32 bytes  (slots >= need_f / need_b,
+ * zero-initialised, peer-visible) and the peer-mapped addresses of the buffers of the ranks it
+ * writes to: en_out[k] = en_in of rank r+1+k, st_out[k] = st_in of rank r-1-k (periodic wrap).
+ * `epoch` must be non-zero, identical on all ranks for one sweep and different from the previous
+ * sweep's.  Halo planes are exchanged as for pb_z_local.  epi_mode: 0 store, 1 out += val,
+ * 2 out = |val| s2, 3 out = max(out, |val| s2).
+ * pb_z_ring_info reports the slots / hops this operator needs on this rank; all zeros means the
+ * fused form is unavailable for it (explicit operator, slab not a multiple of 32 planes, states that
+ * would wrap onto the rank itself) and pb_z_local / pb_z_finish must be used. */
+typedef struct pb_xring {
+  unsigned int epoch;
+  void *en_in, *st_in;
+  void *en_out[3], *st_out[3];
+} pb_xring;
+int pb_z_ring_info(pb_plan *plan, int zop, int *need_f, int *need_b, int *nup, int *ndn);
+int pb_z_ring(pb_plan *plan, int zop, const double *d_val, const double *d_recv_lo, const double *d_recv_hi,
+              double *d_out, const pb_xring *x, int epi_mode, double s2, void *stream);
+/* one directional derivative (PB_OP_DDX.., DD8X.., D2X.., the _ODD variants) with a composite epilogue
+ * (epi_mode as above): the pieces pb_apply's laplacian / ring / divergence are made of */
+int pb_apply_epi(pb_plan *plan, int opcode, const double *d_val, double *d_out, int epi_mode, double s2,
+                 void *stream);
 /* bit r of *mask is set when rank r's interface values enter this rank's correction (0: the
  * operator needs no exchange); slots of d_iface_all belonging to other ranks are never read */
 int pb_z_exchange_ranks(pb_plan *plan, int zop, unsigned long long *mask);
@@ -175,6 +202,11 @@ int pb_host_ring_vector(pb_plan *plan, const double *h_vx, const double *h_vy, c
 long pb_launch_count(void);
 /* of those, launches of the TMA-pipelined persistent sweep kernels (tests assert the fast path ran) */
 long pb_pipe_launch_count(void);
+/* of those, launches of the ring kernel (thread-block clusters for long lines / cross-rank chunk states) */
+long pb_ring_launch_count(void);
+/* ring kernel policy: mode 0 never, 1 where the one-CTA pipelined kernel does not fit (default), 2 wherever
+ * it fits; lines = 16 / 32 / 64 lines per tile (0: automatic); negative values keep the current setting */
+int pb_set_ring(int mode, int lines);
 /* tuning knobs (lines per tile, chunk length); 0 keeps the default.  Affects plans created later. */
 int pb_set_tuning(int lines_yz, int lines_x, int chunk_len);
 

@@ -23,8 +23,14 @@ EXPORTS = [
     "pb_plan_spacing", "pb_plan_set_mesh", "pb_getvar", "pb_getvar_device", "pb_apply",
     "pb_divergence", "pb_grads", "pb_divergence_tensor", "pb_ring_vector", "pb_host_divergence_tensor", "pb_host_ring_vector", "pb_rk4_stage", "pb_reduce", "pb_reduce_device", "pb_z_pack_halo", "pb_z_local",
     "pb_z_finish", "pb_z_exchange_ranks", "pb_peer_exchange", "pb_host_apply", "pb_host_divergence", "pb_host_grads", "pb_launch_count",
-    "pb_pipe_launch_count", "pb_set_tuning",
+    "pb_pipe_launch_count", "pb_set_tuning", "pb_ring_launch_count", "pb_set_ring",
+    "pb_z_ring_info", "pb_z_ring", "pb_apply_epi",
 ]
+
+
+class XRingC(ctypes.Structure):
+    """pb_xring of include/parcop_b200.h."""
+    _fields_ = [("epoch", ctypes.c_uint), ("en_in", _vp), ("st_in", _vp), ("en_out", _vp * 3), ("st_out", _vp * 3)]
 
 
 class ParcopError(RuntimeError):
@@ -64,6 +70,11 @@ def declare(L):
     L.pb_launch_count.restype = ctypes.c_long
     L.pb_pipe_launch_count.restype = ctypes.c_long
     L.pb_set_tuning.argtypes = [i, i, i]
+    L.pb_ring_launch_count.restype = ctypes.c_long
+    L.pb_set_ring.argtypes = [i, i]
+    L.pb_z_ring_info.argtypes = [_vp, i] + [ctypes.POINTER(i)] * 4
+    L.pb_z_ring.argtypes = [_vp, i, _vp, _vp, _vp, _vp, ctypes.POINTER(XRingC), i, d, _vp]
+    L.pb_apply_epi.argtypes = [_vp, i, _vp, _vp, i, d, _vp]
     return L
 
 

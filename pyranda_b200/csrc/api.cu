@@ -44,6 +44,11 @@ struct SweepPlan {
   double *GR = nullptr;   // rank-level reduced-system rows [4][4np]
   int zone_lo = 0, zone_hi = 0;     // rows from either end of the slab the rank-level correction reaches
   unsigned long long rank_mask = 0; // ranks whose interface values enter this rank's correction
+  // the same split line as consecutive chunks of the GLOBAL line (ring kernel): tables of this rank's
+  // chunks from one factorisation of the whole line, and who exchanges which chunk states with whom
+  bool xr_ok = false;
+  SweepDev devx;
+  XRing xr;
   std::vector<void *> owned;
 };
 
@@ -86,6 +91,92 @@ void free_sweep(SweepPlan &sp) {
   for (void *q : sp.owned) cudaFree(q);
   sp.owned.clear();
   sp.built = false;
+}
+
+// A split line as the global line's chunks (ring kernel).  One LU factorisation of the whole line of
+// n rows (circulant limit when periodic): rank r owns chunks r P .. (r + 1) P - 1 of n / 32, every
+// interior rank has constant coefficients from its first row, and the carried-state sums simply run
+// across the slab faces -- the states they need from other ranks are what the kernels exchange.
+int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool periodic) {
+  sp.xr_ok = false;
+  const int n = sp.n, np = sp.np, m = n / np, r = sp.rank;
+  if (m % 32 != 0 || m / 32 > kMaxChunks) return PB_OK;
+  const int P = m / 32, Pg = n / 32;
+  LineTables gt;
+  try { gt = build_line_tables(n, bands, periodic, Pg); }
+  catch (const std::exception &) { return PB_OK; }
+  auto nF = [&](int rank, int q) { return gt.nF[rank * P + q]; };
+  auto nB = [&](int rank, int q) { return gt.nB[rank * P + q]; };
+  auto need_f = [&](int rank) { int v = 0; for (int q = 0; q < P; ++q) v = std::max(v, nF(rank, q) - q); return v; };
+  auto need_b = [&](int rank) { int v = 0; for (int q = 0; q < P; ++q) v = std::max(v, nB(rank, q) - (P - 1 - q)); return v; };
+  XRing xr;
+  memset(&xr, 0, sizeof(xr));
+  xr.on = 1;
+  xr.need_f = need_f(r);
+  xr.need_b = need_b(r);
+  for (int k = 0; k < np - 1; ++k) {  // my top chunks as slots k P .. of rank r + 1 + k, my bottom chunks of rank r - 1 - k
+    int up = r + 1 + k, dn = r - 1 - k;
+    if (periodic) { up %= np; dn = (dn % np + np) % np; }
+    const int cu = up < np ? std::min(P, std::max(0, need_f(up) - k * P)) : 0;
+    const int cd = dn >= 0 ? std::min(P, std::max(0, need_b(dn) - k * P)) : 0;
+    if (cu > 0) { if (k >= kXHops || xr.nup != k) return PB_OK; xr.cnt_up[k] = cu; xr.nup = k + 1; }
+    if (cd > 0) { if (k >= kXHops || xr.ndn != k) return PB_OK; xr.cnt_dn[k] = cd; xr.ndn = k + 1; }
+  }
+  // every state must come from another rank, within the slots a CTA keeps, and a rank that sends to
+  // a rank also hears from it (that is what orders consecutive sweeps on the record buffers)
+  if (xr.need_f > kXExt || xr.need_b > kXExt) return PB_OK;
+  if (xr.need_f > (np - 1) * P || xr.need_b > (np - 1) * P) return PB_OK;
+  for (int rank = 0; rank < np; ++rank)
+    if ((need_f(rank) + P - 1) / P != (need_b(rank) + P - 1) / P && periodic) return PB_OK;
+
+  SweepDev &dv = sp.devx;
+  dv = sp.dev;
+  dv.P = P; dv.C = 32;
+  dv.wrap = 0;
+  for (int q = 0; q < kMaxChunks; ++q) { dv.perm[q] = (unsigned char)q; dv.ctype[q] = 0; dv.nf[q] = dv.nb[q] = 0; }
+  int jmax = 1;
+  for (int q = 0; q < P; ++q) {
+    dv.ctype[q] = gt.ctype[r * P + q];
+    dv.nf[q] = (unsigned char)nF(r, q);
+    dv.nb[q] = (unsigned char)nB(r, q);
+    jmax = std::max(jmax, std::max(nF(r, q), nB(r, q)));
+  }
+  dv.has_const = gt.has_const ? 1 : 0;
+  for (int q = 0; q < 5; ++q) dv.cst[q] = gt.cst[q];
+  dv.cparam = gt.has_const ? 1 : 0;
+  if (dv.cparam)
+    for (int q = 0; q < 32; ++q) {
+      dv.phi0[q] = make_double2(gt.phi[q * 2], gt.phi[q * 2 + 1]);
+      dv.psi0[q] = make_double2(gt.psi[q * 2], gt.psi[q * 2 + 1]);
+    }
+  const size_t nt = (size_t)gt.ntypes * 32;
+  std::vector<double2> luf(nt), phi(nt), psi(nt);
+  std::vector<double4> lub(nt);
+  for (size_t t = 0; t < nt; ++t) {
+    luf[t] = make_double2(gt.luf[t * 2], gt.luf[t * 2 + 1]);
+    phi[t] = make_double2(gt.phi[t * 2], gt.phi[t * 2 + 1]);
+    psi[t] = make_double2(gt.psi[t * 2], gt.psi[t * 2 + 1]);
+    lub[t] = make_double4(gt.lub[t * 4], gt.lub[t * 4 + 1], gt.lub[t * 4 + 2], 0.0);
+  }
+  dv.mstride = jmax + 1;
+  std::vector<double4> Mf((size_t)P * dv.mstride), Mb((size_t)P * dv.mstride);
+  for (int q = 0; q < P; ++q)
+    for (int j = 0; j <= jmax; ++j) {
+      const size_t src = ((size_t)(r * P + q) * (Pg + 1) + j) * 4, dst = (size_t)q * dv.mstride + j;
+      const bool in = j <= Pg;
+      Mf[dst] = in ? make_double4(gt.Mf[src], gt.Mf[src + 1], gt.Mf[src + 2], gt.Mf[src + 3]) : make_double4(0, 0, 0, 0);
+      Mb[dst] = in ? make_double4(gt.Mb[src], gt.Mb[src + 1], gt.Mb[src + 2], gt.Mb[src + 3]) : make_double4(0, 0, 0, 0);
+    }
+  int rcv;
+  if ((rcv = upload(sp, luf, &dv.luf)) != PB_OK) return rcv;
+  if ((rcv = upload(sp, lub, &dv.lub)) != PB_OK) return rcv;
+  if ((rcv = upload(sp, phi, &dv.phi)) != PB_OK) return rcv;
+  if ((rcv = upload(sp, psi, &dv.psi)) != PB_OK) return rcv;
+  if ((rcv = upload(sp, Mf, &dv.Mf)) != PB_OK) return rcv;
+  if ((rcv = upload(sp, Mb, &dv.Mb)) != PB_OK) return rcv;
+  sp.xr = xr;
+  sp.xr_ok = true;
+  return PB_OK;
 }
 
 // One operator along one axis: compact_basetype.f90:65-209 re-expressed for the chunked kernels.
@@ -168,6 +259,7 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic, in
       Mb[t] = make_double4(lt.Mb[t * 4], lt.Mb[t * 4 + 1], lt.Mb[t * 4 + 2], lt.Mb[t * 4 + 3]);
     }
     for (int q = 0; q < P; ++q) { dv.nf[q] = (unsigned char)lt.nF[q]; dv.nb[q] = (unsigned char)lt.nB[q]; }
+    dv.mstride = P + 1;
     {
       int k = 0;
       for (int q = 0; q < P; ++q)
@@ -217,6 +309,7 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic, in
       if ((rcv = upload(sp, GR, &dGR)) != PB_OK) return rcv;
       sp.RC = const_cast<double4 *>(dRC);
       sp.GR = const_cast<double *>(dGR);
+      if ((rcv = build_ring_tables(sp, bands, periodic)) != PB_OK) return rcv;
     }
   }
   return PB_OK;
@@ -327,6 +420,8 @@ const char *pb_last_error(void) { return g_err.c_str(); }
 const char *pb_version(void) { return "parcop_b200 0.1 (sm_100a)"; }
 long pb_launch_count(void) { return launch_count(); }
 long pb_pipe_launch_count(void) { return pipe_launch_count(); }
+long pb_ring_launch_count(void) { return ring_launch_count(); }
+int pb_set_ring(int mode, int lines) { set_ring_kernels(mode, lines); return PB_OK; }
 
 int pb_set_tuning(int lines_yz, int lines_x, int chunk_len) {
   if (lines_yz > 0) set_yz_lines(lines_yz);
@@ -793,6 +888,72 @@ int pb_z_finish(pb_plan *pl, int zop, const double *d_val, const double *iface_a
   PB_CUDA(launch_z_finish(d_out, plane, pl->a[2], sp.RC, sp.GR, sp.np, sp.rank_mask, sp.zone_lo, sp.zone_hi, iface_all,
                           sp.dev.scale, (cudaStream_t)stream));
   return PB_OK;
+}
+
+int pb_z_ring_info(pb_plan *pl, int zop, int *need_f, int *need_b, int *nup, int *ndn) {
+  const int k = zop_kind(zop);
+  if (!pl || k < 0) return fail(PB_ERR_ARG, "bad argument");
+  const SweepPlan &sp = zplan(pl, zop, k);
+  const bool ok = !sp.null_op && sp.split && sp.st.implicit && sp.xr_ok;
+  if (need_f) *need_f = ok ? sp.xr.need_f : 0;
+  if (need_b) *need_b = ok ? sp.xr.need_b : 0;
+  if (nup) *nup = ok ? sp.xr.nup : 0;
+  if (ndn) *ndn = ok ? sp.xr.ndn : 0;
+  return PB_OK;
+}
+
+static int epi_from(int mode, double s2, EpiArgs *e) {
+  if (mode < EPI_STORE || mode > EPI_RING_MAX) return PB_ERR_ARG;
+  e->mode = mode; e->s2 = s2; e->field = nullptr;
+  return PB_OK;
+}
+
+int pb_z_ring(pb_plan *pl, int zop, const double *d_val, const double *recv_lo, const double *recv_hi, double *d_out,
+              const pb_xring *x, int epi_mode, double s2, void *stream) {
+  const int k = zop_kind(zop);
+  if (!pl || k < 0 || !d_val || !d_out || !x) return fail(PB_ERR_ARG, "bad argument");
+  SweepPlan &sp = zplan(pl, zop, k);
+  if (sp.null_op || !sp.split || !sp.st.implicit || !sp.xr_ok)
+    return fail(PB_ERR_UNSUPPORTED, "this z operator has no fused ring form on this partition (pb_z_ring_info reports zeros): use pb_z_local / pb_z_finish");
+  if ((!sp.dev.phys_lo && !recv_lo) || (!sp.dev.phys_hi && !recv_hi)) return fail(PB_ERR_ARG, "missing halo buffer");
+  EpiArgs epi;
+  if (epi_from(epi_mode, s2, &epi) != PB_OK) return fail(PB_ERR_ARG, "bad epilogue mode");
+  XRing xr = sp.xr;
+  xr.epoch = x->epoch;
+  xr.plane = (long)pl->a[0] * pl->a[1];
+  xr.en_in = (const unsigned long long *)x->en_in;
+  xr.st_in = (const unsigned long long *)x->st_in;
+  if ((xr.need_f > 0 && !xr.en_in) || (xr.need_b > 0 && !xr.st_in) || x->epoch == 0) return fail(PB_ERR_ARG, "missing record buffer / epoch 0");
+  for (int h = 0; h < kXHops; ++h) {
+    xr.en_out[h] = (unsigned long long *)x->en_out[h];
+    xr.st_out[h] = (unsigned long long *)x->st_out[h];
+    if ((h < xr.nup && !xr.en_out[h]) || (h < xr.ndn && !xr.st_out[h])) return fail(PB_ERR_ARG, "missing peer record buffer");
+  }
+  // both halo planes or none reach the kernel: a rank at a physical end passes its own buffer for the unused side
+  const double *lo = recv_lo ? recv_lo : recv_hi, *hi = recv_hi ? recv_hi : recv_lo;
+  const cudaError_t err = launch_sweep_ring(sp.st.fam, 0, sp.devx, d_val, d_out, lo, hi, &xr, epi, (cudaStream_t)stream);
+  if (err == cudaErrorNotSupported) return fail(PB_ERR_UNSUPPORTED, "ring kernel: geometry not supported");
+  PB_CUDA(err);
+  return PB_OK;
+}
+
+// one directional operator with a composite epilogue (what pb_apply's laplacian / ring do internally),
+// for callers that assemble composites across ranks
+int pb_apply_epi(pb_plan *pl, int opcode, const double *in, double *out, int epi_mode, double s2, void *stream) {
+  if (!pl || !in || !out) return fail(PB_ERR_ARG, "NULL argument");
+  EpiArgs epi;
+  if (epi_from(epi_mode, s2, &epi) != PB_OK) return fail(PB_ERR_ARG, "bad epilogue mode");
+  cudaStream_t st = (cudaStream_t)stream;
+  int kind, dir;
+  if (opcode >= PB_OP_DDX && opcode <= PB_OP_DDZ) { kind = K_D1; dir = opcode - PB_OP_DDX; }
+  else if (opcode >= PB_OP_DD8X && opcode <= PB_OP_DD8Z) { kind = K_D8; dir = opcode - PB_OP_DD8X; }
+  else if (opcode >= PB_OP_D2X && opcode <= PB_OP_D2Z) { kind = K_D2; dir = opcode - PB_OP_D2X; }
+  else if (opcode >= PB_OP_DDX_ODD && opcode <= PB_OP_DDZ_ODD) return apply_dir(pl, d1_plan(pl, opcode - PB_OP_DDX_ODD, -1), in, out, epi, st);
+  else if (opcode >= PB_OP_DD8X_ODD && opcode <= PB_OP_DD8Z_ODD) {
+    const int d = opcode - PB_OP_DD8X_ODD;
+    return apply_dir(pl, pl->d8_odd[d].built ? pl->d8_odd[d] : pl->sw[K_D8][d], in, out, epi, st);
+  } else return fail(PB_ERR_ARG, "pb_apply_epi: directional derivative opcodes only");
+  return apply_dir(pl, pl->sw[kind][dir], in, out, epi, st);
 }
 
 int pb_peer_exchange(int ncopies, void *const *dst, const void *const *src, const size_t *bytes, int npeers,

@@ -20,14 +20,23 @@
 //   back coalesced.
 #include "sweeps.cuh"
 
+#include <mutex>
+#include <vector>
+
 namespace pb {
 
 std::atomic<long> g_launches{0};
 long launch_count() { return g_launches.load(); }
 std::atomic<long> g_pipe_launches{0};
 long pipe_launch_count() { return g_pipe_launches.load(); }
+std::atomic<long> g_ring_launches{0};
+long ring_launch_count() { return g_ring_launches.load(); }
 int g_reg_kernels = 1;
 int g_pipe_kernels = 1;
+// 0: never, 1: where the one-CTA pipelined kernel does not fit (long lines, short slabs, z-slab rings), 2: wherever it fits
+int g_ring_kernels = getenv("PB_RING") ? atoi(getenv("PB_RING")) : 1;
+static int g_ring_lines = getenv("PB_RING_LINES") ? atoi(getenv("PB_RING_LINES")) : 0;
+void set_ring_kernels(int mode, int lines) { if (mode >= 0) g_ring_kernels = mode; if (lines >= 0) g_ring_lines = lines; }
 // 0: shared-memory kernels, 1: register kernels, 2: register kernels + TMA-pipelined persistent kernels
 void set_reg_kernels(int on) { g_reg_kernels = on >= 1; g_pipe_kernels = on >= 2; }
 int sm_count() {
@@ -42,6 +51,36 @@ int sm_count() {
   return n;
 #endif
 }
+int max_active_clusters_cached(const void *fn, int cl, size_t smem) {
+#ifdef PB_EMULATE
+  (void)fn; (void)cl; (void)smem;
+  return 2;  // two clusters: the tile loop and the prefetch hand-over are exercised
+#else
+  struct Key { const void *fn; int cl; size_t smem; int n; };
+  static std::vector<Key> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Key &k : cache)
+    if (k.fn == fn && k.cl == cl && k.smem == smem) return k.n;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(cl * 2 * sm_count()));
+  cfg.blockDim = dim3(kBlockThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache.push_back(Key{fn, cl, smem, n});
+  return n;
+#endif
+}
+
 static int g_yz_lines = 32;
 static int g_x_lines = 32;
 void set_yz_lines(int nl) { if (nl == 8 || nl == 16 || nl == 32) g_yz_lines = nl; }
@@ -58,6 +97,46 @@ extern template cudaError_t launch_x_f<F_R3, false>(int, const SweepDev &, const
 extern template cudaError_t launch_x_f<F_R4, false>(int, const SweepDev &, const double *, double *, const EpiArgs &, cudaStream_t);
 extern template cudaError_t launch_x_f<F_R4, true>(int, const SweepDev &, const double *, double *, const EpiArgs &, cudaStream_t);
 
+extern template cudaError_t launch_ring_f<F_D1, false>(int, const SweepDev &, const double *, double *, const double *, const double *, const XRing *, cudaStream_t);
+extern template cudaError_t launch_ring_f<F_R3, false>(int, const SweepDev &, const double *, double *, const double *, const double *, const XRing *, cudaStream_t);
+extern template cudaError_t launch_ring_f<F_R4, false>(int, const SweepDev &, const double *, double *, const double *, const double *, const XRing *, cudaStream_t);
+extern template cudaError_t launch_ring_f<F_R4, true>(int, const SweepDev &, const double *, double *, const double *, const double *, const XRing *, cudaStream_t);
+
+// lines per tile of the ring kernel: 256 / lines chunks per CTA must divide the line's chunks into 1, 2, 4 or 8 CTAs
+static int ring_lines(int P, int want) {
+  const int cand[4] = {want, 32, 16, 64};
+  for (int k = 0; k < 4; ++k) {
+    const int nl = cand[k];
+    if (nl != 16 && nl != 32 && nl != 64) continue;
+    const int pl = kBlockThreads / nl;
+    if (P % pl) continue;
+    const int cl = P / pl;
+    if (cl == 1 || cl == 2 || cl == 4 || cl == 8) return nl;
+  }
+  return 0;
+}
+
+cudaError_t launch_sweep_ring(int fam, int lines, const SweepDev &a, const double *v, double *out, const double *halo_lo,
+                              const double *halo_hi, const XRing *xr, const EpiArgs &epi, cudaStream_t st) {
+  if (!a.implicit || a.C != 32) return cudaErrorNotSupported;
+  lines = ring_lines(a.P, lines > 0 ? lines : g_ring_lines);
+  if (!lines) return cudaErrorNotSupported;
+  SweepDev b = a;  // composite epilogues ride on the TMA stores (reduce-add, |.| s^2, reduce-max)
+  b.acc = 0; b.ring = 0;
+  if (epi.mode == EPI_ACC) b.acc = 1;
+  else if (epi.mode == EPI_RING_SET || epi.mode == EPI_RING_MAX) {
+    if (epi.field != nullptr || fam != F_R4 || a.add_v) return cudaErrorNotSupported;
+    b.ring = 1; b.ring_s2 = epi.s2; b.acc = epi.mode == EPI_RING_MAX ? 2 : 0;
+  }
+  switch (fam) {
+    case F_D1: return launch_ring_f<F_D1, false>(lines, b, v, out, halo_lo, halo_hi, xr, st);
+    case F_R3: return launch_ring_f<F_R3, false>(lines, b, v, out, halo_lo, halo_hi, xr, st);
+    default:
+      return a.add_v ? launch_ring_f<F_R4, true>(lines, b, v, out, halo_lo, halo_hi, xr, st)
+                     : launch_ring_f<F_R4, false>(lines, b, v, out, halo_lo, halo_hi, xr, st);
+  }
+}
+
 // lines per tile: as many as fit a 256-thread block (lines * chunks) and ~64 KB of shared memory
 static int pick_lines(int want, int P, size_t row_bytes) {
   int lines = (want == 8 || want == 16 || want == 32) ? want : 32;
@@ -69,6 +148,14 @@ cudaError_t launch_sweep_yz(int fam, int lines, const SweepDev &a, const double 
                             const double *halo_lo, const double *halo_hi, double *iface,
                             const EpiArgs &epi, cudaStream_t st) {
   if (a.P * 8 > kBlockThreads) return cudaErrorInvalidConfiguration;
+  if (g_pipe_kernels && g_ring_kernels && a.implicit && a.C == 32 && iface == nullptr && lines == 0) {
+    // long lines (clusters), short slabs (64-line tiles): the one-CTA pipelined kernel covers 256- and 512-point lines
+    const bool one_cta_fits = a.P == 8 || a.P == 16;
+    if (g_ring_kernels >= 2 || !one_cta_fits) {
+      const cudaError_t err = launch_sweep_ring(fam, 0, a, v, out, halo_lo, halo_hi, nullptr, epi, st);
+      if (err != cudaErrorNotSupported) return err;
+    }
+  }
   lines = pick_lines(lines > 0 ? lines : g_yz_lines, a.P, a.implicit ? (size_t)a.m * sizeof(double) : 0);
   switch (fam) {
     case F_D1: return launch_yz_f<F_D1, false>(lines, a, v, out, halo_lo, halo_hi, iface, epi, st);

@@ -56,6 +56,23 @@ struct SweepDev {
   int ring;              // pipelined kernels, plain-store path: val = |val| * ring_s2 first (ring detector, Cartesian)
   double ring_s2;
   int wstore;            // pipelined kernels: every warp issues the TMA stores of its own chunks (else one thread per block)
+  int mstride;           // entries per chunk row of Mf / Mb (P + 1, or the compact stride of a z-slab line)
+};
+
+// Cross-rank exchange of chunk states inside a z sweep (ring kernel): a z-slab line is the global
+// line cut into chunks; the states of the chunks next to a slab face travel to the neighbouring
+// ranks through peer memory as self-validating records (4 words of {32 data bits, 32-bit epoch}).
+constexpr int kXHops = 3;  // ranks above / below that one rank's chunk states can reach
+constexpr int kXExt = 8;   // chunk states a rank takes in from either side
+struct XRing {
+  int on;
+  unsigned int epoch;
+  int need_f, need_b;                                    // chunk states polled: forward ends from below, backward starts from above
+  int nup, ndn;                                          // ranks written to above / below
+  int cnt_up[kXHops], cnt_dn[kXHops];                    // my top (bottom) chunks rank r+1+k (r-1-k) takes; its slot = k P + e
+  unsigned long long *en_out[kXHops], *st_out[kXHops];   // those ranks' incoming buffers (peer-mapped)
+  const unsigned long long *en_in, *st_in;               // this rank's incoming buffers [slot][line][4]
+  long plane;                                            // lines per xy-plane
 };
 
 struct EpiArgs {
@@ -70,6 +87,10 @@ cudaError_t launch_sweep_yz(int fam, int lines, const SweepDev &a, const double 
                             const EpiArgs &epi, cudaStream_t st);
 cudaError_t launch_sweep_x(int fam, int lines, const SweepDev &a, const double *v, double *out,
                            const EpiArgs &epi, cudaStream_t st);
+// the ring kernel directly: clusters for long lines, cross-rank chunk states for z-slabs (xr may be null)
+cudaError_t launch_sweep_ring(int fam, int lines, const SweepDev &a, const double *v, double *out,
+                              const double *halo_lo, const double *halo_hi, const XRing *xr,
+                              const EpiArgs &epi, cudaStream_t st);
 
 // z-slab helpers
 cudaError_t launch_pack_planes(const double *v, long plane, int m, int h, double *send_lo,
@@ -115,6 +136,8 @@ cudaError_t launch_metrics(long n, const double *const *J9, double dA, double dB
 
 long launch_count();
 long pipe_launch_count();
+long ring_launch_count();
+void set_ring_kernels(int mode, int lines);
 void set_yz_lines(int nl);
 void set_reg_kernels(int on);
 void set_x_lines(int nl);

@@ -1,0 +1,477 @@
+// The "ring" y/z sweep: the pipelined persistent kernel of sweeps.cuh generalised so that the chunks
+// of one grid line may live in different places.  A line is always a ring (periodic) or a row
+// (bounded) of 32-row chunks whose two-value states are combined with the short Mf / Mb sums; what
+// changes is where a chunk's state is found:
+//   * in this CTA's shared memory                        (what sweep_yz_pipe_kernel does),
+//   * in the shared memory of another CTA of the cluster  (lines longer than one CTA's tile: the
+//     CTAs of a thread-block cluster each take ML = 256 * 32 / NL rows of the same NL lines and
+//     read each other's states through distributed shared memory; NL = 32 keeps 256-byte rows
+//     for 512- and 1024-point lines),
+//   * on another GPU                                      (z-slab: the ranks' slabs are consecutive
+//     pieces of the global line; the states of the chunks next to a slab face are written into the
+//     neighbouring ranks' memory over NVLink as self-validating records and polled there, tile by
+//     tile, while the rest of the CTA keeps working).
+// Replaces, for a split z axis, the MPI_Sendrecv + mpi_allgather + redundant reduced solve + spike
+// correction of compact_d1.f90:858-928 / compact_r4.f90:820-877 with ONE kernel per sweep and no
+// correction pass: the result is the global factorisation's solution, row for row.
+#pragma once
+
+namespace pb {
+
+extern int g_ring_kernels;
+int max_active_clusters_cached(const void *fn, int cl, size_t smem);
+
+#ifndef PB_EMULATE
+__device__ __forceinline__ int cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+__device__ __forceinline__ int cl_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return (int)r; }
+__device__ __forceinline__ void cl_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the double2 at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ double2 ld_cl(const double2 *p, int rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_addr(p)), "r"((uint32_t)rank));
+  double2 v;
+  asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ra) : "memory");
+  return v;
+}
+// a chunk state as four words of {32 data bits, epoch}: every word validates itself, so the record
+// needs neither a fence nor a separate flag and may land in any order
+__device__ __forceinline__ void xr_store(unsigned long long *rec, double2 v, unsigned int epoch) {
+  const unsigned long long e = (unsigned long long)epoch << 32;
+  const unsigned long long bx = (unsigned long long)__double_as_longlong(v.x), by = (unsigned long long)__double_as_longlong(v.y);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(rec), "l"((bx & 0xffffffffull) | e), "l"((bx >> 32) | e) : "memory");
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(rec + 2), "l"((by & 0xffffffffull) | e), "l"((by >> 32) | e) : "memory");
+}
+__device__ __forceinline__ bool xr_try_load(const unsigned long long *rec, unsigned int epoch, double2 *v) {
+  unsigned long long w0, w1, w2, w3;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(rec) : "memory");
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(rec + 2) : "memory");
+  const unsigned long long e = (unsigned long long)epoch;
+  if ((w0 >> 32) != e || (w1 >> 32) != e || (w2 >> 32) != e || (w3 >> 32) != e) return false;
+  v->x = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  v->y = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
+  return true;
+}
+__device__ __forceinline__ void xr_pause(unsigned long long &spin) {
+  if (++spin > (1ull << 24)) __trap();  // a neighbour that never arrives must not hang the GPU
+  if (spin > 64) __nanosleep(64);
+}
+#else
+inline int cl_rank() { return emul::t_cluster_rank; }
+inline int cl_size() { return emul::t_cluster_size; }
+inline void cl_sync() { emul::t_cluster_barrier->arrive_and_wait(); }
+inline double2 ld_cl(const double2 *p, int rank) {
+  const char *q = reinterpret_cast<const char *>(emul::t_cluster_smem[rank]) + (reinterpret_cast<const char *>(p) - reinterpret_cast<const char *>(emul::t_smem));
+  return *reinterpret_cast<const double2 *>(q);
+}
+inline void xr_store(unsigned long long *rec, double2 v, unsigned int epoch) {
+  const unsigned long long e = (unsigned long long)epoch << 32;
+  unsigned long long bx, by;
+  std::memcpy(&bx, &v.x, 8); std::memcpy(&by, &v.y, 8);
+  __atomic_store_n(rec + 0, (bx & 0xffffffffull) | e, __ATOMIC_RELEASE);
+  __atomic_store_n(rec + 1, (bx >> 32) | e, __ATOMIC_RELEASE);
+  __atomic_store_n(rec + 2, (by & 0xffffffffull) | e, __ATOMIC_RELEASE);
+  __atomic_store_n(rec + 3, (by >> 32) | e, __ATOMIC_RELEASE);
+}
+inline bool xr_try_load(const unsigned long long *rec, unsigned int epoch, double2 *v) {
+  unsigned long long w[4];
+  for (int k = 0; k < 4; ++k) w[k] = __atomic_load_n(rec + k, __ATOMIC_ACQUIRE);
+  for (int k = 0; k < 4; ++k)
+    if ((w[k] >> 32) != (unsigned long long)epoch) return false;
+  const unsigned long long bx = (w[0] & 0xffffffffull) | (w[1] << 32), by = (w[2] & 0xffffffffull) | (w[3] << 32);
+  std::memcpy(&v->x, &bx, 8); std::memcpy(&v->y, &by, 8);
+  return true;
+}
+inline void xr_pause(unsigned long long &) { std::this_thread::yield(); }  // the other "rank" is another host thread
+#endif
+
+// every chunk handled by this warp has constant coefficients (see warp_all_const in sweeps.cuh)
+template <int NLT, int PL>
+__device__ __forceinline__ bool ring_warp_all_const(const SweepDev &a, int tid, int crank, bool cc) {
+#ifdef PB_EMULATE
+  if (NLT >= 32) return cc;
+  const int per = 32 / NLT, s0 = (tid / NLT) / per * per;
+  bool all = a.has_const != 0;
+  for (int w = 0; w < per; ++w) all = all && a.ctype[crank * PL + a.perm[crank * PL + s0 + w]] == 0;
+  return all;
+#else
+  (void)a; (void)tid; (void)crank;
+  return NLT < 32 ? __all_sync(0xffffffffu, cc) : cc;
+#endif
+}
+
+template <int FAM, int NL, bool ADDV, bool LATE, bool RING>
+__global__ void __launch_bounds__(kBlockThreads, 2)
+sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tmain, const __grid_constant__ TileMap th4,
+                     const __grid_constant__ TileMap tlo, const __grid_constant__ TileMap thi,
+                     const __grid_constant__ TileMap tout, const __grid_constant__ PipeGeo g, const __grid_constant__ XRing xr) {
+  constexpr int CT = 32, H = FT<FAM>::H, HP = 4;
+  constexpr int PL = kBlockThreads / NL;    // chunks of a line per CTA
+  constexpr int ML = PL * CT;               // rows per CTA
+  constexpr int SR = NL >= 32 ? 8 : 16;     // rows of every chunk per round of TMA stores
+  constexpr int WB = NL < 32 ? NL : 32;     // lines per store box (one warp fills it)
+  constexpr int GW = NL / WB;               // store boxes per chunk and round
+  PB_SHARED(S);
+  const int P = a.P;                        // chunks of the line on this rank = cluster size * PL
+  const int CL = cl_size(), crank = cl_rank();
+  double *tile = S;                                                               // [ML + 2 HP][NL]
+  double *stage = S + (size_t)(ML + 2 * HP) * NL;                                 // [PL][GW][SR][WB]
+  double2 *EN = reinterpret_cast<double2 *>(stage + (size_t)PL * SR * NL);         // [PL + kXExt][NL]
+  double2 *ST = EN + (PL + kXExt) * NL;                                           // [PL + kXExt][NL]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(ST + (PL + kXExt) * NL);
+  const int tid = threadIdx.x, l = tid % NL, p = a.perm[crank * PL + tid / NL], lp = crank * PL + p;
+  const int tiles_i = (a.nfast + NL - 1) / NL;
+  const long ntiles = (long)tiles_i * a.nouter;
+  const int type = a.ctype[lp];
+  const bool cc = ring_warp_all_const<NL, PL>(a, tid, crank, a.has_const && type == 0);
+  const bool lo_sp = a.phys_lo && lp == 0, hi_sp = a.phys_hi && lp == P - 1;
+  const double scale = a.scale;
+  const bool rd1 = g.rowdim == 1;
+  // rows -4 .. -1 and ML .. ML+3 of this CTA's piece: the neighbouring CTA's rows, or at the ends of
+  // the rank's line the periodic wrap rows / the neighbouring ranks' planes (none at a physical end)
+  const bool halo_lo = crank > 0 || g.halo, halo_hi = crank < CL - 1 || g.halo;
+  const uint32_t tx_bytes = (uint32_t)((ML + (halo_lo ? HP : 0) + (halo_hi ? HP : 0)) * NL * sizeof(double));
+  const int row0 = crank * ML;
+
+  auto issue = [&](long t) {  // one thread: arm the barrier, describe this CTA's piece of the tile to the TMA unit
+    const int x0 = (int)(t % tiles_i) * NL, o = (int)(t / tiles_i);
+    mbar_expect_tx(bar, tx_bytes);
+    for (int b = 0; b < g.nbox; ++b) {
+      const int row = row0 + b * g.box_rows;
+      tma_load_3d(tile + (size_t)(HP + b * g.box_rows) * NL, &tmain, x0, rd1 ? row : o, rd1 ? o : row, bar);
+    }
+    if (halo_lo) {
+      if (crank > 0) tma_load_3d(tile, &th4, x0, rd1 ? row0 - HP : o, rd1 ? o : row0 - HP, bar);
+      else tma_load_3d(tile, &tlo, x0, rd1 ? g.lo_row : o, rd1 ? o : g.lo_row, bar);
+    }
+    if (halo_hi) {
+      if (crank < CL - 1) tma_load_3d(tile + (size_t)(HP + ML) * NL, &th4, x0, rd1 ? row0 + ML : o, rd1 ? o : row0 + ML, bar);
+      else tma_load_3d(tile + (size_t)(HP + ML) * NL, &thi, x0, rd1 ? g.hi_row : o, rd1 ? o : g.hi_row, bar);
+    }
+  };
+  auto sync_all = [&]() {
+    if (CL > 1) cl_sync();
+    else __syncthreads();
+  };
+  // state of chunk q of this rank's line, q outside [0, P): around the ring, or a neighbouring rank's
+  auto en_get = [&](int q) -> double2 {
+    if (q < 0) {
+      if (!a.wrap) return EN[(PL - q - 1) * NL + l];
+      q += P;
+    }
+    const int owner = q / PL, idx = q - owner * PL;
+    return owner == crank ? EN[idx * NL + l] : ld_cl(EN + idx * NL + l, owner);
+  };
+  auto st_get = [&](int q) -> double2 {
+    if (q >= P) {
+      if (!a.wrap) return ST[(PL + q - P) * NL + l];
+      q -= P;
+    }
+    const int owner = q / PL, idx = q - owner * PL;
+    return owner == crank ? ST[idx * NL + l] : ld_cl(ST + idx * NL + l, owner);
+  };
+
+  if (tid == 0) mbar_init(bar, 1);
+  sync_all();
+  const long ncl = gridDim.x / CL;
+  long t = blockIdx.x / CL;
+  if (tid == 0 && t < ntiles) issue(t);
+#ifdef PB_EMULATE
+  __syncthreads();
+#endif
+  uint32_t parity = 0;
+  const double *tw = tile + (size_t)(p * CT + HP - H) * NL + l;
+
+  for (; t < ntiles; t += ncl) {
+    const int ti = (int)(t % tiles_i), o = (int)(t / tiles_i);
+    const long line0 = (long)ti * NL + (long)o * a.ostride;  // z sweeps: index of the tile's first line in the xy plane
+    double rl[CT];
+
+    mbar_wait(bar, parity);
+    parity ^= 1;
+#ifdef PB_EMULATE
+    __syncthreads();  // the emulated load is a synchronous copy by thread 0
+#endif
+    {  // ---- A: rhs + forward recurrence (zero incoming state), chunk pulled out of the tile ----
+      const double2 *luf = a.luf + (size_t)type * CT;
+      const double l2c = a.cst[0], l1c = a.cst[1];
+      double rm1 = 0.0, rm2 = 0.0;
+      stream_chunk_tile<FAM, CT, NL>(a, tw, lo_sp, hi_sp, [&](auto lrc, double rhs, double) {
+        constexpr int lr = decltype(lrc)::value;
+        double2 c;
+        if (cc) c = make_double2(l2c, l1c);
+        else c = __ldg(luf + lr);
+        double x = fma(-c.x, rm2, rhs);
+        x = fma(-c.y, rm1, x);
+        rl[lr] = x;
+        rm2 = rm1;
+        rm1 = x;
+      });
+      EN[p * NL + l] = make_double2(rm1, rm2);
+      if (xr.on) {
+        const bool lv = ti * NL + l < a.nfast;
+        const int e = P - 1 - lp;  // chunks from the top of the slab
+        for (int k = 0; k < xr.nup; ++k)
+          if (e < xr.cnt_up[k] && lv) xr_store(xr.en_out[k] + ((long)(k * P + e) * xr.plane + line0 + l) * 4, make_double2(rm1, rm2), xr.epoch);
+        const int need = xr.need_f - crank * PL;  // forward end states of the chunks below this slab
+        if (tid < need * NL) {
+          const int e2 = tid / NL, ll = tid - e2 * NL;
+          double2 v = make_double2(0.0, 0.0);
+          if (ti * NL + ll < a.nfast) {
+            const unsigned long long *rec = xr.en_in + ((long)e2 * xr.plane + line0 + ll) * 4;
+            unsigned long long spin = 0;
+            while (!xr_try_load(rec, xr.epoch, &v)) xr_pause(spin);
+          }
+          EN[(PL + e2) * NL + ll] = v;
+        }
+      }
+    }
+    sync_all();  // the tile buffer is free (unless the add-back still reads it), the forward states are visible
+    if (!(ADDV && LATE) && tid == 0 && t + ncl < ntiles) issue(t + ncl);
+
+    {  // ---- B: add the carried forward state, backward recurrence (zero incoming state) ----
+      double2 st = make_double2(0.0, 0.0);
+      {
+        const int nf = a.nf[lp];
+        const double4 *Mp = a.Mf + (size_t)lp * a.mstride;
+        for (int j = 1; j <= nf; ++j) {
+          const double2 en = en_get(lp - j);
+          const double4 M = ldg4(Mp + j);
+          st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
+          st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
+        }
+      }
+      double x1 = 0.0, x2 = 0.0;
+      if (cc) {
+        const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
+        static_for<0, CT>([&](auto jc) {
+          constexpr int r = CT - 1 - decltype(jc)::value;
+          double x = rl[r];
+          x = fma(a.phi0[r].x, st.x, x);
+          x = fma(a.phi0[r].y, st.y, x);
+          x = fma(-u2, x2, x * ip);
+          x = fma(-u1, x1, x);
+          rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
+          x2 = x1;
+          x1 = x;
+        });
+      } else {
+        const double2 *ph = a.phi + (size_t)type * CT;
+        const double4 *lub = a.lub + (size_t)type * CT;
+        static_for<0, CT>([&](auto jc) {
+          constexpr int r = CT - 1 - decltype(jc)::value;
+          const double2 f = __ldg(ph + r);
+          const double4 c = ldg4(lub + r);
+          double x = rl[r];
+          x = fma(f.x, st.x, x);
+          x = fma(f.y, st.y, x);
+          x = fma(-c.y, x1, x);
+          x = fma(-c.z, x2, x);
+          x *= c.x;
+          rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
+          x2 = x1;
+          x1 = x;
+        });
+      }
+      ST[p * NL + l] = make_double2(x1, x2);
+      if (xr.on) {
+        const bool lv = ti * NL + l < a.nfast;
+        for (int k = 0; k < xr.ndn; ++k)
+          if (lp < xr.cnt_dn[k] && lv) xr_store(xr.st_out[k] + ((long)(k * P + lp) * xr.plane + line0 + l) * 4, make_double2(x1, x2), xr.epoch);
+        const int need = xr.need_b - (CL - 1 - crank) * PL;  // backward start states of the chunks above this slab
+        if (tid < need * NL) {
+          const int e2 = tid / NL, ll = tid - e2 * NL;
+          double2 v = make_double2(0.0, 0.0);
+          if (ti * NL + ll < a.nfast) {
+            const unsigned long long *rec = xr.st_in + ((long)e2 * xr.plane + line0 + ll) * 4;
+            unsigned long long spin = 0;
+            while (!xr_try_load(rec, xr.epoch, &v)) xr_pause(spin);
+          }
+          ST[(PL + e2) * NL + ll] = v;
+        }
+      }
+    }
+    sync_all();
+    if (ADDV && LATE && tid == 0 && t + ncl < ntiles) issue(t + ncl);
+
+    {  // ---- D: add the carried backward state, scale / add-back, TMA stores ----
+      double2 tb = make_double2(0.0, 0.0);
+      {
+        const int nb = a.nb[lp];
+        const double4 *Mp = a.Mb + (size_t)lp * a.mstride;
+        for (int j = 1; j <= nb; ++j) {
+          const double2 sv = st_get(lp + j);
+          const double4 M = ldg4(Mp + j);
+          tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
+          tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
+        }
+      }
+      double *sg = stage + (size_t)((p * GW + l / WB) * SR) * WB + (l % WB);
+      auto rowD = [&](auto rc, double gx, double gy, double xl) {
+        constexpr int r = decltype(rc)::value;
+        double val;
+        if (ADDV && LATE) {  // xl already holds scale * x_local + v
+          val = fma(gx * scale, tb.x, xl);
+          val = fma(gy * scale, tb.y, val);
+        } else {
+          double x = fma(gx, tb.x, xl);
+          x = fma(gy, tb.y, x);
+          val = x * scale;
+          if (ADDV) val += tw[(r + H) * NL];  // unreachable: the add-back is always LATE here
+        }
+        if constexpr (RING) val = fabs(val) * a.ring_s2;
+        sg[(r % SR) * WB] = val;
+      };
+      const double2 *ps = a.psi + (size_t)type * CT;
+      static_for<0, CT / SR>([&](auto gc) {
+        constexpr int r0 = decltype(gc)::value * SR;
+        if ((tid & 31) == 0) tma_store_wait_read();  // this warp's previous stores have left its part of the stage
+        __syncwarp();
+        if (cc) {
+          static_for<r0, r0 + SR>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            rowD(rc, a.psi0[r].x, a.psi0[r].y, rl[r]);
+          });
+        } else {
+          static_for<r0, r0 + SR>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            const double2 gq = __ldg(ps + r);
+            rowD(rc, gq.x, gq.y, rl[r]);
+          });
+        }
+        fence_async_smem();
+        __syncwarp();
+        if ((tid & 31) == 0) {  // every warp hands the rows of its own chunks to the TMA unit: no block-wide barrier
+#pragma unroll
+          for (int w = 0; w < (NL < 32 ? 32 / NL : 1); ++w) {
+            const int q = NL < 32 ? a.perm[crank * PL + tid / NL + w] : p;
+            const int x0 = ti * NL + (NL < 32 ? 0 : (l / WB) * WB);
+            const int row = (crank * PL + q) * CT + r0;
+            const int c1 = rd1 ? row : o, c2 = rd1 ? o : row;
+            const double *src = stage + (size_t)((q * GW + (NL < 32 ? 0 : l / WB)) * SR) * WB;
+            if constexpr (RING) {
+              if (a.acc == 2) tma_reduce_max_3d(&tout, x0, c1, c2, src);
+              else tma_store_3d(&tout, x0, c1, c2, src);
+            } else {
+              if (a.acc) tma_reduce_add_3d(&tout, x0, c1, c2, src);
+              else tma_store_3d(&tout, x0, c1, c2, src);
+            }
+          }
+          tma_store_commit();
+        }
+      });
+    }
+  }
+  if ((tid & 31) == 0) tma_store_wait_read();
+  if (CL > 1) cl_sync();  // nobody leaves while a neighbour may still read its states
+}
+
+// Host side: tensor maps, per-CTA chunk order, cluster launch.  Returns cudaErrorNotSupported when
+// the geometry does not fit (the caller falls back to the other kernels).
+template <int FAM, int NL, bool ADDV>
+static cudaError_t launch_yz_ring(const SweepDev &a0, const double *v, double *out, const double *hlo, const double *hhi,
+                                  const XRing *xrp, cudaStream_t st) {
+  constexpr int H = FT<FAM>::H, PL = kBlockThreads / NL, ML = PL * 32, SR = NL >= 32 ? 8 : 16, WB = NL < 32 ? NL : 32;
+  const int m = a0.m;
+  if (a0.C != 32 || !a0.implicit || a0.P % PL != 0 || m != 32 * a0.P || (hlo == nullptr) != (hhi == nullptr)) return cudaErrorNotSupported;
+  const int CL = a0.P / PL;
+  if (CL != 1 && CL != 2 && CL != 4 && CL != 8) return cudaErrorNotSupported;
+  SweepDev a = a0;
+  if (a.mstride == 0) a.mstride = a.P + 1;
+  for (int c = 0; c < CL; ++c) {  // chunk order inside every CTA: table chunks first, so they share warps
+    int k = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int q = 0; q < PL; ++q) {
+        const bool is_const = a.has_const && a.ctype[c * PL + q] == 0;
+        if ((pass == 0) != is_const) a.perm[c * PL + k++] = (unsigned char)q;
+      }
+  }
+  const bool ysweep = a.rstride < a.ostride;
+  const uint64_t ax = (uint64_t)a.nfast;
+  const uint64_t d1 = ysweep ? (uint64_t)m : (uint64_t)a.nouter, d2 = ysweep ? (uint64_t)a.nouter : (uint64_t)m;
+  const uint64_t s1 = (uint64_t)(ysweep ? a.rstride : a.ostride) * 8, s2 = (uint64_t)(ysweep ? a.ostride : a.rstride) * 8;
+  PipeGeo g;
+  g.rowdim = ysweep ? 1 : 2;
+  g.box_rows = ML < 256 ? ML : 256;
+  g.nbox = ML / g.box_rows;
+  g.halo = 0; g.lo_row = 0; g.hi_row = 0;
+  TileMap tmain, th4, tlo, thi, tout;
+  if (!encode_tile_map(&tmain, v, ax, d1, d2, s1, s2, NL, ysweep ? g.box_rows : 1, ysweep ? 1 : g.box_rows)) return cudaErrorNotSupported;
+  if (!encode_tile_map(&th4, v, ax, d1, d2, s1, s2, NL, ysweep ? 4 : 1, ysweep ? 1 : 4)) return cudaErrorNotSupported;
+  tlo = th4; thi = th4;
+  if (!encode_tile_map(&tout, out, ax, d1, d2, s1, s2, WB, ysweep ? SR : 1, ysweep ? 1 : SR, false, a.acc == 2)) return cudaErrorNotSupported;
+  if (hlo != nullptr) {  // z-slab halo planes received from the neighbours: {ax, ay, H} each
+    if (ysweep) return cudaErrorNotSupported;
+    if (!encode_tile_map(&tlo, hlo, ax, d1, H, s1, s2, NL, 1, 4) || !encode_tile_map(&thi, hhi, ax, d1, H, s1, s2, NL, 1, 4))
+      return cudaErrorNotSupported;
+    g.halo = 1; g.lo_row = H - 4; g.hi_row = 0;
+  } else if (a.wrap) {  // periodic: rows m-4..m-1 and 0..3 of the field itself
+    g.halo = 1; g.lo_row = m - 4; g.hi_row = 0;
+  }
+  XRing xr;
+  memset(&xr, 0, sizeof(xr));
+  if (xrp != nullptr) {
+    xr = *xrp;
+    if (xr.on && (ysweep || xr.need_f > kXExt || xr.need_b > kXExt)) return cudaErrorNotSupported;
+  }
+  const size_t smem = ((size_t)(ML + 8) * NL + (size_t)PL * SR * NL) * sizeof(double) + 2 * (size_t)(PL + kXExt) * NL * sizeof(double2) + 16;
+  static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
+  void (*kfn)(SweepDev, TileMap, TileMap, TileMap, TileMap, TileMap, PipeGeo, XRing) = nullptr;
+  int slot = 0;
+  if (a.ring) {
+    if constexpr (!ADDV && FAM == F_R4) kfn = sweep_yz_ring_kernel<FAM, NL, ADDV, false, true>;
+    slot = 1;
+  } else if (ADDV) {
+    if (!late) return cudaErrorNotSupported;
+    if constexpr (ADDV) kfn = sweep_yz_ring_kernel<FAM, NL, ADDV, true, false>;
+  } else {
+    if constexpr (!ADDV) kfn = sweep_yz_ring_kernel<FAM, NL, ADDV, false, false>;
+  }
+  if (kfn == nullptr) return cudaErrorNotSupported;
+  static bool configured[2] = {false, false};
+  if (!configured[slot]) {
+    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured[slot] = true;
+  }
+  const long ntiles = (long)((a.nfast + NL - 1) / NL) * a.nouter;
+  long ncl = CL == 1 ? 2L * sm_count() : (long)max_active_clusters_cached(reinterpret_cast<const void *>(kfn), CL, smem);
+  if (ncl < 1) return cudaErrorNotSupported;
+  if (ntiles < ncl) ncl = ntiles;
+#ifdef PB_EMULATE
+  emul::launch_cluster(dim3((unsigned)(ncl * CL)), CL, dim3(kBlockThreads), smem, [&] { kfn(a, tmain, th4, tlo, thi, tout, g, xr); });
+#else
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(ncl * CL));
+  cfg.blockDim = dim3(kBlockThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, kfn, a, tmain, th4, tlo, thi, tout, g, xr);
+  if (err != cudaSuccess) return err;
+#endif
+  ++g_launches;
+  ++g_pipe_launches;
+  ++g_ring_launches;
+  return cudaGetLastError();
+}
+
+template <int FAM, bool ADDV>
+cudaError_t launch_ring_f(int lines, const SweepDev &a, const double *v, double *out, const double *hlo, const double *hhi,
+                          const XRing *xr, cudaStream_t st) {
+  if (lines == 16) return launch_yz_ring<FAM, 16, ADDV>(a, v, out, hlo, hhi, xr, st);
+  if (lines == 32) return launch_yz_ring<FAM, 32, ADDV>(a, v, out, hlo, hhi, xr, st);
+  if (lines == 64) return launch_yz_ring<FAM, 64, ADDV>(a, v, out, hlo, hhi, xr, st);
+  return cudaErrorNotSupported;
+}
+
+}  // namespace pb

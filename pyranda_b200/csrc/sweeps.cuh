@@ -3,6 +3,7 @@
 #pragma once
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -25,6 +26,7 @@ namespace pb {
 
 extern std::atomic<long> g_launches;
 extern std::atomic<long> g_pipe_launches;
+extern std::atomic<long> g_ring_launches;
 extern int g_reg_kernels;
 extern int g_pipe_kernels;
 int sm_count();
@@ -2036,6 +2038,10 @@ static cudaError_t launch_x_pipe(const SweepDev &a, const double *v, double *out
   ++g_pipe_launches;
   return cudaGetLastError();
 }
+
+}  // namespace pb
+#include "ring.cuh"
+namespace pb {
 
 // ---- launchers -----------------------------------------------------------------------------------
 template <int FAM, int NL, bool PLAIN, bool ADDV>

@@ -4,4 +4,5 @@
 namespace pb {
 template cudaError_t launch_yz_f<F_R4, true>(int, const SweepDev &, const double *, double *, const double *, const double *, double *, const EpiArgs &, cudaStream_t);
 template cudaError_t launch_x_f<F_R4, true>(int, const SweepDev &, const double *, double *, const EpiArgs &, cudaStream_t);
+template cudaError_t launch_ring_f<F_R4, true>(int, const SweepDev &, const double *, double *, const double *, const double *, const XRing *, cudaStream_t);
 }  // namespace pb

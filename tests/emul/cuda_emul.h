@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -67,6 +68,11 @@ namespace emul {
 inline thread_local dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 inline thread_local std::barrier<> *t_barrier = nullptr;
 inline thread_local double *t_smem = nullptr;
+// thread-block clusters: the CTAs of a cluster run concurrently, see each other's shared memory
+// and meet at a cluster-wide barrier
+inline thread_local int t_cluster_rank = 0, t_cluster_size = 1;
+inline thread_local std::barrier<> *t_cluster_barrier = nullptr;
+inline thread_local double *const *t_cluster_smem = nullptr;
 
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body) {
   const unsigned nthreads = block.x * block.y * block.z;
@@ -95,6 +101,39 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
           for (auto &x : th) x.join();
         }
       }
+}
+inline void launch_cluster(dim3 grid, int cl, dim3 block, size_t smem_bytes, const std::function<void()> &body) {
+  const unsigned nthreads = block.x * block.y * block.z;
+  for (unsigned c0 = 0; c0 < grid.x; c0 += (unsigned)cl) {
+    std::vector<std::vector<double>> smem(cl, std::vector<double>(smem_bytes / sizeof(double) + 1));
+    std::vector<double *> sptr(cl);
+    for (int c = 0; c < cl; ++c) sptr[c] = smem[c].data();
+    std::vector<std::unique_ptr<std::barrier<>>> bars;
+    for (int c = 0; c < cl; ++c) bars.emplace_back(new std::barrier<>(nthreads));
+    std::barrier<> cbar(nthreads * cl);
+    auto worker = [&](int c, unsigned t) {
+      t_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      t_blockIdx = dim3(c0 + c, 0, 0);
+      t_blockDim = block;
+      t_gridDim = grid;
+      t_barrier = bars[c].get();
+      t_smem = sptr[c];
+      t_cluster_rank = c;
+      t_cluster_size = cl;
+      t_cluster_barrier = &cbar;
+      t_cluster_smem = sptr.data();
+      body();
+      bars[c]->arrive_and_drop();
+      cbar.arrive_and_drop();
+      t_cluster_rank = 0;
+      t_cluster_size = 1;
+    };
+    std::vector<std::thread> th;
+    th.reserve(nthreads * cl);
+    for (int c = 0; c < cl; ++c)
+      for (unsigned t = 0; t < nthreads; ++t) th.emplace_back(worker, c, t);
+    for (auto &x : th) x.join();
+  }
 }
 }  // namespace emul
 
