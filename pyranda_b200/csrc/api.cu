@@ -100,8 +100,9 @@ void free_sweep(SweepPlan &sp) {
 int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool periodic) {
   sp.xr_ok = false;
   const int n = sp.n, np = sp.np, m = n / np, r = sp.rank;
-  if (m % 32 != 0 || m / 32 > kMaxChunks) return PB_OK;
+  if (m % 32 != 0) return PB_OK;
   const int P = m / 32, Pg = n / 32;
+  if (P != 4 && P != 8 && P != 16 && P != 32) return PB_OK;  // slabs the ring kernel tiles: 128, 256, 512, 1024 planes
   LineTables gt;
   try { gt = build_line_tables(n, bands, periodic, Pg); }
   catch (const std::exception &) { return PB_OK; }

@@ -17,7 +17,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ._lib import OP, ParcopError, check
+import ctypes
+
+from ._lib import OP, ParcopError, XRingC, check
 from .plan import ParcopPlan
 
 # z operator behind each distributed call and its halo width (nor of the stencil)
@@ -36,13 +38,17 @@ class _PeerBuffers:
     The sets alternate per operator, so a rank never overwrites planes its neighbour may still be
     reading (the neighbour's next epoch is ordered after that read)."""
 
-    def __init__(self, lib, group, rank, world, plane, dev):
+    def __init__(self, lib, group, rank, world, plane, dev, slots=0):
         import torch.distributed._symmetric_memory as symm
         self.L = lib
         self.rank, self.world, self.n = rank, world, 4 * plane
         self.set_len = (2 + world) * self.n
         self.flag_off = 2 * self.set_len          # [world] uint64 flags + scratch counter, in doubles
-        self.buf = symm.empty(2 * self.set_len + world + 2, dtype=torch.float64, device=dev)
+        # the fused z sweep (pb_z_ring): incoming chunk-state records, `slots` x plane x 4 words each way
+        self.slots = slots
+        self.rec_off = self.flag_off + ((world + 2 + 1) // 2) * 2
+        self.rec_len = slots * plane * 4
+        self.buf = symm.empty(self.rec_off + 2 * self.rec_len, dtype=torch.float64, device=dev)
         self.buf.zero_()
         self.h = symm.rendezvous(self.buf, dist.group.WORLD if group is None else group)
         self.base = [int(p) for p in self.h.buffer_ptrs]
@@ -64,6 +70,18 @@ class _PeerBuffers:
     def iface_all(self):
         off = self._off("iface")
         return self.buf[off:off + self.world * self.n]
+
+    def ring_args(self, epoch):
+        """pb_xring for this rank: its own record buffers and the peer-mapped ones of the ranks its
+        chunk states travel to (forward end states upwards, backward start states downwards)."""
+        x = XRingC()
+        x.epoch = epoch
+        x.en_in = self.base[self.rank] + 8 * self.rec_off
+        x.st_in = self.base[self.rank] + 8 * (self.rec_off + self.rec_len)
+        for k in range(3):
+            x.en_out[k] = self.base[(self.rank + 1 + k) % self.world] + 8 * self.rec_off
+            x.st_out[k] = self.base[(self.rank - 1 - k) % self.world] + 8 * (self.rec_off + self.rec_len)
+        return x
 
     def exchange(self, copies, peers, stream):
         """copies: (peer, what, slot, source tensor); then the flag handshake with `peers`."""
@@ -109,10 +127,22 @@ class DistributedParcop:
         self._xmask = {}
         self._peers = sorted({r for r in (self.lo_rank(), self.hi_rank()) if r is not None and r != self.rank})
         self._pb = None
+        # which z operators have the fused form (one ring kernel per sweep, chunk states over peer memory)
+        self._ring, slots = {}, 0
+        if self.world > 1 and os.environ.get("PB_NO_RING", "0") != "1":
+            for nm, (opname, _) in _ZOPS.items():
+                if not _IMPLICIT[nm]:
+                    continue
+                v = [ctypes.c_int() for _ in range(4)]
+                check(self.plan.L, self.plan.L.pb_z_ring_info(self.plan._h, OP[opname], *[ctypes.byref(c) for c in v]))
+                if v[0].value + v[1].value > 0:
+                    self._ring[nm] = True
+                    slots = max(slots, v[0].value, v[1].value)
+        self._ring_epoch = 0
         if (self.dev.type == "cuda" and self.world > 1 and self.plane % 2 == 0  # 16-byte aligned planes
                 and os.environ.get("PB_NO_PEER_MEMORY", "0") != "1"):
             try:
-                self._pb = _PeerBuffers(self.plan.L, group, self.rank, self.world, self.plane, self.dev)
+                self._pb = _PeerBuffers(self.plan.L, group, self.rank, self.world, self.plane, self.dev, slots)
             except Exception as exc:  # no IPC / symmetric-memory support: NCCL send/recv instead
                 import warnings
                 warnings.warn("peer-memory exchange unavailable (%s); using NCCL send/recv" % exc)
@@ -121,7 +151,14 @@ class DistributedParcop:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # all ranks or none
         if not ok.item():
             self._pb = None
-        self._tmp = None
+        if self._pb is None:
+            self._ring = {}
+        elif self._ring:  # every rank must take the same path for an operator
+            names = sorted(n for n in _ZOPS if _IMPLICIT[n])
+            have = torch.tensor([1 if n in self._ring else 0 for n in names], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(have, op=dist.ReduceOp.MIN, group=group)
+            self._ring = {n: True for n, h in zip(names, have.tolist()) if h}
+        self._tmp = self._tmp2 = None
         # MPI_CART_SHIFT (comm.f90:186)
         self.lo, self.hi = self.lo_rank(), self.hi_rank()
 
@@ -175,8 +212,11 @@ class DistributedParcop:
                 w.wait()
 
     # ---------------------------------------------------------------- operators
-    def zop_into(self, name, f, out):
-        """One distributed z sweep: halo exchange -> local solve -> all-gather -> finish."""
+    def zop_into(self, name, f, out, epi=0, s2=0.0):
+        """One distributed z sweep.  Fused form (pb_z_ring): halo planes into the neighbours' memory,
+        then ONE kernel that exchanges the chunk states tile by tile and applies the composite epilogue
+        (epi 0 store, 1 out += val, 2 out = |val| s2, 3 out = max(out, |val| s2)).  Otherwise the
+        partitioned form: halo exchange -> local solve -> interface exchange -> correction."""
         opname, h = _ZOPS[name]
         code = OP[opname]
         P, L = self.plan, self.plan.L
@@ -190,11 +230,28 @@ class DistributedParcop:
         if self.world > 1:
             self._halo_exchange(f, h)
         st = self._stream()
-        check(L, L.pb_z_local(P._h, code, f.data_ptr(), recv_lo.data_ptr(), recv_hi.data_ptr(), out.data_ptr(),
+        if name in self._ring:
+            self._ring_epoch += 1
+            x = self._pb.ring_args(self._ring_epoch)
+            check(L, L.pb_z_ring(P._h, code, f.data_ptr(), recv_lo.data_ptr(), recv_hi.data_ptr(), out.data_ptr(),
+                                 ctypes.byref(x), int(epi), float(s2), st))
+            return out
+        dst = out
+        if epi:  # composite epilogue by hand around the partitioned form
+            if self._tmp2 is None:
+                self._tmp2 = self.empty()
+            dst = self._tmp2
+        check(L, L.pb_z_local(P._h, code, f.data_ptr(), recv_lo.data_ptr(), recv_hi.data_ptr(), dst.data_ptr(),
                               iface_local.data_ptr(), st))
         if self.world > 1 and _IMPLICIT[name]:
             self._iface_exchange(code, iface_all, iface_local)
-            check(L, L.pb_z_finish(P._h, code, f.data_ptr(), iface_all.data_ptr(), out.data_ptr(), st))
+            check(L, L.pb_z_finish(P._h, code, f.data_ptr(), iface_all.data_ptr(), dst.data_ptr(), st))
+        if epi == 1:
+            out.add_(dst)
+        elif epi == 2:
+            torch.mul(dst.abs_(), s2, out=out)
+        elif epi == 3:
+            torch.maximum(out, dst.abs_().mul_(s2), out=out)
         return out
 
     def _iface_exchange(self, code, iface_all, iface_local):
@@ -229,52 +286,50 @@ class DistributedParcop:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
 
-    def _local_into(self, opname, f, out):
-        check(self.plan.L, self.plan.L.pb_apply(self.plan._h, OP[opname], f.data_ptr(), out.data_ptr(), self._stream()))
+    def _local_into(self, opname, f, out, epi=0, s2=0.0):
+        L = self.plan.L
+        if epi:
+            check(L, L.pb_apply_epi(self.plan._h, OP[opname], f.data_ptr(), out.data_ptr(), int(epi), float(s2), self._stream()))
+        else:
+            check(L, L.pb_apply(self.plan._h, OP[opname], f.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
     def apply_into(self, name, f, out):
-        """ddx ddy ddz dd8x dd8y dd8z d2x d2y d2z sfilter gfilter gfilterx/y/z laplacian ring."""
+        """ddx ddy ddz dd8x dd8y dd8z d2x d2y d2z sfilter gfilter gfilterx/y/z laplacian ring.  Composites
+        accumulate through the sweeps' own epilogues (TMA reduce-add / reduce-max stores), as on one GPU."""
         if name in ("ddx", "ddy", "ddx_odd", "ddy_odd", "dd4x", "dd4y", "dd8x_odd", "dd8y_odd", "dd8x", "dd8y", "d2x", "d2y", "gfilterx", "gfiltery", "sfilterx", "sfiltery"):
             return self._local_into(name, f, out)
         if name in _ZOPS:
             return self.zop_into(name, f, out)
-        if self._tmp is None:
-            self._tmp = self.empty()
-        tmp = self._tmp
         if name in ("sfilter", "gfilter"):  # operators.f90:849-851,873-875
+            if self._tmp is None:
+                self._tmp = self.empty()
+            tmp = self._tmp
             k = name[0]
             self._local_into(k + "filterx", f, out)
             self._local_into(k + "filtery", out, tmp)
             return self.zop_into(k + "filterz", tmp, out)
         if name == "laplacian":  # operators.f90:523-526
             self._local_into("d2x", f, out)
-            self._local_into("d2y", f, tmp)
-            out.add_(tmp)
-            self.zop_into("d2z", f, tmp)
-            return out.add_(tmp)
+            self._local_into("d2y", f, out, 1)
+            return self.zop_into("d2z", f, out, 1)
         if name == "ring":  # operators.f90:638 with the Cartesian d1 = dx, d2 = dy, d3 = dz
-            self._local_into("dd8x", f, out)
-            out.abs_().mul_(self.plan.dx ** 2)
-            for nm, d in (("dd8y", self.plan.dy),):
-                self._local_into(nm, f, tmp)
-                torch.maximum(out, tmp.abs_().mul_(d ** 2), out=out)
-            self.zop_into("dd8z", f, tmp)
-            return torch.maximum(out, tmp.abs_().mul_(self.plan.dz ** 2), out=out)
+            self._local_into("dd8x", f, out, 2, self.plan.dx ** 2)
+            self._local_into("dd8y", f, out, 3, self.plan.dy ** 2)
+            return self.zop_into("dd8z", f, out, 3, self.plan.dz ** 2)
         raise KeyError(name)
 
     def apply(self, name, f):
         return self.apply_into(name, f, self.empty())
 
+    def _div_into(self, out, fx, fy, fz, bx=True, by=True, bz=True):
+        """ddx + ddy + ddz accumulated in place; b*: the flux is odd across its own symmetry plane."""
+        self._local_into("ddx_odd" if bx else "ddx", fx, out)
+        self._local_into("ddy_odd" if by else "ddy", fy, out, 1)
+        return self.zop_into("ddz_odd" if bz else "ddz", fz, out, 1)
+
     def divergence(self, fx, fy, fz):  # operators.f90:48-52 (each flux is odd across its own symmetry plane)
-        out = self.empty()
-        if self._tmp is None:
-            self._tmp = self.empty()
-        self._local_into("ddx_odd", fx, out)
-        self._local_into("ddy_odd", fy, self._tmp)
-        out.add_(self._tmp)
-        self.zop_into("ddz_odd", fz, self._tmp)
-        return out.add_(self._tmp)
+        return self._div_into(self.empty(), fx, fy, fz)
 
     def divergencetensor(self, fxx, fxy, fxz, fyx, fyy, fyz, fzx, fzy, fzz):
         """operators.f90:97-123 (Cartesian): the divergence of each column; the diagonal components are
@@ -282,31 +337,24 @@ class DistributedParcop:
         if self.plan.coordsys != 0:
             raise ParcopError("divT on a z-slab: only the Cartesian branch is implemented")
         cols = ((fxx, fyx, fzx), (fxy, fyy, fzy), (fxz, fyz, fzz))
-        outs = []
-        if self._tmp is None:
-            self._tmp = self.empty()
-        for c, (a, b, g) in enumerate(cols):
-            out = self.empty()
-            self._local_into("ddx" if c == 0 else "ddx_odd", a, out)
-            self._local_into("ddy" if c == 1 else "ddy_odd", b, self._tmp)
-            out.add_(self._tmp)
-            self.zop_into("ddz" if c == 2 else "ddz_odd", g, self._tmp)
-            outs.append(out.add_(self._tmp))
-        return tuple(outs)
+        return tuple(self._div_into(self.empty(), a, b, g, c != 0, c != 1, c != 2) for c, (a, b, g) in enumerate(cols))
 
     def pringv(self, vx, vy, vz):
         """operators.f90:645-699 with L = 1 (Cartesian): max over directions of max over components of
-        |d8| times the spacing; nine sweeps, three of them distributed."""
+        |d8| times the spacing; nine sweeps with a running maximum, three of them distributed."""
         if self.plan.coordsys != 0:
             raise ParcopError("ringV on a z-slab: only the Cartesian branch is implemented")
-        if self._tmp is None:
-            self._tmp = self.empty()
-        out, tmp = self.empty(), self._tmp
-        out.zero_()
+        out = self.empty()
+        first = True
         for k, (nm, d) in enumerate((("dd8x", self.plan.dx), ("dd8y", self.plan.dy), ("dd8z", self.plan.dz))):
             for c, comp in enumerate((vx, vy, vz)):  # the component normal to a symmetry plane is odd across it (:661-671)
-                self.apply_into(nm + "_odd" if c == k else nm, comp, tmp)
-                torch.maximum(out, tmp.abs_().mul_(d), out=out)
+                op = nm + "_odd" if c == k else nm
+                epi = 2 if first else 3
+                if nm == "dd8z":
+                    self.zop_into(op, comp, out, epi, d)
+                else:
+                    self._local_into(op, comp, out, epi, d)
+                first = False
         return out
 
     def grads(self, f):  # operators.f90:191-193

@@ -59,8 +59,11 @@ for n in ((32, 32, 128 * world), (48, 32, 256 * world)):
             err = rel_linf(eng.apply(name, loc).cpu().numpy(), ref(f)[:, :, sl])
             worst = max(worst, err)
             assert err < 1e-12, (name, n, periodic, rank, err)
-        assert eng._xmask[OP["ddz"]] == "neighbours", eng._xmask
-print("rank", rank, "worst", worst)
+        assert "ddz" in eng._ring or eng._xmask[OP["ddz"]] == "neighbours", (eng._ring, eng._xmask)
+        if os.environ.get("PB_NO_PEER_MEMORY", "0") != "1" and os.environ.get("PB_NO_RING", "0") != "1" and az >= 256:
+            assert "ddz" in eng._ring and "sfilterz" in eng._ring, eng._ring   # the fused sweep ran
+from pyranda_b200 import _lib
+print("rank", rank, "worst", worst, "ring launches", _lib.load().pb_ring_launch_count())
 dist.destroy_process_group()
 """
 
@@ -70,7 +73,8 @@ def _free_port():
 
 
 @pytest.mark.gpu
-def test_zslab_nccl(tmp_path):
+@pytest.mark.parametrize("mode", ["fused", "partitioned-peer", "partitioned-nccl"])
+def test_zslab_nccl(tmp_path, mode):
     import torch
     world = torch.cuda.device_count()
     if world < 2:
@@ -81,6 +85,13 @@ def test_zslab_nccl(tmp_path):
     script.write_text(WORKER.format(root=ROOT))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
-    r = subprocess.run(cmd, env=dict(os.environ, OMP_NUM_THREADS="4"), capture_output=True, text=True, timeout=900)
+    # fused: ring kernel with chunk states over peer memory; partitioned-peer: local solve + correction with the
+    # peer-memory exchange kernel; partitioned-nccl: the same over NCCL send/recv (north_star's plumbing)
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    if mode == "partitioned-peer":
+        env["PB_NO_RING"] = "1"
+    if mode == "partitioned-nccl":
+        env["PB_NO_PEER_MEMORY"] = "1"
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("worst") == world

@@ -144,7 +144,7 @@ OPS = [
 
 
 @pytest.mark.parametrize("periodic", [True, False])
-@pytest.mark.parametrize("n,world,fused", [((20, 3, 256), 2, 3), ((34, 2, 384), 3, 4), ((16, 2, 512), 4, 4), ((8, 2, 768), 2, 4)])
+@pytest.mark.parametrize("n,world,fused", [((20, 3, 256), 2, 3), ((34, 2, 384), 3, 4), ((16, 2, 512), 4, 4), ((16, 2, 1024), 2, 4)])
 def test_fused_zslab_ranks_as_threads(n, world, fused, periodic, oracle_mod, lib):
     worst = _fused_zslab(lib, oracle_mod, n, world, periodic, OPS)
     done = {k: v for k, v in worst.items() if v is not None}
