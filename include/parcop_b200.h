@@ -173,6 +173,14 @@ typedef struct pb_xring {
   unsigned int epoch;
   void *en_in, *st_in;
   void *en_out[3], *st_out[3];
+  /* push = 1: the kernel also moves the halo planes (no separate exchange): halo_dst[0] = the lower
+   * neighbour's upper halo buffer, halo_dst[1] = the upper neighbour's lower halo buffer (NULL at a
+   * physical end), flags / counter / epoch as for pb_peer_exchange */
+  int push, npeers;
+  void *halo_dst[2];
+  void *flag_remote[2], *flag_local[2];
+  unsigned long long halo_epoch;
+  void *counter;
 } pb_xring;
 int pb_z_ring_info(pb_plan *plan, int zop, int *need_f, int *need_b, int *nup, int *ndn);
 int pb_z_ring(pb_plan *plan, int zop, const double *d_val, const double *d_recv_lo, const double *d_recv_hi,

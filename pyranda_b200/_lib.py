@@ -30,7 +30,9 @@ EXPORTS = [
 
 class XRingC(ctypes.Structure):
     """pb_xring of include/parcop_b200.h."""
-    _fields_ = [("epoch", ctypes.c_uint), ("en_in", _vp), ("st_in", _vp), ("en_out", _vp * 3), ("st_out", _vp * 3)]
+    _fields_ = [("epoch", ctypes.c_uint), ("en_in", _vp), ("st_in", _vp), ("en_out", _vp * 3), ("st_out", _vp * 3),
+                ("push", ctypes.c_int), ("npeers", ctypes.c_int), ("halo_dst", _vp * 2), ("flag_remote", _vp * 2),
+                ("flag_local", _vp * 2), ("halo_epoch", ctypes.c_ulonglong), ("counter", _vp)]
 
 
 class ParcopError(RuntimeError):

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libparcop_b200.so")
 SOURCES = ["tables.cpp", "kernels.cu", "api.cu", "sweeps_d1.cu", "sweeps_r3.cu", "sweeps_r4.cu", "sweeps_r4v.cu"]
-DEPS = SOURCES + ["kernels.cuh", "sweeps.cuh", "tables.hpp", os.path.join("..", "..", "include", "parcop_b200.h")]
+DEPS = SOURCES + ["kernels.cuh", "sweeps.cuh", "ring.cuh", "tma.cuh", "tables.hpp", os.path.join("..", "..", "include", "parcop_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 OBJ_DIR = os.path.join(HERE, "build")

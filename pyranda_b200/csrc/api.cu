@@ -930,6 +930,29 @@ int pb_z_ring(pb_plan *pl, int zop, const double *d_val, const double *recv_lo, 
     xr.st_out[h] = (unsigned long long *)x->st_out[h];
     if ((h < xr.nup && !xr.en_out[h]) || (h < xr.ndn && !xr.st_out[h])) return fail(PB_ERR_ARG, "missing peer record buffer");
   }
+  static const int nopoll = getenv("PB_XR_NOPOLL") ? atoi(getenv("PB_XR_NOPOLL")) : 0;  // timing experiments only: results are wrong
+  xr.nopoll = nopoll;
+  xr.push = 0;
+  if (x->push) {
+    if (x->npeers < 0 || x->npeers > 2 || !x->counter || x->halo_epoch == 0) return fail(PB_ERR_ARG, "bad halo push arguments");
+    const long plane = xr.plane;
+    const int h = sp.st.nor;
+    if ((plane * h) % 2) return fail(PB_ERR_UNSUPPORTED, "halo push needs 16-byte aligned planes");
+    xr.push = 1;
+    xr.npeers = x->npeers;
+    xr.push_n = plane * h;
+    xr.push_src[0] = d_val;                                  // my first planes -> the lower neighbour's upper halo
+    xr.push_src[1] = d_val + (long)(pl->a[2] - h) * plane;   // my last planes -> the upper neighbour's lower halo
+    xr.push_dst[0] = (double *)x->halo_dst[0];
+    xr.push_dst[1] = (double *)x->halo_dst[1];
+    for (int q = 0; q < x->npeers; ++q) {
+      if (!x->flag_remote[q] || !x->flag_local[q]) return fail(PB_ERR_ARG, "missing flag address");
+      xr.hflag_remote[q] = (unsigned long long *)x->flag_remote[q];
+      xr.hflag_local[q] = (const volatile unsigned long long *)x->flag_local[q];
+    }
+    xr.hepoch = x->halo_epoch;
+    xr.hcounter = (unsigned int *)x->counter;
+  }
   // both halo planes or none reach the kernel: a rank at a physical end passes its own buffer for the unused side
   const double *lo = recv_lo ? recv_lo : recv_hi, *hi = recv_hi ? recv_hi : recv_lo;
   const cudaError_t err = launch_sweep_ring(sp.st.fam, 0, sp.devx, d_val, d_out, lo, hi, &xr, epi, (cudaStream_t)stream);

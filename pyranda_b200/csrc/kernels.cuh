@@ -73,6 +73,17 @@ struct XRing {
   unsigned long long *en_out[kXHops], *st_out[kXHops];   // those ranks' incoming buffers (peer-mapped)
   const unsigned long long *en_in, *st_in;               // this rank's incoming buffers [slot][line][4]
   long plane;                                            // lines per xy-plane
+  // halo planes pushed by the sweep kernel itself (push = 0: the caller has exchanged them): every CTA
+  // copies its share of this rank's first / last planes into the neighbours' halo buffers, the last
+  // one publishes hepoch in the neighbours' flag words; halo boxes are requested once theirs is seen
+  int push, npeers, nopoll;
+  const double *push_src[2];
+  double *push_dst[2];
+  long push_n;                                           // doubles per copy
+  unsigned long long *hflag_remote[2];
+  const volatile unsigned long long *hflag_local[2];
+  unsigned long long hepoch;
+  unsigned int *hcounter;
 };
 
 struct EpiArgs {

@@ -58,6 +58,11 @@ __device__ __forceinline__ void xr_pause(unsigned long long &spin) {
   if (++spin > (1ull << 24)) __trap();  // a neighbour that never arrives must not hang the GPU
   if (spin > 64) __nanosleep(64);
 }
+__device__ __forceinline__ void xr_fence_sys() { __threadfence_system(); }
+__device__ __forceinline__ unsigned int xr_count(unsigned int *c) { return atomicAdd(c, 1u); }
+__device__ __forceinline__ void xr_flag_set(unsigned long long *f, unsigned long long v) { *reinterpret_cast<volatile unsigned long long *>(f) = v; }
+__device__ __forceinline__ unsigned long long xr_flag_get(const volatile unsigned long long *f) { return *f; }
+__device__ __forceinline__ void xr_fence_tma() { __threadfence_system(); asm volatile("fence.proxy.async;" ::: "memory"); }
 #else
 inline int cl_rank() { return emul::t_cluster_rank; }
 inline int cl_size() { return emul::t_cluster_size; }
@@ -85,6 +90,11 @@ inline bool xr_try_load(const unsigned long long *rec, unsigned int epoch, doubl
   return true;
 }
 inline void xr_pause(unsigned long long &) { std::this_thread::yield(); }  // the other "rank" is another host thread
+inline void xr_fence_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned int xr_count(unsigned int *c) { return __atomic_fetch_add(c, 1u, __ATOMIC_ACQ_REL); }
+inline void xr_flag_set(unsigned long long *f, unsigned long long v) { __atomic_store_n(f, v, __ATOMIC_RELEASE); }
+inline unsigned long long xr_flag_get(const volatile unsigned long long *f) { return __atomic_load_n(const_cast<const unsigned long long *>(f), __ATOMIC_ACQUIRE); }
+inline void xr_fence_tma() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 #endif
 
 // every chunk handled by this warp has constant coefficients (see warp_all_const in sweeps.cuh)
@@ -135,12 +145,21 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   const uint32_t tx_bytes = (uint32_t)((ML + (halo_lo ? HP : 0) + (halo_hi ? HP : 0)) * NL * sizeof(double));
   const int row0 = crank * ML;
 
+  bool halo_seen = !xr.push;
   auto issue = [&](long t) {  // one thread: arm the barrier, describe this CTA's piece of the tile to the TMA unit
     const int x0 = (int)(t % tiles_i) * NL, o = (int)(t / tiles_i);
     mbar_expect_tx(bar, tx_bytes);
     for (int b = 0; b < g.nbox; ++b) {
       const int row = row0 + b * g.box_rows;
       tma_load_3d(tile + (size_t)(HP + b * g.box_rows) * NL, &tmain, x0, rd1 ? row : o, rd1 ? o : row, bar);
+    }
+    if (!halo_seen && g.halo && (crank == 0 || crank == CL - 1)) {  // the neighbours' planes have landed in this rank's halo buffers
+      for (int q = 0; q < xr.npeers; ++q) {
+        unsigned long long spin = 0;
+        while (xr_flag_get(xr.hflag_local[q]) < xr.hepoch) xr_pause(spin);
+      }
+      xr_fence_tma();
+      halo_seen = true;
     }
     if (halo_lo) {
       if (crank > 0) tma_load_3d(tile, &th4, x0, rd1 ? row0 - HP : o, rd1 ? o : row0 - HP, bar);
@@ -174,6 +193,27 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   };
 
   if (tid == 0) mbar_init(bar, 1);
+  if (xr.push) {  // compact_d1.f90:719-735 without a separate pass: my first / last planes into the neighbours' halo buffers
+    for (int c = 0; c < 2; ++c) {
+      if (xr.push_dst[c] == nullptr) continue;
+      const double2 *src = reinterpret_cast<const double2 *>(xr.push_src[c]);
+      double2 *dst = reinterpret_cast<double2 *>(xr.push_dst[c]);
+      const long n2 = xr.push_n / 2, stride = (long)gridDim.x * kBlockThreads;
+      long i = (long)blockIdx.x * kBlockThreads + tid;
+      for (; i + 3 * stride < n2; i += 4 * stride) {
+        const double2 v0 = src[i], v1 = src[i + stride], v2 = src[i + 2 * stride], v3 = src[i + 3 * stride];
+        dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3;
+      }
+      for (; i < n2; i += stride) dst[i] = src[i];
+    }
+    xr_fence_sys();
+    __syncthreads();
+    if (tid == 0 && xr_count(xr.hcounter) == gridDim.x - 1) {
+      *xr.hcounter = 0;
+      xr_fence_sys();
+      for (int q = 0; q < xr.npeers; ++q) xr_flag_set(xr.hflag_remote[q], xr.hepoch);
+    }
+  }
   sync_all();
   const long ncl = gridDim.x / CL;
   long t = blockIdx.x / CL;
@@ -219,7 +259,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         if (tid < need * NL) {
           const int e2 = tid / NL, ll = tid - e2 * NL;
           double2 v = make_double2(0.0, 0.0);
-          if (ti * NL + ll < a.nfast) {
+          if (ti * NL + ll < a.nfast && !xr.nopoll) {
             const unsigned long long *rec = xr.en_in + ((long)e2 * xr.plane + line0 + ll) * 4;
             unsigned long long spin = 0;
             while (!xr_try_load(rec, xr.epoch, &v)) xr_pause(spin);
@@ -284,7 +324,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         if (tid < need * NL) {
           const int e2 = tid / NL, ll = tid - e2 * NL;
           double2 v = make_double2(0.0, 0.0);
-          if (ti * NL + ll < a.nfast) {
+          if (ti * NL + ll < a.nfast && !xr.nopoll) {
             const unsigned long long *rec = xr.st_in + ((long)e2 * xr.plane + line0 + ll) * 4;
             unsigned long long spin = 0;
             while (!xr_try_load(rec, xr.epoch, &v)) xr_pause(spin);
@@ -441,8 +481,19 @@ static cudaError_t launch_yz_ring(const SweepDev &a0, const double *v, double *o
   if (ncl < 1) return cudaErrorNotSupported;
   if (ntiles < ncl) ncl = ntiles;
 #ifdef PB_EMULATE
+  if (xr.push) ncl = 1;  // emulated CTAs run one after the other: the flag handshake of the push needs them all resident
+#endif
+#ifdef PB_EMULATE
   emul::launch_cluster(dim3((unsigned)(ncl * CL)), CL, dim3(kBlockThreads), smem, [&] { kfn(a, tmain, th4, tlo, thi, tout, g, xr); });
 #else
+  static const bool plain1 = getenv("PB_RING_PLAIN_LAUNCH") ? atoi(getenv("PB_RING_PLAIN_LAUNCH")) != 0 : true;
+  if (CL == 1 && plain1) {  // no cluster: an ordinary launch
+    kfn<<<dim3((unsigned)ncl), dim3(kBlockThreads), smem, st>>>(a, tmain, th4, tlo, thi, tout, g, xr);
+    ++g_launches;
+    ++g_pipe_launches;
+    ++g_ring_launches;
+    return cudaGetLastError();
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(ncl * CL));

@@ -567,7 +567,9 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
     }
     T.Mf.assign((size_t)P * (P + 1) * 4, 0.0); T.Mb.assign((size_t)P * (P + 1) * 4, 0.0);
     T.nF.assign(P, 0); T.nB.assign(P, 0);
-    const long double tiny = 1e-22L;
+    // Terms are dropped once the transfer product falls below the rounding unit of the leading
+    // (identity) term: what they would add is below the last bit of the state they are added to.
+    const long double tiny = 2.2e-16L;
     auto mxabs = [](const M2 &x) { return std::max(std::max(fabsl(x.a), fabsl(x.b)), std::max(fabsl(x.c), fabsl(x.d))); };
     auto put4 = [](double *dst, const M2 &x) { dst[0] = (double)x.a; dst[1] = (double)x.b; dst[2] = (double)x.c; dst[3] = (double)x.d; };
     if (cyclic) {

@@ -71,11 +71,21 @@ class _PeerBuffers:
         off = self._off("iface")
         return self.buf[off:off + self.world * self.n]
 
-    def ring_args(self, epoch):
+    def ring_args(self, epoch, lo=None, hi=None, peers=()):
         """pb_xring for this rank: its own record buffers and the peer-mapped ones of the ranks its
-        chunk states travel to (forward end states upwards, backward start states downwards)."""
+        chunk states travel to (forward end states upwards, backward start states downwards); `lo` /
+        `hi` / `peers`: the neighbours whose halo buffers the kernel fills itself."""
         x = XRingC()
         x.epoch = epoch
+        if peers:
+            self.epoch += 1
+            x.push, x.npeers, x.halo_epoch = 1, len(peers), self.epoch
+            x.halo_dst[0] = None if lo is None else self.base[lo] + 8 * self._off("hi")
+            x.halo_dst[1] = None if hi is None else self.base[hi] + 8 * self._off("lo")
+            for q, p in enumerate(peers):
+                x.flag_remote[q] = self.base[p] + 8 * (self.flag_off + self.rank)
+                x.flag_local[q] = self.base[self.rank] + 8 * (self.flag_off + p)
+            x.counter = self.base[self.rank] + 8 * (self.flag_off + self.world)
         x.en_in = self.base[self.rank] + 8 * self.rec_off
         x.st_in = self.base[self.rank] + 8 * (self.rec_off + self.rec_len)
         for k in range(3):
@@ -139,6 +149,7 @@ class DistributedParcop:
                     self._ring[nm] = True
                     slots = max(slots, v[0].value, v[1].value)
         self._ring_epoch = 0
+        self._push = os.environ.get("PB_NO_HALO_PUSH", "0") != "1"  # halo planes moved by the sweep kernel itself
         if (self.dev.type == "cuda" and self.world > 1 and self.plane % 2 == 0  # 16-byte aligned planes
                 and os.environ.get("PB_NO_PEER_MEMORY", "0") != "1"):
             try:
@@ -227,12 +238,14 @@ class DistributedParcop:
             iface_local = self._pb.view("iface", self.rank)
         else:
             recv_lo, recv_hi, iface_all, iface_local = self.recv_lo, self.recv_hi, self.iface_all, self.iface_local
-        if self.world > 1:
+        fused = name in self._ring
+        push = fused and self._push
+        if self.world > 1 and not push:
             self._halo_exchange(f, h)
         st = self._stream()
-        if name in self._ring:
+        if fused:
             self._ring_epoch += 1
-            x = self._pb.ring_args(self._ring_epoch)
+            x = self._pb.ring_args(self._ring_epoch, self.lo, self.hi, self._peers) if push else self._pb.ring_args(self._ring_epoch)
             check(L, L.pb_z_ring(P._h, code, f.data_ptr(), recv_lo.data_ptr(), recv_hi.data_ptr(), out.data_ptr(),
                                  ctypes.byref(x), int(epi), float(s2), st))
             return out

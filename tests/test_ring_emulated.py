@@ -71,7 +71,7 @@ def test_ring_kernel_wherever_it_fits(periodic, oracle_mod, lib):
         lib.pb_set_ring(1, 0)
 
 
-def _fused_zslab(lib, oracle_mod, n, world, periodic, ops):
+def _fused_zslab(lib, oracle_mod, n, world, periodic, ops, push=False):
     """z-slab of `world` ranks as threads: halo planes copied by hand, chunk states exchanged by the
     kernels themselves through the record buffers."""
     from pyranda_b200 import ParcopPlan
@@ -89,6 +89,8 @@ def _fused_zslab(lib, oracle_mod, n, world, periodic, ops):
     st = [np.zeros(cap * plane * 4, dtype=np.uint64) for _ in range(world)]
     epoch = 0
     worst = {}
+    flags = [np.zeros(world, dtype=np.uint64) for _ in range(world)]   # flags[r][p]: set by rank p in rank r's memory
+    counters = [np.zeros(2, dtype=np.uint32) for _ in range(world)]
     for name, h, epi, s2, ref in ops:
         code = OP[name]
         info = [ctypes.c_int() for _ in range(4)]
@@ -104,9 +106,9 @@ def _fused_zslab(lib, oracle_mod, n, world, periodic, ops):
             below, above = r - 1, r + 1
             if periodic:
                 below %= world; above %= world
-            if below >= 0:
+            if below >= 0 and not push:
                 lo[:, :, :h] = slabs[below][:, :, az - h:]
-            if above < world:
+            if above < world and not push:
                 hi[:, :, :h] = slabs[above][:, :, :h]
             halos.append((lo, hi))
         errs = []
@@ -119,6 +121,20 @@ def _fused_zslab(lib, oracle_mod, n, world, periodic, ops):
                 for k in range(3):
                     x.en_out[k] = en[(r + 1 + k) % world].ctypes.data
                     x.st_out[k] = st[(r - 1 - k) % world].ctypes.data
+                if push:  # the kernel moves the halo planes itself and waits for the neighbours' flags
+                    below, above = r - 1, r + 1
+                    if periodic:
+                        below %= world; above %= world
+                    below = below if below >= 0 else None
+                    above = above if above < world else None
+                    peers = sorted({q for q in (below, above) if q is not None})
+                    x.push, x.npeers, x.halo_epoch = 1, len(peers), epoch
+                    x.halo_dst[0] = None if below is None else halos[below][1].ctypes.data
+                    x.halo_dst[1] = None if above is None else halos[above][0].ctypes.data
+                    for q, pr in enumerate(peers):
+                        x.flag_remote[q] = flags[pr].ctypes.data + 8 * r
+                        x.flag_local[q] = flags[r].ctypes.data + 8 * pr
+                    x.counter = counters[r].ctypes.data
                 check(lib, lib.pb_z_ring(plans[r]._h, code, slabs[r].ctypes.data, halos[r][0].ctypes.data, halos[r][1].ctypes.data,
                                          outs[r].ctypes.data, ctypes.byref(x), epi, s2, None))
             except Exception as exc:  # noqa: BLE001
@@ -144,9 +160,10 @@ OPS = [
 
 
 @pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("push", [False, True])
 @pytest.mark.parametrize("n,world,fused", [((20, 3, 256), 2, 3), ((34, 2, 384), 3, 4), ((16, 2, 512), 4, 4), ((16, 2, 1024), 2, 4)])
-def test_fused_zslab_ranks_as_threads(n, world, fused, periodic, oracle_mod, lib):
-    worst = _fused_zslab(lib, oracle_mod, n, world, periodic, OPS)
+def test_fused_zslab_ranks_as_threads(n, world, fused, push, periodic, oracle_mod, lib):
+    worst = _fused_zslab(lib, oracle_mod, n, world, periodic, OPS, push)
     done = {k: v for k, v in worst.items() if v is not None}
     assert len(done) >= (fused if periodic else 4), worst
     assert max(done.values()) < 1e-13, worst
