@@ -183,6 +183,10 @@ typedef struct pb_xring {
   void *counter;
 } pb_xring;
 int pb_z_ring_info(pb_plan *plan, int zop, int *need_f, int *need_b, int *nup, int *ndn);
+/* 0: no fused form; 1: fused, a CTA waits for the neighbours' states of its tile before it uses them
+ * (states from more than one rank away); 2: fused, nobody waits before solving -- a chunk solves with
+ * this rank's states, sends its own at once and adds the neighbours' contribution when it has landed */
+int pb_z_ring_mode(pb_plan *plan, int zop);
 int pb_z_ring(pb_plan *plan, int zop, const double *d_val, const double *d_recv_lo, const double *d_recv_hi,
               double *d_out, const pb_xring *x, int epi_mode, double s2, void *stream);
 /* one directional derivative (PB_OP_DDX.., DD8X.., D2X.., the _ODD variants) with a composite epilogue

@@ -24,7 +24,7 @@ EXPORTS = [
     "pb_divergence", "pb_grads", "pb_divergence_tensor", "pb_ring_vector", "pb_host_divergence_tensor", "pb_host_ring_vector", "pb_rk4_stage", "pb_reduce", "pb_reduce_device", "pb_z_pack_halo", "pb_z_local",
     "pb_z_finish", "pb_z_exchange_ranks", "pb_peer_exchange", "pb_host_apply", "pb_host_divergence", "pb_host_grads", "pb_launch_count",
     "pb_pipe_launch_count", "pb_set_tuning", "pb_ring_launch_count", "pb_set_ring",
-    "pb_z_ring_info", "pb_z_ring", "pb_apply_epi",
+    "pb_z_ring_info", "pb_z_ring", "pb_z_ring_mode", "pb_apply_epi",
 ]
 
 
@@ -76,6 +76,7 @@ def declare(L):
     L.pb_set_ring.argtypes = [i, i]
     L.pb_z_ring_info.argtypes = [_vp, i] + [ctypes.POINTER(i)] * 4
     L.pb_z_ring.argtypes = [_vp, i, _vp, _vp, _vp, _vp, ctypes.POINTER(XRingC), i, d, _vp]
+    L.pb_z_ring_mode.argtypes = [_vp, i]
     L.pb_apply_epi.argtypes = [_vp, i, _vp, _vp, i, d, _vp]
     return L
 

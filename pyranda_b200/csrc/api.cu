@@ -151,13 +151,50 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
       dv.psi0[q] = make_double2(gt.psi[q * 2], gt.psi[q * 2 + 1]);
     }
   const size_t nt = (size_t)gt.ntypes * 32;
-  std::vector<double2> luf(nt), phi(nt), psi(nt);
+  std::vector<double2> luf(nt), phi(nt), psi(nt), chi(nt);
   std::vector<double4> lub(nt);
   for (size_t t = 0; t < nt; ++t) {
     luf[t] = make_double2(gt.luf[t * 2], gt.luf[t * 2 + 1]);
     phi[t] = make_double2(gt.phi[t * 2], gt.phi[t * 2 + 1]);
     psi[t] = make_double2(gt.psi[t * 2], gt.psi[t * 2 + 1]);
+    chi[t] = make_double2(gt.chi[t * 2], gt.chi[t * 2 + 1]);
     lub[t] = make_double4(gt.lub[t * 4], gt.lub[t * 4 + 1], gt.lub[t * 4 + 2], 0.0);
+  }
+  if (dv.cparam)
+    for (int q = 0; q < 32; ++q) dv.chi0[q] = chi[q];
+  // Early form (nobody waits before solving): possible when every exchanged state comes from the
+  // adjacent rank.  The backward states arrive as the rank above computed them from its own chunks;
+  // what this rank's forward states add to them is  sum_j Mb[lp][j] X_e sum_j' Mf[e][j'] EN[c]  with
+  // X_e the first two rows of chi of chunk e above: folded into one 2x2 block per (top chunk lp, top chunk c).
+  static const bool want_early = getenv("PB_XR_EARLY") ? atoi(getenv("PB_XR_EARLY")) != 0 : true;
+  bool early = want_early;
+  for (int rank = 0; rank < np; ++rank)
+    if (need_f(rank) > P || need_b(rank) > P) early = false;
+  std::vector<double4> Bc;
+  int bc_n = 0;
+  if (early && xr.need_b > 0) {
+    const int up = periodic ? (r + 1) % np : r + 1;
+    bc_n = std::max(1, need_f(up));
+    Bc.assign((size_t)xr.need_b * bc_n, make_double4(0, 0, 0, 0));
+    auto at4 = [](const std::vector<double> &v, size_t i) { return make_double4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]); };
+    auto mul = [](const double4 &A, const double4 &B) {  // [[x, y], [z, w]]
+      return make_double4(A.x * B.x + A.y * B.z, A.x * B.y + A.y * B.w, A.z * B.x + A.w * B.z, A.z * B.y + A.w * B.w);
+    };
+    for (int lp = P - xr.need_b; lp < P; ++lp)
+      for (int j = P - lp; j <= nB(r, lp); ++j) {
+        const int e = lp + j - P, g2 = up * P + e, t2 = gt.ctype[g2];
+        const double4 X = make_double4(gt.chi[((size_t)t2 * 32 + 0) * 2], gt.chi[((size_t)t2 * 32 + 0) * 2 + 1],
+                                       gt.chi[((size_t)t2 * 32 + 1) * 2], gt.chi[((size_t)t2 * 32 + 1) * 2 + 1]);
+        const double4 M1 = at4(gt.Mb, (size_t)(r * P + lp) * (Pg + 1) + j);
+        for (int j2 = e + 1; j2 <= nF(up, e); ++j2) {
+          const int c = P + e - j2;  // this rank's chunk whose forward end state enters chunk e above
+          if (c < P - bc_n || c < 0) { early = false; continue; }
+          const double4 M2 = at4(gt.Mf, (size_t)g2 * (Pg + 1) + j2);
+          const double4 T = mul(M1, mul(X, M2));
+          double4 &dst = Bc[(size_t)(lp - (P - xr.need_b)) * bc_n + (c - (P - bc_n))];
+          dst.x += T.x; dst.y += T.y; dst.z += T.z; dst.w += T.w;
+        }
+      }
   }
   dv.mstride = jmax + 1;
   std::vector<double4> Mf((size_t)P * dv.mstride), Mb((size_t)P * dv.mstride);
@@ -175,6 +212,10 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
   if ((rcv = upload(sp, psi, &dv.psi)) != PB_OK) return rcv;
   if ((rcv = upload(sp, Mf, &dv.Mf)) != PB_OK) return rcv;
   if ((rcv = upload(sp, Mb, &dv.Mb)) != PB_OK) return rcv;
+  if ((rcv = upload(sp, chi, &dv.chi)) != PB_OK) return rcv;
+  xr.early = early ? 1 : 0;
+  xr.bc_n = bc_n;
+  if (early && (rcv = upload(sp, Bc, &xr.Bc)) != PB_OK) return rcv;
   sp.xr = xr;
   sp.xr_ok = true;
   return PB_OK;
@@ -208,6 +249,8 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic, in
   {
     static const int wstore = getenv("PB_WARP_STORE") ? atoi(getenv("PB_WARP_STORE")) : 1;
     dv.wstore = wstore;
+    static const int skew = getenv("PB_SKEW_NS") ? atoi(getenv("PB_SKEW_NS")) : 0;
+    dv.skew_ns = skew;
   }
   const int ax = pl->a[0], ay = pl->a[1], az = pl->a[2];
   if (dir == 0) { dv.nfast = ay * az; dv.nouter = 1; dv.rstride = 1; dv.ostride = 0; }
@@ -901,6 +944,14 @@ int pb_z_ring_info(pb_plan *pl, int zop, int *need_f, int *need_b, int *nup, int
   if (nup) *nup = ok ? sp.xr.nup : 0;
   if (ndn) *ndn = ok ? sp.xr.ndn : 0;
   return PB_OK;
+}
+
+int pb_z_ring_mode(pb_plan *pl, int zop) {
+  const int k = zop_kind(zop);
+  if (!pl || k < 0) return 0;
+  const SweepPlan &sp = zplan(pl, zop, k);
+  if (sp.null_op || !sp.split || !sp.st.implicit || !sp.xr_ok) return 0;
+  return sp.xr.early ? 2 : 1;
 }
 
 static int epi_from(int mode, double s2, EpiArgs *e) {

@@ -56,7 +56,10 @@ struct SweepDev {
   int ring;              // pipelined kernels, plain-store path: val = |val| * ring_s2 first (ring detector, Cartesian)
   double ring_s2;
   int wstore;            // pipelined kernels: every warp issues the TMA stores of its own chunks (else one thread per block)
+  int skew_ns;           // persistent kernels: the second wave of CTAs (the co-residents of the first) starts this much later
   int mstride;           // entries per chunk row of Mf / Mb (P + 1, or the compact stride of a z-slab line)
+  const double2 *chi;    // [ntypes][C]  z-slab ring: solution response to a forward state that arrives after the chunk's solve
+  double2 chi0[kParamRows];  // the same for the constant chunk type
 };
 
 // Cross-rank exchange of chunk states inside a z sweep (ring kernel): a z-slab line is the global
@@ -76,6 +79,13 @@ struct XRing {
   // halo planes pushed by the sweep kernel itself (push = 0: the caller has exchanged them): every CTA
   // copies its share of this rank's first / last planes into the neighbours' halo buffers, the last
   // one publishes hepoch in the neighbours' flag words; halo boxes are requested once theirs is seen
+  // early = 1: nobody waits for a neighbour before solving.  A chunk solves with the states of this
+  // rank's chunks, sends its backward start state at once, and adds what the forward states from
+  // below contribute (chi) when they have arrived; the top chunks add, to the backward states from
+  // above, what this rank's own forward states change in them (Bc: [need_b][bc_n] 2x2 blocks applied
+  // to the forward end states of this rank's top bc_n chunks)
+  int early, bc_n;
+  const double4 *Bc;
   int push, npeers, nopoll;
   const double *push_src[2];
   double *push_dst[2];

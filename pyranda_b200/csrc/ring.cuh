@@ -220,6 +220,9 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   if (tid == 0 && t < ntiles) issue(t);
 #ifdef PB_EMULATE
   __syncthreads();
+#else
+  if (a.skew_ns > 0 && blockIdx.x >= gridDim.x / 2)
+    for (int w = 0; w < a.skew_ns; w += 500) __nanosleep(500);
 #endif
   uint32_t parity = 0;
   const double *tw = tile + (size_t)(p * CT + HP - H) * NL + l;
@@ -254,12 +257,12 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         const bool lv = ti * NL + l < a.nfast;
         const int e = P - 1 - lp;  // chunks from the top of the slab
         for (int k = 0; k < xr.nup; ++k)
-          if (e < xr.cnt_up[k] && lv) xr_store(xr.en_out[k] + ((long)(k * P + e) * xr.plane + line0 + l) * 4, make_double2(rm1, rm2), xr.epoch);
-        const int need = xr.need_f - crank * PL;  // forward end states of the chunks below this slab
+          if (e < xr.cnt_up[k] && lv && !(xr.nopoll & 2)) xr_store(xr.en_out[k] + ((long)(k * P + e) * xr.plane + line0 + l) * 4, make_double2(rm1, rm2), xr.epoch);
+        const int need = xr.early ? 0 : xr.need_f - crank * PL;  // waiting form: forward end states of the chunks below this slab
         if (tid < need * NL) {
           const int e2 = tid / NL, ll = tid - e2 * NL;
           double2 v = make_double2(0.0, 0.0);
-          if (ti * NL + ll < a.nfast && !xr.nopoll) {
+          if (ti * NL + ll < a.nfast && !(xr.nopoll & 1)) {
             const unsigned long long *rec = xr.en_in + ((long)e2 * xr.plane + line0 + ll) * 4;
             unsigned long long spin = 0;
             while (!xr_try_load(rec, xr.epoch, &v)) xr_pause(spin);
@@ -274,7 +277,8 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
     {  // ---- B: add the carried forward state, backward recurrence (zero incoming state) ----
       double2 st = make_double2(0.0, 0.0);
       {
-        const int nf = a.nf[lp];
+        int nf = a.nf[lp];
+        if (xr.early && nf > lp) nf = lp;  // early form: this rank's chunks now, the ranks below when their states have arrived
         const double4 *Mp = a.Mf + (size_t)lp * a.mstride;
         for (int j = 1; j <= nf; ++j) {
           const double2 en = en_get(lp - j);
@@ -315,16 +319,45 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           x1 = x;
         });
       }
-      ST[p * NL + l] = make_double2(x1, x2);
-      if (xr.on) {
+      if (xr.on) {  // my backward start state to the ranks below (early form: before the states from below have arrived;
+                    // the receiver adds what its own forward states change in it)
         const bool lv = ti * NL + l < a.nfast;
         for (int k = 0; k < xr.ndn; ++k)
-          if (lp < xr.cnt_dn[k] && lv) xr_store(xr.st_out[k] + ((long)(k * P + lp) * xr.plane + line0 + l) * 4, make_double2(x1, x2), xr.epoch);
-        const int need = xr.need_b - (CL - 1 - crank) * PL;  // backward start states of the chunks above this slab
+          if (lp < xr.cnt_dn[k] && lv && !(xr.nopoll & 2)) xr_store(xr.st_out[k] + ((long)(k * P + lp) * xr.plane + line0 + l) * 4, make_double2(x1, x2), xr.epoch);
+      }
+      if (xr.early && a.nf[lp] > lp) {  // the forward states from below: by now they have usually landed
+        double2 sg2 = make_double2(0.0, 0.0);
+        if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
+          const double4 *Mp = a.Mf + (size_t)lp * a.mstride;
+          const int nfl = a.nf[lp];
+          for (int j = lp + 1; j <= nfl; ++j) {
+            const unsigned long long *rec = xr.en_in + ((long)(j - lp - 1) * xr.plane + line0 + l) * 4;
+            double2 en;
+            unsigned long long spin = 0;
+            while (!xr_try_load(rec, xr.epoch, &en)) xr_pause(spin);
+            const double4 M = ldg4(Mp + j);
+            sg2.x = fma(M.y, en.y, fma(M.x, en.x, sg2.x));
+            sg2.y = fma(M.w, en.y, fma(M.z, en.x, sg2.y));
+          }
+        }
+        const double sc = (ADDV && LATE) ? scale : 1.0;  // the late add-back already holds scale * x + v
+        const double2 *ch = a.chi + (size_t)type * CT;
+        static_for<0, CT>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          const double2 c = cc ? a.chi0[r] : __ldg(ch + r);
+          const double dx = fma(c.y, sg2.y, c.x * sg2.x);
+          rl[r] = fma(dx, sc, rl[r]);
+          if (r == 0) x1 += dx;
+          if (r == 1) x2 += dx;
+        });
+      }
+      ST[p * NL + l] = make_double2(x1, x2);
+      if (xr.on && !xr.early) {
+        const int need = xr.need_b - (CL - 1 - crank) * PL;  // waiting form: backward start states of the chunks above this slab
         if (tid < need * NL) {
           const int e2 = tid / NL, ll = tid - e2 * NL;
           double2 v = make_double2(0.0, 0.0);
-          if (ti * NL + ll < a.nfast && !xr.nopoll) {
+          if (ti * NL + ll < a.nfast && !(xr.nopoll & 1)) {
             const unsigned long long *rec = xr.st_in + ((long)e2 * xr.plane + line0 + ll) * 4;
             unsigned long long spin = 0;
             while (!xr_try_load(rec, xr.epoch, &v)) xr_pause(spin);
@@ -339,8 +372,29 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
     {  // ---- D: add the carried backward state, scale / add-back, TMA stores ----
       double2 tb = make_double2(0.0, 0.0);
       {
-        const int nb = a.nb[lp];
+        int nb = a.nb[lp];
         const double4 *Mp = a.Mb + (size_t)lp * a.mstride;
+        if (xr.early && nb > P - 1 - lp) {  // the chunks above this slab: their states as sent, plus what this rank's forward states add to them
+          if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
+            for (int j = P - lp; j <= nb; ++j) {
+              const unsigned long long *rec = xr.st_in + ((long)(lp + j - P) * xr.plane + line0 + l) * 4;
+              double2 sv;
+              unsigned long long spin = 0;
+              while (!xr_try_load(rec, xr.epoch, &sv)) xr_pause(spin);
+              const double4 M = ldg4(Mp + j);
+              tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
+              tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
+            }
+            const double4 *Bp = xr.Bc + (size_t)(lp - (P - xr.need_b)) * xr.bc_n;
+            for (int c = 0; c < xr.bc_n; ++c) {
+              const double2 en = en_get(P - xr.bc_n + c);
+              const double4 M = ldg4(Bp + c);
+              tb.x = fma(M.y, en.y, fma(M.x, en.x, tb.x));
+              tb.y = fma(M.w, en.y, fma(M.z, en.x, tb.y));
+            }
+          }
+          nb = P - 1 - lp;
+        }
         for (int j = 1; j <= nb; ++j) {
           const double2 sv = st_get(lp + j);
           const double4 M = ldg4(Mp + j);

@@ -1404,6 +1404,9 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   if (tid == 0 && t < ntiles) issue(t);
 #ifdef PB_EMULATE
   __syncthreads();
+#else
+  if (a.skew_ns > 0 && blockIdx.x >= gridDim.x / 2)
+    for (int w = 0; w < a.skew_ns; w += 500) __nanosleep(500);
 #endif
   uint32_t parity = 0;
   const double *tw = tile + (size_t)(s + HP - H) * NL + l;
@@ -1750,6 +1753,9 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
   if (tid == 0 && t < ntiles) issue(t);
 #ifdef PB_EMULATE
   __syncthreads();
+#else
+  if (a.skew_ns > 0 && blockIdx.x >= gridDim.x / 2)
+    for (int w = 0; w < a.skew_ns; w += 500) __nanosleep(500);
 #endif
   uint32_t parity = 0;
 

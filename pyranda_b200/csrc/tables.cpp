@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -496,11 +497,12 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
     for (int k = 0; k < 5; ++k) T.cst[k] = (double)lim[k];
   }
 
-  struct ChunkTab { std::vector<double> luf, lub, phi, psi; };
+  struct ChunkTab { std::vector<double> luf, lub, phi, psi, chi; };
   auto make_chunk = [&](int p, bool use_const) {
     ChunkTab t;
     const int s = p * C;
     t.luf.resize((size_t)C * 2); t.lub.resize((size_t)C * 4); t.phi.resize((size_t)C * 2); t.psi.resize((size_t)C * 2);
+    t.chi.resize((size_t)C * 2);
     std::vector<double> l2(C), l1(C), ip(C), u1(C), u2(C);
     for (int i = 0; i < C; ++i) {
       l2[i] = use_const ? T.cst[0] : L2(s + i); l1[i] = use_const ? T.cst[1] : L1(s + i);
@@ -523,6 +525,16 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
       for (int i = C - 1; i >= 0; --i) {
         const double v = (-u1[i] * x1 - u2[i] * x2) * ip[i];
         t.psi[i * 2 + col] = v;
+        x2 = x1; x1 = v;
+      }
+    }
+    // chi: the backward recurrence (zero incoming state) applied to phi -- what a forward state that
+    // arrives late adds to the chunk's solution
+    for (int col = 0; col < 2; ++col) {
+      double x1 = 0.0, x2 = 0.0;
+      for (int i = C - 1; i >= 0; --i) {
+        const double v = (t.phi[i * 2 + col] - u1[i] * x1 - u2[i] * x2) * ip[i];
+        t.chi[i * 2 + col] = v;
         x2 = x1; x1 = v;
       }
     }
@@ -552,6 +564,7 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
     T.lub.insert(T.lub.end(), t.lub.begin(), t.lub.end());
     T.phi.insert(T.phi.end(), t.phi.begin(), t.phi.end());
     T.psi.insert(T.psi.end(), t.psi.begin(), t.psi.end());
+    T.chi.insert(T.chi.end(), t.chi.begin(), t.chi.end());
   }
 
   // chunk transfer matrices and their truncated products
@@ -569,7 +582,8 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
     T.nF.assign(P, 0); T.nB.assign(P, 0);
     // Terms are dropped once the transfer product falls below the rounding unit of the leading
     // (identity) term: what they would add is below the last bit of the state they are added to.
-    const long double tiny = 2.2e-16L;
+    static const long double tiny_env = getenv("PB_TINY") ? (long double)atof(getenv("PB_TINY")) : 2.2e-16L;
+    const long double tiny = tiny_env;
     auto mxabs = [](const M2 &x) { return std::max(std::max(fabsl(x.a), fabsl(x.b)), std::max(fabsl(x.c), fabsl(x.d))); };
     auto put4 = [](double *dst, const M2 &x) { dst[0] = (double)x.a; dst[1] = (double)x.b; dst[2] = (double)x.c; dst[3] = (double)x.d; };
     if (cyclic) {

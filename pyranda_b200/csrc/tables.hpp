@@ -64,6 +64,7 @@ struct LineTables {
   std::vector<double> lub;          // [ntypes][C][4]  1/pivot, u1, u2, 0
   std::vector<double> phi;          // [ntypes][C][2]  forward response to (r'[s-1], r'[s-2])
   std::vector<double> psi;          // [ntypes][C][2]  backward response to (x[e], x[e+1])
+  std::vector<double> chi;          // [ntypes][C][2]  solution response (backward pass, zero incoming) to the forward state entering the chunk
   // carried state without a serial scan: the state entering chunk p is a short sum over the
   // local end values of the chunks before (after) it, weighted by products of 2x2 chunk transfer
   // matrices; the products decay like rho^(C*distance) and are truncated below 1e-22.

@@ -89,6 +89,7 @@ def _fused_zslab(lib, oracle_mod, n, world, periodic, ops, push=False):
     st = [np.zeros(cap * plane * 4, dtype=np.uint64) for _ in range(world)]
     epoch = 0
     worst = {}
+    modes = set()
     flags = [np.zeros(world, dtype=np.uint64) for _ in range(world)]   # flags[r][p]: set by rank p in rank r's memory
     counters = [np.zeros(2, dtype=np.uint32) for _ in range(world)]
     for name, h, epi, s2, ref in ops:
@@ -98,6 +99,7 @@ def _fused_zslab(lib, oracle_mod, n, world, periodic, ops, push=False):
         if info[0].value + info[1].value == 0:  # states would wrap onto the rank itself: no fused form (SPIKE path)
             worst[name + str(epi)] = None
             continue
+        modes.add(lib.pb_z_ring_mode(plans[0]._h, code))
         epoch += 1
         outs = [np.asfortranarray(np.full((ax, ay, az), 0.5)) for _ in range(world)]
         halos = []
@@ -148,6 +150,7 @@ def _fused_zslab(lib, oracle_mod, n, world, periodic, ops, push=False):
         want = ref(o, f)
         got = np.concatenate(outs, axis=2)
         worst[name + str(epi)] = rel_linf(got, want)
+    worst["modes"] = modes
     return worst
 
 
@@ -164,6 +167,10 @@ OPS = [
 @pytest.mark.parametrize("n,world,fused", [((20, 3, 256), 2, 3), ((34, 2, 384), 3, 4), ((16, 2, 512), 4, 4), ((16, 2, 1024), 2, 4)])
 def test_fused_zslab_ranks_as_threads(n, world, fused, push, periodic, oracle_mod, lib):
     worst = _fused_zslab(lib, oracle_mod, n, world, periodic, OPS, push)
+    modes = worst.pop("modes")
+    assert 2 in modes, modes   # the non-waiting form ran for at least one operator
+    if n[2] // world == 128 and world == 3 and periodic:
+        assert 1 in modes, modes   # the compact filter's states come from two ranks away: the waiting form
     done = {k: v for k, v in worst.items() if v is not None}
     assert len(done) >= (fused if periodic else 4), worst
     assert max(done.values()) < 1e-13, worst
