@@ -167,9 +167,11 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
   // what this rank's forward states add to them is  sum_j Mb[lp][j] X_e sum_j' Mf[e][j'] EN[c]  with
   // X_e the first two rows of chi of chunk e above: folded into one 2x2 block per (top chunk lp, top chunk c).
   static const bool want_early = getenv("PB_XR_EARLY") ? atoi(getenv("PB_XR_EARLY")) != 0 : true;
+  // ... and worthwhile when few states cross a face (first / second / eighth derivative: two chunks): every
+  // consumer polls its own records, which costs more than it hides for the compact filter's six (measured)
   bool early = want_early;
   for (int rank = 0; rank < np; ++rank)
-    if (need_f(rank) > P || need_b(rank) > P) early = false;
+    if (need_f(rank) > std::min(P, 3) || need_b(rank) > std::min(P, 3)) early = false;
   std::vector<double4> Bc;
   int bc_n = 0;
   if (early && xr.need_b > 0) {
