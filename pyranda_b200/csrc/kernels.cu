@@ -325,12 +325,20 @@ cudaError_t launch_peer_exchange(const PeerExchange &x, cudaStream_t st) {
 // pyranda.py:800-804: PHI = dt*F + A*PHI ; U = U + B*PHI
 __global__ void rk4_stage_kernel(long n, double dt, double A, double B, const double *__restrict__ F,
                                  double *__restrict__ PHI, double *__restrict__ U) {
-  PB_GRID_STRIDE(t, n) {
+  PB_GRID_STRIDE(t, n) {  // every product rounded before it is added, as numpy evaluates the reference's lines
+#ifdef PB_EMULATE
     const double tmp1 = A * PHI[t];
     const double phi = dt * F[t] + tmp1;
     PHI[t] = phi;
     const double tmp2 = B * phi;
     U[t] = U[t] + tmp2;
+#else
+    const double tmp1 = __dmul_rn(A, PHI[t]);
+    const double phi = __dadd_rn(__dmul_rn(dt, F[t]), tmp1);
+    PHI[t] = phi;
+    const double tmp2 = __dmul_rn(B, phi);
+    U[t] = __dadd_rn(U[t], tmp2);
+#endif
   }
 }
 cudaError_t launch_rk4_stage(long n, double dt, double A, double B, const double *F, double *PHI, double *U, cudaStream_t st) {

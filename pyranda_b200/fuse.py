@@ -181,10 +181,13 @@ class Fuser:
         self.groups.append({"inputs": inputs, "outs": outs, "stmts": stmts, "kernels": {}, "py": None})
         return len(self.groups) - 1
 
-    def run_group(self, gid, variables):
-        """Evaluates the group into `variables` (fused when every input is a field or a number)."""
+    def run_group(self, gid, variables, out=None):
+        """Evaluates the group into `out` (default: `variables`), fused when every input is a field or a number."""
         g = self.groups[gid]
-        vals = [variables[nm] for nm in g["inputs"]]
+        src_vars = variables
+        if out is not None:
+            variables = out
+        vals = [src_vars[nm] for nm in g["inputs"]]
         kern = self._group_kernel(g, vals) if self.enabled else None
         if kern is None:
             if g["py"] is None:
@@ -239,6 +242,104 @@ class Fuser:
             self.enabled = False
             return None
         return g["kernels"][key], mask, ref
+
+    # ------------------------------------------------------------------ hoisted operator arguments
+    OPERATORS = ("ddx", "ddy", "ddz", "div", "divT", "grad", "filter", "gfilter", "gfilterx", "gfiltery", "gfilterz", "ring",
+                 "ringV", "laplacian", "dd4x", "dd4y", "dd4z", "dd8x", "dd8y", "dd8z")
+
+    def _is_operator_call(self, node):
+        return (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Name)
+                and node.func.value.id == "self" and node.func.attr in self.OPERATORS and not node.keywords)
+
+    def _pure(self, n):
+        if _is_num(n) or self._var_name(n) is not None:
+            return True
+        if not _is_arith(n):
+            return False
+        kids = n.args if isinstance(n, ast.Call) else ([n.operand] if isinstance(n, ast.UnaryOp) else [n.left, n.right])
+        return all(self._pure(k) for k in kids)
+
+    def hoist(self, sources, holder="self._hoisted"):
+        """The flux equations of a deck call operators on arithmetic of the variables:
+        -ddx(:rhou:*:u: - :tauxx:) - ddy(...) ...  Every such argument (over ALL the given sources) moves
+        into ONE multi-output kernel that reads each variable once; the sources come back with the
+        arguments replaced by `holder["hK"]`.  Returns (group id or None, new sources).  Valid because
+        nothing assigns a variable while the right-hand sides of the PDE lines are evaluated."""
+        trees = [ast.parse(src, mode="eval") for src in sources]
+        found, order = {}, []
+
+        def visit(node):
+            for field, old in ast.iter_fields(node):
+                kids = old if isinstance(old, list) else [old]
+                new = []
+                for k in kids:
+                    if isinstance(k, ast.AST):
+                        visit(k)
+                        if self._is_operator_call(node) and field == "args" and _is_arith(k) and self._pure(k):
+                            key = ast.dump(k)
+                            if key not in found:
+                                found[key] = "h%d" % len(order)
+                                order.append((found[key], k))
+                            k = ast.Subscript(value=ast.parse(holder, mode="eval").body, slice=ast.Constant(found[key]), ctx=ast.Load())
+                    new.append(k)
+                setattr(node, field, new if isinstance(old, list) else new[0])
+
+        for t in trees:
+            visit(t)
+        if len(order) < 2:
+            return None, list(sources)
+        for t in trees:
+            ast.fix_missing_locations(t)
+        return self.make_group(order), [ast.unparse(t) for t in trees]
+
+    # ------------------------------------------------------------------ RK4 stage with the flux expression inside
+    @staticmethod
+    def split_stage(src):
+        """`__fz(k, leaf0, leaf1, ...)` at the top of a transformed right-hand side -> (k, source of the
+        tuple of leaves), else None: the stage kernel can then evaluate the flux expression itself."""
+        body = ast.parse(src, mode="eval").body
+        if (isinstance(body, ast.Call) and isinstance(body.func, ast.Name) and body.func.id == "__fz" and body.args
+                and isinstance(body.args[0], ast.Constant) and not body.keywords):
+            tup = ast.Tuple(elts=list(body.args[1:]), ctx=ast.Load())
+            return int(body.args[0].value), ast.unparse(ast.fix_missing_locations(ast.Expression(body=tup)))
+        return None
+
+    def stage(self, idx, vals, dt, A, B, PHI, U):
+        """PHI = dt*F + A*PHI ; U = U + B*PHI (pyranda.py:800-804) with F = spec idx of `vals` evaluated in
+        the same kernel (no flux field is written or read back).  Returns False when the operands do
+        not qualify; the caller then evaluates F and runs the library's stage kernel."""
+        if not self.enabled:
+            return False
+        import torch
+        spec = self.specs[idx]
+        mask = []
+        for v in vals:
+            if isinstance(v, torch.Tensor):
+                if v.dim() == 0 or v.dtype != torch.float64 or not v.is_cuda or v.shape != U.shape or v.stride() != U.stride():
+                    return False
+                mask.append(True)
+            elif isinstance(v, (int, float)) and not isinstance(v, bool):
+                mask.append(False)
+            else:
+                return False
+        if not any(mask) or PHI.stride() != U.stride() or PHI.shape != U.shape or not _dense(U):
+            return False
+        try:
+            rt = self._runtime()
+            key = ("stage",) + tuple(mask)
+            kern = spec.kernels.get(key)
+            if kern is None:
+                kern = spec.kernels[key] = rt.compile(stage_kernel_source(spec.cexpr, mask))
+        except Exception:
+            self.enabled = False
+            return False
+        n = U.numel()
+        args = [n] + [v.data_ptr() if m else float(v) for v, m in zip(vals, mask)] + [float(dt), float(A), float(B), PHI.data_ptr(), U.data_ptr()]
+        types = ([ctypes.c_long] + [ctypes.c_void_p if m else ctypes.c_double for m in mask]
+                 + [ctypes.c_double] * 3 + [ctypes.c_void_p] * 2)
+        rt.launch(kern, n, args, types, torch.cuda.current_stream().cuda_stream)
+        self.launches += 1
+        return True
 
     # ------------------------------------------------------------------ run time
     def call(self, idx, *vals):
@@ -319,6 +420,25 @@ def group_kernel_source(stmts, mask):
     return ("extern \"C\" __global__ void __launch_bounds__(256) fz(%s) {\n"
             "  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {\n"
             "%s\n%s\n  }\n}\n" % (", ".join(params), "\n".join(loads), "\n".join(body)))
+
+
+def stage_kernel_source(cexpr, mask):
+    """The RK4 stage update with the flux expression evaluated in place (same operations and order as
+    the flux kernel followed by rk4_stage_kernel: --fmad=false keeps dt*F + tmp1 two roundings)."""
+    params = ["long n"]
+    loads = []
+    for i, m in enumerate(mask):
+        if m:
+            params.append("const double *__restrict__ a%d" % i)
+            loads.append("    const double v%d = a%d[t];" % (i, i))
+        else:
+            params.append("double v%d" % i)
+    params += ["double dt", "double A", "double B", "double *__restrict__ PHI", "double *__restrict__ U"]
+    return ("extern \"C\" __global__ void __launch_bounds__(256) fz(%s) {\n"
+            "  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {\n"
+            "%s\n    const double F = %s;\n    const double tmp1 = A * PHI[t];\n    const double phi = dt * F + tmp1;\n"
+            "    PHI[t] = phi;\n    const double tmp2 = B * phi;\n    U[t] = U[t] + tmp2;\n  }\n}\n"
+            % (", ".join(params), "\n".join(loads), cexpr))
 
 
 def kernel_source(cexpr, mask):

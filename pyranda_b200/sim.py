@@ -202,13 +202,43 @@ class _Equation:
         lhs, rhs = text.split("=", 1) if assign else (None, text)
         self.lhs = _VAR.findall(lhs) if lhs is not None else None
         self.kind = "PDE" if "ddt(" in text else "ALG"  # pyrandaEq.py:42-43
-        self.src = translate(rhs, user)
+        self.src = _drop_abs_of_ring(translate(rhs, user))
+        self.raw = self.src   # before fusion: the flux plan re-fuses the PDE lines after hoisting their operator arguments
+        self.opaque = bool(user) and any(("userDefined['%s']" % u) in self.src for u in user) or any(
+            k in self.src for k in ("self.bc.", "self.ibm.", "self.random3D", "self.emptyScalar"))
+        self.reads = set(_VAR.findall(rhs))
         self.pure = None  # AST when the right-hand side is arithmetic over variables only (groupable)
         if fuser is not None:  # arithmetic between operator calls -> one generated kernel each (fuse.py)
             if self.kind == "ALG" and self.lhs is not None and len(self.lhs) == 1:
                 self.pure = fuser.pure_tree(self.src)
             self.src = fuser.transform(self.src)
         self.code = compile(self.src, "<eom>", "eval")
+
+
+def _drop_abs_of_ring(src):
+    """abs(ring(f)) == ring(f) bit for bit: the detector is a maximum of |d8 f| * d^2 (operators.f90:615-643),
+    so the deck's abs() around it needs no pass over the field."""
+    import ast
+    try:
+        tree = ast.parse(src, mode="eval")
+    except SyntaxError:
+        return src
+    changed = [False]
+
+    class T(ast.NodeTransformer):
+        def visit_Call(self, node):
+            self.generic_visit(node)
+            f = node.func
+            if (isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "xp" and f.attr == "abs"
+                    and len(node.args) == 1 and not node.keywords):
+                a = node.args[0]
+                if (isinstance(a, ast.Call) and isinstance(a.func, ast.Attribute) and isinstance(a.func.value, ast.Name)
+                        and a.func.value.id == "self" and a.func.attr in ("ring", "ringV")):
+                    changed[0] = True
+                    return a
+            return node
+    tree = T().visit(tree)
+    return ast.unparse(ast.fix_missing_locations(tree)) if changed[0] else src
 
 
 def parse_mesh(text):
@@ -367,7 +397,9 @@ class pyrandaSim:
         from .ibm import ImmersedBoundary
         self.ibm = ImmersedBoundary(self)             # the `IBM` package (pyrandaIBM.py)
         self.fuser = None
-        self._plan = None
+        self._plan = {}
+        self._fplan = None
+        self._hoisted = {}
         if isinstance(backend, CudaBackend) and os.environ.get("PB_NO_FUSE", "0") != "1":
             from .fuse import Fuser
             self.fuser = Fuser(self.xp)
@@ -489,12 +521,61 @@ class pyrandaSim:
             exec(translate(ln, tuple(self.userDefined)), self._ns, local)
         self.updateVars()
 
-    def updateFlux(self):  # pyranda.py:376-394
-        return {eq.lhs[0]: eval(eq.code, self._ns) for eq in self.equations if eq.kind == "PDE"}
+    def _flux_plan(self):
+        """Once per deck: the operator arguments of all PDE lines hoisted into one kernel (fuse.hoist),
+        the lines re-fused, and for lines of the form `arithmetic(operator results)` the split that lets
+        the RK4 stage kernel evaluate that arithmetic itself."""
+        pdes = [eq for eq in self.equations if eq.kind == "PDE"]
+        if self._fplan is not None and self._fplan[0] == len(self.equations):
+            return self._fplan[1]
+        plan = {"gid": None, "items": []}
+        if self.fuser is not None and os.environ.get("PB_NO_HOIST", "0") != "1" and not any(eq.opaque for eq in pdes):
+            gid, srcs = self.fuser.hoist([eq.raw for eq in pdes])
+            plan["gid"] = gid
+            for eq, src in zip(pdes, srcs):
+                fsrc = self.fuser.transform(src)
+                split = self.fuser.split_stage(fsrc)
+                item = {"name": eq.lhs[0], "code": compile(fsrc, "<eom>", "eval"), "stage": None}
+                if split is not None:
+                    item["stage"] = (split[0], compile(split[1], "<eom>", "eval"))
+                plan["items"].append(item)
+        else:
+            plan["items"] = [{"name": eq.lhs[0], "code": eq.code, "stage": None} for eq in pdes]
+        self._fplan = (len(self.equations), plan)
+        return plan
 
-    def _alg_plan(self):
+    def updateFlux(self):  # pyranda.py:376-394
+        plan = self._flux_plan()
+        if plan["gid"] is not None:
+            self.fuser.run_group(plan["gid"], self.variables, out=self._hoisted)
+        flux = {it["name"]: eval(it["code"], self._ns) for it in plan["items"]}
+        self._hoisted.clear()
+        return flux
+
+    def _host_only(self):
+        """Variables nothing on the device depends on during a step: assigned by algebraic lines and read
+        only by lines that assign such variables (the time-step controller's `:dt:` chain, `:cs:` feeding
+        it, diagnostics like `:enst:`).  Between the stages of one rk4() call nobody can look at them, so
+        the lines that only assign them run after the last stage only.  A deck with package calls or user
+        functions (which may read any variable) keeps everything."""
+        if any(eq.opaque for eq in self.equations) or os.environ.get("PB_NO_LAZY", "0") == "1":
+            return set()
+        algs = [eq for eq in self.equations if eq.kind == "ALG" and eq.lhs]
+        dead = set(nm for eq in algs for nm in eq.lhs) - set(self.conserved)
+        changed = True
+        while changed:
+            changed = False
+            for eq in self.equations:
+                keeps = eq.kind == "PDE" or not eq.lhs or any(nm not in dead for nm in eq.lhs)
+                if keeps and (eq.reads & dead):  # a line that runs every stage reads it
+                    dead -= eq.reads
+                    changed = True
+        return dead
+
+    def _alg_plan(self, final=True):
         """Consecutive algebraic equations that are pure arithmetic become one multi-output kernel."""
         plan, run = [], []
+        dead = set() if final else self._host_only()
 
         def flush():
             if len(run) >= 2:
@@ -505,6 +586,8 @@ class pyrandaSim:
         for eq in self.equations:
             if eq.kind != "ALG":
                 continue
+            if eq.lhs and all(nm in dead for nm in eq.lhs):
+                continue  # host-only result, not the last stage
             if self.fuser is not None and eq.pure is not None:
                 run.append(eq)
             else:
@@ -513,11 +596,12 @@ class pyrandaSim:
         flush()
         return plan
 
-    def updateVars(self):  # pyranda.py:397-416
+    def updateVars(self, final=True):  # pyranda.py:397-416
         if self.fuser is not None:
-            if self._plan is None or self._plan[0] != len(self.equations):
-                self._plan = (len(self.equations), self._alg_plan())
-            for kind, item in self._plan[1]:
+            cur = self._plan.get(final)
+            if cur is None or cur[0] != len(self.equations):
+                cur = self._plan[final] = (len(self.equations), self._alg_plan(final))
+            for kind, item in cur[1]:
                 if kind == "group":
                     self.fuser.run_group(item, self.variables)
                     continue
@@ -644,18 +728,46 @@ class pyrandaSim:
                 count[B.storage_key(u)] -= 1
                 self.variables[U] = B.clone(u)
 
+    def _fused_stage(self, dt, A, B, PHI):
+        """One stage on the device: every operator of every PDE line first (as updateFlux does, all
+        right-hand sides before any update), then per conserved variable ONE kernel that evaluates the
+        line's remaining arithmetic and the stage update (no flux field is written and read back)."""
+        plan = self._flux_plan()
+        if plan["gid"] is not None:
+            self.fuser.run_group(plan["gid"], self.variables, out=self._hoisted)
+        pending = []
+        for it in plan["items"]:
+            if it["stage"] is not None:
+                pending.append((it, eval(it["stage"][1], self._ns)))
+            else:
+                pending.append((it, eval(it["code"], self._ns)))
+        self._hoisted.clear()
+        self._unshare_conserved()
+        for it, val in pending:
+            U = it["name"]
+            u = self.B._c(self.variables[U])
+            if it["stage"] is not None:
+                if self.fuser.stage(it["stage"][0], val, dt, A, B, PHI[U], u):
+                    self.variables[U] = u
+                    continue
+                val = self.fuser.call(it["stage"][0], *val)
+            self.variables[U] = self.B.rk4_stage(dt, A, B, val, PHI[U], u)
+
     def rk4(self, time, dt):
         PHI = {U: self.B.zeros() for U in self.conserved}
         time_i = time
         dt = float(dt)  # a device scalar from the time-step controller: the one host read of the step
         self.deltat = dt
         for ii in range(5):
-            FLUX = self.updateFlux()
-            self._unshare_conserved()
-            for U in self.conserved:
-                self.variables[U] = self.B.rk4_stage(dt, self.ARK[ii], self.BRK[ii], FLUX[U], PHI[U], self.variables[U])
+            if self.fuser is not None:
+                self._fused_stage(dt, self.ARK[ii], self.BRK[ii], PHI)
+            else:
+                FLUX = self.updateFlux()
+                self._unshare_conserved()
+                for U in self.conserved:
+                    self.variables[U] = self.B.rk4_stage(dt, self.ARK[ii], self.BRK[ii], FLUX[U], PHI[U], self.variables[U])
             time = time_i + self.ETA[ii] * dt
             self.time = time
-            self.updateVars()
+            self.updateVars(final=(ii == 4))
         self.cycle += 1
         return time

@@ -621,3 +621,77 @@ SYMM_IC = """
 :c: = 1.0 + 3d()
 :dt: = dt.courant(:u:,:v:,:w:,:c:)
 """
+
+
+# examples/3Dadvect.py:14-20,33-97 (BASELINE configs[0]: 3-D advection of a density bump, periodic, the
+# artificial viscosities switched off by their 0.0e-4 factors), strings as written there
+def advect3d_mesh(npts):
+    return tgv_mesh(npts)
+
+
+ADVECT3D_EOM = """
+# Primary Equations of motion here
+ddt(:rho:)  =  -ddx(:rho:*:u:)                  - ddy(:rho:*:v:)                  - ddz(:rho:*:w:)
+ddt(:rhou:) =  -ddx(:rhou:*:u: + :p: - :tauxx:) - ddy(:rhou:*:v: - :tauxy:)       - ddz(:rhou:*:w: - :tauxz:)
+ddt(:rhov:) =  -ddx(:rhov:*:u: - :tauxy:)       - ddy(:rhov:*:v: + :p: - :tauyy:) - ddz(:rhov:*:w: - :tauyz:)
+ddt(:rhow:) =  -ddx(:rhow:*:u: - :tauxz:)       - ddy(:rhow:*:v: - :tauyz:)       - ddz(:rhow:*:w: + :p: - :tauzz:)
+ddt(:Et:)   =  -ddx( (:Et: - :tauxx:)*:u: - :tauxy:*:v: - :tauxz:*:w: ) - ddy( (:Et: - :tauyy:)*:v: -:tauxy:*:u: - :tauyz:*:w:) - ddz( (:Et: - :tauzz:)*:w: - :tauxz:*:u: - :tauyz:*:v: )
+# Conservative filter of the EoM
+:rho:       =  fbar( :rho:  )
+:rhou:      =  fbar( :rhou: )
+:rhov:      =  fbar( :rhov: )
+:rhow:      =  fbar( :rhow: )
+:Et:        =  fbar( :Et:   )
+# Update the primatives and enforce the EOS
+:u:         =  :rhou: / :rho:
+:v:         =  :rhov: / :rho:
+:w:         =  :rhow: / :rho:
+:p:         =  ( :Et: - .5*:rho:*(:u:*:u: + :v:*:v: + :w:*:w:) ) * ( :gamma: - 1.0 )
+# Artificial bulk viscosity 
+:ux:        =  ddx(:u:)
+:vy:        =  ddy(:v:)
+:wz:        =  ddz(:w:)
+:div:       =  :ux: + :vy: + :wz:
+# Remaining cross derivatives
+:uy:        =  ddy(:u:)
+:uz:        =  ddz(:u:)
+:vx:        =  ddx(:v:)
+:vz:        =  ddz(:v:)
+:wy:        =  ddy(:w:)
+:wx:        =  ddx(:w:)
+:enst:      = sqrt( (:uy:-:vx:)**2 + (:uz: - :wx:)**2 + (:vz:-:wy:)**2 )
+:tke:       = :rho:*(:u:*:u: + :v:*:v: + :w:*:w:)
+:S:         = sqrt( :ux:*:ux: + :vy:*:vy: + :wz:*:wz: + .5*((:uy:+:vx:)**2 + (:uz: + :wx:)**2 + (:vz:+:wy:)**2) )
+:mu:        =  gbar( abs(ring(:S:  )) ) * :rho: * 0.0e-4
+:beta:      =  gbar( abs(ring(:div:)) * :rho: )  * 0.0e-4
+:taudia:    =  (:beta:-2./3.*:mu:) *:div:
+:tauxx:     =  2.0*:mu:*:ux:   + :taudia: - :p:
+:tauyy:     =  2.0*:mu:*:vy:   + :taudia: - :p:
+:tauzz:     =  2.0*:mu:*:wz:   + :taudia: - :p:
+:tauxy:     = :mu:*(:uy:+:vx:) + :taudia:
+:tauxz:     = :mu:*(:uz:+:wx:) + :taudia:
+:tauyz:     = :mu:*(:vz:+:wz:) + :taudia:
+:cs:  = sqrt( :p: / :rho: * :gamma: )
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)*.5
+:dt: = numpy.minimum(:dt:,0.2 * dt.diff(:beta:,:rho:))
+:dt: = numpy.minimum(:dt:,0.2 * dt.diff(:mu:,:rho:))
+"""
+
+ADVECT3D_IC = """
+:gamma: = 1.4
+u0 = 1.0
+p0 = 1.0
+rho0 = 1.0
+L = 1.0
+rad = sqrt( (meshx-pi)**2 + (meshy-pi)**2 + (meshz-pi)**2 )
+:w: +=  u0
+:p:  += p0 
+:rho: += rho0*(1.0+ .01* (1.0+tanh( -(rad-.5)/(.5) )) )
+:rhou: = :rho:*:u:
+:rhov: = :rho:*:v:
+:rhow: = :rho:*:w:
+:Et:  = :p: / (:gamma:-1.0) + 0.5*:rho:*(:u:*:u: + :v:*:v: + :w:*:w:)
+:cs:  = sqrt( :p: / :rho: * :gamma: )
+:tke: = :rho:*(:u:*:u: + :v:*:v: + :w:*:w:)
+:dt: = dt.courant(:u:,:v:,:w:,:cs:)
+"""

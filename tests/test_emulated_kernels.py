@@ -158,3 +158,30 @@ def test_emulated_example_decks_on_the_device_backend(case, oracle_mod, emul_lib
     from deck_parity import worst_difference
     n, steps = (16, 2) if case == "RT_3D" else (32, 5)  # the 3-D deck is slow under one-thread-per-CUDA-thread emulation
     assert worst_difference(case, n, oracle_mod, nsteps=steps, lib=emul_lib, tensor_device="cpu") < 1e-11
+
+
+def test_copied_variable_keeps_its_value_through_the_inplace_stage(oracle_mod, emul_lib):
+    """`:phi0: = :phi:` in the initial conditions (examples/simple.py, grid_conv.py, swirl.py): the
+    reference rebinds the conserved array every stage, so phi0 keeps the initial field.  The device
+    stage update is in place and must not drag the copy (or the mesh, `:phi: = meshx`) along; a
+    C-contiguous conserved field must not be walked with the wrong strides either."""
+    from deck_parity import device_sim
+    from oracle_backend import make_sim
+    mesh = "xdom = (0.0, 1.0, 32, periodic=True)\nydom = (0.0, 1.0, 16, periodic=True)\nzdom = (0.0, 1.0, 1)"
+    eom = "ddt(:phi:) = - :c: * ddx(:phi:) - 0.5 * ddy(:phi:)\nddt(:psi:) = - ddx(:psi:)"
+    ic = ":phi: = exp(-(meshx-0.5)**2/0.01)*cos(6.283185307179586*meshy)\n:phi0: = :phi:\n:c: = 1.0\n:psi: = meshx"
+    sims = [make_sim(oracle_mod, "copy", mesh), device_sim("copy", mesh, lib=emul_lib, tensor_device="cpu")]
+    for ss in sims:
+        ss.EOM(eom)
+        ss.setIC(ic)
+    # a conserved field handed over C-contiguous (as a user function would return it)
+    sims[1].variables["phi"] = sims[1].variables["phi"].contiguous()
+    t = [0.0, 0.0]
+    for _ in range(4):
+        for k, ss in enumerate(sims):
+            t[k] = ss.rk4(t[k], 2e-3)
+    a, b = sims
+    for nm in ("phi", "phi0", "psi", "meshx"):
+        assert rel_linf(b.variables[nm].numpy(), a.variables[nm]) < 1e-13, nm
+    assert np.abs(a.variables["phi"] - a.variables["phi0"]).max() > 1e-3          # the field moved ...
+    assert np.abs(b.variables["phi0"].numpy() - a.variables["phi0"]).max() == 0.0  # ... the copy did not

@@ -104,3 +104,45 @@ def test_equation_groups_match_sequential_evaluation():
     g = fz.groups[gid]
     mask = [nm != "gamma" for nm in g["inputs"]]
     assert len(_Nvrtc().compile_to_cubin(group_kernel_source(g["stmts"], mask))) > 100
+
+
+def test_hoisted_flux_arguments_and_stage_split():
+    """fuse.hoist: the operator arguments of all PDE lines in one multi-output group, the lines
+    rewritten to read them; evaluated through the fallback path the fluxes equal the plain ones."""
+    rng = np.random.default_rng(1)
+    sim = _Sim(rng)
+    sim._hoisted = {}
+    fz = Fuser(_NS, enabled=False)
+    import re
+    names = set()
+    for ln in _lines(TGV_EOM):
+        names.update(re.findall(r":([A-Za-z_]\w*):", ln))
+    for nm in names:
+        sim.variables[nm] = rng.uniform(0.5, 1.5, size=(4, 3, 2))
+    ns = {"xp": _NS, "numpy": _NS, "self": sim, "__fz": fz.call}
+    pde = [translate(ln.split("=", 1)[1]) for ln in _lines(TGV_EOM) if "ddt(" in ln]
+    gid, srcs = fz.hoist(pde)
+    assert gid is not None and len(fz.groups[gid]["outs"]) == 15   # 3 directions x 5 equations, all distinct
+    assert len(fz.groups[gid]["inputs"]) == 14                      # rho u v w rhou rhov rhow Et + 6 stresses, each read once
+    fz.run_group(gid, sim.variables, out=sim._hoisted)
+    for src, new in zip(pde, srcs):
+        assert "self._hoisted" in new
+        fsrc = fz.transform(new)
+        split = fz.split_stage(fsrc)
+        assert split is not None                                    # -ddx(.) - ddy(.) - ddz(.): arithmetic of three operator results
+        leaves = eval(split[1], ns)
+        assert len(leaves) == 3
+        assert np.array_equal(eval(src, ns), fz.call(split[0], *leaves))
+        assert np.array_equal(eval(src, ns), eval(fsrc, ns))
+
+
+def test_host_only_lines_are_found():
+    """The `:dt:` chain, `:cs:` and the diagnostics of the Taylor-Green deck are needed by the host only."""
+    from pyranda_b200.sim import pyrandaSim, _Equation
+    eqs = [_Equation(ln) for ln in _lines(TGV_EOM)]
+
+    class S:
+        equations = eqs
+        conserved = [e.lhs[0] for e in eqs if e.kind == "PDE"]
+    dead = pyrandaSim._host_only(S)
+    assert dead == {"dt", "cs", "enst", "tke"}, dead
