@@ -158,7 +158,7 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
     phi[t] = make_double2(gt.phi[t * 2], gt.phi[t * 2 + 1]);
     psi[t] = make_double2(gt.psi[t * 2], gt.psi[t * 2 + 1]);
     chi[t] = make_double2(gt.chi[t * 2], gt.chi[t * 2 + 1]);
-    lub[t] = make_double4(gt.lub[t * 4], gt.lub[t * 4 + 1], gt.lub[t * 4 + 2], 0.0);
+    lub[t] = make_double4(gt.lub[t * 4], gt.lub[t * 4] * gt.lub[t * 4 + 1], gt.lub[t * 4] * gt.lub[t * 4 + 2], 0.0);
   }
   if (dv.cparam)
     for (int q = 0; q < 32; ++q) dv.chi0[q] = chi[q];
@@ -297,7 +297,7 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic, in
       luf[t] = make_double2(lt.luf[t * 2], lt.luf[t * 2 + 1]);
       phi[t] = make_double2(lt.phi[t * 2], lt.phi[t * 2 + 1]);
       psi[t] = make_double2(lt.psi[t * 2], lt.psi[t * 2 + 1]);
-      lub[t] = make_double4(lt.lub[t * 4], lt.lub[t * 4 + 1], lt.lub[t * 4 + 2], 0.0);
+      lub[t] = make_double4(lt.lub[t * 4], lt.lub[t * 4] * lt.lub[t * 4 + 1], lt.lub[t * 4] * lt.lub[t * 4 + 2], 0.0);  // {1/pivot, u1/pivot, u2/pivot}
     }
     std::vector<double4> Mf((size_t)P * (P + 1)), Mb((size_t)P * (P + 1));
     for (size_t t = 0; t < Mf.size(); ++t) {

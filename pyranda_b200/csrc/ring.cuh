@@ -311,9 +311,8 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           double x = rl[r];
           x = fma(f.x, st.x, x);
           x = fma(f.y, st.y, x);
+          x = fma(-c.z, x2, x * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
           x = fma(-c.y, x1, x);
-          x = fma(-c.z, x2, x);
-          x *= c.x;
           rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
           x2 = x1;
           x1 = x;

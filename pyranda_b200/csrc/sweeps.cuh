@@ -383,14 +383,13 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
     double *sp = S + (size_t)(s + C - 1) * NL + l;
     double x1 = 0.0, x2 = 0.0;
     if (cc) {
-      const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+      const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
       auto rowB = [&](double2 f, int j) {
         double t = sp[-(j * NL)];
         t = fma(f.x, st.x, t);
         t = fma(f.y, st.y, t);
+        t = fma(-u2, x2, t * ip);
         t = fma(-u1, x1, t);
-        t = fma(-u2, x2, t);
-        t *= ip;
         sp[-(j * NL)] = t;
         x2 = x1;
         x1 = t;
@@ -412,9 +411,8 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
         double t = sp[-(r * NL)];
         t = fma(f.x, st.x, t);
         t = fma(f.y, st.y, t);
+        t = fma(-c.z, x2, t * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
         t = fma(-c.y, x1, t);
-        t = fma(-c.z, x2, t);
-        t *= c.x;
         sp[-(r * NL)] = t;
         x2 = x1;
         x1 = t;
@@ -776,16 +774,15 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
       const double2 *ph = a.phi + (size_t)type * C;
       double x1 = 0.0, x2 = 0.0;
       if (cc) {
-        const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+        const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
 #pragma unroll 8
         for (int r = C - 1; r >= 0; --r) {
           const double2 f = __ldg(ph + r);
           double t = Sl[r];
           t = fma(f.x, st.x, t);
           t = fma(f.y, st.y, t);
+          t = fma(-u2, x2, t * ip);
           t = fma(-u1, x1, t);
-          t = fma(-u2, x2, t);
-          t *= ip;
           Sl[r] = t;
           x2 = x1;
           x1 = t;
@@ -799,9 +796,8 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
           double t = Sl[r];
           t = fma(f.x, st.x, t);
           t = fma(f.y, st.y, t);
+          t = fma(-c.z, x2, t * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
           t = fma(-c.y, x1, t);
-          t = fma(-c.z, x2, t);
-          t *= c.x;
           Sl[r] = t;
           x2 = x1;
           x1 = t;
@@ -984,15 +980,14 @@ sweep_yz_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict
     }
     double x1 = 0.0, x2 = 0.0;
     if (cc) {
-      const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+      const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
       static_for<0, CT>([&](auto jc) {
         constexpr int r = CT - 1 - decltype(jc)::value;
         double t = rl[r];
         t = fma(a.phi0[r].x, st.x, t);
         t = fma(a.phi0[r].y, st.y, t);
+        t = fma(-u2, x2, t * ip);
         t = fma(-u1, x1, t);
-        t = fma(-u2, x2, t);
-        t *= ip;
         rl[r] = t;
         x2 = x1;
         x1 = t;
@@ -1007,9 +1002,8 @@ sweep_yz_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict
         double t = rl[r];
         t = fma(f.x, st.x, t);
         t = fma(f.y, st.y, t);
+        t = fma(-c.z, x2, t * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
         t = fma(-c.y, x1, t);
-        t = fma(-c.z, x2, t);
-        t *= c.x;
         rl[r] = t;
         x2 = x1;
         x1 = t;
@@ -1193,15 +1187,14 @@ sweep_x_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
     }
     double x1 = 0.0, x2 = 0.0;
     if (cc) {
-      const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+      const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
       static_for<0, CT>([&](auto jc) {
         constexpr int r = CT - 1 - decltype(jc)::value;
         double t = rl[r];
         t = fma(a.phi0[r].x, st.x, t);
         t = fma(a.phi0[r].y, st.y, t);
+        t = fma(-u2, x2, t * ip);
         t = fma(-u1, x1, t);
-        t = fma(-u2, x2, t);
-        t *= ip;
         rl[r] = t;
         x2 = x1;
         x1 = t;
@@ -1216,9 +1209,8 @@ sweep_x_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
         double t = rl[r];
         t = fma(f.x, st.x, t);
         t = fma(f.y, st.y, t);
+        t = fma(-c.z, x2, t * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
         t = fma(-c.y, x1, t);
-        t = fma(-c.z, x2, t);
-        t *= c.x;
         rl[r] = t;
         x2 = x1;
         x1 = t;
@@ -1488,9 +1480,8 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           double x = rl[r];
           x = fma(f.x, st.x, x);
           x = fma(f.y, st.y, x);
+          x = fma(-c.z, x2, x * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
           x = fma(-c.y, x1, x);
-          x = fma(-c.z, x2, x);
-          x *= c.x;
           rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
           if (ADDV && LATE) {
             if (r < 2) xloc[r] = x;
@@ -1848,9 +1839,8 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
         double x = rl[r];
         x = fma(f0, st.x, x);
         x = fma(f1, st.y, x);
+        x = fma(-u2, x2, x * ip);
         x = fma(-u1, x1, x);
-        x = fma(-u2, x2, x);
-        x *= ip;
         if constexpr (ADDV && LATE) {
           if constexpr (r & 1) vv2 = pair(std::integral_constant<int, (r + 3) / 2>{});  // x = 32 p + r - 1, 32 p + r
           rl[r] = fma(x, scale, (r & 1) ? vv2.y : vv2.x);
@@ -1861,7 +1851,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
         x1 = x;
       };
       if (cc) {
-        const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
+        const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
         static_for<0, CT>([&](auto jc) {
           constexpr int r = CT - 1 - decltype(jc)::value;
           rowB(std::integral_constant<int, r>{}, a.phi0[r].x, a.phi0[r].y, ip, u1, u2);
