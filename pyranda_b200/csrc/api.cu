@@ -297,7 +297,10 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic, in
       luf[t] = make_double2(lt.luf[t * 2], lt.luf[t * 2 + 1]);
       phi[t] = make_double2(lt.phi[t * 2], lt.phi[t * 2 + 1]);
       psi[t] = make_double2(lt.psi[t * 2], lt.psi[t * 2 + 1]);
-      lub[t] = make_double4(lt.lub[t * 4], lt.lub[t * 4] * lt.lub[t * 4 + 1], lt.lub[t * 4] * lt.lub[t * 4 + 2], 0.0);  // {1/pivot, u1/pivot, u2/pivot}
+      // y / z kernels: {1/pivot, u1/pivot, u2/pivot} (one operation on the chain through x1); the x kernels sit at
+      // the 128-register limit with the form (t - u1 x1 - u2 x2) / pivot and keep {1/pivot, u1, u2}
+      const double sc = dir == 0 ? 1.0 : lt.lub[t * 4];
+      lub[t] = make_double4(lt.lub[t * 4], sc * lt.lub[t * 4 + 1], sc * lt.lub[t * 4 + 2], 0.0);
     }
     std::vector<double4> Mf((size_t)P * (P + 1)), Mb((size_t)P * (P + 1));
     for (size_t t = 0; t < Mf.size(); ++t) {

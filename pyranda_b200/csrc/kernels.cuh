@@ -34,7 +34,7 @@ struct SweepDev {
   int has_const;        // chunk type 0 has row-independent LU coefficients, kept in cst[]
   double cst[5];        // l2, l1, 1/pivot, u1, u2 of the converged rows
   const double2 *luf;   // [ntypes][C]  {l2, l1}   forward multipliers (rows i-2, i-1)
-  const double4 *lub;   // [ntypes][C]  {1/pivot, u1/pivot, u2/pivot, 0}
+  const double4 *lub;   // [ntypes][C]  y / z sweeps: {1/pivot, u1/pivot, u2/pivot, 0}; x sweeps: {1/pivot, u1, u2, 0}
   const double2 *phi;   // [ntypes][C]  forward response to the state entering the chunk
   const double2 *psi;   // [ntypes][C]  backward response to the state entering the chunk
   const double4 *Mf;    // [P][P+1]     2x2 products giving the forward state entering a chunk

@@ -774,15 +774,16 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
       const double2 *ph = a.phi + (size_t)type * C;
       double x1 = 0.0, x2 = 0.0;
       if (cc) {
-        const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
+        const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
 #pragma unroll 8
         for (int r = C - 1; r >= 0; --r) {
           const double2 f = __ldg(ph + r);
           double t = Sl[r];
           t = fma(f.x, st.x, t);
           t = fma(f.y, st.y, t);
-          t = fma(-u2, x2, t * ip);
           t = fma(-u1, x1, t);
+          t = fma(-u2, x2, t);
+          t *= ip;
           Sl[r] = t;
           x2 = x1;
           x1 = t;
@@ -796,8 +797,9 @@ sweep_x_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v,
           double t = Sl[r];
           t = fma(f.x, st.x, t);
           t = fma(f.y, st.y, t);
-          t = fma(-c.z, x2, t * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
           t = fma(-c.y, x1, t);
+          t = fma(-c.z, x2, t);
+          t *= c.x;
           Sl[r] = t;
           x2 = x1;
           x1 = t;
@@ -1187,14 +1189,15 @@ sweep_x_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
     }
     double x1 = 0.0, x2 = 0.0;
     if (cc) {
-      const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
+      const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
       static_for<0, CT>([&](auto jc) {
         constexpr int r = CT - 1 - decltype(jc)::value;
         double t = rl[r];
         t = fma(a.phi0[r].x, st.x, t);
         t = fma(a.phi0[r].y, st.y, t);
-        t = fma(-u2, x2, t * ip);
         t = fma(-u1, x1, t);
+        t = fma(-u2, x2, t);
+        t *= ip;
         rl[r] = t;
         x2 = x1;
         x1 = t;
@@ -1209,8 +1212,9 @@ sweep_x_reg_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
         double t = rl[r];
         t = fma(f.x, st.x, t);
         t = fma(f.y, st.y, t);
-        t = fma(-c.z, x2, t * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
         t = fma(-c.y, x1, t);
+        t = fma(-c.z, x2, t);
+        t *= c.x;
         rl[r] = t;
         x2 = x1;
         x1 = t;
@@ -1839,8 +1843,9 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
         double x = rl[r];
         x = fma(f0, st.x, x);
         x = fma(f1, st.y, x);
-        x = fma(-u2, x2, x * ip);
         x = fma(-u1, x1, x);
+        x = fma(-u2, x2, x);
+        x *= ip;
         if constexpr (ADDV && LATE) {
           if constexpr (r & 1) vv2 = pair(std::integral_constant<int, (r + 3) / 2>{});  // x = 32 p + r - 1, 32 p + r
           rl[r] = fma(x, scale, (r & 1) ? vv2.y : vv2.x);
@@ -1851,7 +1856,7 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
         x1 = x;
       };
       if (cc) {
-        const double ip = a.cst[2], u1 = a.cst[2] * a.cst[3], u2 = a.cst[2] * a.cst[4];
+        const double ip = a.cst[2], u1 = a.cst[3], u2 = a.cst[4];
         static_for<0, CT>([&](auto jc) {
           constexpr int r = CT - 1 - decltype(jc)::value;
           rowB(std::integral_constant<int, r>{}, a.phi0[r].x, a.phi0[r].y, ip, u1, u2);
