@@ -417,6 +417,27 @@ def parity_block(world, rank, local, dev):
             "tolerance": 1e-12, "against": "oracle/parcop_oracle.c (CPU restatement of the reference), same inputs", "z_path": paths}
 
 
+def other_configs(world, rank):
+    """BASELINE configs[3] (RT3D, bounded x, z-slab over the ranks; 1.5 N x N x N with N = 512 on 8 GPUs, the same
+    points per GPU -- N = 256 -- on one) and configs[4] (curvilinear cylinder 1024 x 512 x 64, one GPU), a few
+    RK4 steps each through the deck interpreter (tools/run_configs.py).  Failures are reported, not fatal."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    out = {}
+    try:
+        import run_configs
+        npts = {1: 256, 8: 512}.get(world)
+        if npts is not None:
+            out["rt3d"] = run_configs.run_rt3d(npts, 2)
+        if world == 1:
+            torch.cuda.empty_cache()
+            out["cylinder_curv"] = run_configs.run_cylinder(1024, 512, 64, 2)
+    except Exception as exc:  # noqa: BLE001
+        out["error"] = "%s: %s" % (type(exc).__name__, exc)
+    torch.cuda.empty_cache()
+    return out or None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -432,6 +453,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong_1024 block")
     ap.add_argument("--no-bounded", action="store_true", help="skip the per_op_bounded block")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[3] / configs[4] (RT3D, curvilinear cylinder)")
     ap.add_argument("--tgv-n", type=int, default=256)
     args = ap.parse_args()
     quiet_stdout()
@@ -515,6 +537,9 @@ def main():
     bounded = None if args.no_bounded else bounded_block(world, rank, local, dev, peak, n)
     strong = None if (args.no_strong or args.global_n) else strong_1024_block(world, rank, local, dev, peak)
     parity = None if args.no_parity else parity_block(world, rank, local, dev)
+    configs = None
+    if not args.no_configs:
+        configs = other_configs(world, rank)
 
     if rank != 0:
         if world > 1:
@@ -543,7 +568,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": K, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.global_n else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": cfg,
-            "per_op": per_op, "per_op_bounded": bounded, "strong_1024": strong, "parity": parity, "tgv": tgv, "roofline": roofline,
+            "per_op": per_op, "per_op_bounded": bounded, "strong_1024": strong, "parity": parity, "configs": configs, "tgv": tgv,
+            "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     emit(line)
     if world > 1:

@@ -432,7 +432,7 @@ Partition build_partition(int m, const std::vector<double> &bands, bool cyclic, 
   return part;
 }
 
-LineTables build_line_tables(int m, const std::vector<double> &bands, bool cyclic, int P) {
+LineTables build_line_tables(int m, const std::vector<double> &bands, bool cyclic, int P, double cut) {
   if (P < 1 || m % P != 0) throw std::invalid_argument("build_line_tables: P must divide m");
   const int C = m / P;
   if (C < 8) throw std::invalid_argument("build_line_tables: chunk shorter than 8 rows");
@@ -585,8 +585,8 @@ LineTables build_line_tables(int m, const std::vector<double> &bands, bool cycli
     T.nF.assign(P, 0); T.nB.assign(P, 0);
     // Terms are dropped once the transfer product falls below the rounding unit of the leading
     // (identity) term: what they would add is below the last bit of the state they are added to.
-    static const long double tiny_env = getenv("PB_TINY") ? (long double)atof(getenv("PB_TINY")) : 2.2e-16L;
-    const long double tiny = tiny_env;
+    static const long double tiny_env = getenv("PB_TINY") ? (long double)atof(getenv("PB_TINY")) : 0.0L;
+    const long double tiny = tiny_env > 0.0L ? tiny_env : (cut > 0.0 ? (long double)cut : 2.2e-16L);
     auto mxabs = [](const M2 &x) { return std::max(std::max(fabsl(x.a), fabsl(x.b)), std::max(fabsl(x.c), fabsl(x.d))); };
     auto put4 = [](double *dst, const M2 &x) { dst[0] = (double)x.a; dst[1] = (double)x.b; dst[2] = (double)x.c; dst[3] = (double)x.d; };
     if (cyclic) {

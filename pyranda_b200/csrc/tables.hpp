@@ -72,7 +72,8 @@ struct LineTables {
   std::vector<double> Mb;           // [P][P+1][4]  Mb[p][j] applies to the start values of chunk (p+j) mod P
   std::vector<int> nF, nB;          // [P] number of terms kept (including the identity term)
 };
-LineTables build_line_tables(int m, const std::vector<double> &bands, bool cyclic, int P);
+// cut: carried-state terms whose transfer product is below this are dropped (0: the default, the rounding unit)
+LineTables build_line_tables(int m, const std::vector<double> &bands, bool cyclic, int P, double cut = 0.0);
 
 // bands: m rows x 5, row i multiplies x[i-2..i+2]; entries that fall outside [0,m) are couplings
 // to the other end when `cyclic`, and are ignored otherwise.

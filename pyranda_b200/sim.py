@@ -345,6 +345,18 @@ def curvilinear_coordinates(opt, lo=(0, 0, 0), shape=None):
     x, y, z = (np.asfortranarray(a) for a in np.meshgrid(*ax, indexing="ij"))
     fn = opt.get("function")
     if fn:
+        # a function of index ARRAYS (numpy fancy indexing, as the example decks' lambdas allow) fills the
+        # whole block at once; anything else is evaluated point by point like pyrandaMesh.makeMesh does
+        try:
+            I, J, K = np.meshgrid(*[np.arange(shape[d]) + lo[d] for d in range(3)], indexing="ij")
+            got = fn(I, J, K)
+            arrs = [np.asfortranarray(np.broadcast_to(np.asarray(g, dtype=np.float64), shape)) for g in got]
+            if len(arrs) == 3:
+                probe = [(0, 0, 0), (shape[0] - 1, shape[1] - 1, shape[2] - 1), (shape[0] // 2, shape[1] // 3, shape[2] // 2)]
+                if all(np.allclose([a[q] for a in arrs], fn(q[0] + lo[0], q[1] + lo[1], q[2] + lo[2]), rtol=0, atol=0) for q in probe):
+                    return tuple(arrs)
+        except Exception:
+            pass
         for i in range(shape[0]):
             for j in range(shape[1]):
                 for k in range(shape[2]):
