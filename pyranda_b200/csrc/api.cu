@@ -167,11 +167,10 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
   // what this rank's forward states add to them is  sum_j Mb[lp][j] X_e sum_j' Mf[e][j'] EN[c]  with
   // X_e the first two rows of chi of chunk e above: folded into one 2x2 block per (top chunk lp, top chunk c).
   static const bool want_early = getenv("PB_XR_EARLY") ? atoi(getenv("PB_XR_EARLY")) != 0 : true;
-  // ... and worthwhile when few states cross a face (first / second / eighth derivative: two chunks): every
-  // consumer polls its own records, which costs more than it hides for the compact filter's six (measured)
+  static const int early_max = getenv("PB_XR_EARLY_MAX") ? atoi(getenv("PB_XR_EARLY_MAX")) : kXExt;
   bool early = want_early;
   for (int rank = 0; rank < np; ++rank)
-    if (need_f(rank) > std::min(P, 3) || need_b(rank) > std::min(P, 3)) early = false;
+    if (need_f(rank) > std::min(P, early_max) || need_b(rank) > std::min(P, early_max)) early = false;
   std::vector<double4> Bc;
   int bc_n = 0;
   if (early && xr.need_b > 0) {
@@ -983,6 +982,11 @@ int pb_z_ring(pb_plan *pl, int zop, const double *d_val, const double *recv_lo, 
   xr.en_in = (const unsigned long long *)x->en_in;
   xr.st_in = (const unsigned long long *)x->st_in;
   if ((xr.need_f > 0 && !xr.en_in) || (xr.need_b > 0 && !xr.st_in) || x->epoch == 0) return fail(PB_ERR_ARG, "missing record buffer / epoch 0");
+#ifndef PB_EMULATE
+  if (((uintptr_t)x->en_in | (uintptr_t)x->st_in) & 31) return fail(PB_ERR_ARG, "record buffers must be 32-byte aligned");
+  for (int h = 0; h < kXHops; ++h)
+    if (((uintptr_t)x->en_out[h] | (uintptr_t)x->st_out[h]) & 31) return fail(PB_ERR_ARG, "record buffers must be 32-byte aligned");
+#endif
   for (int h = 0; h < kXHops; ++h) {
     xr.en_out[h] = (unsigned long long *)x->en_out[h];
     xr.st_out[h] = (unsigned long long *)x->st_out[h];

@@ -41,13 +41,13 @@ __device__ __forceinline__ double2 ld_cl(const double2 *p, int rank) {
 __device__ __forceinline__ void xr_store(unsigned long long *rec, double2 v, unsigned int epoch) {
   const unsigned long long e = (unsigned long long)epoch << 32;
   const unsigned long long bx = (unsigned long long)__double_as_longlong(v.x), by = (unsigned long long)__double_as_longlong(v.y);
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(rec), "l"((bx & 0xffffffffull) | e), "l"((bx >> 32) | e) : "memory");
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(rec + 2), "l"((by & 0xffffffffull) | e), "l"((by >> 32) | e) : "memory");
+  // one 256-bit store per record (a whole 32-byte sector crosses the link in one piece)
+  asm volatile("st.relaxed.sys.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(rec), "l"((bx & 0xffffffffull) | e), "l"((bx >> 32) | e),
+               "l"((by & 0xffffffffull) | e), "l"((by >> 32) | e) : "memory");
 }
 __device__ __forceinline__ bool xr_try_load(const unsigned long long *rec, unsigned int epoch, double2 *v) {
   unsigned long long w0, w1, w2, w3;
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(rec) : "memory");
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(rec + 2) : "memory");
+  asm volatile("ld.relaxed.sys.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(rec) : "memory");
   const unsigned long long e = (unsigned long long)epoch;
   if ((w0 >> 32) != e || (w1 >> 32) != e || (w2 >> 32) != e || (w3 >> 32) != e) return false;
   v->x = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
@@ -59,6 +59,8 @@ __device__ __forceinline__ void xr_pause(unsigned long long &spin) {
   if (spin > 64) __nanosleep(64);
 }
 __device__ __forceinline__ void xr_fence_sys() { __threadfence_system(); }
+// barrier `id` (1..15) among `count` threads (whole warps): the chunks that take states from a neighbouring rank
+__device__ __forceinline__ void xr_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ unsigned int xr_count(unsigned int *c) { return atomicAdd(c, 1u); }
 __device__ __forceinline__ void xr_flag_set(unsigned long long *f, unsigned long long v) { *reinterpret_cast<volatile unsigned long long *>(f) = v; }
 __device__ __forceinline__ unsigned long long xr_flag_get(const volatile unsigned long long *f) { return *f; }
@@ -112,11 +114,13 @@ __device__ __forceinline__ bool ring_warp_all_const(const SweepDev &a, int tid, 
 #endif
 }
 
-template <int FAM, int NL, bool ADDV, bool LATE, bool RING>
+// CLUSTER = false: one CTA per line tile (no distributed shared memory, plain block barriers)
+template <int FAM, int NL, bool ADDV, bool LATE, bool RING, bool CLUSTER>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tmain, const __grid_constant__ TileMap th4,
                      const __grid_constant__ TileMap tlo, const __grid_constant__ TileMap thi,
-                     const __grid_constant__ TileMap tout, const __grid_constant__ PipeGeo g, const __grid_constant__ XRing xr) {
+                     const __grid_constant__ TileMap tout, const __grid_constant__ PipeGeo g, const __grid_constant__ XRing xr,
+                     const double *__restrict__ v) {
   constexpr int CT = 32, H = FT<FAM>::H, HP = 4;
   constexpr int PL = kBlockThreads / NL;    // chunks of a line per CTA
   constexpr int ML = PL * CT;               // rows per CTA
@@ -125,7 +129,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   constexpr int GW = NL / WB;               // store boxes per chunk and round
   PB_SHARED(S);
   const int P = a.P;                        // chunks of the line on this rank = cluster size * PL
-  const int CL = cl_size(), crank = cl_rank();
+  const int CL = CLUSTER ? cl_size() : 1, crank = CLUSTER ? cl_rank() : 0;
   double *tile = S;                                                               // [ML + 2 HP][NL]
   double *stage = S + (size_t)(ML + 2 * HP) * NL;                                 // [PL][GW][SR][WB]
   double2 *EN = reinterpret_cast<double2 *>(stage + (size_t)PL * SR * NL);         // [PL + kXExt][NL]
@@ -171,7 +175,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
     }
   };
   auto sync_all = [&]() {
-    if (CL > 1) cl_sync();
+    if (CLUSTER && CL > 1) cl_sync();
     else __syncthreads();
   };
   // state of chunk q of this rank's line, q outside [0, P): around the ring, or a neighbouring rank's
@@ -180,6 +184,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       if (!a.wrap) return EN[(PL - q - 1) * NL + l];
       q += P;
     }
+    if constexpr (!CLUSTER) return EN[q * NL + l];
     const int owner = q / PL, idx = q - owner * PL;
     return owner == crank ? EN[idx * NL + l] : ld_cl(EN + idx * NL + l, owner);
   };
@@ -188,10 +193,18 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       if (!a.wrap) return ST[(PL + q - P) * NL + l];
       q -= P;
     }
+    if constexpr (!CLUSTER) return ST[q * NL + l];
     const int owner = q / PL, idx = q - owner * PL;
     return owner == crank ? ST[idx * NL + l] : ld_cl(ST + idx * NL + l, owner);
   };
 
+#ifndef PB_EMULATE
+  // early form: the warps that hold a chunk taking forward states from below / backward states from above
+  // fetch one record per thread into shared memory and meet at their own barrier
+  const bool pollF = xr.early && lp < xr.need_f, pollB = xr.early && lp >= P - xr.need_b;
+  const bool warpF = xr.early && __any_sync(0xffffffffu, pollF), warpB = xr.early && __any_sync(0xffffffffu, pollB);
+  const int nbarF = xr.early ? __syncthreads_count(warpF) : 0, nbarB = xr.early ? __syncthreads_count(warpB) : 0;
+#endif
   if (tid == 0) mbar_init(bar, 1);
   if (xr.push) {  // compact_d1.f90:719-735 without a separate pass: my first / last planes into the neighbours' halo buffers
     for (int c = 0; c < 2; ++c) {
@@ -324,16 +337,41 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         for (int k = 0; k < xr.ndn; ++k)
           if (lp < xr.cnt_dn[k] && lv && !(xr.nopoll & 2)) xr_store(xr.st_out[k] + ((long)(k * P + lp) * xr.plane + line0 + l) * 4, make_double2(x1, x2), xr.epoch);
       }
+#ifndef PB_EMULATE
+      if (warpF) {  // one record per thread of the chunks next to the lower face, then everybody who needs them reads shared memory
+        if (pollF) {
+          double2 en = make_double2(0.0, 0.0);
+          if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
+            const unsigned long long *rec = xr.en_in + ((long)lp * xr.plane + line0 + l) * 4;
+            unsigned long long spin = 0;
+            while (!xr_try_load(rec, xr.epoch, &en)) xr_pause(spin);
+          }
+          EN[(PL + lp) * NL + l] = en;
+        }
+        __syncwarp();
+        xr_bar(1, nbarF);
+      }
+#endif
       if (xr.early && a.nf[lp] > lp) {  // the forward states from below: by now they have usually landed
         double2 sg2 = make_double2(0.0, 0.0);
         if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
           const double4 *Mp = a.Mf + (size_t)lp * a.mstride;
           const int nfl = a.nf[lp];
           for (int j = lp + 1; j <= nfl; ++j) {
-            const unsigned long long *rec = xr.en_in + ((long)(j - lp - 1) * xr.plane + line0 + l) * 4;
             double2 en;
+#ifdef PB_EMULATE
+            const unsigned long long *rec = xr.en_in + ((long)(j - lp - 1) * xr.plane + line0 + l) * 4;
             unsigned long long spin = 0;
             while (!xr_try_load(rec, xr.epoch, &en)) xr_pause(spin);
+#else
+            if (warpF) {
+              en = EN[(PL + j - lp - 1) * NL + l];
+            } else {  // a consumer outside the fetching warps (cannot happen for equal state counts per chunk): its own fetch
+              const unsigned long long *rec = xr.en_in + ((long)(j - lp - 1) * xr.plane + line0 + l) * 4;
+              unsigned long long spin = 0;
+              while (!xr_try_load(rec, xr.epoch, &en)) xr_pause(spin);
+            }
+#endif
             const double4 M = ldg4(Mp + j);
             sg2.x = fma(M.y, en.y, fma(M.x, en.x, sg2.x));
             sg2.y = fma(M.w, en.y, fma(M.z, en.x, sg2.y));
@@ -373,13 +411,38 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       {
         int nb = a.nb[lp];
         const double4 *Mp = a.Mb + (size_t)lp * a.mstride;
+#ifndef PB_EMULATE
+        if (warpB) {  // one record per thread of the chunks next to the upper face
+          if (pollB) {
+            double2 sv = make_double2(0.0, 0.0);
+            if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
+              const unsigned long long *rec = xr.st_in + ((long)(lp - (P - xr.need_b)) * xr.plane + line0 + l) * 4;
+              unsigned long long spin = 0;
+              while (!xr_try_load(rec, xr.epoch, &sv)) xr_pause(spin);
+            }
+            ST[(PL + lp - (P - xr.need_b)) * NL + l] = sv;
+          }
+          __syncwarp();
+          xr_bar(2, nbarB);
+        }
+#endif
         if (xr.early && nb > P - 1 - lp) {  // the chunks above this slab: their states as sent, plus what this rank's forward states add to them
           if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
             for (int j = P - lp; j <= nb; ++j) {
-              const unsigned long long *rec = xr.st_in + ((long)(lp + j - P) * xr.plane + line0 + l) * 4;
               double2 sv;
+#ifdef PB_EMULATE
+              const unsigned long long *rec = xr.st_in + ((long)(lp + j - P) * xr.plane + line0 + l) * 4;
               unsigned long long spin = 0;
               while (!xr_try_load(rec, xr.epoch, &sv)) xr_pause(spin);
+#else
+              if (warpB) {
+                sv = ST[(PL + lp + j - P) * NL + l];
+              } else {
+                const unsigned long long *rec = xr.st_in + ((long)(lp + j - P) * xr.plane + line0 + l) * 4;
+                unsigned long long spin = 0;
+                while (!xr_try_load(rec, xr.epoch, &sv)) xr_pause(spin);
+              }
+#endif
               const double4 M = ldg4(Mp + j);
               tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
               tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
@@ -402,6 +465,13 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         }
       }
       double *sg = stage + (size_t)((p * GW + l / WB) * SR) * WB + (l % WB);
+      // add-back that is not LATE: the input left the tile when the prefetch started, it is read again (from L2)
+      const double *pv = v;
+      if (ADDV && !LATE) {
+        int xi = ti * NL + l;
+        if (xi >= a.nfast) xi = a.nfast - 1;
+        pv = v + (long)xi + (long)o * a.ostride + (long)(lp * CT) * a.rstride;
+      }
       auto rowD = [&](auto rc, double gx, double gy, double xl) {
         constexpr int r = decltype(rc)::value;
         double val;
@@ -412,7 +482,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           double x = fma(gx, tb.x, xl);
           x = fma(gy, tb.y, x);
           val = x * scale;
-          if (ADDV) val += tw[(r + H) * NL];  // unreachable: the add-back is always LATE here
+          if (ADDV) val += __ldg(pv + (long)r * a.rstride);
         }
         if constexpr (RING) val = fabs(val) * a.ring_s2;
         sg[(r % SR) * WB] = val;
@@ -458,7 +528,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
     }
   }
   if ((tid & 31) == 0) tma_store_wait_read();
-  if (CL > 1) cl_sync();  // nobody leaves while a neighbour may still read its states
+  if (CLUSTER && CL > 1) cl_sync();  // nobody leaves while a neighbour may still read its states
 }
 
 // Host side: tensor maps, per-CTA chunk order, cluster launch.  Returns cudaErrorNotSupported when
@@ -511,19 +581,28 @@ static cudaError_t launch_yz_ring(const SweepDev &a0, const double *v, double *o
   }
   const size_t smem = ((size_t)(ML + 8) * NL + (size_t)PL * SR * NL) * sizeof(double) + 2 * (size_t)(PL + kXExt) * NL * sizeof(double2) + 16;
   static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
-  void (*kfn)(SweepDev, TileMap, TileMap, TileMap, TileMap, TileMap, PipeGeo, XRing) = nullptr;
+  void (*kfn)(SweepDev, TileMap, TileMap, TileMap, TileMap, TileMap, PipeGeo, XRing, const double *) = nullptr;
   int slot = 0;
+  const bool cl1 = CL == 1;
   if (a.ring) {
-    if constexpr (!ADDV && FAM == F_R4) kfn = sweep_yz_ring_kernel<FAM, NL, ADDV, false, true>;
+    if constexpr (!ADDV && FAM == F_R4) kfn = cl1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, false, true, false> : sweep_yz_ring_kernel<FAM, NL, ADDV, false, true, true>;
     slot = 1;
   } else if (ADDV) {
-    if (!late) return cudaErrorNotSupported;
-    if constexpr (ADDV) kfn = sweep_yz_ring_kernel<FAM, NL, ADDV, true, false>;
+    // filters: the add-back from the tile (LATE) keeps the tile until the backward pass, so the next tile is
+    // requested one phase later; re-reading the input from L2 instead (request after the forward pass) measured
+    // slower on one GPU and across ranks (profiles/r2_xr_variants_2gpu.log)
+    static const int xr_late = getenv("PB_XR_LATE") ? atoi(getenv("PB_XR_LATE")) : 1;
+    const bool use_late = xr.on ? xr_late != 0 : late;
+    if constexpr (ADDV) {
+      if (use_late) { kfn = cl1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, true, false, false> : sweep_yz_ring_kernel<FAM, NL, ADDV, true, false, true>; slot = 0; }
+      else { kfn = cl1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, false, false, false> : sweep_yz_ring_kernel<FAM, NL, ADDV, false, false, true>; slot = 2; }
+    }
   } else {
-    if constexpr (!ADDV) kfn = sweep_yz_ring_kernel<FAM, NL, ADDV, false, false>;
+    if constexpr (!ADDV) kfn = cl1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, false, false, false> : sweep_yz_ring_kernel<FAM, NL, ADDV, false, false, true>;
   }
   if (kfn == nullptr) return cudaErrorNotSupported;
-  static bool configured[2] = {false, false};
+  static bool configured[6] = {false, false, false, false, false, false};
+  slot = 2 * slot + (cl1 ? 0 : 1);
   if (!configured[slot]) {
     cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -537,11 +616,11 @@ static cudaError_t launch_yz_ring(const SweepDev &a0, const double *v, double *o
   if (xr.push) ncl = 1;  // emulated CTAs run one after the other: the flag handshake of the push needs them all resident
 #endif
 #ifdef PB_EMULATE
-  emul::launch_cluster(dim3((unsigned)(ncl * CL)), CL, dim3(kBlockThreads), smem, [&] { kfn(a, tmain, th4, tlo, thi, tout, g, xr); });
+  emul::launch_cluster(dim3((unsigned)(ncl * CL)), CL, dim3(kBlockThreads), smem, [&] { kfn(a, tmain, th4, tlo, thi, tout, g, xr, v); });
 #else
   static const bool plain1 = getenv("PB_RING_PLAIN_LAUNCH") ? atoi(getenv("PB_RING_PLAIN_LAUNCH")) != 0 : true;
   if (CL == 1 && plain1) {  // no cluster: an ordinary launch
-    kfn<<<dim3((unsigned)ncl), dim3(kBlockThreads), smem, st>>>(a, tmain, th4, tlo, thi, tout, g, xr);
+    kfn<<<dim3((unsigned)ncl), dim3(kBlockThreads), smem, st>>>(a, tmain, th4, tlo, thi, tout, g, xr, v);
     ++g_launches;
     ++g_pipe_launches;
     ++g_ring_launches;
@@ -560,7 +639,7 @@ static cudaError_t launch_yz_ring(const SweepDev &a0, const double *v, double *o
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, kfn, a, tmain, th4, tlo, thi, tout, g, xr);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, kfn, a, tmain, th4, tlo, thi, tout, g, xr, v);
   if (err != cudaSuccess) return err;
 #endif
   ++g_launches;

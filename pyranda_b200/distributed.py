@@ -46,7 +46,7 @@ class _PeerBuffers:
         self.flag_off = 2 * self.set_len          # [world] uint64 flags + scratch counter, in doubles
         # the fused z sweep (pb_z_ring): incoming chunk-state records, `slots` x plane x 4 words each way
         self.slots = slots
-        self.rec_off = self.flag_off + ((world + 2 + 1) // 2) * 2
+        self.rec_off = self.flag_off + ((world + 2 + 3) // 4) * 4   # records are 32-byte aligned
         self.rec_len = slots * plane * 4
         self.buf = symm.empty(self.rec_off + 2 * self.rec_len, dtype=torch.float64, device=dev)
         self.buf.zero_()
