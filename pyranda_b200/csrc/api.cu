@@ -102,7 +102,7 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
   const int n = sp.n, np = sp.np, m = n / np, r = sp.rank;
   if (m % 32 != 0) return PB_OK;
   const int P = m / 32, Pg = n / 32;
-  if (P != 4 && P != 8 && P != 16 && P != 32) return PB_OK;  // slabs the ring kernel tiles: 128, 256, 512, 1024 planes
+  if (P != 4 && P != 8 && P != 16) return PB_OK;  // slabs one CTA's tile covers: 128, 256, 512 planes
   LineTables gt;
   try { gt = build_line_tables(n, bands, periodic, Pg); }
   catch (const std::exception &) { return PB_OK; }
@@ -167,7 +167,10 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
   // what this rank's forward states add to them is  sum_j Mb[lp][j] X_e sum_j' Mf[e][j'] EN[c]  with
   // X_e the first two rows of chi of chunk e above: folded into one 2x2 block per (top chunk lp, top chunk c).
   static const bool want_early = getenv("PB_XR_EARLY") ? atoi(getenv("PB_XR_EARLY")) != 0 : true;
-  static const int early_max = getenv("PB_XR_EARLY_MAX") ? atoi(getenv("PB_XR_EARLY_MAX")) : kXExt;
+  // ... and worthwhile when few states cross a face: measured on 2 GPUs at 512^3 per GPU, ddz 0.52 -> 0.47 ms (two
+  // states per face, the waits vanish) but the compact filter 0.80 -> 0.89 ms (six states: the correction and
+  // closure sums cost more than the waits they remove) -- profiles/r2_xr_variants_2gpu.log
+  static const int early_max = getenv("PB_XR_EARLY_MAX") ? atoi(getenv("PB_XR_EARLY_MAX")) : 3;
   bool early = want_early;
   for (int rank = 0; rank < np; ++rank)
     if (need_f(rank) > std::min(P, early_max) || need_b(rank) > std::min(P, early_max)) early = false;

@@ -104,8 +104,11 @@ extern template cudaError_t launch_ring_f<F_R4, true>(int, const SweepDev &, con
 
 // lines per tile of the ring kernel: 256 / lines chunks per CTA must divide the line's chunks into 1, 2, 4 or 8 CTAs
 static int ring_lines(int P, int want) {
-  const int cand[4] = {want, 32, 16, 64};
-  for (int k = 0; k < 4; ++k) {
+  // one CTA per line tile when the line has 4 / 8 / 16 chunks (64 / 32 / 16 lines); longer lines: 32-line tiles
+  // over a cluster (256-byte rows measured best at 1024 points)
+  const int one = P == 4 ? 64 : (P == 8 ? 32 : (P == 16 ? 16 : 0));
+  const int cand[5] = {want, one, 32, 16, 64};
+  for (int k = 0; k < 5; ++k) {
     const int nl = cand[k];
     if (nl != 16 && nl != 32 && nl != 64) continue;
     const int pl = kBlockThreads / nl;

@@ -115,7 +115,8 @@ __device__ __forceinline__ bool ring_warp_all_const(const SweepDev &a, int tid, 
 }
 
 // CLUSTER = false: one CTA per line tile (no distributed shared memory, plain block barriers)
-template <int FAM, int NL, bool ADDV, bool LATE, bool RING, bool CLUSTER>
+// XRM: 0 no cross-rank exchange, 1 waiting form, 2 early form (see XRing)
+template <int FAM, int NL, bool ADDV, bool LATE, bool RING, bool CLUSTER, int XRM>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tmain, const __grid_constant__ TileMap th4,
                      const __grid_constant__ TileMap tlo, const __grid_constant__ TileMap thi,
@@ -149,7 +150,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   const uint32_t tx_bytes = (uint32_t)((ML + (halo_lo ? HP : 0) + (halo_hi ? HP : 0)) * NL * sizeof(double));
   const int row0 = crank * ML;
 
-  bool halo_seen = !xr.push;
+  bool halo_seen = XRM == 0 || !xr.push;
   auto issue = [&](long t) {  // one thread: arm the barrier, describe this CTA's piece of the tile to the TMA unit
     const int x0 = (int)(t % tiles_i) * NL, o = (int)(t / tiles_i);
     mbar_expect_tx(bar, tx_bytes);
@@ -157,7 +158,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       const int row = row0 + b * g.box_rows;
       tma_load_3d(tile + (size_t)(HP + b * g.box_rows) * NL, &tmain, x0, rd1 ? row : o, rd1 ? o : row, bar);
     }
-    if (!halo_seen && g.halo && (crank == 0 || crank == CL - 1)) {  // the neighbours' planes have landed in this rank's halo buffers
+    if (XRM != 0 && !halo_seen && g.halo && (crank == 0 || crank == CL - 1)) {  // the neighbours' planes have landed in this rank's halo buffers
       for (int q = 0; q < xr.npeers; ++q) {
         unsigned long long spin = 0;
         while (xr_flag_get(xr.hflag_local[q]) < xr.hepoch) xr_pause(spin);
@@ -181,7 +182,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   // state of chunk q of this rank's line, q outside [0, P): around the ring, or a neighbouring rank's
   auto en_get = [&](int q) -> double2 {
     if (q < 0) {
-      if (!a.wrap) return EN[(PL - q - 1) * NL + l];
+      if (XRM != 0 && !a.wrap) return EN[(PL - q - 1) * NL + l];
       q += P;
     }
     if constexpr (!CLUSTER) return EN[q * NL + l];
@@ -190,7 +191,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   };
   auto st_get = [&](int q) -> double2 {
     if (q >= P) {
-      if (!a.wrap) return ST[(PL + q - P) * NL + l];
+      if (XRM != 0 && !a.wrap) return ST[(PL + q - P) * NL + l];
       q -= P;
     }
     if constexpr (!CLUSTER) return ST[q * NL + l];
@@ -201,12 +202,12 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
 #ifndef PB_EMULATE
   // early form: the warps that hold a chunk taking forward states from below / backward states from above
   // fetch one record per thread into shared memory and meet at their own barrier
-  const bool pollF = xr.early && lp < xr.need_f, pollB = xr.early && lp >= P - xr.need_b;
-  const bool warpF = xr.early && __any_sync(0xffffffffu, pollF), warpB = xr.early && __any_sync(0xffffffffu, pollB);
-  const int nbarF = xr.early ? __syncthreads_count(warpF) : 0, nbarB = xr.early ? __syncthreads_count(warpB) : 0;
+  const bool pollF = XRM == 2 && lp < xr.need_f, pollB = XRM == 2 && lp >= P - xr.need_b;
+  const bool warpF = XRM == 2 && __any_sync(0xffffffffu, pollF), warpB = XRM == 2 && __any_sync(0xffffffffu, pollB);
+  const int nbarF = XRM == 2 ? __syncthreads_count(warpF) : 0, nbarB = XRM == 2 ? __syncthreads_count(warpB) : 0;
 #endif
   if (tid == 0) mbar_init(bar, 1);
-  if (xr.push) {  // compact_d1.f90:719-735 without a separate pass: my first / last planes into the neighbours' halo buffers
+  if (XRM != 0 && xr.push) {  // compact_d1.f90:719-735 without a separate pass: my first / last planes into the neighbours' halo buffers
     for (int c = 0; c < 2; ++c) {
       if (xr.push_dst[c] == nullptr) continue;
       const double2 *src = reinterpret_cast<const double2 *>(xr.push_src[c]);
@@ -266,12 +267,12 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         rm1 = x;
       });
       EN[p * NL + l] = make_double2(rm1, rm2);
-      if (xr.on) {
+      if constexpr (XRM != 0) {
         const bool lv = ti * NL + l < a.nfast;
         const int e = P - 1 - lp;  // chunks from the top of the slab
         for (int k = 0; k < xr.nup; ++k)
           if (e < xr.cnt_up[k] && lv && !(xr.nopoll & 2)) xr_store(xr.en_out[k] + ((long)(k * P + e) * xr.plane + line0 + l) * 4, make_double2(rm1, rm2), xr.epoch);
-        const int need = xr.early ? 0 : xr.need_f - crank * PL;  // waiting form: forward end states of the chunks below this slab
+        const int need = XRM == 2 ? 0 : xr.need_f - crank * PL;  // waiting form: forward end states of the chunks below this slab
         if (tid < need * NL) {
           const int e2 = tid / NL, ll = tid - e2 * NL;
           double2 v = make_double2(0.0, 0.0);
@@ -291,7 +292,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       double2 st = make_double2(0.0, 0.0);
       {
         int nf = a.nf[lp];
-        if (xr.early && nf > lp) nf = lp;  // early form: this rank's chunks now, the ranks below when their states have arrived
+        if (XRM == 2 && nf > lp) nf = lp;  // early form: this rank's chunks now, the ranks below when their states have arrived
         const double4 *Mp = a.Mf + (size_t)lp * a.mstride;
         for (int j = 1; j <= nf; ++j) {
           const double2 en = en_get(lp - j);
@@ -331,14 +332,14 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           x1 = x;
         });
       }
-      if (xr.on) {  // my backward start state to the ranks below (early form: before the states from below have arrived;
+      if constexpr (XRM != 0) {  // my backward start state to the ranks below (early form: before the states from below have arrived;
                     // the receiver adds what its own forward states change in it)
         const bool lv = ti * NL + l < a.nfast;
         for (int k = 0; k < xr.ndn; ++k)
           if (lp < xr.cnt_dn[k] && lv && !(xr.nopoll & 2)) xr_store(xr.st_out[k] + ((long)(k * P + lp) * xr.plane + line0 + l) * 4, make_double2(x1, x2), xr.epoch);
       }
 #ifndef PB_EMULATE
-      if (warpF) {  // one record per thread of the chunks next to the lower face, then everybody who needs them reads shared memory
+      if (XRM == 2 && warpF) {  // one record per thread of the chunks next to the lower face, then everybody who needs them reads shared memory
         if (pollF) {
           double2 en = make_double2(0.0, 0.0);
           if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
@@ -352,7 +353,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         xr_bar(1, nbarF);
       }
 #endif
-      if (xr.early && a.nf[lp] > lp) {  // the forward states from below: by now they have usually landed
+      if (XRM == 2 && a.nf[lp] > lp) {  // the forward states from below: by now they have usually landed
         double2 sg2 = make_double2(0.0, 0.0);
         if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
           const double4 *Mp = a.Mf + (size_t)lp * a.mstride;
@@ -389,7 +390,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         });
       }
       ST[p * NL + l] = make_double2(x1, x2);
-      if (xr.on && !xr.early) {
+      if constexpr (XRM == 1) {
         const int need = xr.need_b - (CL - 1 - crank) * PL;  // waiting form: backward start states of the chunks above this slab
         if (tid < need * NL) {
           const int e2 = tid / NL, ll = tid - e2 * NL;
@@ -412,7 +413,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         int nb = a.nb[lp];
         const double4 *Mp = a.Mb + (size_t)lp * a.mstride;
 #ifndef PB_EMULATE
-        if (warpB) {  // one record per thread of the chunks next to the upper face
+        if (XRM == 2 && warpB) {  // one record per thread of the chunks next to the upper face
           if (pollB) {
             double2 sv = make_double2(0.0, 0.0);
             if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
@@ -426,7 +427,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           xr_bar(2, nbarB);
         }
 #endif
-        if (xr.early && nb > P - 1 - lp) {  // the chunks above this slab: their states as sent, plus what this rank's forward states add to them
+        if (XRM == 2 && nb > P - 1 - lp) {  // the chunks above this slab: their states as sent, plus what this rank's forward states add to them
           if (ti * NL + l < a.nfast && !(xr.nopoll & 1)) {
             for (int j = P - lp; j <= nb; ++j) {
               double2 sv;
@@ -584,25 +585,29 @@ static cudaError_t launch_yz_ring(const SweepDev &a0, const double *v, double *o
   void (*kfn)(SweepDev, TileMap, TileMap, TileMap, TileMap, TileMap, PipeGeo, XRing, const double *) = nullptr;
   int slot = 0;
   const bool cl1 = CL == 1;
+  const int xrm = xr.on ? (xr.early ? 2 : 1) : 0;
+  if (xrm != 0 && !cl1) return cudaErrorNotSupported;  // a z-slab line is one CTA's tile (128, 256 or 512 planes)
+  // filters: the add-back from the tile (LATE) keeps the tile until the backward pass, so the next tile is
+  // requested one phase later; re-reading the input from L2 instead (request after the forward pass) measured
+  // slower on one GPU and across ranks (profiles/r2_xr_variants_2gpu.log)
+#define PB_RING_PICK(LATEV, RINGV)                                                                               \
+  (cl1 ? (xrm == 0 ? sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, false, 0>                                 \
+                   : xrm == 1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, false, 1>                      \
+                              : sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, false, 2>)                     \
+       : sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, true, 0>)
   if (a.ring) {
-    if constexpr (!ADDV && FAM == F_R4) kfn = cl1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, false, true, false> : sweep_yz_ring_kernel<FAM, NL, ADDV, false, true, true>;
+    if constexpr (!ADDV && FAM == F_R4) kfn = PB_RING_PICK(false, true);
     slot = 1;
   } else if (ADDV) {
-    // filters: the add-back from the tile (LATE) keeps the tile until the backward pass, so the next tile is
-    // requested one phase later; re-reading the input from L2 instead (request after the forward pass) measured
-    // slower on one GPU and across ranks (profiles/r2_xr_variants_2gpu.log)
-    static const int xr_late = getenv("PB_XR_LATE") ? atoi(getenv("PB_XR_LATE")) : 1;
-    const bool use_late = xr.on ? xr_late != 0 : late;
-    if constexpr (ADDV) {
-      if (use_late) { kfn = cl1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, true, false, false> : sweep_yz_ring_kernel<FAM, NL, ADDV, true, false, true>; slot = 0; }
-      else { kfn = cl1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, false, false, false> : sweep_yz_ring_kernel<FAM, NL, ADDV, false, false, true>; slot = 2; }
-    }
+    if (!late) return cudaErrorNotSupported;
+    if constexpr (ADDV) kfn = PB_RING_PICK(true, false);
   } else {
-    if constexpr (!ADDV) kfn = cl1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, false, false, false> : sweep_yz_ring_kernel<FAM, NL, ADDV, false, false, true>;
+    if constexpr (!ADDV) kfn = PB_RING_PICK(false, false);
   }
+#undef PB_RING_PICK
   if (kfn == nullptr) return cudaErrorNotSupported;
-  static bool configured[6] = {false, false, false, false, false, false};
-  slot = 2 * slot + (cl1 ? 0 : 1);
+  static bool configured[8] = {false, false, false, false, false, false, false, false};
+  slot = 4 * slot + (cl1 ? xrm : 3);
   if (!configured[slot]) {
     cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
