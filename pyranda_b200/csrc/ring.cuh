@@ -273,8 +273,8 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         for (int k = 0; k < xr.nup; ++k)
           if (e < xr.cnt_up[k] && lv && !(xr.nopoll & 2)) xr_store(xr.en_out[k] + ((long)(k * P + e) * xr.plane + line0 + l) * 4, make_double2(rm1, rm2), xr.epoch);
         const int need = XRM == 2 ? 0 : xr.need_f - crank * PL;  // waiting form: forward end states of the chunks below this slab
-        if (tid < need * NL) {
-          const int e2 = tid / NL, ll = tid - e2 * NL;
+        for (int idx = tid; idx < need * NL; idx += kBlockThreads) {  // 64-line tiles have more records than threads
+          const int e2 = idx / NL, ll = idx - e2 * NL;
           double2 v = make_double2(0.0, 0.0);
           if (ti * NL + ll < a.nfast && !(xr.nopoll & 1)) {
             const unsigned long long *rec = xr.en_in + ((long)e2 * xr.plane + line0 + ll) * 4;
@@ -392,8 +392,8 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
       ST[p * NL + l] = make_double2(x1, x2);
       if constexpr (XRM == 1) {
         const int need = xr.need_b - (CL - 1 - crank) * PL;  // waiting form: backward start states of the chunks above this slab
-        if (tid < need * NL) {
-          const int e2 = tid / NL, ll = tid - e2 * NL;
+        for (int idx = tid; idx < need * NL; idx += kBlockThreads) {
+          const int e2 = idx / NL, ll = idx - e2 * NL;
           double2 v = make_double2(0.0, 0.0);
           if (ti * NL + ll < a.nfast && !(xr.nopoll & 1)) {
             const unsigned long long *rec = xr.st_in + ((long)e2 * xr.plane + line0 + ll) * 4;

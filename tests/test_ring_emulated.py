@@ -173,4 +173,4 @@ def test_fused_zslab_ranks_as_threads(n, world, fused, push, periodic, oracle_mo
         assert 1 in modes, modes   # the compact filter's states come from two ranks away: the waiting form
     done = {k: v for k, v in worst.items() if v is not None}
     assert len(done) >= (fused if periodic else 4), worst
-    assert max(done.values()) < 1e-13, worst
+    assert max(done.values()) < 2e-14, worst   # a dropped far-chunk state of the compact filter is 4e-12
