@@ -256,8 +256,10 @@ __device__ __forceinline__ void stream_chunk(const SweepDev &a, const double *__
         if (k == H) {
           if (lastblk) pl = pend;  // the next row to load is row m
         }
-        ring[k] = __ldg(pl);
-        pl += rs;
+        if (!(lastblk && k >= 2 * H)) {  // rows past m + H - 1 are never used (and a halo buffer holds only H planes)
+          ring[k] = __ldg(pl);
+          pl += rs;
+        }
         emit(b + k, rhs, vc);
       });
     }
@@ -329,6 +331,7 @@ sweep_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict__ v
       return halo_lo ? __ldg(halo_lo + base + (long)(r + H) * rs) : 0.0;
     }
     if (r >= m) {
+      if (r >= m + H) return 0.0;  // look-ahead past the stencil: never used, and a halo buffer holds only H planes
       if (a.wrap) return __ldg(vp + (long)(r - m) * rs);
       return halo_hi ? __ldg(halo_hi + base + (long)(r - m) * rs) : 0.0;
     }
@@ -510,6 +513,7 @@ explicit_yz_kernel(const __grid_constant__ SweepDev a, const double *__restrict_
       return halo_lo ? __ldg(halo_lo + base + (long)(r + H) * rs) : 0.0;
     }
     if (r >= m) {
+      if (r >= m + H) return 0.0;  // look-ahead past the stencil: never used, and a halo buffer holds only H planes
       if (a.wrap) return __ldg(vp + (long)(r - m) * rs);
       return halo_hi ? __ldg(halo_hi + base + (long)(r - m) * rs) : 0.0;
     }

@@ -93,5 +93,6 @@ def test_zslab_nccl(tmp_path, mode):
     if mode == "partitioned-nccl":
         env["PB_NO_PEER_MEMORY"] = "1"
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    at = r.stderr.find("Traceback")
+    assert r.returncode == 0, r.stdout[-1500:] + (r.stderr[at:at + 3000] if at >= 0 else r.stderr[-3000:])
     assert r.stdout.count("worst") == world
