@@ -164,7 +164,8 @@ OPS = [
 
 @pytest.mark.parametrize("periodic", [True, False])
 @pytest.mark.parametrize("push", [False, True])
-@pytest.mark.parametrize("n,world,fused", [((20, 3, 256), 2, 3), ((34, 2, 384), 3, 4), ((16, 2, 512), 4, 4), ((16, 2, 1024), 2, 4)])
+@pytest.mark.parametrize("n,world,fused", [((20, 3, 256), 2, 3), ((34, 2, 384), 3, 4), ((16, 2, 512), 4, 4), ((16, 2, 1024), 2, 4),
+                                           ((64, 64, 1024), 8, 4)])   # the bench line's parity slab at 8 ranks: 64-line tiles, 128-plane slabs
 def test_fused_zslab_ranks_as_threads(n, world, fused, push, periodic, oracle_mod, lib):
     worst = _fused_zslab(lib, oracle_mod, n, world, periodic, OPS, push)
     modes = worst.pop("modes")
