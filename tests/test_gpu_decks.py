@@ -88,3 +88,39 @@ def test_taylor_green_64_hundred_steps(oracle_mod):
     for nm, grad in (("mu", "S"), ("beta", "div")):
         d = np.abs(gpu.variables[nm].cpu().numpy() - ref.variables[nm]).max() * np.abs(ref.variables[grad]).max()
         assert d < 1e-12 * p, (nm, d / p)
+
+
+def test_restart_and_viz_dump_on_device_fields(tmp_path):
+    """§8 f4 on the device backend (pyranda.py:431-470,475-588): writeRestart / readRestart stage the
+    device state through the host once and the restarted run continues bit for bit; ss.write dumps the
+    device fields as legacy VTK with the reference's file names."""
+    import os
+    from decks import TGV_EOM, TGV_IC, tgv_mesh
+    from pyranda_b200.sim import pyrandaSim
+    a = pyrandaSim("tgv", tgv_mesh(64))
+    a.EOM(TGV_EOM)
+    a.setIC(TGV_IC)
+    t = 0.0
+    for _ in range(2):
+        t = a.rk4(t, float(a.variables["dt"]) * 0.5)
+    a.writeRestart(tmp_path / "state")
+    for _ in range(2):
+        t = a.rk4(t, float(a.variables["dt"]) * 0.5)
+    b = pyrandaSim("tgv", tgv_mesh(64))
+    tb = b.readRestart(tmp_path / "state")
+    assert b.cycle == 2 and len(b.equations) == len(a.equations)
+    for _ in range(2):
+        tb = b.rk4(tb, float(b.variables["dt"]) * 0.5)
+    assert tb == t
+    for nm in ("rho", "rhou", "Et", "p", "mu"):
+        assert np.array_equal(a.variables[nm].cpu().numpy(), b.variables[nm].cpu().numpy()), nm
+    path = a.write(["rho", "p"], root=str(tmp_path))
+    assert path.endswith(os.path.join("vis%07d" % a.cycle, "proc-000000.%07d.vtk" % a.cycle))
+    raw = open(path, "rb").read()
+    n = 64 ** 3
+    assert b"DIMENSIONS 64 64 64" in raw
+    tag = b"SCALARS p float\nLOOKUP_TABLE default\n"
+    at = raw.index(tag) + len(tag)
+    p = np.frombuffer(raw[at:at + 4 * n], dtype=">f4")
+    want = a.variables["p"].permute(2, 1, 0).contiguous().cpu().numpy().ravel()   # x fastest
+    assert np.allclose(p, want, rtol=1e-6, atol=1e-7)

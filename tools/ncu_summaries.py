@@ -2,7 +2,7 @@
 """Turn the ncu outputs a gpurun call brings back into the small text summaries kept in profiles/.
 
   python tools/ncu_summaries.py launches <launches.csv> <out.txt>     per-kernel launch list -> share of step
-  python tools/ncu_summaries.py raw <report.ncu-rep> <out.txt>        --set full capture -> key metrics/launch
+  python tools/ncu_summaries.py raw <report.ncu-rep | raw.csv> <out.txt>   --set full capture -> key metrics/launch
 
 The launch list comes from `ncu --metrics gpu__time_duration.sum --clock-control none --csv`, the
 report from `ncu --set full --clock-control none --import-source on` (B200_PROFILING.md).
@@ -56,7 +56,10 @@ def launches(path, out):
 
 
 def raw(rep, out):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # the raw page already dumped on the GPU box (`ncu -i x.ncu-rep --page raw --csv`)
+        txt = open(rep, errors="replace").read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     with open(out, "w") as f:
