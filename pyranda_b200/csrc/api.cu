@@ -171,7 +171,11 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
   // states per face, the waits vanish) but the compact filter 0.80 -> 0.89 ms (six states: the correction and
   // closure sums cost more than the waits they remove) -- profiles/r2_xr_variants_2gpu.log
   static const int early_max = getenv("PB_XR_EARLY_MAX") ? atoi(getenv("PB_XR_EARLY_MAX")) : 3;
-  bool early = want_early;
+  // ... and, of those, for the first derivative only: the second / eighth derivative kernels (larger right-hand
+  // sides, 56-64-byte spill frames) measured slower in the early form, dd8z 0.71 vs 0.62 ms and d2z 0.63 vs 0.55 ms
+  // against ddz 0.48 vs 0.53 ms (2 GPUs, 512^3 per GPU, gpurun r2af in profiles/r2_xr_variants_2gpu.log)
+  static const bool early_all = getenv("PB_XR_EARLY_ALL") ? atoi(getenv("PB_XR_EARLY_ALL")) != 0 : false;
+  bool early = want_early && (early_all || sp.st.fam == F_D1);
   for (int rank = 0; rank < np; ++rank)
     if (need_f(rank) > std::min(P, early_max) || need_b(rank) > std::min(P, early_max)) early = false;
   std::vector<double4> Bc;

@@ -19,6 +19,7 @@
 namespace pb {
 
 extern int g_ring_kernels;
+constexpr int kXSum = 8;  // most terms of a carried-state sum (the host checks the tables against it)
 int max_active_clusters_cached(const void *fn, int cl, size_t smem);
 
 #ifndef PB_EMULATE
@@ -116,7 +117,8 @@ __device__ __forceinline__ bool ring_warp_all_const(const SweepDev &a, int tid, 
 
 // CLUSTER = false: one CTA per line tile (no distributed shared memory, plain block barriers)
 // XRM: 0 no cross-rank exchange, 1 waiting form, 2 early form (see XRing)
-template <int FAM, int NL, bool ADDV, bool LATE, bool RING, bool CLUSTER, int XRM>
+// TAB: some chunk of the line reads coefficient tables (see sweep_yz_pipe_kernel)
+template <int FAM, int NL, bool ADDV, bool LATE, bool RING, bool CLUSTER, int XRM, bool TAB>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tmain, const __grid_constant__ TileMap th4,
                      const __grid_constant__ TileMap tlo, const __grid_constant__ TileMap thi,
@@ -294,11 +296,27 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
         int nf = a.nf[lp];
         if (XRM == 2 && nf > lp) nf = lp;  // early form: this rank's chunks now, the ranks below when their states have arrived
         const double4 *Mp = a.Mf + (size_t)lp * a.mstride;
-        for (int j = 1; j <= nf; ++j) {
-          const double2 en = en_get(lp - j);
-          const double4 M = ldg4(Mp + j);
-          st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
-          st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
+        // unrolled with a guard: the loads of all terms leave together (as a counted loop the sum exposed one
+        // shared + one table load latency per term: 11 % of the filter kernel's samples, profiles/r2_xr_kernel_single_gpu_ncu.txt)
+        // (cluster form: the states come through distributed shared memory and the counted loop measured faster,
+        // 1024^3 ddy 3.5 vs 4.4 ms)
+        if constexpr (CLUSTER) {
+          for (int j = 1; j <= nf; ++j) {
+            const double2 en = en_get(lp - j);
+            const double4 M = ldg4(Mp + j);
+            st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
+            st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
+          }
+        } else {
+#pragma unroll
+          for (int j = 1; j <= kXSum; ++j) {
+            if (j <= nf) {
+              const double2 en = en_get(lp - j);
+              const double4 M = ldg4(Mp + j);
+              st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
+              st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
+            }
+          }
         }
       }
       double x1 = 0.0, x2 = 0.0;
@@ -316,21 +334,53 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           x1 = x;
         });
       } else {
-        const double2 *ph = a.phi + (size_t)type * CT;
-        const double4 *lub = a.lub + (size_t)type * CT;
-        static_for<0, CT>([&](auto jc) {
-          constexpr int r = CT - 1 - decltype(jc)::value;
-          const double2 f = __ldg(ph + r);
-          const double4 c = ldg4(lub + r);
-          double x = rl[r];
-          x = fma(f.x, st.x, x);
-          x = fma(f.y, st.y, x);
-          x = fma(-c.z, x2, x * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
-          x = fma(-c.y, x1, x);
-          rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
-          x2 = x1;
-          x1 = x;
-        });
+        if constexpr (TAB) {
+          // table chunks: coefficients kTabAhead rows ahead of the chain (see sweep_yz_pipe_kernel)
+          const double2 *ph = a.phi + (size_t)type * CT;
+          const double4 *lub = a.lub + (size_t)type * CT;
+          double2 pf[kTabAhead];
+          double pc[kTabAhead][3];
+#pragma unroll
+          for (int k = 0; k < kTabAhead; ++k) {
+            pf[k] = __ldg(ph + (CT - 1 - k));
+            const double4 c4 = ldg4(lub + (CT - 1 - k));
+            pc[k][0] = c4.x; pc[k][1] = c4.y; pc[k][2] = c4.z;
+          }
+          static_for<0, CT>([&](auto jc) {
+            constexpr int j = decltype(jc)::value, r = CT - 1 - j, slot = j % kTabAhead;
+            const double2 f = pf[slot];
+            const double cx = pc[slot][0], cy = pc[slot][1], cz = pc[slot][2];
+            if constexpr (r - kTabAhead >= 0) {
+              pf[slot] = __ldg(ph + (r - kTabAhead));
+              const double4 c4 = ldg4(lub + (r - kTabAhead));
+              pc[slot][0] = c4.x; pc[slot][1] = c4.y; pc[slot][2] = c4.z;
+            }
+            double x = rl[r];
+            x = fma(f.x, st.x, x);
+            x = fma(f.y, st.y, x);
+            x = fma(-cz, x2, x * cx);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
+            x = fma(-cy, x1, x);
+            rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
+            x2 = x1;
+            x1 = x;
+          });
+        } else {
+          const double2 *ph = a.phi + (size_t)type * CT;
+          const double4 *lub = a.lub + (size_t)type * CT;
+          static_for<0, CT>([&](auto jc) {
+            constexpr int r = CT - 1 - decltype(jc)::value;
+            const double2 f = __ldg(ph + r);
+            const double4 c = ldg4(lub + r);
+            double x = rl[r];
+            x = fma(f.x, st.x, x);
+            x = fma(f.y, st.y, x);
+            x = fma(-c.z, x2, x * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
+            x = fma(-c.y, x1, x);
+            rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
+            x2 = x1;
+            x1 = x;
+          });
+        }
       }
       if constexpr (XRM != 0) {  // my backward start state to the ranks below (early form: before the states from below have arrived;
                     // the receiver adds what its own forward states change in it)
@@ -438,7 +488,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
 #else
               if (warpB) {
                 sv = ST[(PL + lp + j - P) * NL + l];
-              } else {
+        } else {
                 const unsigned long long *rec = xr.st_in + ((long)(lp + j - P) * xr.plane + line0 + l) * 4;
                 unsigned long long spin = 0;
                 while (!xr_try_load(rec, xr.epoch, &sv)) xr_pause(spin);
@@ -458,11 +508,23 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           }
           nb = P - 1 - lp;
         }
-        for (int j = 1; j <= nb; ++j) {
-          const double2 sv = st_get(lp + j);
-          const double4 M = ldg4(Mp + j);
-          tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
-          tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
+        if constexpr (CLUSTER) {
+          for (int j = 1; j <= nb; ++j) {
+            const double2 sv = st_get(lp + j);
+            const double4 M = ldg4(Mp + j);
+            tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
+            tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
+          }
+        } else {
+#pragma unroll
+          for (int j = 1; j <= kXSum; ++j) {
+            if (j <= nb) {
+              const double2 sv = st_get(lp + j);
+              const double4 M = ldg4(Mp + j);
+              tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
+              tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
+            }
+          }
         }
       }
       double *sg = stage + (size_t)((p * GW + l / WB) * SR) * WB + (l % WB);
@@ -499,10 +561,16 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
             rowD(rc, a.psi0[r].x, a.psi0[r].y, rl[r]);
           });
         } else {
+          constexpr int NQ = TAB ? SR : 1;  // table instantiation: the rows of the group at once
+          double2 gq[NQ];
+          if constexpr (TAB) {
+#pragma unroll
+            for (int k = 0; k < SR; ++k) gq[k] = __ldg(ps + r0 + k);
+          }
           static_for<r0, r0 + SR>([&](auto rc) {
             constexpr int r = decltype(rc)::value;
-            const double2 gq = __ldg(ps + r);
-            rowD(rc, gq.x, gq.y, rl[r]);
+            if constexpr (!TAB) gq[0] = __ldg(ps + r);
+            rowD(rc, gq[TAB ? r - r0 : 0].x, gq[TAB ? r - r0 : 0].y, rl[r]);
           });
         }
         fence_async_smem();
@@ -544,6 +612,8 @@ static cudaError_t launch_yz_ring(const SweepDev &a0, const double *v, double *o
   if (CL != 1 && CL != 2 && CL != 4 && CL != 8) return cudaErrorNotSupported;
   SweepDev a = a0;
   if (a.mstride == 0) a.mstride = a.P + 1;
+  for (int q = 0; q < a.P; ++q)
+    if (a.nf[q] > kXSum || a.nb[q] > kXSum) return cudaErrorNotSupported;
   for (int c = 0; c < CL; ++c) {  // chunk order inside every CTA: table chunks first, so they share warps
     int k = 0;
     for (int pass = 0; pass < 2; ++pass)
@@ -590,11 +660,14 @@ static cudaError_t launch_yz_ring(const SweepDev &a0, const double *v, double *o
   // filters: the add-back from the tile (LATE) keeps the tile until the backward pass, so the next tile is
   // requested one phase later; re-reading the input from L2 instead (request after the forward pass) measured
   // slower on one GPU and across ranks (profiles/r2_xr_variants_2gpu.log)
-#define PB_RING_PICK(LATEV, RINGV)                                                                               \
-  (cl1 ? (xrm == 0 ? sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, false, 0>                                 \
-                   : xrm == 1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, false, 1>                      \
-                              : sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, false, 2>)                     \
-       : sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, true, 0>)
+  bool tab = !a.has_const;  // any chunk on the table path?
+  for (int q = 0; q < a.P; ++q) tab = tab || a.ctype[q] != 0;
+#define PB_RING_PICK1(LATEV, RINGV, TABV)                                                                         \
+  (cl1 ? (xrm == 0 ? sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, false, 0, TABV>                            \
+                   : xrm == 1 ? sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, false, 1, TABV>                 \
+                              : sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, false, 2, TABV>)                \
+       : sweep_yz_ring_kernel<FAM, NL, ADDV, LATEV, RINGV, true, 0, TABV>)
+#define PB_RING_PICK(LATEV, RINGV) (tab ? PB_RING_PICK1(LATEV, RINGV, true) : PB_RING_PICK1(LATEV, RINGV, false))
   if (a.ring) {
     if constexpr (!ADDV && FAM == F_R4) kfn = PB_RING_PICK(false, true);
     slot = 1;
@@ -605,9 +678,10 @@ static cudaError_t launch_yz_ring(const SweepDev &a0, const double *v, double *o
     if constexpr (!ADDV) kfn = PB_RING_PICK(false, false);
   }
 #undef PB_RING_PICK
+#undef PB_RING_PICK1
   if (kfn == nullptr) return cudaErrorNotSupported;
-  static bool configured[8] = {false, false, false, false, false, false, false, false};
-  slot = 4 * slot + (cl1 ? xrm : 3);
+  static bool configured[16] = {false, false, false, false, false, false, false, false, false, false, false, false, false, false, false, false};
+  slot = 2 * (4 * slot + (cl1 ? xrm : 3)) + (tab ? 1 : 0);
   if (!configured[slot]) {
     cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

@@ -1310,6 +1310,11 @@ __device__ __forceinline__ int warp_other_chunk(const SweepDev &a, int tid, int 
 // (periodic wrap rows or z-slab halo planes are extra boxes), so every chunk runs the same code with
 // compile-time shared-memory offsets.
 
+#ifndef PB_TAB_AHEAD
+#define PB_TAB_AHEAD 4
+#endif
+constexpr int kTabAhead = PB_TAB_AHEAD;  // rows of table coefficients in flight in the backward pass of a table chunk
+
 struct PipeGeo {
   int rowdim;          // tensor-map dimension the sweep runs along (1: y, 2: z)
   int nbox, box_rows;  // main boxes per tile
@@ -1360,7 +1365,10 @@ __device__ __forceinline__ void stream_chunk_tile(const SweepDev &a, const doubl
 }
 
 // RING: the plain-store path writes |val| s^2 (ring detector with a constant length scale)
-template <int FAM, int NL, bool PLAIN, bool ADDV, bool LATE, bool RING>
+// TAB: the line has chunks that read coefficient tables (first / last chunks of a bounded line; periodic lines
+// and interior z-slabs have none).  The table instantiation keeps the coefficient loads ahead of the recurrence
+// with a register ring; the other one is the kernel as tuned on periodic lines.
+template <int FAM, int NL, bool PLAIN, bool ADDV, bool LATE, bool RING, bool TAB>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ TileMap tmain,
                      const __grid_constant__ TileMap tlo, const __grid_constant__ TileMap thi,
@@ -1380,7 +1388,11 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   const long rs = a.rstride;
   const int s = p * CT;
   const int type = a.ctype[p];
-  const bool cc = warp_all_const<NL>(a, tid, a.has_const && type == 0);
+  // lines without table chunks: the second / eighth derivative kernels run 6-10 % faster with the table code
+  // compiled out, the first derivative and the filter kernels 7-9 % slower (register allocation at the 128
+  // limit; gpurun logs r2ab / r2ac in profiles/r2_table_path_variants.log) -- so only the former drop it
+  constexpr bool kNoTables = !TAB && FAM != F_D1 && !ADDV;
+  const bool cc = kNoTables ? true : warp_all_const<NL>(a, tid, a.has_const && type == 0);
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
   const double scale = a.scale;
   const uint32_t tx_bytes = (uint32_t)((m + (g.halo ? 2 * HP : 0)) * NL * sizeof(double));
@@ -1479,25 +1491,63 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           x1 = x;
         });
       } else {
-        const double2 *ph = a.phi + (size_t)type * CT;
-        const double4 *lub = a.lub + (size_t)type * CT;
-        static_for<0, CT>([&](auto jc) {
-          constexpr int r = CT - 1 - decltype(jc)::value;
-          const double2 f = __ldg(ph + r);
-          const double4 c = ldg4(lub + r);
-          double x = rl[r];
-          x = fma(f.x, st.x, x);
-          x = fma(f.y, st.y, x);
-          x = fma(-c.z, x2, x * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
-          x = fma(-c.y, x1, x);
-          rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
-          if (ADDV && LATE) {
-            if (r < 2) xloc[r] = x;
-            if (r >= CT - 2) xloc[r - (CT - 4)] = x;
+        if constexpr (TAB) {
+          // table chunks: the coefficients of row r - kTabAhead are requested while row r is solved (a row of the
+          // chain is shorter than an L1 hit; left to the compiler the loads sat one row ahead and this warp took
+          // 4.7x a constant warp through this phase, profiles/r2_bounded_table_path_ncu.txt)
+          const double2 *ph = a.phi + (size_t)type * CT;
+          const double4 *lub = a.lub + (size_t)type * CT;
+          double2 pf[kTabAhead];
+          double pc[kTabAhead][3];
+#pragma unroll
+          for (int k = 0; k < kTabAhead; ++k) {
+            pf[k] = __ldg(ph + (CT - 1 - k));
+            const double4 c4 = ldg4(lub + (CT - 1 - k));
+            pc[k][0] = c4.x; pc[k][1] = c4.y; pc[k][2] = c4.z;
           }
-          x2 = x1;
-          x1 = x;
-        });
+          static_for<0, CT>([&](auto jc) {
+            constexpr int j = decltype(jc)::value, r = CT - 1 - j, slot = j % kTabAhead;
+            const double2 f = pf[slot];
+            const double cx = pc[slot][0], cy = pc[slot][1], cz = pc[slot][2];
+            if constexpr (r - kTabAhead >= 0) {
+              pf[slot] = __ldg(ph + (r - kTabAhead));
+              const double4 c4 = ldg4(lub + (r - kTabAhead));
+              pc[slot][0] = c4.x; pc[slot][1] = c4.y; pc[slot][2] = c4.z;
+            }
+            double x = rl[r];
+            x = fma(f.x, st.x, x);
+            x = fma(f.y, st.y, x);
+            x = fma(-cz, x2, x * cx);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
+            x = fma(-cy, x1, x);
+            rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
+            if (ADDV && LATE) {
+              if (r < 2) xloc[r] = x;
+              if (r >= CT - 2) xloc[r - (CT - 4)] = x;
+            }
+            x2 = x1;
+            x1 = x;
+          });
+        } else {
+          const double2 *ph = a.phi + (size_t)type * CT;
+          const double4 *lub = a.lub + (size_t)type * CT;
+          static_for<0, CT>([&](auto jc) {
+            constexpr int r = CT - 1 - decltype(jc)::value;
+            const double2 f = __ldg(ph + r);
+            const double4 c = ldg4(lub + r);
+            double x = rl[r];
+            x = fma(f.x, st.x, x);
+            x = fma(f.y, st.y, x);
+            x = fma(-c.z, x2, x * c.x);  // lub = {1/pivot, u1/pivot, u2/pivot}: one operation on the chain through x1
+            x = fma(-c.y, x1, x);
+            rl[r] = (ADDV && LATE) ? fma(x, scale, tw[(r + H) * NL]) : x;
+            if (ADDV && LATE) {
+              if (r < 2) xloc[r] = x;
+              if (r >= CT - 2) xloc[r - (CT - 4)] = x;
+            }
+            x2 = x1;
+            x1 = x;
+          });
+        }
       }
       ST[p * NL + l] = make_double2(x1, x2);
     }
@@ -1581,10 +1631,18 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
             if (r >= CT - 2) xi[r - (CT - 4)] = x;
           });
         } else {
+          // plain stores of a table instantiation: the 16 rows of the group at once, nothing waits on a load in the
+          // middle of the stores (the read-modify-write epilogues already hold a 16-row window of the old output)
+          constexpr int NQ = (PLAIN && TAB) ? 16 : 1;
+          double2 gq[NQ];
+          if constexpr (PLAIN && TAB) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) gq[k] = __ldg(ps + r0 + k);
+          }
           static_for<r0, r0 + 16>([&](auto rc) {
             constexpr int r = decltype(rc)::value;
-            const double2 gq = __ldg(ps + r);
-            const double x = rowD(rc, gq.x, gq.y, rl[r]);
+            if constexpr (!(PLAIN && TAB)) gq[0] = __ldg(ps + r);
+            const double x = rowD(rc, gq[(PLAIN && TAB) ? r - r0 : 0].x, gq[(PLAIN && TAB) ? r - r0 : 0].y, rl[r]);
             if (r < 2) xi[r] = x;
             if (r >= CT - 2) xi[r - (CT - 4)] = x;
           });
@@ -1664,16 +1722,21 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
   static const bool late = getenv("PB_ADDV_LATE") ? atoi(getenv("PB_ADDV_LATE")) != 0 : true;
   void (*kfn)(SweepDev, TileMap, TileMap, TileMap, TileMap, PipeGeo, const double *, double *, double *, EpiArgs) = nullptr;
   int slot;
+  bool tab = !a.has_const;  // any chunk on the table path?
+  for (int q = 0; q < a.P; ++q) tab = tab || a.ctype[q] != 0;
+#define PB_PIPE_PICK(LATEV, RINGV) (tab ? sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, LATEV, RINGV, true> : sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, LATEV, RINGV, false>)
   if (a.ring) {
-    if constexpr (PLAIN && !ADDV && FAM == F_R4) kfn = sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, false, true>;
+    if constexpr (PLAIN && !ADDV && FAM == F_R4) kfn = PB_PIPE_PICK(false, true);
     slot = 2;
   } else if (ADDV && late) {
-    kfn = sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, true, false>; slot = 1;
+    kfn = PB_PIPE_PICK(true, false); slot = 1;
   } else {
-    kfn = sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, false, false>; slot = 0;
+    kfn = PB_PIPE_PICK(false, false); slot = 0;
   }
+#undef PB_PIPE_PICK
   if (kfn == nullptr) return cudaErrorNotSupported;
-  static bool configured[3] = {false, false, false};
+  slot = 2 * slot + (tab ? 1 : 0);
+  static bool configured[6] = {false, false, false, false, false, false};
   if (!configured[slot]) {
     cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

@@ -19,6 +19,7 @@ import ctypes
 import math
 
 _BIN = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/"}
+_CMP = {ast.Lt: "<", ast.LtE: "<=", ast.Gt: ">", ast.GtE: ">="}
 _CFUN = {"sqrt": "sqrt", "abs": "fabs", "sin": "sin", "cos": "cos", "tanh": "tanh", "exp": "exp",
          "minimum": "fmin", "maximum": "fmax"}
 
@@ -33,6 +34,10 @@ def _is_arith(node):
     if isinstance(node, ast.UnaryOp):
         return isinstance(node.op, (ast.USub, ast.UAdd))
     if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Name):
+        if node.func.value.id == "xp" and node.func.attr == "where" and not node.keywords:
+            # xp.where(a < b, x, y) with one ordering comparison: a select in the generated kernel
+            c = node.args[0] if len(node.args) == 3 else None
+            return isinstance(c, ast.Compare) and len(c.ops) == 1 and type(c.ops[0]) in _CMP
         return node.func.value.id == "xp" and node.func.attr in _CFUN and not node.keywords
     return False
 
@@ -98,6 +103,12 @@ class Fuser:
             c, p = self._emit(node.operand, leaves, keys)
             s = "-" if isinstance(node.op, ast.USub) else "+"
             return "(%s%s)" % (s, c), "(%s%s)" % (s, p)
+        if isinstance(node, ast.Call) and node.func.attr == "where":
+            cmp_ = node.args[0]
+            (lc, lp), (rc, rp) = self._emit(cmp_.left, leaves, keys), self._emit(cmp_.comparators[0], leaves, keys)
+            (ac, ap), (bc, bp) = self._emit(node.args[1], leaves, keys), self._emit(node.args[2], leaves, keys)
+            op = _CMP[type(cmp_.ops[0])]
+            return ("((%s %s %s) ? %s : %s)" % (lc, op, rc, ac, bc), "xp.where((%s %s %s), %s, %s)" % (lp, op, rp, ap, bp))
         if isinstance(node, ast.Call):
             parts = [self._emit(a, leaves, keys) for a in node.args]
             return ("%s(%s)" % (_CFUN[node.func.attr], ", ".join(c for c, _ in parts)),

@@ -146,3 +146,27 @@ def test_host_only_lines_are_found():
         conserved = [e.lhs[0] for e in eqs if e.kind == "PDE"]
     dead = pyrandaSim._host_only(S)
     assert dead == {"dt", "cs", "enst", "tke"}, dead
+
+
+def test_where_with_a_comparison_is_one_fused_select():
+    """xp.where(a < b, x, y) (the immersed-boundary package's masked algebra, pyranda_b200/ibm.py) becomes one
+    generated kernel with a select; the fallback evaluation equals the plain one and NVRTC takes the source."""
+    rng = np.random.default_rng(1)
+    sdf, val, tx, g0, lens = (rng.standard_normal((6, 5, 4)) for _ in range(5))
+    fz = Fuser(_NS, enabled=False)
+    for src in ("xp.where(sdf <= epsi, val + cfl * gl * (tx * g0), val)", "c - xp.where(sdf < lens, normal, 0.0) * a",
+                "xp.where(sdf < lens, 0.0, normal / sdf)", "xp.where(sdf >= 0.5, xp.sqrt(xp.abs(val)), 0.0)"):
+        loc = dict(sdf=sdf, epsi=0.0, val=val, cfl=0.5, gl=np.abs(g0), tx=tx, g0=g0, lens=lens, c=val, normal=tx, a=g0)
+        out = fz.transform(src)
+        assert out.startswith("__fz(") and "where" not in out, out   # the whole expression is one fused call
+        got = eval(out, {"xp": _NS, "__fz": fz.call}, loc)
+        assert np.array_equal(got, eval(src, {"xp": _NS}, loc))
+    spec = fz.specs[0]
+    assert "?" in spec.cexpr
+    try:
+        from pyranda_b200.fuse import _Nvrtc
+        rt = _Nvrtc()
+    except Exception:
+        pytest.skip("NVRTC bindings not importable here")
+    for spec in fz.specs:
+        rt.compile_to_cubin(kernel_source(spec.cexpr, [True] * spec.nleaves))

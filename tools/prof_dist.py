@@ -17,7 +17,8 @@ rank, world = dist.get_rank(), dist.get_world_size()
 n = int(sys.argv[1]); reps = int(sys.argv[2]); ops = sys.argv[3:] or ["ddz", "sfilter", "gfilter"]
 gz = int(os.environ.get("PB_GLOBAL_NZ", n * world))
 L = 2 * np.pi
-eng = DistributedParcop(n, n, gz, 0, L, 0, L, 0, L, periodic=(True,) * 3, device=local)
+per = os.environ.get("PB_BOUNDED", "0") != "1"
+eng = DistributedParcop(n, n, gz, 0, L, 0, L, 0, L, periodic=(per,) * 3, device=local)
 f = eng.empty(); f.copy_(torch.rand(tuple(reversed(eng.plan.shape)), dtype=torch.float64, device="cuda").permute(2, 1, 0))
 out = eng.empty()
 for name in ops:
