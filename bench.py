@@ -36,8 +36,9 @@ SWEEPS = {"ddx": 1, "ddy": 1, "ddz": 1, "sfilter": 3, "gfilter": 3}
 BYTES_PER_POINT = {"ddx": 16, "ddy": 16, "ddz": 16, "sfilter": 48, "gfilter": 48}
 METRIC = "fp64 Gpoints/s (operator applications x points / s), compact ddx+ddy+ddz+filter+gfilter"
 NPER = 512  # points per side per GPU
-# ncu --set full, 512^3 ddz launch: 1.073867 GB read + 1.035293 GB written (profiles/r1_v7_tma_kernels_ncu_full.txt)
-NCU_TRAFFIC_DDZ_512 = 2109160000
+# ncu --set full, 512^3 launch of the periodic y/z sweep kernel (the kernel of ddy and ddz): 1.076544 GB read + 1.034750 GB
+# written (profiles/r2_pipe_and_ring_kernels_ncu_full.txt; round 1: 1.073867 + 1.035293, profiles/r1_v7_tma_kernels_ncu_full.txt)
+NCU_TRAFFIC_DDZ_512 = 2111294000
 
 
 def bench_config(world, n, global_n=0):
@@ -552,7 +553,7 @@ def main():
     ach = 16.0 * npts / (per_op_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "sweep_yz_pipe_kernel<D1,16> (%s, one launch per application)" % dom, "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_DDZ_512 if (n == 512 and world == 1 and not args.global_n) else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the ddz launch in profiles/r1_v7_tma_kernels_ncu_full.txt",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the sweep_yz_pipe_kernel<D1,16> launch in profiles/r2_pipe_and_ring_kernels_ncu_full.txt",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": 16 * npts}
     tgv = None
