@@ -40,7 +40,8 @@ class ImmersedBoundary:
         if code is None:
             fz = getattr(self.sim, "fuser", None)
             code = self._code[src] = compile(fz.transform(src) if fz is not None else src, "<ibm>", "eval")
-        return eval(code, self.sim._ns, local)
+        ns = getattr(self.sim, "_ns", None)
+        return eval(code, ns if ns is not None else {"xp": self.sim.xp}, local)
 
     def _extend(self, sdf, g, val, epsi):
         """pyrandaIBM.py:75-89: march `val` along grad(phi) where phi <= epsi, filtering each step."""
