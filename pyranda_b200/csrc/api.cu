@@ -428,6 +428,34 @@ int apply_dir_slab(pb_plan *pl, SweepPlan &sp, const double *in, double *out, in
   return PB_OK;
 }
 
+// An explicit z sweep (the Gaussian filter) restricted to planes [first, first + cnt): the slab is a
+// short line whose neighbours' planes act as halo planes (compact_r4.f90:640-656 does the same with the
+// planes received from the neighbouring ranks).  The first / last slab of a periodic axis wraps around
+// the field; those of a bounded axis keep the one-sided closure rows.  Host-array pipeline only.
+int apply_z_explicit_slab(pb_plan *pl, SweepPlan &sp, const double *in, double *out, int first, int cnt, cudaStream_t st) {
+  if (!sp.built || sp.null_op || sp.split || sp.st.implicit || sp.dir != 2 || cnt % sp.dev.C != 0)
+    return fail(PB_ERR_STATE, "slab z sweeps need a local explicit operator and whole chunks");
+  const int az = pl->a[2], H = 4;
+  const long plane = (long)pl->a[0] * pl->a[1];
+  const bool lo_end = first == 0, hi_end = first + cnt == az;
+  SweepDev dv = sp.dev;
+  dv.m = cnt;
+  dv.P = cnt / dv.C;
+  dv.wrap = 0;
+  dv.phys_lo = lo_end ? sp.dev.phys_lo : 0;
+  dv.phys_hi = hi_end ? sp.dev.phys_hi : 0;
+  const double *hlo = nullptr, *hhi = nullptr;
+  if (!lo_end) hlo = in + (long)(first - H) * plane;
+  else if (sp.dev.wrap) hlo = in + (long)(az - H) * plane;
+  if (!hi_end) hhi = in + (long)(first + cnt) * plane;
+  else if (sp.dev.wrap) hhi = in;
+  if ((lo_end && !sp.dev.wrap && !sp.dev.phys_lo) || (hi_end && !sp.dev.wrap && !sp.dev.phys_hi))
+    return fail(PB_ERR_STATE, "slab z sweeps need a periodic axis or closure rows at its ends");
+  const long off = (long)first * plane;
+  PB_CUDA(launch_sweep_yz(sp.st.fam, 0, dv, in + off, out + off, hlo, hhi, nullptr, kStore, st));
+  return PB_OK;
+}
+
 double *mesh_arr(const pb_plan *pl, const char *name) {
   auto it = pl->mesh.find(name);
   return it == pl->mesh.end() ? nullptr : it->second;
@@ -1112,6 +1140,8 @@ static int copy_slab(pb_plan *pl, void *dst, const void *src, bool along_z, int 
   return PB_OK;
 }
 
+static long sz_chunk(const SweepPlan *sz) { return (sz && sz->built && sz->dev.C > 0) ? sz->dev.C : 1L << 30; }
+
 static int host_apply_pipelined(pb_plan *pl, SweepPlan *sx, SweepPlan *sy, SweepPlan *sz, const double *h_val, double *h_out,
                                 bool *done) {
   *done = false;
@@ -1120,8 +1150,10 @@ static int host_apply_pipelined(pb_plan *pl, SweepPlan *sx, SweepPlan *sy, Sweep
   for (SweepPlan *s : all)
     if (s) { if (!s->built || s->null_op || s->split) return PB_OK; ++nsw; }
   const int az = pl->a[2], ay = pl->a[1];
-  const int NS = 8;
-  if (nsw == 0 || az < 2 * NS || ay < 2 * NS) return PB_OK;
+  static const int ns_env = getenv("PB_HOST_SLABS") ? atoi(getenv("PB_HOST_SLABS")) : 0;
+  int NS = ns_env > 0 ? ns_env : 16;  // slabs per field: fill and drain of the pipeline cost 1 / NS of the copy time each
+  while (NS > 1 && (az < 2 * NS || ay < 2 * NS)) NS >>= 1;
+  if (nsw == 0 || NS < 4) return PB_OK;
   int rc;
   double *d0, *d1, *d2;
   if ((rc = get_scratch(pl, 4, &d0)) || (rc = get_scratch(pl, 5, &d1)) || (rc = get_scratch(pl, 6, &d2))) return rc;
@@ -1130,6 +1162,45 @@ static int host_apply_pipelined(pb_plan *pl, SweepPlan *sx, SweepPlan *sy, Sweep
   auto slab = [&](int n, int s, int *first, int *cnt) { *first = (int)((long)n * s / NS); *cnt = (int)((long)n * (s + 1) / NS) - *first; };
   PB_CUDA(cudaStreamSynchronize(0));  // earlier work of the caller on the default stream
   const bool zin = sx || sy;           // the input arrives in z-slabs unless only z is swept
+  // Explicit z sweep after x / y (the Gaussian filter): a z-slab of the result needs the x / y-swept planes of
+  // its own slab and four planes of either neighbour, so slab s - 1 is swept along z and sent back as soon as
+  // slab s has passed x and y -- input and output copies overlap instead of following each other.  On a
+  // periodic axis slab 0 also needs the last planes and leaves last.
+  static const bool no_stream = getenv("PB_HOST_NO_ZSTREAM") != nullptr;
+  int NZ = NS;  // slabs of whole chunks
+  while (NZ >= 4 && az % (NZ * sz_chunk(sz)) != 0) NZ >>= 1;
+  if (sz && zin && !sz->st.implicit && !no_stream && NZ >= 4 && az / NZ >= 8 &&
+      (sz->dev.wrap || (sz->dev.phys_lo && sz->dev.phys_hi))) {
+    const bool wrap = sz->dev.wrap != 0;
+    const int NS = NZ;
+    auto slab = [&](int n, int s, int *first, int *cnt) { *first = (int)((long)n * s / NS); *cnt = (int)((long)n * (s + 1) / NS) - *first; };
+    double *Y = (sx && sy) ? d2 : d1, *fin = (Y == d1) ? d2 : d1;  // x / y-swept field, result
+    auto zsweep = [&](int s) -> int {
+      int f, c, r2;
+      slab(az, s, &f, &c);
+      if ((r2 = apply_z_explicit_slab(pl, *sz, Y, fin, f, c, sC)) != PB_OK) return r2;
+      PB_CUDA(cudaEventRecord(pl->hev[NS + s], sC));
+      PB_CUDA(cudaStreamWaitEvent(sOut, pl->hev[NS + s], 0));
+      return copy_slab(pl, h_out, fin, true, f, c, cudaMemcpyDeviceToHost, sOut);
+    };
+    for (int s = 0; s < NS; ++s) {
+      int f, c;
+      slab(az, s, &f, &c);
+      if ((rc = copy_slab(pl, d0, h_val, true, f, c, cudaMemcpyHostToDevice, sIn)) != PB_OK) return rc;
+      PB_CUDA(cudaEventRecord(pl->hev[s], sIn));
+      PB_CUDA(cudaStreamWaitEvent(sC, pl->hev[s], 0));
+      const double *cur = d0;
+      if (sx) { if ((rc = apply_dir_slab(pl, *sx, cur, d1, f, c, sC)) != PB_OK) return rc; cur = d1; }
+      if (sy) { if ((rc = apply_dir_slab(pl, *sy, cur, cur == d1 ? d2 : d1, f, c, sC)) != PB_OK) return rc; }
+      if (s >= 1 && (s - 1 > 0 || !wrap)) { if ((rc = zsweep(s - 1)) != PB_OK) return rc; }
+    }
+    if ((rc = zsweep(NS - 1)) != PB_OK) return rc;
+    if (wrap) { if ((rc = zsweep(0)) != PB_OK) return rc; }
+    PB_CUDA(cudaStreamSynchronize(sOut));
+    PB_CUDA(cudaStreamSynchronize(sC));
+    *done = true;
+    return PB_OK;
+  }
   for (int s = 0; s < NS; ++s) {
     int f, c;
     slab(zin ? az : ay, s, &f, &c);

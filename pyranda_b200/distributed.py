@@ -24,6 +24,7 @@ from .plan import ParcopPlan
 
 # z operator behind each distributed call and its halo width (nor of the stencil)
 _ZOPS = {"ddz": ("ddz", 3), "ddz_odd": ("ddz_odd", 3), "dd4z": ("dd4z", 3), "dd8z": ("dd8z", 4), "dd8z_odd": ("dd8z_odd", 4), "d2z": ("d2z", 3), "sfilterz": ("sfilterz", 4), "gfilterz": ("gfilterz", 4)}
+_LOCAL_OPS = ("ddx", "ddy", "ddx_odd", "ddy_odd", "dd4x", "dd4y", "dd8x_odd", "dd8y_odd", "dd8x", "dd8y", "d2x", "d2y", "gfilterx", "gfiltery", "sfilterx", "sfiltery")
 _IMPLICIT = {"ddz": True, "ddz_odd": True, "dd4z": False, "dd8z": True, "dd8z_odd": True, "d2z": True, "sfilterz": True, "gfilterz": False}
 
 
@@ -310,7 +311,7 @@ class DistributedParcop:
     def apply_into(self, name, f, out):
         """ddx ddy ddz dd8x dd8y dd8z d2x d2y d2z sfilter gfilter gfilterx/y/z laplacian ring.  Composites
         accumulate through the sweeps' own epilogues (TMA reduce-add / reduce-max stores), as on one GPU."""
-        if name in ("ddx", "ddy", "ddx_odd", "ddy_odd", "dd4x", "dd4y", "dd8x_odd", "dd8y_odd", "dd8x", "dd8y", "d2x", "d2y", "gfilterx", "gfiltery", "sfilterx", "sfiltery"):
+        if name in _LOCAL_OPS:
             return self._local_into(name, f, out)
         if name in _ZOPS:
             return self.zop_into(name, f, out)
@@ -375,6 +376,11 @@ class DistributedParcop:
 
     def apply_host_into(self, name, a_in, a_out):
         """Host arrays in / out (the f2py call shape) around the distributed device operator."""
+        if name in _LOCAL_OPS and self.dev.type == "cuda":
+            # x / y sweeps are local to a z-slab: the plan's own slab pipeline (input copy, sweeps and output copy
+            # of different slabs overlap on three streams, pb_host_apply)
+            torch.cuda.current_stream().synchronize()
+            return self.plan.apply_host_into(name, a_in, a_out)
         if not hasattr(self, "_hin"):
             self._hin, self._hout = self.empty(), self.empty()
         self._planes(self._hin).copy_(torch.from_numpy(a_in.T), non_blocking=True)

@@ -46,6 +46,17 @@ def test_emulated_operators_match_oracle(periodic, oracle_mod, emul_lib):
 
 
 @pytest.mark.parametrize("periodic", [True, False])
+def test_emulated_host_pipeline_streams_the_gaussian_filter(periodic, oracle_mod, emul_lib):
+    """pb_host_apply moves host arrays in slabs; the explicit filter's z sweep runs slab by slab behind the
+    x / y sweeps (neighbouring slabs' planes as halo planes, wrap planes / closure rows at the ends)."""
+    o, p, f = _pair((16, 32, 64), periodic, oracle_mod, emul_lib)
+    for name in ("gfilter", "sfilter", "ddx", "ddy", "ddz"):
+        assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < 1e-13, (name, periodic)
+    for d in (1, 2, 3):
+        assert rel_linf(p.gfilterdir(f, d), o.dir_op("gf", d - 1, f)) < 1e-13, (d, periodic)
+
+
+@pytest.mark.parametrize("periodic", [True, False])
 def test_emulated_tensor_divergence_and_vector_ring(periodic, oracle_mod, emul_lib):
     """divergenceTensor and pRingV (parcop.f90:213-223,324-333), Cartesian."""
     o, p, f = _pair((32, 24, 20), periodic, oracle_mod, emul_lib)

@@ -44,6 +44,9 @@ for n in ((32, 48, 32 * world), (64, 64, 64 * world)):
         hin = np.asfortranarray(f[:, :, sl]); hout = np.empty_like(hin, order="F")
         eng.apply_host_into("ddz", hin, hout)
         assert rel_linf(hout, o.ddz(f)[:, :, sl]) < 1e-12
+        for name, ref in (("ddx", o.ddx), ("ddy", o.ddy)):  # local directions: the rank's own slab pipeline
+            eng.apply_host_into(name, hin, hout)
+            assert rel_linf(hout, ref(f)[:, :, sl]) < 1e-12, (name, n, periodic, rank)
 # long slabs: neighbour-only interface exchange and the pipelined kernels with halo planes
 from pyranda_b200._lib import OP
 for n in ((32, 32, 128 * world), (48, 32, 256 * world)):
