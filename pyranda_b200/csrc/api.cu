@@ -134,6 +134,7 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
   dv = sp.dev;
   dv.P = P; dv.C = 32;
   dv.wrap = 0;
+  dv.mconst = 0;  // the products of a slab's chunks come from the tables of the global line
   for (int q = 0; q < kMaxChunks; ++q) { dv.perm[q] = (unsigned char)q; dv.ctype[q] = 0; dv.nf[q] = dv.nb[q] = 0; }
   int jmax = 1;
   for (int q = 0; q < P; ++q) {
@@ -317,6 +318,24 @@ int build_sweep(pb_plan *pl, SweepPlan &sp, int kind, int dir, bool periodic, in
     }
     for (int q = 0; q < P; ++q) { dv.nf[q] = (unsigned char)lt.nF[q]; dv.nb[q] = (unsigned char)lt.nB[q]; }
     dv.mstride = P + 1;
+    {  // one row of products for every chunk (circulant lines): a copy in the kernel parameters
+      static const bool off = getenv("PB_NO_MCONST") != nullptr;
+      bool same = !off && lt.nF[0] >= 1 && lt.nB[0] >= 1 && lt.nF[0] <= kMTerms && lt.nB[0] <= kMTerms;
+      for (int q = 1; q < P && same; ++q) {
+        same = lt.nF[q] == lt.nF[0] && lt.nB[q] == lt.nB[0];
+        for (int j = 1; j <= lt.nF[0] && same; ++j)
+          same = memcmp(&Mf[(size_t)q * (P + 1) + j], &Mf[j], sizeof(double4)) == 0;
+        for (int j = 1; j <= lt.nB[0] && same; ++j)
+          same = memcmp(&Mb[(size_t)q * (P + 1) + j], &Mb[j], sizeof(double4)) == 0;
+      }
+      dv.mconst = same ? 1 : 0;
+      dv.nf0 = same ? lt.nF[0] : 0;
+      dv.nb0 = same ? lt.nB[0] : 0;
+      for (int j = 0; j < kMTerms; ++j) {
+        dv.Mf0[j] = (same && j < lt.nF[0]) ? Mf[j + 1] : make_double4(0, 0, 0, 0);
+        dv.Mb0[j] = (same && j < lt.nB[0]) ? Mb[j + 1] : make_double4(0, 0, 0, 0);
+      }
+    }
     {
       int k = 0;
       for (int q = 0; q < P; ++q)

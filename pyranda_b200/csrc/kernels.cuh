@@ -10,6 +10,7 @@ namespace pb {
 
 constexpr int kMaxChunks = 32;
 constexpr int kParamRows = 32;   // chunk length up to which the constant-chunk tables ride in the kernel parameters
+constexpr int kMTerms = 8;       // transfer products per direction that fit the parameter copy (SweepDev::Mf0 / Mb0)
 constexpr int kBlockThreads = 256; // every sweep block has at most this many threads
 
 // epilogue applied when a sweep writes its result
@@ -58,6 +59,10 @@ struct SweepDev {
   int wstore;            // pipelined kernels: every warp issues the TMA stores of its own chunks (else one thread per block)
   int skew_ns;           // persistent kernels: the second wave of CTAs (the co-residents of the first) starts this much later
   int mstride;           // entries per chunk row of Mf / Mb (P + 1, or the compact stride of a z-slab line)
+  // lines whose chunks all share ONE row of transfer products (periodic lines): the products ride in the kernel
+  // parameters, so the carried-state sums take them as constant-bank operands and load nothing
+  int mconst, nf0, nb0;
+  double4 Mf0[kMTerms], Mb0[kMTerms];
   const double2 *chi;    // [ntypes][C]  z-slab ring: solution response to a forward state that arrives after the chunk's solve
   double2 chi0[kParamRows];  // the same for the constant chunk type
 };

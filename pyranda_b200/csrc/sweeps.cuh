@@ -1302,6 +1302,34 @@ __device__ __forceinline__ int warp_other_chunk(const SweepDev &a, int tid, int 
 #endif
 }
 
+// carried-state sum of a line whose chunks share one row of transfer products (SweepDev::mconst): the same terms
+// in the same order as the table loop, with the products as constant-bank operands of the fmas
+template <int NLT, bool FWD, int NT = kMTerms>
+__device__ __forceinline__ double2 state_sum_const(const SweepDev &a, const double2 *E, int p, int P, int l) {
+  double2 s = make_double2(0.0, 0.0);
+  const int n = FWD ? a.nf0 : a.nb0;
+  static_for<1, NT + 1>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    if (j <= n) {
+      int q = FWD ? p - j : p + j;
+      if (FWD) { if (q < 0) q += P; }
+      else { if (q >= P) q -= P; }
+      const double2 e = E[q * NLT + l];
+      const double4 M = FWD ? a.Mf0[j - 1] : a.Mb0[j - 1];
+      s.x = fma(M.y, e.y, fma(M.x, e.x, s.x));
+      s.y = fma(M.w, e.y, fma(M.z, e.x, s.y));
+    }
+  });
+  return s;
+}
+
+#ifndef PB_MCONST
+#define PB_MCONST 1
+#endif
+#ifndef PB_MCONST_ALL  // experiment: the seven-point families too, with a four-term bound
+#define PB_MCONST_ALL 0
+#endif
+
 // ---- pipelined sweeps: persistent CTAs, next tile prefetched by TMA --------------------------------
 // The register kernels above only have loads in flight during their forward phase.  Here a CTA
 // walks over tiles; as soon as every thread has pulled its chunk of the current tile out of shared
@@ -1392,6 +1420,11 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
   // compiled out, the first derivative and the filter kernels 7-9 % slower (register allocation at the 128
   // limit; gpurun logs r2ab / r2ac in profiles/r2_table_path_variants.log) -- so only the former drop it
   constexpr bool kNoTables = !TAB && FAM != F_D1 && !ADDV;
+  // transfer products of the carried-state sums as constant-bank operands (SweepDev::Mf0 / Mb0) instead of loads:
+  // the nine-point family gains 7-9 % (filter 1.44 -> 1.32 ms at 512^3), the first / second derivative kernels lose
+  // 4-10 % with the same change (gpurun r2bb, profiles/r2_const_products_ab.log), so only the former take it
+  constexpr bool kMConst = PB_MCONST && (FAM == F_R4 || PB_MCONST_ALL) && !TAB;
+  constexpr int kMT = FAM == F_R4 ? kMTerms : 4;
   const bool cc = kNoTables ? true : warp_all_const<NL>(a, tid, a.has_const && type == 0);
   const bool lo_sp = a.phys_lo && p == 0, hi_sp = a.phys_hi && p == P - 1;
   const double scale = a.scale;
@@ -1459,7 +1492,9 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
     double xloc[4] = {0.0, 0.0, 0.0, 0.0};  // late add-back: local solution of the four interface rows
     {  // ---- B: add the carried forward state, backward recurrence (zero incoming state) ----
       double2 st = make_double2(0.0, 0.0);
-      {
+      if constexpr (kMConst) {  // the launcher sends lines without a shared row of products to the TAB kernel
+        st = state_sum_const<NL, true, kMT>(a, EN, p, P, l);
+      } else {
         const int nf = a.nf[p];
         const double4 *Mp = a.Mf + (size_t)p * (P + 1);
         for (int j = 1; j <= nf; ++j) {
@@ -1572,7 +1607,9 @@ sweep_yz_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
 
     {  // ---- D: add the carried backward state, scale / add-back / epilogue, store ----
       double2 tb = make_double2(0.0, 0.0);
-      {
+      if constexpr (kMConst) {
+        tb = state_sum_const<NL, false, kMT>(a, ST, p, P, l);
+      } else {
         const int nb = a.nb[p];
         const double4 *Mp = a.Mb + (size_t)p * (P + 1);
         for (int j = 1; j <= nb; ++j) {
@@ -1724,6 +1761,8 @@ static cudaError_t launch_yz_pipe(const SweepDev &a, const double *v, double *ou
   int slot;
   bool tab = !a.has_const;  // any chunk on the table path?
   for (int q = 0; q < a.P; ++q) tab = tab || a.ctype[q] != 0;
+  if (PB_MCONST && FAM == F_R4 && !a.mconst) tab = true;  // the other instantiation takes its transfer products from the parameters
+  if (PB_MCONST_ALL && FAM != F_R4 && (!a.mconst || a.nf0 > 4 || a.nb0 > 4)) tab = true;
 #define PB_PIPE_PICK(LATEV, RINGV) (tab ? sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, LATEV, RINGV, true> : sweep_yz_pipe_kernel<FAM, NL, PLAIN, ADDV, LATEV, RINGV, false>)
   if (a.ring) {
     if constexpr (PLAIN && !ADDV && FAM == F_R4) kfn = PB_PIPE_PICK(false, true);
@@ -1891,7 +1930,9 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
 
     if constexpr (implicit) {  // ---- B ----
       double2 st = make_double2(0.0, 0.0);
-      {
+      if (PB_MCONST && FAM == F_R4 && a.mconst) {  // nine-point family only, as in the y / z kernel
+        st = state_sum_const<NLX, true>(a, EN, p, P, l);
+      } else {
         const int nf = a.nf[p];
         const double4 *Mp = a.Mf + (size_t)p * (P + 1);
         for (int j = 1; j <= nf; ++j) {
@@ -1947,15 +1988,19 @@ sweep_x_pipe_kernel(const __grid_constant__ SweepDev a, const __grid_constant__ 
     {  // ---- D: carried backward state, then 16 rows of every chunk at a time through the stage ----
       double2 tbk = make_double2(0.0, 0.0);
       if constexpr (implicit) {
-        const int nb = a.nb[p];
-        const double4 *Mp = a.Mb + (size_t)p * (P + 1);
-        for (int j = 1; j <= nb; ++j) {
-          int q = p + j;
-          if (q >= P) q -= P;
-          const double2 sv = ST[q * NLX + l];
-          const double4 M = ldg4(Mp + j);
-          tbk.x = fma(M.y, sv.y, fma(M.x, sv.x, tbk.x));
-          tbk.y = fma(M.w, sv.y, fma(M.z, sv.x, tbk.y));
+        if (PB_MCONST && FAM == F_R4 && a.mconst) {
+          tbk = state_sum_const<NLX, false>(a, ST, p, P, l);
+        } else {
+          const int nb = a.nb[p];
+          const double4 *Mp = a.Mb + (size_t)p * (P + 1);
+          for (int j = 1; j <= nb; ++j) {
+            int q = p + j;
+            if (q >= P) q -= P;
+            const double2 sv = ST[q * NLX + l];
+            const double4 M = ldg4(Mp + j);
+            tbk.x = fma(M.y, sv.y, fma(M.x, sv.x, tbk.x));
+            tbk.y = fma(M.w, sv.y, fma(M.z, sv.x, tbk.y));
+          }
         }
       }
       const double2 *ps = a.psi + (size_t)type * CT;
