@@ -214,6 +214,28 @@ int build_ring_tables(SweepPlan &sp, const std::vector<double> &bands, bool peri
       Mf[dst] = in ? make_double4(gt.Mf[src], gt.Mf[src + 1], gt.Mf[src + 2], gt.Mf[src + 3]) : make_double4(0, 0, 0, 0);
       Mb[dst] = in ? make_double4(gt.Mb[src], gt.Mb[src + 1], gt.Mb[src + 2], gt.Mb[src + 3]) : make_double4(0, 0, 0, 0);
     }
+  {  // chunks of a periodic global line share one row of products: a copy in the kernel parameters (SweepDev::Mf0 / Mb0)
+    static const bool off = getenv("PB_NO_MCONST") != nullptr;
+    int qf = 0, qb = 0;
+    for (int q = 1; q < P; ++q) {
+      if (dv.nf[q] > dv.nf[qf]) qf = q;
+      if (dv.nb[q] > dv.nb[qb]) qb = q;
+    }
+    bool same = !off && dv.nf[qf] <= kMTerms && dv.nb[qb] <= kMTerms;
+    for (int q = 0; q < P && same; ++q) {
+      for (int j = 1; j <= dv.nf[q] && same; ++j)
+        same = memcmp(&Mf[(size_t)q * dv.mstride + j], &Mf[(size_t)qf * dv.mstride + j], sizeof(double4)) == 0;
+      for (int j = 1; j <= dv.nb[q] && same; ++j)
+        same = memcmp(&Mb[(size_t)q * dv.mstride + j], &Mb[(size_t)qb * dv.mstride + j], sizeof(double4)) == 0;
+    }
+    dv.mconst = same ? 1 : 0;
+    dv.nf0 = same ? dv.nf[qf] : 0;
+    dv.nb0 = same ? dv.nb[qb] : 0;
+    for (int j = 0; j < kMTerms; ++j) {
+      dv.Mf0[j] = (same && j < dv.nf[qf]) ? Mf[(size_t)qf * dv.mstride + j + 1] : make_double4(0, 0, 0, 0);
+      dv.Mb0[j] = (same && j < dv.nb[qb]) ? Mb[(size_t)qb * dv.mstride + j + 1] : make_double4(0, 0, 0, 0);
+    }
+  }
   int rcv;
   if ((rcv = upload(sp, luf, &dv.luf)) != PB_OK) return rcv;
   if ((rcv = upload(sp, lub, &dv.lub)) != PB_OK) return rcv;

@@ -125,6 +125,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
                      const __grid_constant__ TileMap tout, const __grid_constant__ PipeGeo g, const __grid_constant__ XRing xr,
                      const double *__restrict__ v) {
   constexpr int CT = 32, H = FT<FAM>::H, HP = 4;
+  constexpr bool kRingMConst = PB_MCONST && FAM == F_R4 && !CLUSTER && kXSum <= kMTerms;
   constexpr int PL = kBlockThreads / NL;    // chunks of a line per CTA
   constexpr int ML = PL * CT;               // rows per CTA
   constexpr int SR = NL >= 32 ? 8 : 16;     // rows of every chunk per round of TMA stores
@@ -312,7 +313,8 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           for (int j = 1; j <= kXSum; ++j) {
             if (j <= nf) {
               const double2 en = en_get(lp - j);
-              const double4 M = ldg4(Mp + j);
+              // nine-point family on periodic lines: the products are kernel parameters (see sweep_yz_pipe_kernel)
+              const double4 M = (kRingMConst && a.mconst) ? a.Mf0[j - 1] : ldg4(Mp + j);
               st.x = fma(M.y, en.y, fma(M.x, en.x, st.x));
               st.y = fma(M.w, en.y, fma(M.z, en.x, st.y));
             }
@@ -520,7 +522,7 @@ sweep_yz_ring_kernel(const __grid_constant__ SweepDev a, const __grid_constant__
           for (int j = 1; j <= kXSum; ++j) {
             if (j <= nb) {
               const double2 sv = st_get(lp + j);
-              const double4 M = ldg4(Mp + j);
+              const double4 M = (kRingMConst && a.mconst) ? a.Mb0[j - 1] : ldg4(Mp + j);
               tb.x = fma(M.y, sv.y, fma(M.x, sv.x, tb.x));
               tb.y = fma(M.w, sv.y, fma(M.z, sv.x, tb.y));
             }
