@@ -1154,8 +1154,11 @@ int pb_z_exchange_ranks(pb_plan *pl, int zop, unsigned long long *mask) {
 // at ~100x the bandwidth), so the field moves in slabs and the three engines overlap:
 //   one-direction operators: slab s is copied in while slab s-1 is swept and slab s-2 copied out
 //     (slabs of z-planes for x / y sweeps, slabs of y-rows for z sweeps);
-//   filter / gfilter (x -> y -> z): x and y sweeps run per z-slab as the slabs arrive, the z sweep
-//     runs per y-slab and each finished slab leaves while the next is swept.
+//   compact filter (x -> y -> z): x and y sweeps run per z-slab as the slabs arrive, the z sweep
+//     runs per y-slab and each finished slab leaves while the next is swept (every output plane depends
+//     on every input plane, so the two copies cannot overlap);
+//   Gaussian filter: its z sweep is explicit, so a z-slab of the result leaves as soon as the next slab
+//     has passed x and y (apply_z_explicit_slab) -- copies in and out overlap as for one direction.
 // Anything else (composites, curvilinear weighting, null or split directions) takes the plain path.
 static int host_pipeline_ready(pb_plan *pl, size_t nev) {
   for (int k = 0; k < 3; ++k)

@@ -684,9 +684,26 @@ class pyrandaSim:
         return path
 
     # ---- restart (pyranda.py:475-588: the whole state, for a later run) ----
-    def writeRestart(self, path):
-        """One .npz with every variable (fields staged device -> host, numbers as they are), the
-        equation strings, time, cycle and the last time step.  Off the step loop: the only D2H of a run."""
+    def _restart_file(self, path, suffix):
+        """`path` as given on one rank; on a z-slab every rank has its own file (`<path>.proc-NNNNN`).  Without a
+        path: `restart_<cycle or suffix>/proc-NNNNN.npz`, the directory naming of pyranda.py:484-490."""
+        lo = getattr(self.PyMPI, "chunk_3d_lo", (0, 0, 0))
+        az = max(int(getattr(self.PyMPI, "az", self.nz)), 1)
+        rank, split = int(lo[2] // az), az < self.nz
+        if path is None:
+            d = "restart" + (suffix if suffix else "_" + str(self.cycle).zfill(7))
+            os.makedirs(d, exist_ok=True)
+            return os.path.join(d, "proc-%s.npz" % str(rank).zfill(5))
+        path = str(path)
+        if split:
+            path = (path[:-4] if path.endswith(".npz") else path) + ".proc-%s.npz" % str(rank).zfill(5)
+        return path if path.endswith(".npz") else path + ".npz"
+
+    def writeRestart(self, path=None, suffix=None):
+        """One .npz per rank with every variable (fields staged device -> host, numbers as they are), the
+        equation strings, time, cycle, the last time step and the rank's extents.  A bare `ss.writeRestart()`
+        works as in the reference (pyranda.py:475-490).  Off the step loop: the only D2H of a run."""
+        path = self._restart_file(path, suffix)
         fields, scalars = {}, {}
         for nm, val in self.variables.items():
             if self.B.isfield(val) and getattr(val, "ndim", 3) == 3:
@@ -695,15 +712,20 @@ class pyrandaSim:
                 scalars[nm] = float(val)
         meta = {"time": self.time, "cycle": self.cycle, "deltat": float(self.deltat), "scalars": scalars,
                 "equations": [eq.text for eq in self.equations], "nn": [self.nx, self.ny, self.nz]}
+        meta["lo"] = [int(v) for v in getattr(self.PyMPI, "chunk_3d_lo", (0, 0, 0))]
         np.savez(path, __meta__=np.array(repr(meta)), **fields)
+        return path
 
-    def readRestart(self, path):
-        """Restores a state written by writeRestart on a simulation built with the same mesh."""
+    def readRestart(self, path=None, suffix=None):
+        """Restores a state written by writeRestart on a simulation built with the same mesh and partition."""
         import ast as _ast
-        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz") as z:
+        with np.load(self._restart_file(path, suffix)) as z:
             meta = _ast.literal_eval(str(z["__meta__"]))
             if list(meta["nn"]) != [self.nx, self.ny, self.nz]:
                 raise ValueError("restart was written on a %s grid" % (meta["nn"],))
+            lo = [int(v) for v in getattr(self.PyMPI, "chunk_3d_lo", (0, 0, 0))]
+            if list(meta.get("lo", lo)) != lo:
+                raise ValueError("restart was written by the rank at %s, this rank starts at %s" % (meta["lo"], lo))
             if not self.equations:
                 self.EOM("\n".join(meta["equations"]))
             for key in z.files:

@@ -301,3 +301,15 @@ def test_restart_roundtrip(oracle_mod, tmp_path):
     assert tb == t
     for nm in ("rho", "rhou", "Et", "p", "mu"):
         assert np.array_equal(a.variables[nm], b.variables[nm]), nm
+    # the reference's call shape: no arguments -> restart_<cycle>/proc-NNNNN.npz (pyranda.py:475-490)
+    import os
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        written = a.writeRestart()
+        assert written == os.path.join("restart_%s" % str(a.cycle).zfill(7), "proc-00000.npz") and os.path.exists(written)
+        c = make_sim(oracle_mod, "tgv", tgv_mesh(16))
+        c.cycle = a.cycle
+        assert c.readRestart() == t and np.array_equal(c.variables["rho"], a.variables["rho"])
+    finally:
+        os.chdir(cwd)
