@@ -445,6 +445,30 @@ def _make_backend():
             dist.all_gather(pieces, part, group=self.eng.group)
             return torch.cat(pieces, dim=-1)
 
+        def ghost_host(self, a):
+            """pyrandaMPI.ghost with np = 1 on a z-slab (pyrandaMPI.py:514-556): the field on the host with one plane
+            of either neighbouring rank appended.  The planes at the two ends of the axis are clipped as the reference
+            does (periodic or not), so the first / last rank gain one plane and the others two: the VTK blocks of a dump
+            share a plane instead of leaving a gap.  Off the step loop (viz dumps only)."""
+            eng = self.eng
+            t = self._f(a)
+            lo_plane, hi_plane = t[:, :, 0].contiguous(), t[:, :, -1].contiguous()
+            below = above = None
+            ops = []
+            if eng.rank > 0:
+                below = torch.empty_like(lo_plane)
+                g = eng._global_rank(eng.rank - 1)
+                ops += [dist.P2POp(dist.isend, lo_plane, g, eng.group), dist.P2POp(dist.irecv, below, g, eng.group)]
+            if eng.rank < eng.world - 1:
+                above = torch.empty_like(hi_plane)
+                g = eng._global_rank(eng.rank + 1)
+                ops += [dist.P2POp(dist.isend, hi_plane, g, eng.group), dist.P2POp(dist.irecv, above, g, eng.group)]
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            parts = ([below.unsqueeze(2)] if below is not None else []) + [t] + ([above.unsqueeze(2)] if above is not None else [])
+            return torch.cat(parts, dim=2).cpu().numpy()
+
         def _op(self, name, v): return self.eng.apply(name, self._f(v))
         def ddx(self, v): return self._op("ddx", v)
         def ddy(self, v): return self._op("ddy", v)

@@ -647,8 +647,8 @@ class pyrandaSim:
         `<root>/vis<cycle>/proc-<rank>.<cycle>.vtk` plus the `pyranda.visit` index, with the
         reference's names (pyranda.py:440-470).  Binary, big-endian float32 as VTK requires; CYCLE and
         TIME field data as pyrandaIO.py:79-84.  Off the step loop: each variable is staged device ->
-        host once.  Blocks are written without the reference's one-plane ghost overlap
-        (pyrandaMPI.ghost), so the pieces of a z-slab run abut instead of sharing a plane."""
+        host once.  On a z-slab every block carries one plane of its neighbours (the reference's
+        pyrandaMPI.ghost, pyrandaIO.py:62-67,107-108), so the pieces of a dump share a plane."""
         names = list(wVars) if wVars else list(self.conserved)
         root = self.name if root is None else root
         rank = int(self.PyMPI.chunk_3d_lo[2] // max(self.PyMPI.az, 1))
@@ -656,7 +656,8 @@ class pyrandaSim:
         dump = "vis" + str(self.cycle).zfill(7)
         os.makedirs(os.path.join(root, dump), exist_ok=True)
         path = os.path.join(root, dump, "proc-%s.%s.vtk" % (str(rank).zfill(6), str(self.cycle).zfill(7)))
-        host = lambda a: np.asarray(self.B.tohost(a), dtype=np.float64)
+        ghost = getattr(self.B, "ghost_host", None)  # z-slab backends: neighbour planes appended
+        host = lambda a: np.asarray(ghost(a) if ghost is not None else self.B.tohost(a), dtype=np.float64)
         xyz = [host(self.variables[k]) for k in ("meshx", "meshy", "meshz")]
         ax, ay, az = xyz[0].shape
         with open(path, "wb") as fid:

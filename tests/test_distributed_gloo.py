@@ -172,6 +172,18 @@ g, l = ref.variables["rho"], par.variables["rho"]
 for name, axes in (("yzsum", (1, 2)), ("xzsum", (0, 2)), ("xysum", (0, 1)), ("xsum", (0,)), ("ysum", (1,)), ("zsum", (2,))):
     got = getattr(par.PyMPI, name)(l).numpy()
     assert got.shape == g.sum(axis=axes).shape and np.abs(got - g.sum(axis=axes)).max() < 1e-11 * np.abs(g.sum(axis=axes)).max(), name
+# viz dump from the z-slab: every block carries one plane of its neighbours (pyrandaMPI.ghost, pyrandaIO.py:62-67,107-108)
+root = os.path.join({tmp!r}, "viz")
+path = par.write(["rho"], root=root)
+raw = open(path, "rb").read()
+planes = 16 + (1 if world > 1 else 0) + (1 if 0 < rank < world - 1 else 0)
+assert ("DIMENSIONS 24 16 %d" % planes).encode() in raw, raw[:300]
+gh = par.B.ghost_host(par.variables["rho"])
+lo = rank * 16 - (1 if rank > 0 else 0)
+assert gh.shape == (24, 16, planes) and np.abs(gh - g[:, :, lo:lo + planes]).max() < 1e-11 * np.abs(g).max()
+dist.barrier()
+if rank == 0:
+    assert "!NBLOCKS %d" % world in open(os.path.join(root, "pyranda.visit")).read()
 print("rank", rank, "worst", worst)
 dist.destroy_process_group()
 """
@@ -184,7 +196,7 @@ def test_distributed_interpreter_gloo(tmp_path):
     subprocess.check_call(["make", "-C", EMUL, "-s"])
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
     script = tmp_path / "sim_worker.py"
-    script.write_text(SIM_WORKER.format(root=ROOT, emul=EMUL))
+    script.write_text(SIM_WORKER.format(root=ROOT, emul=EMUL, tmp=str(tmp_path)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
     r = subprocess.run(cmd, env=dict(os.environ, OMP_NUM_THREADS="2"), capture_output=True, text=True, timeout=1500)

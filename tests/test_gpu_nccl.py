@@ -44,6 +44,12 @@ for n in ((32, 48, 32 * world), (64, 64, 64 * world)):
         hin = np.asfortranarray(f[:, :, sl]); hout = np.empty_like(hin, order="F")
         eng.apply_host_into("ddz", hin, hout)
         assert rel_linf(hout, o.ddz(f)[:, :, sl]) < 1e-12
+        # neighbour planes for viz dumps (pyrandaMPI.ghost): P2P over NCCL on the device fields
+        from pyranda_b200.distributed import _make_backend
+        gh = _make_backend()(eng).ghost_host(loc)
+        g_lo = rank * az - (1 if rank > 0 else 0)
+        g_n = az + (1 if rank > 0 else 0) + (1 if rank < world - 1 else 0)
+        assert gh.shape == (n[0], n[1], g_n) and np.array_equal(gh, f[:, :, g_lo:g_lo + g_n]), (rank, gh.shape)
         for name, ref in (("ddx", o.ddx), ("ddy", o.ddy)):  # local directions: the rank's own slab pipeline
             eng.apply_host_into(name, hin, hout)
             assert rel_linf(hout, ref(f)[:, :, sl]) < 1e-12, (name, n, periodic, rank)

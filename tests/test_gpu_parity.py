@@ -39,6 +39,23 @@ def test_unary_operators_host_arrays(n, periodic, oracle_mod):
 
 
 @pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("n", [(64, 64, 256), (48, 40, 512), (32, 64, 128)])
+def test_host_pipeline_streamed_gaussian_filter(n, periodic, oracle_mod):
+    """Host arrays whose z extent splits into slabs of whole 32-row chunks: the Gaussian filter's z sweep runs slab by
+    slab behind x / y (api.cu host_apply_pipelined, apply_z_explicit_slab); the other operators take the slab pipeline."""
+    from pyranda_b200 import _lib
+    L = _lib.load()
+    o, p, f = _pair(n, periodic, oracle_mod)
+    c0 = L.pb_launch_count()
+    assert rel_linf(p.gfilter(f), o.gfilter(f)) < TOL, (n, periodic)
+    slabs = (L.pb_launch_count() - c0) // 3
+    assert slabs in (4, 8, 16) and n[2] % (32 * slabs) == 0, "the streamed path did not run"
+    for name in ("sfilter", "ddz", "ddy"):
+        assert rel_linf(getattr(p, name)(f), getattr(o, name)(f)) < TOL, (name, n, periodic)
+    assert rel_linf(p.gfilterdir(f, 3), o.gfilterdir(f, 3)) < TOL
+
+
+@pytest.mark.parametrize("periodic", [True, False])
 def test_div_grad(periodic, oracle_mod):
     o, p, f = _pair((48, 64, 32), periodic, oracle_mod)
     g = np.asfortranarray(np.cos(f) + 0.3 * f)
