@@ -117,7 +117,7 @@ for ss in (ref, par):
 sl = slice(rank * 16, (rank + 1) * 16)
 assert abs(float(par.variables["dt"]) - float(ref.variables["dt"])) < 1e-13 * float(ref.variables["dt"])
 t1 = t2 = 0.0
-for _ in range(3):
+for _ in range(2):
     dt = float(ref.variables["dt"]) * 0.5
     t1 = ref.rk4(t1, dt)
     t2 = par.rk4(t2, dt)
@@ -136,7 +136,7 @@ for ss in (ref, par):
     ss.EOM(eom)
     ss.setIC(BC_IC)
 t1 = t2 = 0.0
-for _ in range(3):
+for _ in range(2):
     t1 = ref.rk4(t1, 1.0e-3)
     t2 = par.rk4(t2, 1.0e-3)
 a, b = par.variables["phi"].numpy(), ref.variables["phi"][:, :, sl]
@@ -208,7 +208,8 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, pytest.param(4, marks=pytest.mark.skipif(
+    not os.environ.get("PB_SLOW_TESTS"), reason="four emulated ranks take minutes on the CPU box (PB_SLOW_TESTS=1 to include)"))])
 def test_zslab_gloo(world, tmp_path):
     subprocess.check_call(["make", "-C", EMUL, "-s"])
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
